@@ -1,0 +1,109 @@
+"""CPU checks of the tap-GEMM host plan (weight packing, tap tables, phases) through the numpy emulator."""
+import torch
+import torch.nn.functional as F
+
+from oracle.tapgemm_emu import emulate
+from wdno_b200.tapgemm import TapGemm
+
+
+def cl(x):  # [B,C,D,H,W] -> fp16 channels-last [B,D,H,W,C]
+    return x.permute(0, 2, 3, 4, 1).contiguous().to(torch.float16)
+
+
+def uncl(y):  # [B,D,H,W,C] -> [B,C,D,H,W] fp32
+    return y.permute(0, 4, 1, 2, 3).float()
+
+
+def test_conv3x3x3_concat_bias_stats():
+    torch.manual_seed(0)
+    B, D, H, W = 1, 5, 6, 7
+    x0 = torch.randn(B, 16, D, H, W).half().float()
+    x1 = torch.randn(B, 16, D, H, W).half().float()
+    w = (torch.randn(24, 32, 3, 3, 3) * 0.1).half().float()
+    bias = torch.randn(24)
+    plan = TapGemm(w, bias, src_channels=(16, 16), device="cpu", n_tile=32)
+    out, stats = emulate(plan, cl(x0), cl(x1), want_stats=True, groups=3)
+    ref = F.conv3d(torch.cat([x0, x1], 1), w, bias, padding=1)
+    assert torch.allclose(uncl(out), ref, atol=1e-4, rtol=1e-4)
+    rs = ref.reshape(B, 3, -1)
+    assert torch.allclose(stats[:, :, 0].float(), rs.sum(-1), atol=1e-2)
+    assert torch.allclose(stats[:, :, 1].float(), (rs ** 2).sum(-1), rtol=1e-4)
+
+
+def test_conv7_init_padded_channels():
+    torch.manual_seed(1)
+    B, D, H, W = 1, 4, 5, 6
+    x = torch.zeros(B, 48, D, H, W)
+    x[:, :42] = torch.randn(B, 42, D, H, W).half().float()
+    w = (torch.randn(16, 42, 7, 7, 7) * 0.05).half().float()
+    plan = TapGemm(w, None, src_channels=(48,), device="cpu", kc=16)
+    out, _ = emulate(plan, cl(x))
+    ref = F.conv3d(x[:, :42], w, None, padding=3)
+    assert torch.allclose(uncl(out), ref, atol=2e-4, rtol=1e-4)
+
+
+def test_linear_1x1_resid_and_fp32_out():
+    torch.manual_seed(2)
+    B, D, H, W = 2, 3, 4, 5
+    x = torch.randn(B, 32, D, H, W).half().float()
+    w = (torch.randn(42, 32) * 0.1).half().float()
+    b = torch.randn(42)
+    plan = TapGemm(w, b, device="cpu")
+    out, _ = emulate(plan, cl(x), out_fp32_bfchw=True)
+    ref = F.conv3d(x, w[:, :, None, None, None], b)
+    assert torch.allclose(out.permute(0, 2, 1, 3, 4), ref, atol=1e-4, rtol=1e-4)
+    w2 = (torch.randn(32, 32) * 0.1).half().float()
+    plan2 = TapGemm(w2, None, device="cpu")
+    out2, _ = emulate(plan2, cl(x), resid=cl(x))
+    ref2 = F.conv3d(x, w2[:, :, None, None, None]) + x
+    assert torch.allclose(uncl(out2), ref2, atol=1e-4, rtol=1e-4)
+
+
+def test_down144_and_up144():
+    torch.manual_seed(3)
+    B, D, H, W = 1, 2, 8, 8
+    x = torch.randn(B, 16, D, H, W).half().float()
+    wd = (torch.randn(16, 16, 1, 4, 4) * 0.1).half().float()
+    bd = torch.randn(16)
+    plan = TapGemm(wd, bd, kind="down144", device="cpu", n_tile=16)
+    out, _ = emulate(plan, cl(x))
+    ref = F.conv3d(x, wd, bd, stride=(1, 2, 2), padding=(0, 1, 1))
+    assert torch.allclose(uncl(out), ref, atol=1e-4, rtol=1e-4)
+    wu = (torch.randn(16, 16, 1, 4, 4) * 0.1).half().float()
+    bu = torch.randn(16)
+    plan_u = TapGemm(wu, bu, kind="up144", device="cpu", n_tile=16)
+    out_u, _ = emulate(plan_u, cl(x))
+    ref_u = F.conv_transpose3d(x, wu, bu, stride=(1, 2, 2), padding=(0, 1, 1))
+    assert torch.allclose(uncl(out_u), ref_u, atol=1e-4, rtol=1e-4)
+
+
+def test_burgers_unshuffle_and_up2conv_2d():
+    torch.manual_seed(4)
+    B, H, W = 2, 8, 8
+    x = torch.randn(B, 16, H, W).half().float()
+    w = (torch.randn(32, 64, 1, 1) * 0.1).half().float()
+    b = torch.randn(32)
+    plan = TapGemm(w, b, kind="unshuffle", device="cpu", n_tile=32)
+    out, _ = emulate(plan, cl(x[:, :, None]))
+    xu = x.reshape(B, 16, 4, 2, 4, 2).permute(0, 1, 3, 5, 2, 4).reshape(B, 64, 4, 4)
+    ref = F.conv2d(xu, w, b)
+    assert torch.allclose(uncl(out)[:, :, 0], ref, atol=1e-4, rtol=1e-4)
+    w3 = (torch.randn(16, 16, 3, 3) * 0.1).half().float()
+    plan3 = TapGemm(w3, None, up2=True, device="cpu", n_tile=16)
+    out3, _ = emulate(plan3, cl(x[:, :, None]))
+    ref3 = F.conv2d(F.interpolate(x, scale_factor=2, mode="nearest"), w3, padding=1)
+    assert torch.allclose(uncl(out3)[:, :, 0], ref3, atol=1e-4, rtol=1e-4)
+
+
+def test_fused_affine_silu_on_load():
+    torch.manual_seed(5)
+    B, D, H, W = 2, 2, 4, 4
+    x = torch.randn(B, 16, D, H, W).half().float()
+    a = torch.randn(B, 16)
+    c = torch.randn(B, 16)
+    w = (torch.randn(16, 16, 3, 3, 3) * 0.1).half().float()
+    plan = TapGemm(w, None, device="cpu", n_tile=16)
+    out, _ = emulate(plan, cl(x), coef0=(a, c))
+    act = F.silu(x * a[:, :, None, None, None] + c[:, :, None, None, None]).half().float()
+    ref = F.conv3d(act, w, padding=1)
+    assert torch.allclose(uncl(out), ref, atol=2e-3, rtol=1e-3)

@@ -1,0 +1,354 @@
+"""Host-side plans for the tcgen05 tap-GEMM kernel (csrc/tapgemm.cu, C ABI: wdno_tapgemm).
+
+A `TapGemm` owns the fp16 weight tiles of one dense layer, re-packed from the reference's
+`state_dict` tensor into the kernel's tile order, plus the tap / K-set / N-chunk tables.  Calling it
+enqueues one kernel on the current torch CUDA stream.  Layer kinds (reference call sites):
+
+  conv       nn.Conv3d / nn.Conv2d / nn.Linear with "same" padding or 1x1
+             (video_diffusion_pytorch_conv3d.py:192,216,238-239,291-292,393,471; unet.py:133,162,190-192,233-234,317,369)
+  down144    nn.Conv3d(dim, dim, (1,4,4), (1,2,2), (0,1,1))            (conv3d.py:162-163)
+  up144      nn.ConvTranspose3d(dim, dim, (1,4,4), (1,2,2), (0,1,1))   (conv3d.py:159-160)
+  unshuffle  Rearrange('b c (h p1) (w p2) -> b (c p1 p2) h w') + Conv2d(4c, c', 1)   (unet.py:41-45)
+  conv+up2   nn.Upsample(scale_factor=2, 'nearest') + Conv2d(3, padding=1)           (unet.py:35-39): kind='conv', up2=True
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import KSet, NChunk, Tap, TapGemmParams
+
+_SMEM_LIMIT = 227 * 1024
+_BAR_BYTES = 512
+
+
+def _device_bytes(ctypes_array, device):
+    raw = bytes(ctypes_array)
+    t = torch.frombuffer(bytearray(raw), dtype=torch.uint8).clone()
+    return t.to(device)
+
+
+def _round_up(a, b):
+    return (a + b - 1) // b * b
+
+
+class TapGemm:
+    def __init__(self, weight, bias=None, *, kind="conv", src_channels=None, up2=False,
+                 n_tile=None, device=None, kc=None):
+        """weight: fp32 tensor in the reference layout of the layer kind (see module docstring)."""
+        w = weight.detach().to(torch.float32).cpu()
+        self.kind = kind
+        self.up2 = bool(up2)
+        self.device = torch.device(device if device is not None else "cuda")
+        if w.dim() == 2:  # nn.Linear [out, in]
+            w = w[:, :, None, None, None]
+        elif w.dim() == 4:  # nn.Conv2d [out, in, kh, kw]
+            w = w[:, :, None]
+        assert w.dim() == 5
+        if kind == "up144":
+            self.cin, self.cout = w.shape[0], w.shape[1]
+        elif kind == "unshuffle":
+            self.cout, self.cin = w.shape[0], w.shape[1] // 4
+        else:
+            self.cout, self.cin = w.shape[0], w.shape[1]
+        self.src_channels = tuple(src_channels) if src_channels is not None else (self.cin,)
+        assert sum(self.src_channels) >= self.cin
+        self.w = w
+        self.bias = None
+        if kind == "conv":
+            self.KD, self.KH, self.KW = w.shape[2:]
+        elif kind in ("down144", "up144"):
+            assert tuple(w.shape[2:]) == (1, 4, 4)
+            self.KD, self.KH, self.KW = 1, 3, 3
+        elif kind == "unshuffle":
+            assert tuple(w.shape[2:]) == (1, 1, 1)
+            self.KD, self.KH, self.KW = 1, 1, 1
+        else:
+            raise ValueError(kind)
+        assert self.KD % 2 == 1 and self.KH % 2 == 1 and self.KW % 2 == 1
+        if n_tile is None:
+            n_tile = 64 if self.cout >= 64 else _round_up(self.cout, 16)
+        self.N = int(n_tile)
+        self.cout_pad = _round_up(self.cout, self.N)
+        self.kc_override = kc
+        if bias is not None:
+            b = torch.zeros(self.cout_pad if kind != "up144" else self.cout_pad, dtype=torch.float32)
+            b[: self.cout] = bias.detach().float().cpu()
+            self.bias = b.to(self.device)
+        self._packed = {}   # KC -> dict(wpacked, chunks, sets, taps, n_chunks, tables kept alive)
+        self._launch = {}   # geometry key -> (params, keepalive)
+
+    # ------------------------------------------------------------------ packing
+    def _virtual_cin(self):
+        """total channels of the (concatenated) sources"""
+        return sum(self.src_channels)
+
+    def _pack(self, KC):
+        if KC in self._packed:
+            return self._packed[KC]
+        N, kind = self.N, self.kind
+        w = self.w
+        ctot = self._virtual_cin()
+        assert ctot % KC == 0, f"source channels {ctot} not a multiple of KC={KC}"
+        for c in self.src_channels[:-1]:
+            assert c % KC == 0, "concat boundary must be KC-aligned"
+        nck = ctot // KC            # channel chunks
+        ncn = self.cout_pad // N    # cout chunks
+
+        def src_of(chunk):
+            ch = chunk * KC
+            for si, c in enumerate(self.src_channels):
+                if ch < c:
+                    return si, ch
+                ch -= c
+            raise AssertionError
+
+        taps, sets, chunks, tiles = [], [], [], []
+
+        def tile_from(wslice):
+            """wslice: [N, KC] fp32 (rows = output channels) -> [KC/8, N, 8]"""
+            return wslice.reshape(N, KC // 8, 8).permute(1, 0, 2).contiguous()
+
+        def padded_w(wfull):
+            """[cout, cin, ...] -> zero-padded to [cout_pad, ctot, ...]"""
+            out = torch.zeros((self.cout_pad, ctot) + tuple(wfull.shape[2:]), dtype=torch.float32)
+            out[: wfull.shape[0], : wfull.shape[1]] = wfull
+            return out
+
+        if kind == "conv":
+            wp = padded_w(w)
+            KD, KH, KW = self.KD, self.KH, self.KW
+            tap_list = [(kz, ky, kx) for kz in range(KD) for ky in range(KH) for kx in range(KW)]
+            # one shared tap table (shift filled at launch: depends on Wp) -> store (kz,ky,kx)
+            for (kz, ky, kx) in tap_list:
+                taps.append((kz, ky, kx))
+            for ck in range(nck):
+                s, ch = src_of(ck)
+                sets.append(dict(src=s, ch_off=ch, ph_y=0, ph_x=0, tap_begin=0, tap_count=len(tap_list)))
+            # vectorised packing: [NC, N, nck, KC/8, 8, T] -> [NC, nck, T, KC/8, N, 8]
+            T = len(tap_list)
+            wr = wp.reshape(ncn, N, nck, KC // 8, 8, T).permute(0, 2, 5, 3, 1, 4).contiguous()
+            wpacked = wr.reshape(-1)
+            per_chunk_tiles = nck * T
+            for cn in range(ncn):
+                chunks.append(dict(out_ch_off=cn * N, n_valid=min(N, self.cout - cn * N), ph_y=0, ph_x=0,
+                                   set_begin=0, set_count=nck, n_tiles=per_chunk_tiles,
+                                   w_tile_off=cn * per_chunk_tiles))
+        elif kind == "down144":
+            wp = padded_w(w)  # [cout_pad, ctot, 1, 4, 4]
+            # phase a (row parity of the source pixel), taps (tky -> ky):  a=0: {1:1, 2:3} ; a=1: {0:0, 1:2}
+            ph = {0: [(1, 1), (2, 3)], 1: [(0, 0), (1, 2)]}
+            tile_list = []
+            for a in (0, 1):
+                for b in (0, 1):
+                    tb = len(taps)
+                    pairs = [(tky, ky, tkx, kx) for (tky, ky) in ph[a] for (tkx, kx) in ph[b]]
+                    for (tky, ky, tkx, kx) in pairs:
+                        taps.append((0, tky, tkx))
+                    for ck in range(nck):
+                        s, ch = src_of(ck)
+                        sets.append(dict(src=s, ch_off=ch, ph_y=a, ph_x=b, tap_begin=tb, tap_count=4,
+                                         _pairs=pairs, _ck=ck))
+            per_chunk = 0
+            for cn in range(ncn):
+                for st in sets:
+                    for (tky, ky, tkx, kx) in st["_pairs"]:
+                        ck = st["_ck"]
+                        tile_list.append(tile_from(wp[cn * N:(cn + 1) * N, ck * KC:(ck + 1) * KC, 0, ky, kx]))
+                if cn == 0:
+                    per_chunk = len(tile_list)
+                chunks.append(dict(out_ch_off=cn * N, n_valid=min(N, self.cout - cn * N), ph_y=0, ph_x=0,
+                                   set_begin=0, set_count=len(sets), n_tiles=per_chunk, w_tile_off=cn * per_chunk))
+            wpacked = torch.stack(tile_list).reshape(-1)
+        elif kind == "up144":
+            # w: [cin, cout, 1, 4, 4]; out phase A: taps (tky -> ky): A=0: {1:1, 0:3} ; A=1: {2:0, 1:2}
+            wt = torch.zeros((self.cout_pad, ctot, 4, 4), dtype=torch.float32)
+            wt[: self.cout, : self.cin] = w[:, :, 0].permute(1, 0, 2, 3)
+            ph = {0: [(0, 3), (1, 1)], 1: [(1, 2), (2, 0)]}
+            tile_list = []
+            for A in (0, 1):
+                for Bp in (0, 1):
+                    pairs = [(tky, ky, tkx, kx) for (tky, ky) in ph[A] for (tkx, kx) in ph[Bp]]
+                    tb = len(taps)
+                    for (tky, ky, tkx, kx) in pairs:
+                        taps.append((0, tky, tkx))
+                    sb = len(sets)
+                    for ck in range(nck):
+                        s, ch = src_of(ck)
+                        sets.append(dict(src=s, ch_off=ch, ph_y=0, ph_x=0, tap_begin=tb, tap_count=4))
+                    for cn in range(ncn):
+                        t0 = len(tile_list)
+                        for ck in range(nck):
+                            for (tky, ky, tkx, kx) in pairs:
+                                tile_list.append(tile_from(wt[cn * N:(cn + 1) * N, ck * KC:(ck + 1) * KC, ky, kx]))
+                        chunks.append(dict(out_ch_off=cn * N, n_valid=min(N, self.cout - cn * N), ph_y=A, ph_x=Bp,
+                                           set_begin=sb, set_count=nck, n_tiles=len(tile_list) - t0, w_tile_off=t0))
+            wpacked = torch.stack(tile_list).reshape(-1)
+        elif kind == "unshuffle":
+            # w: [cout, 4*cin, 1,1,1] with input channel index c*4 + p1*2 + p2
+            w4 = w[:, :, 0, 0, 0].reshape(self.cout, self.cin, 2, 2)
+            wp = torch.zeros((self.cout_pad, ctot, 2, 2), dtype=torch.float32)
+            wp[: self.cout, : self.cin] = w4
+            taps.append((0, 0, 0))
+            tile_list = []
+            for a in (0, 1):
+                for b in (0, 1):
+                    for ck in range(nck):
+                        s, ch = src_of(ck)
+                        sets.append(dict(src=s, ch_off=ch, ph_y=a, ph_x=b, tap_begin=0, tap_count=1, _ck=ck))
+            per_chunk = len(sets)
+            for cn in range(ncn):
+                for st in sets:
+                    ck = st["_ck"]
+                    tile_list.append(tile_from(wp[cn * N:(cn + 1) * N, ck * KC:(ck + 1) * KC, st["ph_y"], st["ph_x"]]))
+                chunks.append(dict(out_ch_off=cn * N, n_valid=min(N, self.cout - cn * N), ph_y=0, ph_x=0,
+                                   set_begin=0, set_count=len(sets), n_tiles=per_chunk, w_tile_off=cn * per_chunk))
+            wpacked = torch.stack(tile_list).reshape(-1)
+        else:
+            raise ValueError(kind)
+
+        sets_c = (KSet * len(sets))(*[KSet(s["src"], s["ch_off"], s["ph_y"], s["ph_x"], s["tap_begin"], s["tap_count"])
+                                       for s in sets])
+        chunks_c = (NChunk * len(chunks))(*[NChunk(c["out_ch_off"], c["n_valid"], c["ph_y"], c["ph_x"], c["set_begin"],
+                                                   c["set_count"], c["n_tiles"], 0, c["w_tile_off"]) for c in chunks])
+        pk = dict(
+            wpacked=wpacked.to(torch.float16).to(self.device),
+            sets=_device_bytes(sets_c, self.device),
+            chunks=_device_bytes(chunks_c, self.device),
+            taps_kyx=taps, n_chunks=len(chunks),
+            taps_dev={},  # Wp -> device tap table
+        )
+        self._packed[KC] = pk
+        return pk
+
+    # ------------------------------------------------------------------ geometry / smem plan
+    def _plan(self, B, D, H, W):
+        """(B, D, H, W) = tap grid (== output grid before depth-to-space)."""
+        key = (B, D, H, W)
+        if key in self._launch:
+            return self._launch[key]
+        KD, KH, KW = self.KD, self.KH, self.KW
+        Wp = W + KW - 1
+        maxshift = (KH - 1) * Wp + (KW - 1)
+        ZT = min(4, D)
+        PT = max(1, 4 // ZT)
+        if self.N > 64:
+            while ZT * PT * 128 > 512:
+                PT = max(1, PT - 1)
+        P = ZT + KD - 1
+        S = 128 * PT + maxshift
+        ctot = self._virtual_cin()
+        btile = lambda kc: self.N * kc * 2
+        cands = [self.kc_override] if self.kc_override else [64, 32, 16]
+        best = None  # (score, KC, S_pad, NSLOT, NBST)
+        for KC in cands:
+            if ctot % KC or any(c % KC for c in self.src_channels[:-1]):
+                continue
+            CH = KC // 8
+            rem = {8: 1, 4: 2, 2: 4}[CH]
+            S_pad = S + ((rem - S) % 8)
+            slot = CH * S_pad * 16
+            found = None
+            for nslot in range(min(12, P + 2), P - 1, -1):
+                for nbst in (6, 4, 3, 2):
+                    if _BAR_BYTES + _round_up(nslot * slot, 128) + nbst * btile(KC) <= _SMEM_LIMIT:
+                        found = (nslot, nbst)
+                        break
+                if found:
+                    break
+            if not found:
+                continue
+            # prefer a full ring (P+2 slots) with >=4 weight stages; among equals the larger KC
+            score = (min(found[0] - P, 2), min(found[1], 4), KC)
+            if best is None or score > best[0]:
+                best = (score, KC, S_pad, found[0], found[1])
+        if best is None:
+            raise ValueError(f"tapgemm: no shared-memory plan for grid {(B, D, H, W)} taps {(KD, KH, KW)}")
+        choice = best[1:]
+        KC, S_pad, NSLOT, NBST = choice
+        pk = self._pack(KC)
+        if Wp not in pk["taps_dev"]:
+            tl = pk["taps_kyx"]
+            taps_c = (Tap * len(tl))(*[Tap(kz, ky * Wp + kx) for (kz, ky, kx) in tl])
+            pk["taps_dev"][Wp] = _device_bytes(taps_c, self.device)
+        taps_dev = pk["taps_dev"][Wp]
+        positions = H * Wp
+        ptiles = (positions + 128 * PT - 1) // (128 * PT)
+        zgroups = (D + ZT - 1) // ZT
+        n_units = B * zgroups * ptiles * pk["n_chunks"]
+        sms = (torch.cuda.get_device_properties(self.device).multi_processor_count
+               if self.device.type == "cuda" else 148)
+        p = TapGemmParams()
+        p.src_mode = {"conv": 2 if self.up2 else 0, "down144": 1, "unshuffle": 1, "up144": 0}[self.kind]
+        p.B, p.D, p.H, p.W = B, D, H, W
+        p.KD, p.pz, p.py, p.px = KD, KD // 2, KH // 2, KW // 2
+        p.Wp, p.maxshift = Wp, maxshift
+        p.ZT, p.PT, p.KC, p.N, p.n_chunks = ZT, PT, KC, self.N, pk["n_chunks"]
+        p.chunks = pk["chunks"].data_ptr()
+        p.sets = pk["sets"].data_ptr()
+        p.taps = taps_dev.data_ptr()
+        p.wpacked = pk["wpacked"].data_ptr()
+        p.NSLOT, p.NBST, p.S_pad = NSLOT, NBST, S_pad
+        p.grid = max(1, min(n_units, sms))
+        self._launch[key] = p
+        return p
+
+    # ------------------------------------------------------------------ launch
+    def __call__(self, src0, src1=None, *, coef0=None, coef1=None, out=None, resid=None, stats=None,
+                 groups=8, out_fp32_bfchw=False):
+        """src*: fp16 [B, D, Hs, Ws, C] contiguous.  coef*: (a, c) fp32 [B, C] pairs -> silu(a*x+c) fused on load.
+        Returns the output tensor (fp16 [B, D, Ho, Wo, Cout], or fp32 [B, D, Cout, H, W] if out_fp32_bfchw)."""
+        L = _lib.lib()
+        assert src0.dtype == torch.float16 and src0.is_contiguous() and src0.dim() == 5
+        B, D, Hs, Ws, C0 = src0.shape
+        if self.kind in ("down144", "unshuffle"):
+            H, W = Hs // 2, Ws // 2
+        elif self.kind == "conv" and self.up2:
+            H, W = Hs * 2, Ws * 2
+        else:
+            H, W = Hs, Ws
+        p0 = self._plan(B, D, H, W)
+        p = TapGemmParams.from_buffer_copy(p0)
+        assert C0 == self.src_channels[0], (C0, self.src_channels)
+        p.src[0] = src0.data_ptr()
+        p.src_c[0] = C0
+        if src1 is not None:
+            assert src1.dtype == torch.float16 and src1.is_contiguous() and src1.shape[:4] == src0.shape[:4]
+            assert src1.shape[4] == self.src_channels[1]
+            p.src[1] = src1.data_ptr()
+            p.src_c[1] = src1.shape[4]
+        else:
+            assert len(self.src_channels) == 1
+        for i, cf in enumerate((coef0, coef1)):
+            if cf is not None:
+                a, c = cf
+                assert a.dtype == torch.float32 and c.dtype == torch.float32 and a.is_contiguous() and c.is_contiguous()
+                assert a.shape == (B, self.src_channels[i]) and c.shape == a.shape
+                p.coef_a[i] = a.data_ptr()
+                p.coef_c[i] = c.data_ptr()
+        Ho, Wo = (2 * H, 2 * W) if self.kind == "up144" else (H, W)
+        if out_fp32_bfchw:
+            assert self.kind == "conv"
+            if out is None:
+                out = torch.empty((B, D, self.cout, H, W), dtype=torch.float32, device=src0.device)
+            assert out.dtype == torch.float32 and out.is_contiguous() and out.shape == (B, D, self.cout, H, W)
+            p.out_mode, p.out_c = 2, self.cout
+        else:
+            if out is None:
+                out = torch.empty((B, D, Ho, Wo, self.cout), dtype=torch.float16, device=src0.device)
+            assert out.dtype == torch.float16 and out.is_contiguous() and out.shape == (B, D, Ho, Wo, self.cout)
+            assert self.cout % 8 == 0
+            p.out_mode, p.out_c = (1 if self.kind == "up144" else 0), self.cout
+        p.out = out.data_ptr()
+        if self.bias is not None:
+            p.bias = self.bias.data_ptr()
+        if resid is not None:
+            assert resid.dtype == torch.float16 and resid.is_contiguous() and resid.shape == out.shape
+            p.resid = resid.data_ptr()
+        if stats is not None:
+            assert stats.dtype == torch.float64 and stats.is_contiguous() and stats.numel() == B * groups * 2
+            assert self.cout % groups == 0 and (self.cout // groups) % 8 == 0
+            p.stats = stats.data_ptr()
+            p.G, p.cpg = groups, self.cout // groups
+        _lib.check(L.wdno_tapgemm(C.byref(p), _lib.current_stream_ptr()), "tapgemm")
+        return out
