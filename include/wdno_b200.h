@@ -103,6 +103,71 @@ typedef struct {
 int64_t wdno_tapgemm_smem_bytes(const wdno_tapgemm_params* p);
 int wdno_tapgemm(const wdno_tapgemm_params* p, void* stream);
 
+
+/* ------------------------------------------------------------------------------------------
+ * U-Net helper kernels (HBM-bound).  reference: conv3d.py:139-151,165-174,189-230,405-410 ;
+ * burgers/ddpm_burgers/unet.py:55-65,82-108,129-181
+ * ------------------------------------------------------------------------------------------ */
+/* x fp32 [B,F,C,H,W] -> out fp16 channels-last [B,F,H,W,Cp] (channels C..Cp-1 zero) */
+int wdno_pack_bfchw_f16(const float* x, void* out, int B, int F, int C, int H, int W, int Cp, void* stream);
+/* GroupNorm statistics (double [B][G][2] = sum,sumsq over `count` elements) -> per-(b,channel) affine
+ * a,c with  GN(y)*(scale+1)+shift == a*y + c ; scale_shift = [B][ss_stride] rows (scale[C] | shift[C]) or NULL */
+int wdno_gn_finalize(const double* stats, const float* gamma, const float* beta, const float* scale_shift,
+                     int ss_stride, float* a, float* c, int B, int C, int G, double count, float eps, void* stream);
+/* out = silu(a*y + c) (+ resid) ; y,resid,out fp16 [B, vox_per_sample, C] */
+int wdno_gn_silu_add(const void* y, const float* a, const float* c, const void* resid, void* out, int B, int C,
+                     int64_t vox_per_sample, void* stream);
+/* channel LayerNorm without bias: (x-mean)*rsqrt(var+eps)*gamma over C for each of nvox voxels (fp16 in/out) */
+int wdno_chan_layernorm(const void* x, const float* gamma, void* out, int64_t nvox, int C, float eps, void* stream);
+/* emb = W2*gelu(W1*sinusoid(time)+b1)+b2 ; also writes silu(emb).  time fp32 [B] */
+int wdno_time_mlp(const float* time, const float* w1, const float* b1, const float* w2, const float* b2, float* emb,
+                  float* emb_silu, int B, int dim, int tdim, float theta, void* stream);
+/* out[b][j] = bias[j] + sum_k in[b][k]*w[j][k] (fp32; all ResnetBlock.mlp Linear layers concatenated along j) */
+int wdno_small_linear(const float* in, const float* w, const float* bias, float* out, int B, int K, int J, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * attention cores (4 heads x 32).  reference: conv3d.py:232-258,277-353 ; unet.py:183-259
+ * token index of (sequence s, token t) = (s / inner)*outerT + (s % inner)*innerT + t*tokT ;
+ * qkv fp16 [tokens][384] (q|k|v, each 4x32), out fp16 [tokens][128]
+ * ------------------------------------------------------------------------------------------ */
+int wdno_softmax_attn(const void* qkv, void* out, const float* bias /*[4][n][n] or NULL*/,
+                      const float* rot_cos /*[n][16] or NULL*/, const float* rot_sin, int64_t n_seq, int n_tok,
+                      int64_t inner, int64_t outerT, int64_t innerT, int64_t tokT, float scale, void* stream);
+/* qkv fp16 [n_img][n_pos][384] -> out fp16 [n_img][n_pos][128] */
+int wdno_linear_attn(const void* qkv, void* out, int64_t n_img, int n_pos, float scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * diffusion step algebra on the fp32 state [B,F,C,H,W] (Burgers: F=1).
+ * reference: smoke/ddpm/diffusion_2d.py:689-699,723-754,769-785,851-933,970-976,988-1050 ;
+ *            burgers/ddpm_burgers/diffusion_1d.py:172-182,205-258,276-307,310-460,520-645
+ * A condition program is the reference's sequence of in-place slice assignments; later ops override earlier.
+ * ------------------------------------------------------------------------------------------ */
+#define WDNO_MAX_COND_OPS 8
+typedef struct {
+  int32_t f0, f1, c0, c1, y0, y1, x0, x1; /* destination box (half-open) */
+  const float* src;                       /* NULL = fill with zero */
+  int64_t sb, sf, sc, sy, sx;             /* source strides (elements) */
+  int32_t of, oc, oy, ox;                 /* source index = dst index - offset */
+} wdno_cond_op;
+
+/* coef_dev (device float[8]): DDIM {sqrt_recip_ac[t], sqrt_recipm1_ac[t], sqrt(ac[t_next]), c, sigma, last_flag, gscale, 0}
+ *                             DDPM {sqrt_recip_ac[t], sqrt_recipm1_ac[t], post_mean_coef1, post_mean_coef2, exp(.5*logvar)|0, 0, gscale, 0}
+ * cond_mode: 0 never, 1 all but the last step (smoke), 2 always (Burgers).  noise / guidance may be NULL. */
+int wdno_ddim_step(float* x, const float* eps, const float* noise, const float* guidance, const float* coef_dev,
+                   const wdno_cond_op* ops_host, int n_ops, int B, int F, int C, int H, int W, int cond_mode, void* stream);
+int wdno_ddpm_step(float* x, const float* eps, const float* noise, const float* guidance, const float* coef_dev,
+                   const wdno_cond_op* ops_host, int n_ops, int B, int F, int C, int H, int W, int cond_mode, void* stream);
+int wdno_apply_conditions(float* x, const wdno_cond_op* ops_host, int n_ops, int B, int F, int C, int H, int W, void* stream);
+int wdno_predict_x0(const float* x, const float* eps, const float* coef_dev, float* x0, int64_t total, int clip, void* stream);
+int wdno_q_sample(const float* x0, const float* noise, const float* sqrt_ac, const float* sqrt_1mac, const int64_t* t,
+                  float* out, int B, int64_t per_sample, void* stream);
+/* acc[b] += sum (pred-target)^2 * w[c]   (w NULL, length 1 or length C) */
+int wdno_mse_weighted(const float* pred, const float* target, const float* w, int w_len, int B, int F, int C, int H, int W,
+                      double* acc, void* stream);
+/* CUDA-graph support: copy step *step_dev's scalars (time_table[s], coef_table[s][8]) into time_out[B] / coef_out[8], ++step */
+int wdno_step_begin(int* step_dev, const float* time_table, const float* coef_table, float* time_out, float* coef_out,
+                    int B, int n_steps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

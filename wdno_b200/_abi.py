@@ -5,9 +5,35 @@ P = C.c_void_p
 I = C.c_int32
 L64 = C.c_int64
 F = C.c_float
+D = C.c_double
+
+
+class CondOp(C.Structure):
+    _fields_ = [("f0", I), ("f1", I), ("c0", I), ("c1", I), ("y0", I), ("y1", I), ("x0", I), ("x1", I),
+                ("src", P), ("sb", L64), ("sf", L64), ("sc", L64), ("sy", L64), ("sx", L64),
+                ("of", I), ("oc", I), ("oy", I), ("ox", I)]
+
+
+MAX_COND_OPS = 8
 
 # name -> argtypes ; restype is always int
-SIGNATURES = {}
+SIGNATURES = {
+    "wdno_pack_bfchw_f16": [P, P, I, I, I, I, I, I, P],
+    "wdno_gn_finalize": [P, P, P, P, I, P, P, I, I, I, D, F, P],
+    "wdno_gn_silu_add": [P, P, P, P, P, I, I, L64, P],
+    "wdno_chan_layernorm": [P, P, P, L64, I, F, P],
+    "wdno_time_mlp": [P, P, P, P, P, P, P, I, I, I, F, P],
+    "wdno_small_linear": [P, P, P, P, I, I, I, P],
+    "wdno_softmax_attn": [P, P, P, P, P, L64, I, L64, L64, L64, L64, F, P],
+    "wdno_linear_attn": [P, P, L64, I, F, P],
+    "wdno_ddim_step": [P, P, P, P, P, P, I, I, I, I, I, I, I, P],
+    "wdno_ddpm_step": [P, P, P, P, P, P, I, I, I, I, I, I, I, P],
+    "wdno_apply_conditions": [P, P, I, I, I, I, I, I, P],
+    "wdno_predict_x0": [P, P, P, P, L64, I, P],
+    "wdno_q_sample": [P, P, P, P, P, P, I, L64, P],
+    "wdno_mse_weighted": [P, P, P, I, I, I, I, I, I, P, P],
+    "wdno_step_begin": [P, P, P, P, P, I, I, P],
+}
 
 
 def bind(lib):

@@ -1,0 +1,292 @@
+// HBM-bound helper kernels of the U-Net forward: layout packing, GroupNorm finalisation, fused
+// GroupNorm-apply+SiLU+residual, channel LayerNorm, time-embedding MLPs.
+// Reference arithmetic: smoke/video_diffusion_pytorch/video_diffusion_pytorch_conv3d.py:139-151 (SinusoidalPosEmb),
+// 165-174 (LayerNorm), 189-230 (Block / ResnetBlock), 405-410 (time_mlp); burgers/ddpm_burgers/unet.py:55-65,82-108,129-181.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <algorithm>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace wdno {
+
+// ------------------------------------------------------------------ pack [B,F,C,H,W] fp32 -> [B,F,H,W,Cp] fp16
+// One block per (b, f, y): smem transpose so that both the fp32 reads (along x) and fp16 writes (along c) coalesce.
+__global__ void pack_bfchw_kernel(const float* __restrict__ x, __half* __restrict__ out, int C, int H, int W, int Cp) {
+  extern __shared__ float tile[];  // [C][W+1]
+  const int bfy = blockIdx.x;
+  const int y = bfy % H;
+  const int bf = bfy / H;
+  const float* src = x + (static_cast<size_t>(bf) * C * H + y) * W;
+  for (int i = threadIdx.x; i < C * W; i += blockDim.x) {
+    const int c = i / W, xx = i - c * W;
+    tile[c * (W + 1) + xx] = src[static_cast<size_t>(c) * H * W + xx];
+  }
+  __syncthreads();
+  __half* dst = out + (static_cast<size_t>(bf) * H + y) * W * Cp;
+  for (int i = threadIdx.x; i < W * Cp; i += blockDim.x) {
+    const int xx = i / Cp, c = i - xx * Cp;
+    dst[i] = __float2half_rn(c < C ? tile[c * (W + 1) + xx] : 0.f);
+  }
+}
+
+// ------------------------------------------------------------------ GroupNorm finalise
+// stats[b][g] = (sum, sumsq) over cpg channels x nvox voxels  ->  per-(b,channel) affine a,c such that
+// GN(y)*(scale+1)+shift == a*y + c.   ss = [B][2C] (scale | shift) or NULL.
+__global__ void gn_finalize_kernel(const double* __restrict__ stats, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, const float* __restrict__ ss, int ss_stride,
+                                   float* __restrict__ a, float* __restrict__ c, int B, int C, int G, double count,
+                                   float eps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * C) return;
+  const int b = i / C, ch = i - b * C;
+  const int g = ch / (C / G);
+  const double s = stats[(static_cast<size_t>(b) * G + g) * 2];
+  const double q = stats[(static_cast<size_t>(b) * G + g) * 2 + 1];
+  const double mean = s / count;
+  double var = q / count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  float ga = gamma[ch] * rstd;
+  float be = beta[ch] - static_cast<float>(mean) * ga;
+  if (ss != nullptr) {
+    const float sc = ss[static_cast<size_t>(b) * ss_stride + ch] + 1.0f;
+    const float sh = ss[static_cast<size_t>(b) * ss_stride + C + ch];
+    ga *= sc;
+    be = be * sc + sh;
+  }
+  a[i] = ga;
+  c[i] = be;
+}
+
+// ------------------------------------------------------------------ out = silu(a*y + c) (+ r)
+__global__ void gn_silu_add_kernel(const __half* __restrict__ y, const float* __restrict__ a, const float* __restrict__ c,
+                                   const __half* __restrict__ r, __half* __restrict__ out, int C, size_t vox_per_sample,
+                                   size_t total_chunks) {
+  // one thread per 8 channels (16 B)
+  const int cpv = C >> 3;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total_chunks;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t vox = i / cpv;
+    const int ch = static_cast<int>(i - vox * cpv) * 8;
+    const int b = static_cast<int>(vox / vox_per_sample);
+    const uint4 yv = __ldg(reinterpret_cast<const uint4*>(y) + i);
+    const float4 a0 = __ldg(reinterpret_cast<const float4*>(a + static_cast<size_t>(b) * C + ch));
+    const float4 a1 = __ldg(reinterpret_cast<const float4*>(a + static_cast<size_t>(b) * C + ch + 4));
+    const float4 c0 = __ldg(reinterpret_cast<const float4*>(c + static_cast<size_t>(b) * C + ch));
+    const float4 c1 = __ldg(reinterpret_cast<const float4*>(c + static_cast<size_t>(b) * C + ch + 4));
+    const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    const float cv[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+    const __half2* yh = reinterpret_cast<const __half2*>(&yv);
+    float f[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 t = __half22float2(yh[k]);
+      f[2 * k] = t.x;
+      f[2 * k + 1] = t.y;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float v = fmaf(av[k], f[k], cv[k]);
+      f[k] = v / (1.0f + __expf(-v));
+    }
+    if (r != nullptr) {
+      const uint4 rv = __ldg(reinterpret_cast<const uint4*>(r) + i);
+      const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 t = __half22float2(rh[k]);
+        f[2 * k] += t.x;
+        f[2 * k + 1] += t.y;
+      }
+    }
+    uint4 ov;
+    __half2* oh = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) oh[k] = __floats2half2_rn(f[2 * k], f[2 * k + 1]);
+    reinterpret_cast<uint4*>(out)[i] = ov;
+  }
+}
+
+// ------------------------------------------------------------------ channel LayerNorm (no bias): (x-mean)*rsqrt(var+eps)*gamma
+// LPV lanes cooperate on one voxel; each lane owns C/(8*LPV) 16-byte chunks.
+template <int LPV, int CPL>
+__global__ void chan_layernorm_kernel(const __half* __restrict__ x, const float* __restrict__ gamma,
+                                      __half* __restrict__ out, size_t nvox, float eps) {
+  constexpr int C = LPV * CPL * 8;
+  const size_t gt = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  const size_t vox = gt / LPV;
+  const int l = static_cast<int>(gt % LPV);
+  const bool active = vox < nvox;
+  float f[CPL * 8];
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < CPL; ++k) {
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (active) v = __ldg(reinterpret_cast<const uint4*>(x + vox * C) + k * LPV + l);
+    const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 t = __half22float2(h[j]);
+      f[k * 8 + 2 * j] = t.x;
+      f[k * 8 + 2 * j + 1] = t.y;
+      sum += t.x + t.y;
+    }
+  }
+#pragma unroll
+  for (int sh = LPV / 2; sh > 0; sh >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, sh);
+  const float mean = sum * (1.0f / C);
+  float sq = 0.f;
+#pragma unroll
+  for (int k = 0; k < CPL * 8; ++k) {
+    const float d = f[k] - mean;
+    sq += d * d;
+  }
+#pragma unroll
+  for (int sh = LPV / 2; sh > 0; sh >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, sh);
+  const float rstd = rsqrtf(sq * (1.0f / C) + eps);
+  if (!active) return;
+#pragma unroll
+  for (int k = 0; k < CPL; ++k) {
+    const int ch = (k * LPV + l) * 8;
+    uint4 ov;
+    __half2* oh = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float g0 = __ldg(gamma + ch + 2 * j), g1 = __ldg(gamma + ch + 2 * j + 1);
+      oh[j] = __floats2half2_rn((f[k * 8 + 2 * j] - mean) * rstd * g0, (f[k * 8 + 2 * j + 1] - mean) * rstd * g1);
+    }
+    reinterpret_cast<uint4*>(out + vox * C)[k * LPV + l] = ov;
+  }
+}
+
+// ------------------------------------------------------------------ time embedding
+// t_emb = W2 * gelu(W1 * sinusoid(time) + b1) + b2 ; one block per sample.  Writes emb and silu(emb).
+__global__ void time_mlp_kernel(const float* __restrict__ time, const float* __restrict__ w1, const float* __restrict__ b1,
+                                const float* __restrict__ w2, const float* __restrict__ b2, float* __restrict__ emb,
+                                float* __restrict__ emb_silu, int dim, int tdim, float theta) {
+  extern __shared__ float sh[];  // [dim] sinusoid, [tdim] hidden
+  float* s0 = sh;
+  float* s1 = sh + dim;
+  const int b = blockIdx.x;
+  const float t = time[b];
+  const int half = dim / 2;
+  const float step = logf(theta) / static_cast<float>(half - 1);
+  for (int i = threadIdx.x; i < dim; i += blockDim.x) {
+    const int k = (i < half) ? i : i - half;
+    const float e = t * expf(-step * static_cast<float>(k));
+    s0[i] = (i < half) ? sinf(e) : cosf(e);
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < tdim; j += blockDim.x) {
+    float acc = b1[j];
+    const float* wr = w1 + static_cast<size_t>(j) * dim;
+    for (int k = 0; k < dim; ++k) acc = fmaf(wr[k], s0[k], acc);
+    s1[j] = 0.5f * acc * (1.0f + erff(acc * 0.70710678118654752f));  // exact GELU
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < tdim; j += blockDim.x) {
+    float acc = b2[j];
+    const float* wr = w2 + static_cast<size_t>(j) * tdim;
+    for (int k = 0; k < tdim; ++k) acc = fmaf(wr[k], s1[k], acc);
+    emb[static_cast<size_t>(b) * tdim + j] = acc;
+    emb_silu[static_cast<size_t>(b) * tdim + j] = acc / (1.0f + expf(-acc));
+  }
+}
+
+// out[b][j] = bias[j] + sum_k in[b][k] * w[j][k]   (all ResnetBlock.mlp Linear layers concatenated along j)
+__global__ void small_linear_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
+                                    float* __restrict__ out, int B, int K, int J) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= J) return;
+  const float* wr = w + static_cast<size_t>(warp) * K;
+  for (int b = 0; b < B; ++b) {
+    float acc = 0.f;
+    for (int k = lane; k < K; k += 32) acc = fmaf(wr[k], in[static_cast<size_t>(b) * K + k], acc);
+#pragma unroll
+    for (int sh = 16; sh > 0; sh >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sh);
+    if (lane == 0) out[static_cast<size_t>(b) * J + warp] = acc + bias[warp];
+  }
+}
+
+}  // namespace wdno
+
+using namespace wdno;
+
+extern "C" int wdno_pack_bfchw_f16(const float* x, void* out, int B, int F, int C, int H, int W, int Cp, void* stream) {
+  if (!x || !out || B < 1 || F < 1 || C < 1 || H < 1 || W < 1 || Cp < C || (Cp % 8))
+    return set_error(WDNO_E_INVALID, "pack_bfchw_f16: bad arguments");
+  const size_t smem = static_cast<size_t>(C) * (W + 1) * sizeof(float);
+  if (smem > 48 * 1024) return set_error(WDNO_E_INVALID, "pack_bfchw_f16: C*(W+1) too large");
+  pack_bfchw_kernel<<<B * F * H, 256, smem, static_cast<cudaStream_t>(stream)>>>(x, static_cast<__half*>(out), C, H, W, Cp);
+  return check_launch("pack_bfchw_f16");
+}
+
+extern "C" int wdno_gn_finalize(const double* stats, const float* gamma, const float* beta, const float* scale_shift,
+                                int ss_stride, float* a, float* c, int B, int C, int G, double count, float eps,
+                                void* stream) {
+  if (!stats || !gamma || !beta || !a || !c || B < 1 || C < 1 || G < 1 || (C % G) || count <= 0)
+    return set_error(WDNO_E_INVALID, "gn_finalize: bad arguments");
+  const int n = B * C;
+  gn_finalize_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(stats, gamma, beta, scale_shift,
+                                                                                    ss_stride, a, c, B, C, G, count, eps);
+  return check_launch("gn_finalize");
+}
+
+extern "C" int wdno_gn_silu_add(const void* y, const float* a, const float* c, const void* resid, void* out, int B, int C,
+                                int64_t vox_per_sample, void* stream) {
+  if (!y || !a || !c || !out || B < 1 || C < 8 || (C % 8) || vox_per_sample < 1)
+    return set_error(WDNO_E_INVALID, "gn_silu_add: bad arguments");
+  const size_t chunks = static_cast<size_t>(B) * vox_per_sample * (C / 8);
+  const int grid = static_cast<int>(std::min<size_t>((chunks + 255) / 256, static_cast<size_t>(num_sms()) * 16));
+  gn_silu_add_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(y), a, c, static_cast<const __half*>(resid), static_cast<__half*>(out), C,
+      static_cast<size_t>(vox_per_sample), chunks);
+  return check_launch("gn_silu_add");
+}
+
+extern "C" int wdno_chan_layernorm(const void* x, const float* gamma, void* out, int64_t nvox, int C, float eps,
+                                   void* stream) {
+  if (!x || !gamma || !out || nvox < 1) return set_error(WDNO_E_INVALID, "chan_layernorm: bad arguments");
+  const __half* xi = static_cast<const __half*>(x);
+  __half* o = static_cast<__half*>(out);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int threads = 256;
+#define WDNO_LN(LPV, CPL)                                                                              \
+  {                                                                                                    \
+    const size_t total = static_cast<size_t>(nvox) * LPV;                                              \
+    chan_layernorm_kernel<LPV, CPL><<<static_cast<unsigned>((total + threads - 1) / threads), threads, 0, st>>>( \
+        xi, gamma, o, static_cast<size_t>(nvox), eps);                                                 \
+  }
+  switch (C) {
+    case 64: WDNO_LN(8, 1); break;
+    case 128: WDNO_LN(16, 1); break;
+    case 256: WDNO_LN(32, 1); break;
+    case 512: WDNO_LN(32, 2); break;
+    case 1024: WDNO_LN(32, 4); break;
+    default: return set_error(WDNO_E_INVALID, "chan_layernorm: C must be 64/128/256/512/1024");
+  }
+#undef WDNO_LN
+  return check_launch("chan_layernorm");
+}
+
+extern "C" int wdno_time_mlp(const float* time, const float* w1, const float* b1, const float* w2, const float* b2,
+                             float* emb, float* emb_silu, int B, int dim, int tdim, float theta, void* stream) {
+  if (!time || !w1 || !b1 || !w2 || !b2 || !emb || !emb_silu || B < 1 || dim < 4 || (dim % 2) || tdim < 1)
+    return set_error(WDNO_E_INVALID, "time_mlp: bad arguments");
+  const size_t smem = static_cast<size_t>(dim + tdim) * sizeof(float);
+  time_mlp_kernel<<<B, 256, smem, static_cast<cudaStream_t>(stream)>>>(time, w1, b1, w2, b2, emb, emb_silu, dim, tdim, theta);
+  return check_launch("time_mlp");
+}
+
+extern "C" int wdno_small_linear(const float* in, const float* w, const float* bias, float* out, int B, int K, int J,
+                                 void* stream) {
+  if (!in || !w || !bias || !out || B < 1 || K < 1 || J < 1) return set_error(WDNO_E_INVALID, "small_linear: bad arguments");
+  const int threads = 256;
+  const int grid = (J * 32 + threads - 1) / threads;
+  small_linear_kernel<<<grid, threads, 0, static_cast<cudaStream_t>(stream)>>>(in, w, bias, out, B, K, J);
+  return check_launch("small_linear");
+}

@@ -1,0 +1,407 @@
+"""Unet3D_with_Conv3D on the B200 engine.
+
+Same constructor, attribute names and `state_dict()` keys as the reference
+(smoke/video_diffusion_pytorch/video_diffusion_pytorch_conv3d.py:357-472), so reference checkpoints load
+unchanged; `forward(x, time)` (conv3d.py:487-574) runs entirely in libwdno_b200.so kernels:
+
+  pack -> tap-GEMM(7^3) -> [LN -> tap-GEMM(qkv) -> softmax-attn(rotary,bias) -> tap-GEMM(out)+res] ->
+  ResnetBlocks as  tap-GEMM(3^3, GN partial sums in the epilogue) -> gn_finalize -> tap-GEMM(3^3, GN-apply+SiLU
+  fused into the operand load) -> gn_finalize -> silu+residual ; linear attention ; (1,4,4) down / transposed up
+  as tap lists on the same kernel ; final 1x1 writes fp32 eps in the reference [B,F,C,H,W] layout.
+
+The torch sub-modules below only HOLD parameters (they are never called).
+"""
+import math
+
+import torch
+from torch import nn
+
+from . import ops
+from .tapgemm import TapGemm
+
+
+def _holder():
+    return nn.Module()
+
+
+class _RotaryHolder(nn.Module):
+    """parameter layout of rotary_embedding_torch.RotaryEmbedding(dim): `freqs` [dim/2], not trainable"""
+
+    def __init__(self, dim, theta=10000):
+        super().__init__()
+        self.freqs = nn.Parameter(1.0 / (theta ** (torch.arange(0, dim, 2)[: dim // 2].float() / dim)), requires_grad=False)
+
+
+def _block(dim, dim_out, groups):
+    m = _holder()
+    m.proj = nn.Conv3d(dim, dim_out, (3, 3, 3), padding=(1, 1, 1))
+    m.norm = nn.GroupNorm(groups, dim_out)
+    m.act = nn.SiLU()
+    return m
+
+
+def _resnet(dim, dim_out, time_emb_dim, groups):
+    m = _holder()
+    m.mlp = nn.Sequential(nn.SiLU(), nn.Linear(time_emb_dim, dim_out * 2)) if time_emb_dim is not None else None
+    m.block1 = _block(dim, dim_out, groups)
+    m.block2 = _block(dim_out, dim_out, groups)
+    m.res_conv = nn.Conv3d(dim, dim_out, 1) if dim != dim_out else nn.Identity()
+    return m
+
+
+def _layernorm(dim):
+    m = _holder()
+    m.gamma = nn.Parameter(torch.ones(1, dim, 1, 1, 1))
+    return m
+
+
+def _prenorm_residual(dim, fn):
+    """Residual(PreNorm(dim, fn)) -> keys  fn.norm.gamma , fn.fn.<...>"""
+    pre = _holder()
+    pre.fn = fn
+    pre.norm = _layernorm(dim)
+    res = _holder()
+    res.fn = pre
+    return res
+
+
+def _attention(dim, heads, dim_head, rotary):
+    m = _holder()
+    if rotary is not None:
+        m.rotary_emb = rotary
+    hidden = heads * dim_head
+    m.to_qkv = nn.Linear(dim, hidden * 3, bias=False)
+    m.to_out = nn.Linear(hidden, dim, bias=False)
+    return m
+
+
+def _einops_wrap(fn):
+    m = _holder()
+    m.fn = fn
+    return m
+
+
+def _spatial_linear_attention(dim, heads, dim_head=32):
+    m = _holder()
+    hidden = heads * dim_head
+    m.to_qkv = nn.Conv2d(dim, hidden * 3, 1, bias=False)
+    m.to_out = nn.Conv2d(hidden, dim, 1)
+    return m
+
+
+class Unet3D_with_Conv3D(nn.Module):
+    def __init__(self, dim, cond_dim=None, out_dim=None, dim_mults=(1, 2, 4, 8), channels=6, attn_heads=4,
+                 attn_dim_head=32, use_bert_text_cond=False, init_dim=None, init_kernel_size=7,
+                 use_sparse_linear_attn=True, block_type="resnet", resnet_groups=8):
+        super().__init__()
+        if cond_dim is not None or use_bert_text_cond:
+            raise NotImplementedError("text/cond embedding is dead code in WDNO (never constructed); not built")
+        if attn_heads != 4 or attn_dim_head != 32:
+            raise NotImplementedError("the attention kernels are built for the reference defaults heads=4, dim_head=32")
+        if not use_sparse_linear_attn:
+            raise NotImplementedError("use_sparse_linear_attn=False is never used by WDNO")
+        assert init_kernel_size % 2 == 1
+        self.channels = channels
+        self.self_condition = False
+        self.has_cond = False
+        self.null_cond_emb = None
+        self.dim = dim
+        self.groups = resnet_groups
+        self.heads, self.dim_head = attn_heads, attn_dim_head
+
+        rotary = _RotaryHolder(min(32, attn_dim_head))
+        temporal = lambda d: _einops_wrap(_attention(d, attn_heads, attn_dim_head, rotary))
+        tb = _holder()
+        tb.relative_attention_bias = nn.Embedding(32, attn_heads)
+        self.time_rel_pos_bias = tb
+        self.rel_pos_max_distance = 32
+
+        init_dim = init_dim if init_dim is not None else dim
+        k = init_kernel_size
+        self.init_conv = nn.Conv3d(channels, init_dim, (k, k, k), padding=(k // 2,) * 3)
+        self.init_temporal_attn = _prenorm_residual(init_dim, temporal(init_dim))
+        dims = [init_dim, *[dim * m for m in dim_mults]]
+        in_out = list(zip(dims[:-1], dims[1:]))
+        time_dim = dim * 4
+        self.time_mlp = nn.Sequential(nn.Identity(), nn.Linear(dim, time_dim), nn.GELU(), nn.Linear(time_dim, time_dim))
+
+        self.downs = nn.ModuleList([])
+        self.ups = nn.ModuleList([])
+        nres = len(in_out)
+        for ind, (di, do) in enumerate(in_out):
+            last = ind >= nres - 1
+            self.downs.append(nn.ModuleList([
+                _resnet(di, do, time_dim, resnet_groups),
+                _resnet(do, do, time_dim, resnet_groups),
+                _prenorm_residual(do, _spatial_linear_attention(do, attn_heads)),
+                _prenorm_residual(do, temporal(do)),
+                nn.Conv3d(do, do, (1, 4, 4), (1, 2, 2), (0, 1, 1)) if not last else nn.Identity(),
+            ]))
+        mid = dims[-1]
+        self.mid_block1 = _resnet(mid, mid, time_dim, resnet_groups)
+        self.mid_spatial_attn = _prenorm_residual(mid, _einops_wrap(_attention(mid, attn_heads, 32, None)))
+        self.mid_temporal_attn = _prenorm_residual(mid, temporal(mid))
+        self.mid_block2 = _resnet(mid, mid, time_dim, resnet_groups)
+        for ind, (di, do) in enumerate(reversed(in_out)):
+            last = ind >= nres - 1
+            self.ups.append(nn.ModuleList([
+                _resnet(do * 2, di, time_dim, resnet_groups),
+                _resnet(di, di, time_dim, resnet_groups),
+                _prenorm_residual(di, _spatial_linear_attention(di, attn_heads)),
+                _prenorm_residual(di, temporal(di)),
+                nn.ConvTranspose3d(di, di, (1, 4, 4), (1, 2, 2), (0, 1, 1)) if not last else nn.Identity(),
+            ]))
+        out_dim = out_dim if out_dim is not None else channels
+        self.out_dim = out_dim
+        self.final_conv = nn.Sequential(_resnet(dim * 2, dim, None, resnet_groups), nn.Conv3d(dim, out_dim, 1))
+        self._engine = None
+
+    # ---- engine lifetime: plans are rebuilt whenever parameters may have changed
+    def invalidate(self):
+        self._engine = None
+
+    def _apply(self, fn, *a, **k):
+        self._engine = None
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, *a, **k):
+        self._engine = None
+        return super().load_state_dict(*a, **k)
+
+    def engine(self):
+        if self._engine is None:
+            self._engine = Unet3DEngine(self)
+        return self._engine
+
+    def forward_with_cond_scale(self, *args, cond_scale=2.0, **kwargs):
+        # has_cond is always False in WDNO -> identical to forward (conv3d.py:474-485)
+        return self.forward(*args, **kwargs)
+
+    def forward(self, x, time, cond=None, null_cond_prob=0.0, focus_present_mask=None, prob_focus_present=0.0):
+        """x [B, F, C, H, W] fp32 CUDA, time [B] -> eps [B, F, C, H, W] fp32.  (focus_present_mask: the reference draws
+        an all-False mask for prob_focus_present=0, which leaves attention unmasked; other values are not supported.)"""
+        if focus_present_mask is not None or prob_focus_present != 0.0:
+            raise NotImplementedError("focus_present_mask is never used by WDNO")
+        if not x.is_cuda:
+            raise RuntimeError("wdno_b200 runs on a CUDA (sm_100a) device only; there is no CPU path")
+        return self.engine().forward(x, time)
+
+
+class _ResnetPlan:
+    pass
+
+
+class Unet3DEngine:
+    """Plans + packed weights for one parameter snapshot of a Unet3D_with_Conv3D."""
+
+    def __init__(self, m):
+        dev = next(m.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("wdno_b200: move the model to a CUDA device before calling it")
+        self.dev = dev
+        self.m = m
+        self.groups = m.groups
+        self.scale = m.dim_head ** -0.5
+        f32 = lambda t: t.detach().to(dev, torch.float32).contiguous()
+        self.cin = m.channels
+        self.cin_pad = (m.channels + 15) // 16 * 16
+        self.init_conv = TapGemm(m.init_conv.weight, m.init_conv.bias, src_channels=(self.cin_pad,), device=dev)
+        self.tw1, self.tb1 = f32(m.time_mlp[1].weight), f32(m.time_mlp[1].bias)
+        self.tw2, self.tb2 = f32(m.time_mlp[3].weight), f32(m.time_mlp[3].bias)
+        self.dim = m.dim
+        # all ResnetBlock.mlp Linear layers concatenated -> one launch per forward
+        self._mlp_w, self._mlp_b, self._mlp_off = [], [], 0
+        self.stats_slots = 0
+
+        self.init_tattn = self._attn_plan(m.init_temporal_attn, temporal=True)
+        self.downs = []
+        for b1, b2, sattn, tattn, down in m.downs:
+            self.downs.append(dict(
+                b1=self._resnet_plan(b1, None), b2=self._resnet_plan(b2, None),
+                sattn=self._lin_attn_plan(sattn), tattn=self._attn_plan(tattn, temporal=True),
+                down=None if isinstance(down, nn.Identity) else TapGemm(down.weight, down.bias, kind="down144", device=dev)))
+        self.mid1 = self._resnet_plan(m.mid_block1, None)
+        self.mid_sattn = self._attn_plan(m.mid_spatial_attn, temporal=False)
+        self.mid_tattn = self._attn_plan(m.mid_temporal_attn, temporal=True)
+        self.mid2 = self._resnet_plan(m.mid_block2, None)
+        self.ups = []
+        for b1, b2, sattn, tattn, up in m.ups:
+            cin = b1.block1.proj.weight.shape[1]
+            self.ups.append(dict(
+                b1=self._resnet_plan(b1, (cin // 2, cin // 2)), b2=self._resnet_plan(b2, None),
+                sattn=self._lin_attn_plan(sattn), tattn=self._attn_plan(tattn, temporal=True),
+                up=None if isinstance(up, nn.Identity) else TapGemm(up.weight, up.bias, kind="up144", device=dev)))
+        fc = m.final_conv[0]
+        cin = fc.block1.proj.weight.shape[1]
+        self.final_block = self._resnet_plan(fc, (cin // 2, cin // 2))
+        self.final_conv = TapGemm(m.final_conv[1].weight, m.final_conv[1].bias, device=dev)
+        self.mlp_w = torch.cat(self._mlp_w, 0).contiguous() if self._mlp_w else None
+        self.mlp_b = torch.cat(self._mlp_b, 0).contiguous() if self._mlp_b else None
+        self.freqs = m.init_temporal_attn.fn.fn.fn.rotary_emb.freqs.detach().float().cpu()
+        self.rel_emb = m.time_rel_pos_bias.relative_attention_bias.weight.detach().float().cpu()
+        self.max_distance = m.rel_pos_max_distance
+        self._tables = {}
+        self.launches = 0
+
+    # ------------------------------------------------------------ plan builders
+    def _f32(self, t):
+        return t.detach().to(self.dev, torch.float32).contiguous()
+
+    def _resnet_plan(self, blk, src_channels):
+        p = _ResnetPlan()
+        w1 = blk.block1.proj.weight
+        p.cout = w1.shape[0]
+        p.conv1 = TapGemm(w1, blk.block1.proj.bias, src_channels=src_channels, device=self.dev)
+        p.conv2 = TapGemm(blk.block2.proj.weight, blk.block2.proj.bias, device=self.dev)
+        p.g1, p.b1 = self._f32(blk.block1.norm.weight), self._f32(blk.block1.norm.bias)
+        p.g2, p.b2 = self._f32(blk.block2.norm.weight), self._f32(blk.block2.norm.bias)
+        p.res = None
+        if not isinstance(blk.res_conv, nn.Identity):
+            p.res = TapGemm(blk.res_conv.weight, blk.res_conv.bias, src_channels=src_channels, device=self.dev)
+        p.ss_off = None
+        if blk.mlp is not None:
+            p.ss_off = self._mlp_off
+            self._mlp_w.append(self._f32(blk.mlp[1].weight))
+            self._mlp_b.append(self._f32(blk.mlp[1].bias))
+            self._mlp_off += 2 * p.cout
+        p.stat1, p.stat2 = self.stats_slots, self.stats_slots + 1
+        self.stats_slots += 2
+        return p
+
+    def _attn_plan(self, res, temporal):
+        attn = res.fn.fn.fn
+        return dict(gamma=self._f32(res.fn.norm.gamma.reshape(-1)),
+                    qkv=TapGemm(attn.to_qkv.weight, None, device=self.dev),
+                    out=TapGemm(attn.to_out.weight, None, device=self.dev), temporal=temporal)
+
+    def _lin_attn_plan(self, res):
+        attn = res.fn.fn
+        return dict(gamma=self._f32(res.fn.norm.gamma.reshape(-1)),
+                    qkv=TapGemm(attn.to_qkv.weight, None, device=self.dev),
+                    out=TapGemm(attn.to_out.weight, attn.to_out.bias, device=self.dev))
+
+    def _rel_tables(self, n):
+        """T5 relative-position bias [heads][n][n] (conv3d.py:74-112) and rotary cos/sin [n][16]."""
+        if n in self._tables:
+            return self._tables[n]
+        pos = torch.arange(n)
+        rel = pos[None, :] - pos[:, None]
+        nb = self.rel_emb.shape[0]
+        k = -rel
+        half = nb // 2
+        ret = (k < 0).long() * half
+        k = k.abs()
+        max_exact = half // 2
+        small = k < max_exact
+        large = max_exact + (torch.log(k.float() / max_exact) / math.log(self.max_distance / max_exact)
+                             * (half - max_exact)).long()
+        large = torch.min(large, torch.full_like(large, half - 1))
+        bucket = ret + torch.where(small, k, large)
+        bias = self.rel_emb[bucket].permute(2, 0, 1).contiguous().to(self.dev)
+        ang = torch.arange(n, dtype=torch.float32)[:, None] * self.freqs[None, :]
+        tabs = (bias, (ang.cos().contiguous().to(self.dev), ang.sin().contiguous().to(self.dev)))
+        self._tables[n] = tabs
+        return tabs
+
+    # ------------------------------------------------------------ blocks
+    def _resnet(self, p, src0, src1, ss, stats):
+        B, D, H, W, _ = src0.shape
+        count = float(D * H * W * (p.cout // self.groups))
+        st1, st2 = stats[p.stat1], stats[p.stat2]
+        y1 = p.conv1(src0, src1, stats=st1, groups=self.groups)
+        a1, c1 = ops.gn_finalize(st1, p.g1, p.b1, ss if p.ss_off is not None else None, p.ss_off or 0,
+                                 0 if ss is None else ss.shape[1], B, p.cout, self.groups, count)
+        y2 = p.conv2(y1, coef0=(a1, c1), stats=st2, groups=self.groups)
+        a2, c2 = ops.gn_finalize(st2, p.g2, p.b2, None, 0, 0, B, p.cout, self.groups, count)
+        self.launches += 4
+        if p.res is None:
+            self.launches += 1
+            return ops.gn_silu_add(y2, a2, c2, resid=src0)
+        h = ops.gn_silu_add(y2, a2, c2, resid=None)
+        self.launches += 2
+        return p.res(src0, src1, resid=h)
+
+    def _temporal_attn(self, ap, x):
+        B, D, H, W, C = x.shape
+        bias, rot = self._rel_tables(D)
+        xn = ops.chan_layernorm(x, ap["gamma"])
+        qkv = ap["qkv"](xn)
+        o = ops.softmax_attn(qkv, B * H * W, D, H * W, D * H * W, 1, H * W, self.scale, bias=bias, rot=rot)
+        self.launches += 4
+        return ap["out"](o, resid=x)
+
+    def _mid_spatial_attn(self, ap, x):
+        B, D, H, W, C = x.shape
+        xn = ops.chan_layernorm(x, ap["gamma"])
+        qkv = ap["qkv"](xn)
+        o = ops.softmax_attn(qkv, B * D, H * W, 1, H * W, 0, 1, self.scale)
+        self.launches += 4
+        return ap["out"](o, resid=x)
+
+    def _linear_attn(self, ap, x):
+        B, D, H, W, C = x.shape
+        xn = ops.chan_layernorm(x, ap["gamma"])
+        qkv = ap["qkv"](xn)
+        o = ops.linear_attn(qkv, B * D, H * W, self.scale)
+        self.launches += 4
+        return ap["out"](o, resid=x)
+
+    # ------------------------------------------------------------ forward
+    def forward(self, x, time, taps=None):
+        """taps: optional dict receiving named fp16 channels-last intermediates (per-layer parity tests)."""
+        rec = (lambda k, v: taps.__setitem__(k, v)) if taps is not None else (lambda k, v: None)
+        self.launches = 0
+        x = x.contiguous().float()
+        B = x.shape[0]
+        tf = time.to(device=x.device, dtype=torch.float32).contiguous()
+        emb, emb_silu = ops.time_mlp(tf, self.tw1, self.tb1, self.tw2, self.tb2)
+        ss = ops.small_linear(emb_silu, self.mlp_w, self.mlp_b)
+        stats = torch.zeros((self.stats_slots, B, self.groups, 2), dtype=torch.float64, device=x.device)
+        xin = ops.pack_bfchw_f16(x, self.cin_pad)
+        h = self.init_conv(xin)
+        self.launches += 5
+        rec("init_conv", h)
+        h = self._temporal_attn(self.init_tattn, h)
+        rec("init_temporal_attn", h)
+        r = h
+        skips = []
+        for i, lv in enumerate(self.downs):
+            h = self._resnet(lv["b1"], h, None, ss, stats)
+            rec(f"downs.{i}.0", h)
+            h = self._resnet(lv["b2"], h, None, ss, stats)
+            rec(f"downs.{i}.1", h)
+            h = self._linear_attn(lv["sattn"], h)
+            rec(f"downs.{i}.2", h)
+            h = self._temporal_attn(lv["tattn"], h)
+            rec(f"downs.{i}.3", h)
+            skips.append(h)
+            if lv["down"] is not None:
+                h = lv["down"](h)
+                self.launches += 1
+                rec(f"downs.{i}.4", h)
+        h = self._resnet(self.mid1, h, None, ss, stats)
+        rec("mid_block1", h)
+        h = self._mid_spatial_attn(self.mid_sattn, h)
+        rec("mid_spatial_attn", h)
+        h = self._temporal_attn(self.mid_tattn, h)
+        rec("mid_temporal_attn", h)
+        h = self._resnet(self.mid2, h, None, ss, stats)
+        rec("mid_block2", h)
+        for i, lv in enumerate(self.ups):
+            h = self._resnet(lv["b1"], h, skips.pop(), ss, stats)
+            rec(f"ups.{i}.0", h)
+            h = self._resnet(lv["b2"], h, None, ss, stats)
+            rec(f"ups.{i}.1", h)
+            h = self._linear_attn(lv["sattn"], h)
+            rec(f"ups.{i}.2", h)
+            h = self._temporal_attn(lv["tattn"], h)
+            rec(f"ups.{i}.3", h)
+            if lv["up"] is not None:
+                h = lv["up"](h)
+                self.launches += 1
+                rec(f"ups.{i}.4", h)
+        h = self._resnet(self.final_block, h, r, None, stats)
+        rec("final_conv.0", h)
+        out = self.final_conv(h, out_fp32_bfchw=True)
+        self.launches += 1
+        return out
