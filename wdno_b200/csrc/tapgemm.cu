@@ -202,84 +202,111 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const wdno_tapgemm
     }
   } else if (warp == kBWarp) {
     // ============================================================ B (weight tile) producer
-    if (lane == 0) {
-      uint32_t bt = 0;
-      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-        const UnitCoord uc = decode_unit(u, p.n_chunks, ptiles, zgroups);
-        const wdno_nchunk ci = p.chunks[uc.nc];
-        const uint8_t* wsrc = static_cast<const uint8_t*>(p.wpacked) + static_cast<size_t>(ci.w_tile_off) * btile_bytes;
-        for (int i = 0; i < ci.n_tiles; ++i, ++bt) {
-          const int stage = bt % p.NBST;
-          const uint32_t par = (bt / p.NBST) & 1u;
-          ptx::mbar_wait(&bars->b_empty[stage], par ^ 1u);
-          ptx::mbar_arrive_expect_tx(&bars->b_full[stage], btile_bytes);
-          ptx::bulk_g2s(b_base + static_cast<size_t>(stage) * btile_bytes, wsrc + static_cast<size_t>(i) * btile_bytes,
-                        btile_bytes, &bars->b_full[stage]);
+    // warp-uniform control flow, one elected lane issues the bulk copies
+    uint32_t bst = 0, bph = 0;
+    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+      const int nc = u % p.n_chunks;
+      const wdno_nchunk ci = p.chunks[nc];
+      const uint8_t* wsrc = static_cast<const uint8_t*>(p.wpacked) + static_cast<size_t>(ci.w_tile_off) * btile_bytes;
+      for (int i = 0; i < ci.n_tiles; ++i) {
+        ptx::mbar_wait(&bars->b_empty[bst], bph ^ 1u);
+        if (ptx::elect_one()) {
+          ptx::mbar_arrive_expect_tx(&bars->b_full[bst], btile_bytes);
+          ptx::bulk_g2s(b_base + static_cast<size_t>(bst) * btile_bytes, wsrc + static_cast<size_t>(i) * btile_bytes,
+                        btile_bytes, &bars->b_full[bst]);
         }
+        __syncwarp();
+        if (++bst == static_cast<uint32_t>(p.NBST)) { bst = 0; bph ^= 1u; }
       }
     }
   } else if (warp == kMmaWarp) {
-    // ============================================================ MMA issuer (one thread)
-    if (lane == 0) {
-      const uint32_t idesc = ptx::make_idesc_f16(p.N, 0);
-      const uint32_t slab_u32 = ptx::smem_u32(slab_base);
-      const uint32_t b_u32 = ptx::smem_u32(b_base);
-      const int ksteps = p.KC >> 4;
-      uint32_t g = 0, bt = 0, ucnt = 0;
-      for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++ucnt) {
-        const UnitCoord uc = decode_unit(u, p.n_chunks, ptiles, zgroups);
-        const wdno_nchunk ci = p.chunks[uc.nc];
-        const int buf = ucnt % NBUF;
-        ptx::mbar_wait(&bars->acc_empty[buf], ((ucnt / NBUF) & 1u) ^ 1u);
-        ptx::tc_fence_after();
-        const uint32_t acc0 = tmem_base + static_cast<uint32_t>(buf * NACC * NPAD);
-        bool first = true;
-        for (int si = 0; si < ci.set_count; ++si) {
-          const wdno_kset st = p.sets[ci.set_begin + si];
-          const uint32_t g0 = g;
-          g += P;
-          for (int j = 0; j < p.ZT; ++j) {
-            const uint32_t gj = g0 + j;
-            ptx::mbar_wait(&bars->slab_full[gj % p.NSLOT], (gj / p.NSLOT) & 1u);
+    // ============================================================ MMA issuer
+    // The whole warp runs the warp-uniform control flow (so descriptors stay in uniform registers and no
+    // per-operand waterfall loops are generated); one elected lane issues tcgen05.mma / tcgen05.commit.
+    // Ring positions are tracked incrementally -- no integer division on this path.
+    const uint32_t idesc = ptx::make_idesc_f16(p.N, 0);
+    const uint32_t desc_hi = 8u | (1u << 14);                        // SBO = 128 B, descriptor version 1
+    const uint32_t a_lo0 = (ptx::smem_u32(slab_base) >> 4) + (static_cast<uint32_t>(p.S_pad) << 16);  // LBO = S_pad*16
+    const uint32_t b_lo0 = (ptx::smem_u32(b_base) >> 4) + (static_cast<uint32_t>(p.N) << 16);         // LBO = N*16
+    const uint32_t slot_u = slot_bytes >> 4, btile_u = btile_bytes >> 4;
+    const uint32_t a_kstep = 2u * static_cast<uint32_t>(p.S_pad), b_kstep = 2u * static_cast<uint32_t>(p.N);
+    const int ksteps = p.KC >> 4;
+    const uint32_t nslot = static_cast<uint32_t>(p.NSLOT);
+    uint32_t s0 = 0, sph = 0;   // ring slot / phase of plane 0 of the current K-set
+    uint32_t bst = 0, bph = 0;  // weight stage / phase
+    uint32_t ucnt = 0;
+    for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++ucnt) {
+      const int nc = u % p.n_chunks;
+      const wdno_nchunk ci = p.chunks[nc];
+      const uint32_t buf = (NBUF == 2) ? (ucnt & 1u) : 0u;
+      const uint32_t aph = (NBUF == 2) ? ((ucnt >> 1) & 1u) : (ucnt & 1u);
+      ptx::mbar_wait(&bars->acc_empty[buf], aph ^ 1u);
+      ptx::tc_fence_after();
+      const uint32_t acc0 = tmem_base + buf * static_cast<uint32_t>(NACC * NPAD);
+      uint32_t accum = 0u;
+      for (int si = 0; si < ci.set_count; ++si) {
+        const wdno_kset st = p.sets[ci.set_begin + si];
+        for (int j = 0; j < p.ZT; ++j) {
+          uint32_t s = s0 + j, ph = sph;
+          if (s >= nslot) { s -= nslot; ph ^= 1u; }
+          ptx::mbar_wait(&bars->slab_full[s], ph);
+        }
+        int cur_kz = 0;
+        const wdno_tap* tp_ptr = p.taps + st.tap_begin;
+        for (int t = 0; t < st.tap_count; ++t) {
+          const wdno_tap tp = tp_ptr[t];
+          while (cur_kz < tp.kz) {
+            // plane cur_kz is dead: release it; plane cur_kz + ZT becomes needed
+            uint32_t sd = s0 + cur_kz;
+            if (sd >= nslot) sd -= nslot;
+            if (ptx::elect_one()) ptx::tc_commit(&bars->slab_empty[sd]);
+            __syncwarp();
+            uint32_t sn = s0 + cur_kz + p.ZT, ph = sph;
+            if (sn >= nslot) { sn -= nslot; ph ^= 1u; }
+            ptx::mbar_wait(&bars->slab_full[sn], ph);
+            ++cur_kz;
           }
-          int cur_kz = 0;
-          for (int t = 0; t < st.tap_count; ++t, ++bt) {
-            const wdno_tap tp = p.taps[st.tap_begin + t];
-            while (cur_kz < tp.kz) {
-              // plane cur_kz is dead: release it; plane cur_kz + ZT becomes needed
-              const uint32_t gd = g0 + cur_kz;
-              ptx::tc_commit(&bars->slab_empty[gd % p.NSLOT]);
-              const uint32_t gn = g0 + cur_kz + p.ZT;
-              ptx::mbar_wait(&bars->slab_full[gn % p.NSLOT], (gn / p.NSLOT) & 1u);
-              ++cur_kz;
-            }
-            const int stage = bt % p.NBST;
-            ptx::mbar_wait(&bars->b_full[stage], (bt / p.NBST) & 1u);
-            ptx::tc_fence_after();
-            const uint32_t bs = b_u32 + static_cast<uint32_t>(stage) * btile_bytes;
+          ptx::mbar_wait(&bars->b_full[bst], bph);
+          ptx::tc_fence_after();
+          if (ptx::elect_one()) {
+            const uint32_t b_lo = b_lo0 + bst * btile_u;
             for (int za = 0; za < p.ZT; ++za) {
-              const uint32_t gp = g0 + tp.kz + za;
-              const uint32_t as = slab_u32 + (gp % p.NSLOT) * slot_bytes;
+              uint32_t sa = s0 + tp.kz + za;
+              if (sa >= nslot) sa -= nslot;
+              const uint32_t a_lo = a_lo0 + sa * slot_u + static_cast<uint32_t>(tp.shift);
               for (int pi = 0; pi < p.PT; ++pi) {
-                const uint32_t a_pos = as + static_cast<uint32_t>(tp.shift + pi * 128) * 16u;
                 const uint32_t dcol = acc0 + static_cast<uint32_t>((za * p.PT + pi) * NPAD);
+                uint32_t al = a_lo + static_cast<uint32_t>(pi * 128), bl = b_lo;
+                uint32_t acc_flag = accum;
                 for (int k = 0; k < ksteps; ++k) {
-                  const uint64_t ad = ptx::make_desc_kmajor_noswz(a_pos + 2u * k * lbo_a, lbo_a, 128u);
-                  const uint64_t bd = ptx::make_desc_kmajor_noswz(bs + 2u * k * lbo_b, lbo_b, 128u);
-                  ptx::tc_mma_f16(dcol, ad, bd, idesc, (first && k == 0) ? 0u : 1u);
+                  const uint64_t ad = (static_cast<uint64_t>(desc_hi) << 32) | al;
+                  const uint64_t bd = (static_cast<uint64_t>(desc_hi) << 32) | bl;
+                  ptx::tc_mma_f16(dcol, ad, bd, idesc, acc_flag);
+                  acc_flag = 1u;
+                  al += a_kstep;
+                  bl += b_kstep;
                 }
               }
             }
-            first = false;
-            ptx::tc_commit(&bars->b_empty[stage]);
+            ptx::tc_commit(&bars->b_empty[bst]);
           }
+          __syncwarp();
+          accum = 1u;
+          if (++bst == static_cast<uint32_t>(p.NBST)) { bst = 0; bph ^= 1u; }
+        }
+        if (ptx::elect_one()) {
           for (int j = cur_kz; j < P; ++j) {
-            const uint32_t gd = g0 + j;
-            ptx::tc_commit(&bars->slab_empty[gd % p.NSLOT]);
+            uint32_t sd = s0 + j;
+            if (sd >= nslot) sd -= nslot;
+            ptx::tc_commit(&bars->slab_empty[sd]);
           }
         }
-        ptx::tc_commit(&bars->acc_full[buf]);
+        __syncwarp();
+        s0 += static_cast<uint32_t>(P);
+        if (s0 >= nslot) { s0 -= nslot; sph ^= 1u; }
       }
+      if (ptx::elect_one()) ptx::tc_commit(&bars->acc_full[buf]);
+      __syncwarp();
     }
   } else {
     // ============================================================ epilogue warps 0..3
@@ -290,13 +317,14 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const wdno_tapgemm
     for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++ucnt) {
       const UnitCoord uc = decode_unit(u, p.n_chunks, ptiles, zgroups);
       const wdno_nchunk ci = p.chunks[uc.nc];
-      const int buf = ucnt % NBUF;
+      const uint32_t buf = (NBUF == 2) ? (ucnt & 1u) : 0u;
+      const uint32_t aph = (NBUF == 2) ? ((ucnt >> 1) & 1u) : (ucnt & 1u);
       const int o0 = uc.pt * 128 * p.PT;
       const int z0 = uc.zg * p.ZT;
       float s1[16], s2[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
-      ptx::mbar_wait(&bars->acc_full[buf], (ucnt / NBUF) & 1u);
+      ptx::mbar_wait(&bars->acc_full[buf], aph);
       ptx::tc_fence_after();
       for (int a = 0; a < NACC; ++a) {
         const int za = a / p.PT, pi = a - za * p.PT;
