@@ -168,6 +168,25 @@ int wdno_mse_weighted(const float* pred, const float* target, const float* w, in
 int wdno_step_begin(int* step_dev, const float* time_table, const float* coef_table, float* time_out, float* coef_out,
                     int B, int n_steps, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * separable DWT / IDWT along one axis of an fp32 tensor viewed as [outer][N][inner] (element strides).
+ * Replaces the arithmetic of the third-party libraries the reference calls (not vendored in its tree):
+ * pytorch_wavelets afb1d/sfb1d ('zero', 'periodization') and ptwt==0.1.6 wavedec3/waverec3 ('zero');
+ * call sites: smoke/inference_2d.py:37-46,141-147,178-186,220-254 ; burgers/eval_ddpm_burgers.py:134-136,188-194 ;
+ * burgers/ddpm_burgers/test_util.py:186-203.
+ *   analysis : lo/hi[i] = sum_k X(2i + k - off) * taps[k]      (X zero-extended, or periodic with odd N edge-repeated)
+ *   synthesis: y[m] = sum_{k:(m+off-k) even} lo((m+off-k)/2)*taps_lo[k] + hi(..)*taps_hi[k]
+ * taps are HOST arrays (<= WDNO_MAX_TAPS).  The adjoints used by gradient guidance are the same two kernels
+ * with the synthesis / analysis taps swapped in (see wdno_b200/wavelets.py).
+ * ------------------------------------------------------------------------------------------ */
+#define WDNO_MAX_TAPS 20
+int wdno_dwt_analysis_axis(const float* x, float* lo, float* hi, int64_t outer, int N, int64_t inner, int nout,
+                           int64_t x_ostride, int64_t lo_ostride, int64_t hi_ostride, const float* taps_lo_host,
+                           const float* taps_hi_host, int L, int off, int periodic, void* stream);
+int wdno_dwt_synthesis_axis(const float* lo, const float* hi, float* y, int64_t outer, int n, int64_t inner, int Nout,
+                            int64_t lo_ostride, int64_t hi_ostride, int64_t y_ostride, const float* taps_lo_host,
+                            const float* taps_hi_host, int L, int off, int periodic, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

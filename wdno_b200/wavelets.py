@@ -1,0 +1,326 @@
+"""DWT / IDWT with the call signatures of the third-party libraries WDNO uses, on the CUDA kernels of csrc/dwt.cu.
+
+    DWTForward(J, mode, wave)(x) -> (Yl, [Yh...])       pytorch_wavelets       (inference_2d.py:178-180,244-246;
+    DWTInverse(mode, wave)((Yl, Yh)) -> x                                       eval_ddpm_burgers.py:134-136,188-194)
+    DWT1DForward / DWT1DInverse                          pytorch_wavelets       (test_util.py:186-187; inference_2d.py:43-46)
+    wavedec3(x, wavelet, mode='zero', level=1) -> [Yl, {aad..ddd}]   ptwt 0.1.6 (inference_2d.py:41,141,184,250)
+    waverec3([Yl, {...}], wavelet) -> x                                        (inference_2d.py:141,220)
+    Wavelet(name)                                        pywt.Wavelet stand-in (filter banks of SURVEY.md row a21)
+
+Every transform is differentiable (torch.autograd.Function whose backward is the adjoint pass on the same kernels),
+which is what the reference's gradient guidance needs (inference_2d.py:30-66, eval_ddpm_burgers.py:108-147).
+fp32 CUDA tensors only; there is no CPU path.
+"""
+import ctypes as C
+import math
+
+import torch
+from torch import nn
+
+from . import _lib
+
+_S2 = math.sqrt(2.0)
+_DEC = {
+    "bior1.3": ([_S2 * v / 16.0 for v in (-1, 1, 8, 8, 1, -1)], [_S2 * v / 2.0 for v in (0, 0, -1, 1, 0, 0)]),
+    "bior2.4": ([_S2 * v / 128.0 for v in (0, 3, -6, -16, 38, 90, 38, -16, -6, 3)],
+                [_S2 * v / 4.0 for v in (0, 0, 0, 1, -2, 1, 0, 0, 0, 0)]),
+    "haar": ([_S2 / 2.0, _S2 / 2.0], [-_S2 / 2.0, _S2 / 2.0]),
+}
+
+
+class Wavelet:
+    """pywt.Wavelet stand-in: .name, .dec_lo, .dec_hi, .rec_lo, .rec_hi, .dec_len"""
+
+    def __init__(self, name):
+        if isinstance(name, Wavelet):
+            name = name.name
+        if hasattr(name, "name") and not isinstance(name, str):
+            name = name.name
+        if name not in _DEC:
+            raise ValueError(f"wavelet {name!r} not built (have {sorted(_DEC)})")
+        self.name = name
+        self.dec_lo, self.dec_hi = list(_DEC[name][0]), list(_DEC[name][1])
+        self.rec_lo = [((-1.0) ** (k + 1)) * v for k, v in enumerate(self.dec_hi)]
+        self.rec_hi = [((-1.0) ** k) * v for k, v in enumerate(self.dec_lo)]
+        self.dec_len = self.rec_len = len(self.dec_lo)
+
+    @property
+    def filter_bank(self):
+        return self.dec_lo, self.dec_hi, self.rec_lo, self.rec_hi
+
+
+def _wave(w):
+    return w if isinstance(w, Wavelet) else Wavelet(w)
+
+
+def _farr(v):
+    return (C.c_float * len(v))(*v)
+
+
+def _check(x):
+    if not (torch.is_tensor(x) and x.is_cuda):
+        raise RuntimeError("wdno_b200.wavelets: CUDA tensors only (no CPU path)")
+
+
+# ---------------------------------------------------------------- raw axis passes
+def _mode_id(mode):
+    if mode in ("zero", "constant"):
+        return 0
+    if mode in ("periodization", "per"):
+        return 1
+    raise ValueError(f"padding mode {mode!r} not built (zero / periodization)")
+
+
+def _analysis_raw(x, axis, t_lo, t_hi, off, periodic, nout, lo=None, hi=None):
+    """x contiguous fp32; returns (lo, hi) (or writes into given views that are contiguous beyond `axis`)."""
+    x = x.contiguous()
+    axis = axis % x.dim()
+    N = x.shape[axis]
+    outer = int(math.prod(x.shape[:axis])) if axis > 0 else 1
+    inner = int(math.prod(x.shape[axis + 1:])) if axis < x.dim() - 1 else 1
+    oshape = list(x.shape)
+    oshape[axis] = nout
+    if lo is None:
+        lo = torch.empty(oshape, dtype=torch.float32, device=x.device)
+    if hi is None:
+        hi = torch.empty(oshape, dtype=torch.float32, device=x.device)
+    _lib.check(_lib.lib().wdno_dwt_analysis_axis(
+        x.data_ptr(), lo.data_ptr(), hi.data_ptr(), outer, N, inner, nout, N * inner, _ostride(lo, axis, nout, inner),
+        _ostride(hi, axis, nout, inner), _farr(t_lo), _farr(t_hi), len(t_lo), off, periodic, _lib.current_stream_ptr()),
+        "dwt_analysis_axis")
+    return lo, hi
+
+
+def _ostride(t, axis, n, inner):
+    """outer stride (elements) of a tensor/view whose dims from `axis` on are contiguous and dims before it are
+    uniformly strided (plain tensors, or a band slice of a stacked tensor)"""
+    if t.dim() == 0 or axis == 0:
+        return n * inner
+    assert t.stride(axis) == inner, "sub-band view must be contiguous from the transform axis on"
+    return t.stride(axis - 1)
+
+
+def _synthesis_raw(lo, hi, axis, t_lo, t_hi, off, periodic, nout):
+    axis = axis % lo.dim()
+    n = lo.shape[axis]
+    outer = int(math.prod(lo.shape[:axis])) if axis > 0 else 1
+    inner = int(math.prod(lo.shape[axis + 1:])) if axis < lo.dim() - 1 else 1
+    oshape = list(lo.shape)
+    oshape[axis] = nout
+    y = torch.empty(oshape, dtype=torch.float32, device=lo.device)
+    _lib.check(_lib.lib().wdno_dwt_synthesis_axis(
+        lo.data_ptr(), hi.data_ptr(), y.data_ptr(), outer, n, inner, nout, _ostride(lo, axis, n, inner),
+        _ostride(hi, axis, n, inner), nout * inner, _farr(t_lo), _farr(t_hi), len(t_lo), off, periodic,
+        _lib.current_stream_ptr()), "dwt_synthesis_axis")
+    return y
+
+
+def _uniform_outer(t, axis):
+    """True if dims before `axis` collapse to one uniformly strided outer dim and dims from axis on are contiguous"""
+    if not t.is_cuda:
+        return False
+    exp = 1
+    for d in range(t.dim() - 1, axis - 1, -1):
+        if t.shape[d] != 1 and t.stride(d) != exp:
+            return False
+        exp *= t.shape[d]
+    st = None
+    for d in range(axis - 1, -1, -1):
+        if st is None:
+            st = t.stride(d)
+            run = st * t.shape[d]
+        else:
+            if t.shape[d] != 1 and t.stride(d) != run:
+                return False
+            run = t.stride(d) * t.shape[d]
+    return True
+
+
+def _prep(t, axis):
+    t = t.to(torch.float32)
+    return t if _uniform_outer(t, axis % t.dim()) else t.contiguous()
+
+
+def _geom(N, L, mode):
+    """-> (nout, off, periodic) of the analysis along an axis of length N"""
+    if _mode_id(mode) == 0:
+        return (N + L - 1) // 2, L - 2, 0
+    return (N + (N & 1)) // 2, L // 2 - 1, 1
+
+
+class _Analysis(torch.autograd.Function):
+    """(lo, hi) = afb1d(x) along `axis` (Appendix A.1 / A.3)"""
+
+    @staticmethod
+    def forward(ctx, x, axis, wname, mode):
+        w = Wavelet(wname)
+        L = w.dec_len
+        x = x.to(torch.float32).contiguous()
+        N = x.shape[axis]
+        nout, off, per = _geom(N, L, mode)
+        ctx.cfg = (axis, wname, mode, N)
+        return _analysis_raw(x, axis, w.dec_lo[::-1], w.dec_hi[::-1], off, per, nout)
+
+    @staticmethod
+    def backward(ctx, glo, ghi):
+        axis, wname, mode, N = ctx.cfg
+        w = Wavelet(wname)
+        L = w.dec_len
+        _, off, per = _geom(N, L, mode)
+        glo, ghi = _prep(glo, axis), _prep(ghi, axis)
+        if per:
+            Np = N + (N & 1)
+            g = _synthesis_raw(glo, ghi, axis, w.dec_lo[::-1], w.dec_hi[::-1], off, 1, Np)
+            if Np != N:  # the repeated edge sample folds back onto the last real sample
+                idx = [slice(None)] * g.dim()
+                idx[axis] = slice(0, N)
+                gx = g[tuple(idx)].clone()
+                last, ext = list(idx), list(idx)
+                last[axis], ext[axis] = slice(N - 1, N), slice(N, N + 1)
+                gx[tuple(last)] += g[tuple(ext)]
+                g = gx
+        else:
+            g = _synthesis_raw(glo, ghi, axis, w.dec_lo[::-1], w.dec_hi[::-1], off, 0, N)
+        return g, None, None, None
+
+
+class _Synthesis(torch.autograd.Function):
+    """y = sfb1d(lo, hi) along `axis` (Appendix A.2 / A.3)"""
+
+    @staticmethod
+    def forward(ctx, lo, hi, axis, wname, mode):
+        w = Wavelet(wname)
+        L = w.dec_len
+        lo, hi = _prep(lo, axis), _prep(hi, axis)
+        n = lo.shape[axis]
+        per = _mode_id(mode)
+        nout = 2 * n if per else 2 * n - L + 2
+        off = L // 2 - 1 if per else L - 2
+        ctx.cfg = (axis, wname, mode, n, off, per)
+        return _synthesis_raw(lo, hi, axis, w.rec_lo, w.rec_hi, off, per, nout)
+
+    @staticmethod
+    def backward(ctx, gy):
+        axis, wname, mode, n, off, per = ctx.cfg
+        w = Wavelet(wname)
+        gy = gy.to(torch.float32).contiguous()
+        glo, ghi = _analysis_raw(gy, axis, w.rec_lo, w.rec_hi, off, per, n)
+        return glo, ghi, None, None, None
+
+
+def afb1d(x, wave, mode, axis=-1):
+    _check(x)
+    return _Analysis.apply(x, axis % x.dim(), _wave(wave).name, mode)
+
+
+def sfb1d(lo, hi, wave, mode, axis=-1):
+    _check(lo)
+    return _Synthesis.apply(lo, hi, axis % lo.dim(), _wave(wave).name, mode)
+
+
+# ---------------------------------------------------------------- pytorch_wavelets-style modules
+class DWTForward(nn.Module):
+    def __init__(self, J=1, wave="db1", mode="zero"):
+        super().__init__()
+        self.J, self.wave, self.mode = J, _wave(wave), mode
+
+    def forward(self, x):
+        """x [B,C,H,W] -> (Yl [B,C,H',W'], [Yh_j [B,C,3,H_j,W_j]], finest first); bands (LH, HL, HH)"""
+        _check(x)
+        ll, yh = x, []
+        for _ in range(self.J):
+            lo_w, hi_w = afb1d(ll, self.wave, self.mode, axis=-1)
+            ll, lh = afb1d(lo_w, self.wave, self.mode, axis=-2)
+            hl, hh = afb1d(hi_w, self.wave, self.mode, axis=-2)
+            yh.append(torch.stack((lh, hl, hh), dim=2))
+        return ll, yh
+
+
+class DWTInverse(nn.Module):
+    def __init__(self, wave="db1", mode="zero"):
+        super().__init__()
+        self.wave, self.mode = _wave(wave), mode
+
+    def forward(self, coeffs):
+        yl, yh = coeffs
+        _check(yl)
+        ll = yl
+        for h in yh[::-1]:
+            if h is None:
+                h = torch.zeros(ll.shape[0], ll.shape[1], 3, ll.shape[-2], ll.shape[-1], device=ll.device)
+            if ll.shape[-2] > h.shape[-2]:
+                ll = ll[..., :-1, :]
+            if ll.shape[-1] > h.shape[-1]:
+                ll = ll[..., :-1]
+            lh, hl, hh = h[:, :, 0], h[:, :, 1], h[:, :, 2]
+            lo = sfb1d(ll, lh, self.wave, self.mode, axis=-2)
+            hi = sfb1d(hl, hh, self.wave, self.mode, axis=-2)
+            ll = sfb1d(lo, hi, self.wave, self.mode, axis=-1)
+        return ll
+
+
+class DWT1DForward(nn.Module):
+    def __init__(self, J=1, wave="db1", mode="zero"):
+        super().__init__()
+        self.J, self.wave, self.mode = J, _wave(wave), mode
+
+    def forward(self, x):
+        """x [B,C,N] -> (lo, [hi_j], finest first)"""
+        _check(x)
+        lo, his = x, []
+        for _ in range(self.J):
+            lo, hi = afb1d(lo, self.wave, self.mode, axis=-1)
+            his.append(hi)
+        return lo, his
+
+
+class DWT1DInverse(nn.Module):
+    def __init__(self, wave="db1", mode="zero"):
+        super().__init__()
+        self.wave, self.mode = _wave(wave), mode
+
+    def forward(self, coeffs):
+        lo, his = coeffs
+        _check(lo)
+        for hi in his[::-1]:
+            if hi is None:
+                hi = torch.zeros_like(lo)
+            if lo.shape[-1] > hi.shape[-1]:
+                lo = lo[..., :-1]
+            lo = sfb1d(lo, hi, self.wave, self.mode, axis=-1)
+        return lo
+
+
+# ---------------------------------------------------------------- ptwt-style 3-D transform
+KEYS3 = ("aad", "ada", "add", "daa", "dad", "dda", "ddd")
+
+
+def wavedec3(data, wavelet, *, mode="zero", level=1):
+    """data [B,D,H,W] -> [aaa, {aad, ada, add, daa, dad, dda, ddd}] ; letters index (D,H,W), a = low-pass"""
+    _check(data)
+    if level != 1:
+        raise NotImplementedError("WDNO only uses level=1 (inference_2d.py:41,184,250)")
+    if _mode_id(mode) != 0:
+        raise NotImplementedError("WDNO only uses mode='zero' for the 3-D transform")
+    w = _wave(wavelet)
+    out = {}
+    for kd, xd in zip("ad", afb1d(data, w, "zero", axis=1)):
+        for kh, xh in zip("ad", afb1d(xd, w, "zero", axis=2)):
+            for kw, xw in zip("ad", afb1d(xh, w, "zero", axis=3)):
+                out[kd + kh + kw] = xw
+    return [out["aaa"], {k: out[k] for k in KEYS3}]
+
+
+def waverec3(coeffs, wavelet):
+    w = _wave(wavelet)
+    aaa, d = coeffs[0], coeffs[1]
+    _check(aaa)
+    b = dict(d)
+    b["aaa"] = aaa
+    xd = {}
+    for kd in "ad":
+        xh = {}
+        for kh in "ad":
+            xh[kh] = sfb1d(b[kd + kh + "a"], b[kd + kh + "d"], w, "zero", axis=3)
+        xd[kd] = sfb1d(xh["a"], xh["d"], w, "zero", axis=2)
+    return sfb1d(xd["a"], xd["d"], w, "zero", axis=1)
