@@ -1,0 +1,57 @@
+"""The C-ABI library loads without a GPU and exports every symbol include/wdno_b200.h declares; argument
+validation errors surface as ValueError with the library's message (no compute calls here)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from wdno_b200 import build
+    build.build()
+    from wdno_b200 import _lib
+    return _lib.lib()
+
+
+def test_exports_every_declared_symbol(lib):
+    hdr = open(os.path.join(ROOT, "include", "wdno_b200.h")).read()
+    names = sorted(set(re.findall(r"\b(wdno_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 20
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    from wdno_b200 import _abi
+    declared = set(names) - {"wdno_last_error", "wdno_version", "wdno_device_cc", "wdno_tapgemm", "wdno_tapgemm_smem_bytes"}
+    assert declared == set(_abi.SIGNATURES), declared ^ set(_abi.SIGNATURES)
+
+
+def test_struct_layouts_match_header():
+    from wdno_b200 import _abi, _lib
+    assert C.sizeof(_lib.Tap) == 8 and C.sizeof(_lib.KSet) == 24 and C.sizeof(_lib.NChunk) == 40
+    assert C.sizeof(_lib.TapGemmParams) == 216
+    assert C.sizeof(_abi.CondOp) == 96
+
+
+def test_invalid_arguments_are_rejected_without_a_gpu(lib):
+    from wdno_b200 import _lib
+    p = _lib.TapGemmParams()
+    rc = lib.wdno_tapgemm(C.byref(p), None)
+    assert rc == -1 and b"KC" in lib.wdno_last_error()
+    with pytest.raises(ValueError):
+        _lib.check(rc, "tapgemm")
+    assert lib.wdno_chan_layernorm(None, None, None, 0, 64, 1e-5, None) == -1
+    assert lib.wdno_dwt_analysis_axis(None, None, None, 1, 1, 1, 1, 1, 1, 1, None, None, 6, 4, 0, None) == -1
+
+
+def test_product_path_has_no_cpu_fallback():
+    import torch
+    from wdno_b200.unet3d import Unet3D_with_Conv3D
+    from wdno_b200 import wavelets
+    m = Unet3D_with_Conv3D(dim=64, dim_mults=(1, 2, 4), channels=42)
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 24, 42, 40, 40), torch.zeros(1))
+    with pytest.raises(RuntimeError):
+        wavelets.wavedec3(torch.zeros(1, 8, 8, 8), "bior1.3")

@@ -281,40 +281,69 @@ class GaussianDiffusion(nn.Module):
         return design, gs
 
     # ------------------------------------------------------------ samplers
+    def _runner(self, kind, shape, N_upsample, init, control, low, gs):
+        """StepRunner with STATIC state / noise / condition buffers, cached across sample() calls so the captured
+        CUDA graph is reused; a new call only copies its conditions into the static buffers."""
+        dev = self.betas.device
+        key = (kind, tuple(shape), N_upsample, control is not None and self.is_condition_control, low is not None,
+               self.sampling_timesteps, float(self.ddim_sampling_eta), gs is not None, self.use_cuda_graph)
+        cache = self.__dict__.setdefault("_runners", {})
+        r = cache.get(key)
+        if r is None or r.model_engine is not self.model.engine():
+            coef_shape = self._coef_shape(N_upsample)
+            static = dict(init=torch.empty_like(init, dtype=torch.float32, device=dev).contiguous(),
+                          control=None if control is None else torch.empty_like(control, dtype=torch.float32, device=dev).contiguous(),
+                          low=None if low is None else torch.empty_like(low, dtype=torch.float32, device=dev).contiguous())
+            keep, prog = self._conditions(shape, coef_shape, static["init"], static["control"], static["low"])
+            if kind == "ddim":
+                times, table = ddim_tables(self, self.ddim_sampling_eta, gs)
+            else:
+                times, table = ddpm_tables(self, gs)
+            x = torch.empty(tuple(shape), dtype=torch.float32, device=dev)
+            r = StepRunner(self.model, x, times, table, prog, kind, 1 if kind == "ddim" else 2,
+                           use_graph=self.use_cuda_graph)
+            r.static, r.keep, r.model_engine = static, keep, self.model.engine()
+            cache.clear()  # one live runner: its static buffers are sized for the workload
+            cache[key] = r
+        for k, v in (("init", init), ("control", control), ("low", low)):
+            if r.static[k] is not None:
+                r.static[k].copy_(v, non_blocking=True)
+        r.step.zero_()
+        return r
+
     @torch.no_grad()
     def ddim_sample(self, shape, N_upsample=0, design_fn=None, design_guidance="standard", init=None, init_u=None,
                     control=None, low=None, device=None):
         dev = self.betas.device
-        coef_shape = self._coef_shape(N_upsample)
         design, gs = self._guidance(design_fn, design_guidance, low, init, init_u)
-        times, table = ddim_tables(self, self.ddim_sampling_eta, gs)
-        img = self._randn(shape, dev)
-        keep, prog = self._conditions(shape, coef_shape, init, control, low)
-        ops.apply_conditions(img, prog)
-        run = StepRunner(self.model, img, times, table, prog, "ddim", 1, use_graph=self.use_cuda_graph)
-        for i in range(len(times)):
-            last = i == len(times) - 1
+        assert init is not None
+        run = self._runner("ddim", shape, N_upsample, init, control if self.is_condition_control else None,
+                           low if self.is_super_model else None, gs)
+        run.x.copy_(self._randn(shape, dev))
+        ops.apply_conditions(run.x, run.prog)
+        n = len(run.times)
+        for i in range(n):
+            last = i == n - 1
             if not last:
                 run.noise.copy_(self._randn(shape, dev)) if self._noise_source is not None else run.noise.normal_()
             if design is not None:
                 run.step_guided(not last, design)
             else:
                 run.step_graph(not last)
-        self.last_launches_per_step = getattr(self.model, "engine", lambda: None)() and self.model.engine().launches + 2
-        return img
+        self.last_launches_per_step = self.model.engine().launches + 2
+        return run.x.clone()
 
     @torch.no_grad()
     def p_sample_loop(self, shape, N_upsample=0, design_fn=None, design_guidance="standard", return_all_timesteps=None,
                       init=None, init_u=None, control=None, low=None, device=None):
         dev = self.betas.device
-        coef_shape = self._coef_shape(N_upsample)
         design, gs = self._guidance(design_fn, design_guidance, low, init, init_u)
-        times, table = ddpm_tables(self, gs)
-        x = self._randn(list(shape), dev)
-        keep, prog = self._conditions(shape, coef_shape, init, control, low)
-        ops.apply_conditions(x, prog)
-        run = StepRunner(self.model, x, times, table, prog, "ddpm", 2, use_graph=self.use_cuda_graph)
-        for i, t in enumerate(times):
+        assert init is not None
+        run = self._runner("ddpm", shape, N_upsample, init, control if self.is_condition_control else None,
+                           low if self.is_super_model else None, gs)
+        run.x.copy_(self._randn(list(shape), dev))
+        ops.apply_conditions(run.x, run.prog)
+        for i, t in enumerate(run.times):
             with_noise = t > 0
             if with_noise:
                 run.noise.copy_(self._randn(shape, dev)) if self._noise_source is not None else run.noise.normal_()
@@ -322,7 +351,8 @@ class GaussianDiffusion(nn.Module):
                 run.step_guided(with_noise, design)
             else:
                 run.step_graph(with_noise)
-        return x
+        self.last_launches_per_step = self.model.engine().launches + 2
+        return run.x.clone()
 
     @torch.no_grad()
     def sample(self, batch_size=16, N_upsample=0, design_fn=None, design_guidance="standard", init=None, init_u=None,

@@ -350,5 +350,18 @@ class TapGemm:
             assert self.cout % groups == 0 and (self.cout // groups) % 8 == 0
             p.stats = stats.data_ptr()
             p.G, p.cpg = groups, self.cout // groups
+        tm = TapGemm.timing
+        if tm is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         _lib.check(L.wdno_tapgemm(C.byref(p), _lib.current_stream_ptr()), "tapgemm")
+        if tm is not None:
+            e1.record()
+            flops = 2.0 * B * D * H * W * self.cout * self.cin * self.w.shape[2] * self.w.shape[3] * self.w.shape[4]
+            if self.kind == "unshuffle":
+                flops *= 4
+            tm.append((e0, e1, flops, (self.kind, self.cin, self.cout, self.KD, self.KH, self.KW, B, D, H, W)))
         return out
+
+    # bench.py sets this to a list to collect (start event, end event, algorithmic FLOPs, shape) per launch
+    timing = None
