@@ -97,6 +97,10 @@ typedef struct {
   /* shared-memory plan */
   int32_t NSLOT, NBST, S_pad;
   int32_t grid;           /* persistent CTAs to launch (<= #SM) */
+  int32_t TPS;            /* weight tiles per bulk-copy stage */
+  int32_t reuse;          /* 1: (1x1 layers) slabs of all K-sets stay resident while every N-chunk is computed */
+  int32_t n_taps;         /* entries of taps[] (<= 384; copied to shared memory) */
+  int32_t pad_;
 } wdno_tapgemm_params;
 
 /* bytes of dynamic shared memory the plan needs, or <0 */

@@ -201,13 +201,29 @@ def run_case(i):
         res["ms_init7"] = ms
         res["tflops_init7"] = 2 * 343 * 42 * 64 * 16 * 38400 / ms / 1e9
         res["err"] = 0.0
+    elif i == 12:
+        res["name"] = "1x1 with resident slabs over N-chunks: 64->384 (24x40x40), 256->384 (24x10x10), 512->128 + resid"
+        errs = []
+        for cin, cout, hw in ((64, 384, 40), (256, 384, 10), (128, 256, 10)):
+            x = rnd(2, cin, 24, hw, hw)
+            w = rnd(cout, cin, scale=0.1)
+            plan = TapGemm(w, None, device=dev)
+            out = plan(cl(x))
+            errs.append(relerr(uncl(out), F.conv3d(x, w[:, :, None, None, None])))
+        x0, x1 = rnd(2, 256, 24, 10, 10), rnd(2, 256, 24, 10, 10)
+        w, b, r = rnd(128, 512, scale=0.05), rnd(128), rnd(2, 128, 24, 10, 10)
+        plan = TapGemm(w, b, src_channels=(256, 256), device=dev)
+        out = plan(cl(x0), cl(x1), resid=cl(r))
+        errs.append(relerr(uncl(out), F.conv3d(torch.cat([x0, x1], 1), w[:, :, None, None, None], b) + r))
+        res["errs"] = errs
+        res["err"] = max(errs)
     else:
         return None
     torch.cuda.synchronize()
     return res
 
 
-NCASES = 12
+NCASES = 13
 
 
 def main():

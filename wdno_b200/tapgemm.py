@@ -19,7 +19,7 @@ from . import _lib
 from ._lib import KSet, NChunk, Tap, TapGemmParams
 
 _SMEM_LIMIT = 227 * 1024
-_BAR_BYTES = 512
+_BAR_BYTES = 512 + 384 * 8  # barriers + shared-memory tap table
 
 
 def _device_bytes(ctypes_array, device):
@@ -223,49 +223,71 @@ class TapGemm:
 
     # ------------------------------------------------------------------ geometry / smem plan
     def _plan(self, B, D, H, W):
-        """(B, D, H, W) = tap grid (== output grid before depth-to-space)."""
+        """(B, D, H, W) = tap grid (== output grid before depth-to-space).  Chooses the accumulator shape (ZT x PT),
+        K-set width KC, slab ring depth, weight stages (TPS tiles per bulk copy) and whether 1x1 layers keep their
+        slabs resident across N-chunks, all under the 227 KB shared-memory budget."""
         key = (B, D, H, W)
         if key in self._launch:
             return self._launch[key]
         KD, KH, KW = self.KD, self.KH, self.KW
         Wp = W + KW - 1
         maxshift = (KH - 1) * Wp + (KW - 1)
-        ZT = min(4, D)
-        PT = max(1, 4 // ZT)
-        if self.N > 64:
-            while ZT * PT * 128 > 512:
-                PT = max(1, PT - 1)
-        P = ZT + KD - 1
-        S = 128 * PT + maxshift
         ctot = self._virtual_cin()
+        ncn = self.cout_pad // self.N
+        is_1x1 = self.kind == "conv" and KD == KH == KW == 1
         btile = lambda kc: self.N * kc * 2
-        cands = [self.kc_override] if self.kc_override else [64, 32, 16]
-        best = None  # (score, KC, S_pad, NSLOT, NBST)
-        for KC in cands:
-            if ctot % KC or any(c % KC for c in self.src_channels[:-1]):
-                continue
+
+        def fit(KC, ZT, PT, want_slots, min_slots):
+            """-> (S_pad, NSLOT, NBST, TPS) or None"""
             CH = KC // 8
+            S = 128 * PT + maxshift
             rem = {8: 1, 4: 2, 2: 4}[CH]
             S_pad = S + ((rem - S) % 8)
             slot = CH * S_pad * 16
-            found = None
-            for nslot in range(min(12, P + 2), P - 1, -1):
-                for nbst in (6, 4, 3, 2):
-                    if _BAR_BYTES + _round_up(nslot * slot, 128) + nbst * btile(KC) <= _SMEM_LIMIT:
-                        found = (nslot, nbst)
+            tps0 = max(1, min(16384 // btile(KC), 16))
+            for nslot in range(min(12, want_slots), min_slots - 1, -1):
+                for tps in sorted({tps0, max(1, tps0 // 2), 1}, reverse=True):
+                    for nbst in (4, 3, 2):
+                        if _BAR_BYTES + _round_up(nslot * slot, 128) + nbst * tps * btile(KC) <= _SMEM_LIMIT:
+                            return S_pad, nslot, nbst, tps
+            return None
+
+        kcs = [self.kc_override] if self.kc_override else [64, 32, 16]
+        kcs = [k for k in kcs if ctot % k == 0 and not any(c % k for c in self.src_channels[:-1])]
+        plan = None
+        if is_1x1 and ncn > 1:
+            # A-stationary: all K-sets of a work item stay in the slab ring while every N-chunk is computed
+            for KC in kcs:
+                sets = ctot // KC
+                for ZT in (min(4, D), min(2, D), 1):
+                    need = sets * ZT
+                    if need > 12:
+                        continue
+                    f = fit(KC, ZT, 1, min(12, need + ZT), need)
+                    if f:
+                        plan = (KC, ZT, 1, 1) + f
                         break
-                if found:
+                if plan:
                     break
-            if not found:
-                continue
-            # prefer a full ring (P+2 slots) with >=4 weight stages; among equals the larger KC
-            score = (min(found[0] - P, 2), min(found[1], 4), KC)
-            if best is None or score > best[0]:
-                best = (score, KC, S_pad, found[0], found[1])
-        if best is None:
-            raise ValueError(f"tapgemm: no shared-memory plan for grid {(B, D, H, W)} taps {(KD, KH, KW)}")
-        choice = best[1:]
-        KC, S_pad, NSLOT, NBST = choice
+        if plan is None:
+            ZT = min(4, D)
+            PT = max(1, 4 // ZT)
+            if self.N > 64:
+                while ZT * PT * 128 > 512:
+                    PT = max(1, PT - 1)
+            P = ZT + KD - 1
+            best = None
+            for KC in kcs:
+                f = fit(KC, ZT, PT, P + 2, P)
+                if not f:
+                    continue
+                score = (min(f[1] - P, 2), KC)  # prefer a full ring (P+2 slots), then the larger KC
+                if best is None or score > best[0]:
+                    best = (score, (KC, ZT, PT, 0) + f)
+            if best is None:
+                raise ValueError(f"tapgemm: no shared-memory plan for grid {(B, D, H, W)} taps {(KD, KH, KW)}")
+            plan = best[1]
+        KC, ZT, PT, reuse, S_pad, NSLOT, NBST, TPS = plan
         pk = self._pack(KC)
         if Wp not in pk["taps_dev"]:
             tl = pk["taps_kyx"]
@@ -275,7 +297,7 @@ class TapGemm:
         positions = H * Wp
         ptiles = (positions + 128 * PT - 1) // (128 * PT)
         zgroups = (D + ZT - 1) // ZT
-        n_units = B * zgroups * ptiles * pk["n_chunks"]
+        n_work = B * zgroups * ptiles * (1 if reuse else pk["n_chunks"])
         sms = (torch.cuda.get_device_properties(self.device).multi_processor_count
                if self.device.type == "cuda" else 148)
         p = TapGemmParams()
@@ -289,7 +311,9 @@ class TapGemm:
         p.taps = taps_dev.data_ptr()
         p.wpacked = pk["wpacked"].data_ptr()
         p.NSLOT, p.NBST, p.S_pad = NSLOT, NBST, S_pad
-        p.grid = max(1, min(n_units, sms))
+        p.TPS, p.reuse = TPS, reuse
+        p.n_taps = len(pk["taps_kyx"])
+        p.grid = max(1, min(n_work, sms))
         self._launch[key] = p
         return p
 
