@@ -73,6 +73,132 @@ __device__ __forceinline__ Work decode_work(int w, int n_chunks, int ptiles, int
 
 __device__ __forceinline__ float silu_f(float v) { return v / (1.0f + __expf(-v)); }
 
+// ------------------------------------------------------------------ MMA issue
+// All MMAs of one weight tile: ZT*PT accumulators x KS k-steps, fully unrolled, operands in registers.
+template <int ZT, int PT, int KS>
+__device__ __forceinline__ void issue_tile(uint32_t a_tap_lo, uint32_t s_kz, uint32_t nslot, uint32_t slot_u, uint32_t b_lo,
+                                           uint32_t acc0, uint32_t npad, uint32_t a_kstep, uint32_t b_kstep, uint32_t idesc,
+                                           uint32_t accum) {
+  constexpr uint64_t kDescHi = static_cast<uint64_t>(8u | (1u << 14)) << 32;  // SBO = 128 B, descriptor version 1
+#pragma unroll
+  for (int za = 0; za < ZT; ++za) {
+    uint32_t sa = s_kz + za;
+    if (sa >= nslot) sa -= nslot;
+    const uint32_t a_lo = a_tap_lo + sa * slot_u;
+#pragma unroll
+    for (int pi = 0; pi < PT; ++pi) {
+      const uint32_t dcol = acc0 + static_cast<uint32_t>(za * PT + pi) * npad;
+#pragma unroll
+      for (int k = 0; k < KS; ++k) {
+        const uint64_t ad = kDescHi | (a_lo + static_cast<uint32_t>(pi * 128) + static_cast<uint32_t>(k) * a_kstep);
+        const uint64_t bd = kDescHi | (b_lo + static_cast<uint32_t>(k) * b_kstep);
+        ptx::tc_mma_f16(dcol, ad, bd, idesc, (k == 0) ? accum : 1u);
+      }
+    }
+  }
+}
+
+// The whole warp runs the warp-uniform control flow (waits, ring bookkeeping); one elected lane issues the MMAs of a
+// whole weight stage (TPS taps of one kz group) and the tcgen05.commit that frees it.  No divisions on this path.
+template <int ZT, int PT, int KS>
+__device__ __forceinline__ void mma_role(const wdno_tapgemm_params& p, Bars* bars, const wdno_tap* s_taps, uint32_t tmem_base,
+                                         const uint8_t* slab_base, const uint8_t* b_base, int n_work, int ptiles, int zgroups) {
+  constexpr int NACC = ZT * PT;
+  const uint32_t N = static_cast<uint32_t>(p.N);
+  const uint32_t npad = (N <= 64) ? 64u : 128u;
+  const bool two_buf = NACC * npad * 2 <= 512;
+  const int KD = p.KD, TPS = p.TPS, n_chunks = p.n_chunks, reuse = p.reuse;
+  const int P = ZT + KD - 1;
+  const uint32_t nslot = static_cast<uint32_t>(p.NSLOT), nbst = static_cast<uint32_t>(p.NBST);
+  const uint32_t idesc = ptx::make_idesc_f16(p.N, 0);
+  const uint32_t S_pad = static_cast<uint32_t>(p.S_pad);
+  const uint32_t slot_u = (static_cast<uint32_t>(p.KC >> 3) * S_pad * 16u) >> 4;
+  const uint32_t btile_u = (N * static_cast<uint32_t>(p.KC) * 2u) >> 4, bstage_u = btile_u * static_cast<uint32_t>(TPS);
+  const uint32_t a_lo0 = (ptx::smem_u32(slab_base) >> 4) + (S_pad << 16);  // start | LBO = S_pad*16 B
+  const uint32_t b_lo0 = (ptx::smem_u32(b_base) >> 4) + (N << 16);         // start | LBO = N*16 B
+  const uint32_t a_kstep = 2u * S_pad, b_kstep = 2u * N;
+  uint32_t s0 = 0, sph = 0;   // ring slot / phase of plane 0 of the current K-set
+  uint32_t bst = 0, bph = 0;  // weight stage / phase
+  uint32_t acnt = 0;          // accumulator-buffer use counter
+  for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+    const int nc0 = reuse ? 0 : (w % n_chunks);
+    const int nc1 = reuse ? n_chunks : nc0 + 1;
+    const uint32_t su = s0, suph = sph;  // ring position at the start of this work item
+    for (int nc = nc0; nc < nc1; ++nc, ++acnt) {
+      const wdno_nchunk ci = p.chunks[nc];
+      const bool first_pass = (nc == nc0), last_pass = (nc == nc1 - 1);
+      if (reuse) { s0 = su; sph = suph; }
+      const uint32_t buf = two_buf ? (acnt & 1u) : 0u;
+      const uint32_t aph = two_buf ? ((acnt >> 1) & 1u) : (acnt & 1u);
+      ptx::mbar_wait(&bars->acc_empty[buf], aph ^ 1u);
+      ptx::tc_fence_after();
+      const uint32_t acc0 = tmem_base + buf * static_cast<uint32_t>(NACC) * npad;
+      uint32_t accum = 0u;
+      for (int si = 0; si < ci.set_count; ++si) {
+        const wdno_kset st = p.sets[ci.set_begin + si];
+        const int groups_per_kz = (st.tap_count / KD) / TPS;
+        if (first_pass) {
+#pragma unroll
+          for (int j = 0; j < ZT; ++j) {
+            uint32_t s = s0 + j, ph = sph;
+            if (s >= nslot) { s -= nslot; ph ^= 1u; }
+            ptx::mbar_wait(&bars->slab_full[s], ph);
+          }
+        }
+        const wdno_tap* tp_ptr = s_taps + st.tap_begin;
+        for (int kz = 0; kz < KD; ++kz) {
+          uint32_t s_kz = s0 + kz;
+          if (s_kz >= nslot) s_kz -= nslot;
+          if (kz > 0) {
+            // plane kz-1 is dead: release it; plane kz+ZT-1 becomes needed (KD > 1 never uses slab reuse)
+            uint32_t sd = s0 + kz - 1;
+            if (sd >= nslot) sd -= nslot;
+            if (ptx::elect_one()) ptx::tc_commit(&bars->slab_empty[sd]);
+            __syncwarp();
+            uint32_t sn = s0 + kz + ZT - 1, ph = sph;
+            if (sn >= nslot) { sn -= nslot; ph ^= 1u; }
+            ptx::mbar_wait(&bars->slab_full[sn], ph);
+          }
+          for (int g = 0; g < groups_per_kz; ++g) {
+            ptx::mbar_wait(&bars->b_full[bst], bph);
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
+              uint32_t b_lo = b_lo0 + bst * bstage_u;
+              uint32_t af = accum;
+#pragma unroll 1
+              for (int i = 0; i < TPS; ++i) {
+                const uint32_t shift = static_cast<uint32_t>(tp_ptr[i].shift);
+                issue_tile<ZT, PT, KS>(a_lo0 + shift, s_kz, nslot, slot_u, b_lo, acc0, npad, a_kstep, b_kstep, idesc, af);
+                af = 1u;
+                b_lo += btile_u;
+              }
+              ptx::tc_commit(&bars->b_empty[bst]);
+            }
+            __syncwarp();
+            accum = 1u;
+            tp_ptr += TPS;
+            if (++bst == nbst) { bst = 0; bph ^= 1u; }
+          }
+        }
+        if (last_pass) {
+          if (ptx::elect_one()) {
+            for (int j = KD - 1; j < P; ++j) {
+              uint32_t sd = s0 + j;
+              if (sd >= nslot) sd -= nslot;
+              ptx::tc_commit(&bars->slab_empty[sd]);
+            }
+          }
+          __syncwarp();
+        }
+        s0 += static_cast<uint32_t>(P);
+        if (s0 >= nslot) { s0 -= nslot; sph ^= 1u; }
+      }
+      if (ptx::elect_one()) ptx::tc_commit(&bars->acc_full[buf]);
+      __syncwarp();
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const wdno_tapgemm_params p) {
   extern __shared__ __align__(128) uint8_t smem[];
   Bars* bars = reinterpret_cast<Bars*>(smem);
@@ -223,8 +349,8 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const wdno_tapgemm
       for (int nc = wk.nc0; nc < wk.nc1; ++nc) {
         const wdno_nchunk ci = p.chunks[nc];
         const uint8_t* wsrc = static_cast<const uint8_t*>(p.wpacked) + static_cast<size_t>(ci.w_tile_off) * btile_bytes;
-        for (int i = 0; i < ci.n_tiles; i += p.TPS) {
-          const uint32_t cnt = static_cast<uint32_t>(min(p.TPS, ci.n_tiles - i));
+        for (int i = 0; i < ci.n_tiles; i += p.TPS) {  // the plan guarantees TPS | taps of every kz group
+          const uint32_t cnt = static_cast<uint32_t>(p.TPS);
           ptx::mbar_wait(&bars->b_empty[bst], bph ^ 1u);
           if (ptx::elect_one()) {
             ptx::mbar_arrive_expect_tx(&bars->b_full[bst], cnt * btile_bytes);
@@ -237,110 +363,17 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const wdno_tapgemm
       }
     }
   } else if (warp == kMmaWarp) {
-    // ============================================================ MMA issuer
-    // The whole warp runs the warp-uniform control flow (so descriptors stay in uniform registers and no
-    // per-operand waterfall loops are generated); one elected lane issues tcgen05.mma / tcgen05.commit.
-    // Ring positions are tracked incrementally -- no integer division on this path.
-    const uint32_t idesc = ptx::make_idesc_f16(p.N, 0);
-    const uint32_t desc_hi = 8u | (1u << 14);                        // SBO = 128 B, descriptor version 1
-    const uint32_t a_lo0 = (ptx::smem_u32(slab_base) >> 4) + (static_cast<uint32_t>(p.S_pad) << 16);  // LBO = S_pad*16
-    const uint32_t b_lo0 = (ptx::smem_u32(b_base) >> 4) + (static_cast<uint32_t>(p.N) << 16);         // LBO = N*16
-    const uint32_t slot_u = slot_bytes >> 4, btile_u = btile_bytes >> 4, bstage_u = bstage_bytes >> 4;
-    const uint32_t a_kstep = 2u * static_cast<uint32_t>(p.S_pad), b_kstep = 2u * static_cast<uint32_t>(p.N);
-    const int ksteps = p.KC >> 4;
-    const uint32_t nslot = static_cast<uint32_t>(p.NSLOT);
-    uint32_t s0 = 0, sph = 0;   // ring slot / phase of plane 0 of the current K-set
-    uint32_t bst = 0, bph = 0;  // weight stage / phase
-    uint32_t acnt = 0;          // accumulator-buffer use counter
-    for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-      const Work wk = decode_work(w, p.n_chunks, ptiles, zgroups, p.reuse);
-      const uint32_t su = s0, suph = sph;  // ring position at the start of this work item
-      for (int nc = wk.nc0; nc < wk.nc1; ++nc, ++acnt) {
-        const wdno_nchunk ci = p.chunks[nc];
-        const bool first_pass = (nc == wk.nc0), last_pass = (nc == wk.nc1 - 1);
-        if (p.reuse) { s0 = su; sph = suph; }
-        const uint32_t buf = (NBUF == 2) ? (acnt & 1u) : 0u;
-        const uint32_t aph = (NBUF == 2) ? ((acnt >> 1) & 1u) : (acnt & 1u);
-        ptx::mbar_wait(&bars->acc_empty[buf], aph ^ 1u);
-        ptx::tc_fence_after();
-        const uint32_t acc0 = tmem_base + buf * static_cast<uint32_t>(NACC * NPAD);
-        uint32_t accum = 0u;
-        int ti = 0;  // tile index inside this chunk's weight stream
-        for (int si = 0; si < ci.set_count; ++si) {
-          const wdno_kset st = p.sets[ci.set_begin + si];
-          if (first_pass) {
-            for (int j = 0; j < p.ZT; ++j) {
-              uint32_t s = s0 + j, ph = sph;
-              if (s >= nslot) { s -= nslot; ph ^= 1u; }
-              ptx::mbar_wait(&bars->slab_full[s], ph);
-            }
-          }
-          int cur_kz = 0;
-          const wdno_tap* tp_ptr = s_taps + st.tap_begin;
-          for (int t = 0; t < st.tap_count; ++t, ++ti) {
-            const wdno_tap tp = tp_ptr[t];
-            while (cur_kz < tp.kz) {
-              // plane cur_kz is dead: release it; plane cur_kz + ZT becomes needed (KD > 1 never uses reuse)
-              uint32_t sd = s0 + cur_kz;
-              if (sd >= nslot) sd -= nslot;
-              if (ptx::elect_one()) ptx::tc_commit(&bars->slab_empty[sd]);
-              __syncwarp();
-              uint32_t sn = s0 + cur_kz + p.ZT, ph = sph;
-              if (sn >= nslot) { sn -= nslot; ph ^= 1u; }
-              ptx::mbar_wait(&bars->slab_full[sn], ph);
-              ++cur_kz;
-            }
-            const int tin = ti % p.TPS;
-            if (tin == 0) {
-              ptx::mbar_wait(&bars->b_full[bst], bph);
-              ptx::tc_fence_after();
-            }
-            const bool stage_done = (tin == p.TPS - 1) || (ti == ci.n_tiles - 1);
-            if (ptx::elect_one()) {
-              const uint32_t b_lo = b_lo0 + bst * bstage_u + static_cast<uint32_t>(tin) * btile_u;
-              for (int za = 0; za < p.ZT; ++za) {
-                uint32_t sa = s0 + tp.kz + za;
-                if (sa >= nslot) sa -= nslot;
-                const uint32_t a_lo = a_lo0 + sa * slot_u + static_cast<uint32_t>(tp.shift);
-                for (int pi = 0; pi < p.PT; ++pi) {
-                  const uint32_t dcol = acc0 + static_cast<uint32_t>((za * p.PT + pi) * NPAD);
-                  uint32_t al = a_lo + static_cast<uint32_t>(pi * 128), bl = b_lo;
-                  uint32_t acc_flag = accum;
-                  for (int k = 0; k < ksteps; ++k) {
-                    const uint64_t ad = (static_cast<uint64_t>(desc_hi) << 32) | al;
-                    const uint64_t bd = (static_cast<uint64_t>(desc_hi) << 32) | bl;
-                    ptx::tc_mma_f16(dcol, ad, bd, idesc, acc_flag);
-                    acc_flag = 1u;
-                    al += a_kstep;
-                    bl += b_kstep;
-                  }
-                }
-              }
-              if (stage_done) ptx::tc_commit(&bars->b_empty[bst]);
-            }
-            __syncwarp();
-            accum = 1u;
-            if (stage_done) {
-              if (++bst == static_cast<uint32_t>(p.NBST)) { bst = 0; bph ^= 1u; }
-            }
-          }
-          if (last_pass) {
-            if (ptx::elect_one()) {
-              for (int j = cur_kz; j < P; ++j) {
-                uint32_t sd = s0 + j;
-                if (sd >= nslot) sd -= nslot;
-                ptx::tc_commit(&bars->slab_empty[sd]);
-              }
-            }
-            __syncwarp();
-          }
-          s0 += static_cast<uint32_t>(P);
-          if (s0 >= nslot) { s0 -= nslot; sph ^= 1u; }
-        }
-        if (ptx::elect_one()) ptx::tc_commit(&bars->acc_full[buf]);
-        __syncwarp();
-      }
-    }
+    // ============================================================ MMA issuer (templated on the accumulator shape)
+    const int ks = p.KC >> 4;
+#define WDNO_MMA(ZT_, PT_) \
+    if (ks == 1) mma_role<ZT_, PT_, 1>(p, bars, s_taps, tmem_base, slab_base, b_base, n_work, ptiles, zgroups); \
+    else if (ks == 2) mma_role<ZT_, PT_, 2>(p, bars, s_taps, tmem_base, slab_base, b_base, n_work, ptiles, zgroups); \
+    else mma_role<ZT_, PT_, 4>(p, bars, s_taps, tmem_base, slab_base, b_base, n_work, ptiles, zgroups);
+    if (p.ZT == 4) { WDNO_MMA(4, 1) }
+    else if (p.ZT == 2) { WDNO_MMA(2, 1) }
+    else if (p.PT == 4) { WDNO_MMA(1, 4) }
+    else { WDNO_MMA(1, 1) }
+#undef WDNO_MMA
   } else {
     // ============================================================ epilogue warps 0..3
     const int row = warp * 32 + lane;
@@ -503,6 +536,9 @@ static int validate(const wdno_tapgemm_params* p) {
   if (p->NBST < 2 || p->NBST > kMaxBStages) return set_error(WDNO_E_INVALID, "tapgemm: NBST must be in [2,8]");
   if (p->n_taps < 1 || p->n_taps > kMaxTaps) return set_error(WDNO_E_INVALID, "tapgemm: n_taps must be in [1,384]");
   if (p->TPS < 1 || p->TPS > 64) return set_error(WDNO_E_INVALID, "tapgemm: TPS must be in [1,64]");
+  if (p->ZT != 4 && p->ZT != 2 && p->ZT != 1) return set_error(WDNO_E_INVALID, "tapgemm: ZT must be 4, 2 or 1");
+  if (p->ZT > 1 && p->PT != 1) return set_error(WDNO_E_INVALID, "tapgemm: PT must be 1 when ZT > 1");
+  if (p->ZT == 1 && p->PT != 1 && p->PT != 4) return set_error(WDNO_E_INVALID, "tapgemm: PT must be 1 or 4 when ZT == 1");
   if (p->reuse && p->KD != 1) return set_error(WDNO_E_INVALID, "tapgemm: slab reuse needs KD == 1");
   if (p->S_pad < 128 * p->PT + p->maxshift) return set_error(WDNO_E_INVALID, "tapgemm: S_pad smaller than slab");
   if (p->S_pad >= 16384) return set_error(WDNO_E_INVALID, "tapgemm: S_pad too large for descriptor");

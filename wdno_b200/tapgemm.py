@@ -244,9 +244,10 @@ class TapGemm:
             rem = {8: 1, 4: 2, 2: 4}[CH]
             S_pad = S + ((rem - S) % 8)
             slot = CH * S_pad * 16
-            tps0 = max(1, min(16384 // btile(KC), 16))
+            tpk = {"conv": KH * KW, "down144": 4, "up144": 4, "unshuffle": 1}[self.kind]  # taps per kz group
+            divs = [d for d in range(tpk, 0, -1) if tpk % d == 0 and (d * btile(KC) <= 16384 or d == 1)]
             for nslot in range(min(12, want_slots), min_slots - 1, -1):
-                for tps in sorted({tps0, max(1, tps0 // 2), 1}, reverse=True):
+                for tps in divs:
                     for nbst in (4, 3, 2):
                         if _BAR_BYTES + _round_up(nslot * slot, 128) + nbst * tps * btile(KC) <= _SMEM_LIMIT:
                             return S_pad, nslot, nbst, tps
@@ -259,7 +260,7 @@ class TapGemm:
             # A-stationary: all K-sets of a work item stay in the slab ring while every N-chunk is computed
             for KC in kcs:
                 sets = ctot // KC
-                for ZT in (min(4, D), min(2, D), 1):
+                for ZT in [z for z in (4, 2, 1) if z <= D]:
                     need = sets * ZT
                     if need > 12:
                         continue
@@ -270,8 +271,8 @@ class TapGemm:
                 if plan:
                     break
         if plan is None:
-            ZT = min(4, D)
-            PT = max(1, 4 // ZT)
+            ZT = 4 if D >= 4 else (2 if D >= 2 else 1)
+            PT = 4 if ZT == 1 else 1
             if self.N > 64:
                 while ZT * PT * 128 > 512:
                     PT = max(1, PT - 1)
