@@ -121,8 +121,9 @@ int wdno_gn_finalize(const double* stats, const float* gamma, const float* beta,
 /* out = silu(a*y + c) (+ resid) ; y,resid,out fp16 [B, vox_per_sample, C] */
 int wdno_gn_silu_add(const void* y, const float* a, const float* c, const void* resid, void* out, int B, int C,
                      int64_t vox_per_sample, void* stream);
-/* channel LayerNorm without bias: (x-mean)*rsqrt(var+eps)*gamma over C for each of nvox voxels (fp16 in/out) */
-int wdno_chan_layernorm(const void* x, const float* gamma, void* out, int64_t nvox, int C, float eps, void* stream);
+/* channel LayerNorm without bias: (x-mean)*rsqrt(var+eps)*gamma (+ resid) over C for each of nvox voxels (fp16 in/out) */
+int wdno_chan_layernorm(const void* x, const float* gamma, const void* resid, void* out, int64_t nvox, int C, float eps,
+                        void* stream);
 /* emb = W2*gelu(W1*sinusoid(time)+b1)+b2 ; also writes silu(emb).  time fp32 [B] */
 int wdno_time_mlp(const float* time, const float* w1, const float* b1, const float* w2, const float* b2, float* emb,
                   float* emb_silu, int B, int dim, int tdim, float theta, void* stream);

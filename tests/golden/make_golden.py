@@ -56,5 +56,34 @@ def smoke_fixture():
     print("smoke_ddim4", out["sample_norm"])
 
 
+def burgers_fixture():
+    b = ref_loader.burgers()
+    torch.manual_seed(0)
+    m = b.Unet2D(dim=128, dim_mults=[1, 2, 4, 8], channels=9, out_dim=9, resnet_block_groups=1).eval()
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(2, 9, 64, 64, generator=g)
+    t = torch.tensor([17, 803])
+    with torch.no_grad():
+        y = m(x, t)
+    out = dict(weights_checksum=checksum(m.state_dict()), x_checksum=float(x.double().abs().sum()), t=t, y=y.clone(),
+               y_norm=float(y.norm()))
+    # config C1: DDIM (4 steps here), eta = 0.5 (eta = 1 gives sqrt of a rounding-negative number at t=999 in the
+    # reference itself), u0 + f conditioning, padded 41x60 coefficients
+    gd = b.GaussianDiffusion(m, seq_length=(64, 64), is_wavelet=True, pad_mode="periodization", wave_type="bior2.4",
+                             padded_shape=[41, 60], ori_shape=[81, 120], timesteps=1000, sampling_timesteps=4,
+                             ddim_sampling_eta=0.5, is_condition_u0=True, is_condition_f=True)
+    u0 = torch.randn(2, 32, 64, generator=g)
+    f = torch.randn(2, 4, 64, 64, generator=g)
+    with patched_randn(NoiseTape(12)), torch.no_grad():
+        smp = gd.sample(batch_size=2, u_init=u0, f=f)
+    out.update(u0_checksum=float(u0.double().abs().sum()), sample=smp.clone(), sample_norm=float(smp.norm()), steps=4,
+               eta=0.5, tape_seed=12)
+    torch.save(out, os.path.join(HERE, "burgers_unet2d_ddim4.pt"))
+    print("burgers", out["weights_checksum"], out["y_norm"], out["sample_norm"])
+
+
 if __name__ == "__main__":
-    smoke_fixture()
+    if len(sys.argv) < 2 or sys.argv[1] == "smoke":
+        smoke_fixture()
+    if len(sys.argv) < 2 or sys.argv[1] == "burgers":
+        burgers_fixture()

@@ -42,7 +42,7 @@ def test_invalid_arguments_are_rejected_without_a_gpu(lib):
     assert rc == -1 and b"KC" in lib.wdno_last_error()
     with pytest.raises(ValueError):
         _lib.check(rc, "tapgemm")
-    assert lib.wdno_chan_layernorm(None, None, None, 0, 64, 1e-5, None) == -1
+    assert lib.wdno_chan_layernorm(None, None, None, None, 0, 64, 1e-5, None) == -1
     assert lib.wdno_dwt_analysis_axis(None, None, None, 1, 1, 1, 1, 1, 1, 1, None, None, 6, 4, 0, None) == -1
 
 

@@ -149,3 +149,63 @@ def test_engine_state_dict_keys_match_reference():
     assert all(a[k].shape == b[k].shape for k in a)
     # same construction order => same default-init weights under the same seed
     assert all(torch.equal(a[k], b[k]) for k in a)
+
+
+def _burgers_pair(S, eta, T=1000, dim=32, u0=True, uT=False, f=True):
+    from oracle.unet2d import Unet2DOracle
+    b = ref_loader.burgers()
+    torch.manual_seed(0)
+    m = b.Unet2D(dim=dim, dim_mults=[1, 2, 4, 8], channels=9, out_dim=9, resnet_block_groups=1).eval()
+    _perturb_norms(m)
+    gd = b.GaussianDiffusion(m, seq_length=(64, 64), is_wavelet=True, pad_mode="periodization", wave_type="bior2.4",
+                             padded_shape=[41, 60], ori_shape=[81, 120], timesteps=T, sampling_timesteps=S,
+                             ddim_sampling_eta=eta, loss_layer_weight=torch.linspace(0.5, 2, 9).reshape(1, 9, 1, 1),
+                             is_condition_u0=u0, is_condition_uT=uT, is_condition_f=f)
+    return b, m, gd, Unet2DOracle(m.state_dict())
+
+
+def test_unet2d_oracle_matches_reference():
+    b, m, gd, orc = _burgers_pair(3, 1.0)
+    x = torch.randn(2, 9, 64, 64)
+    t = torch.tensor([7, 950])
+    with torch.no_grad():
+        assert torch.allclose(m(x, t), orc(x, t), atol=1e-5, rtol=1e-5)
+
+
+def test_burgers_samplers_and_losses_oracle_match_reference():
+    from oracle import diffusion as D
+    b, m, gd, orc = _burgers_pair(3, 0.5, uT=True)  # eta=1 makes sqrt(1-an-sigma^2) NaN at t=999 in the reference too
+    u0, uT, f = torch.randn(2, 32, 64), torch.randn(2, 32, 64), torch.randn(2, 4, 64, 64)
+    with patched_randn(NoiseTape(3)), torch.no_grad():
+        ref = gd.sample(batch_size=2, u_init=u0, u_final=uT, f=f)
+    sch = D.schedule("cosine", 1000)
+    assert torch.equal(sch["alphas_cumprod"], gd.alphas_cumprod)
+    with torch.no_grad():
+        got = D.burgers_ddim_sample(orc, sch, (2, 9, 64, 64), 3, 0.5, NoiseTape(3), [41, 60], u0, uT, f)
+    assert torch.allclose(ref, got, atol=2e-5, rtol=1e-5)
+    b, m, gd, orc = _burgers_pair(None, 0.0, T=4)
+    with patched_randn(NoiseTape(4)), torch.no_grad():
+        ref = gd.sample(batch_size=2, u_init=u0, f=f)
+    sch = D.schedule("cosine", 4)
+    with torch.no_grad():
+        got = D.burgers_ddpm_sample(orc, sch, (2, 9, 64, 64), NoiseTape(4), [41, 60], u0, None, f, T=4)
+    assert torch.allclose(ref, got, atol=2e-5, rtol=1e-5)
+    x0 = torch.randn(2, 9, 64, 64).clamp(-1, 1)
+    t = torch.tensor([0, 3])
+    noise = torch.randn_like(x0)
+    with torch.no_grad():
+        ref_l = gd.p_losses(x0.clone(), t, noise.clone())
+        got_l = D.burgers_p_losses(orc, sch, x0, t, noise, [41, 60], gd.loss_layer_weight, cond_u0=True, cond_uT=False,
+                                   cond_f=True)
+    assert abs(float(ref_l) - float(got_l)) < 1e-5 * max(1.0, abs(float(ref_l)))
+
+
+def test_burgers_engine_state_dict_matches_reference():
+    from wdno_b200.unet2d import Unet2D
+    b = ref_loader.burgers()
+    torch.manual_seed(0)
+    ref = b.Unet2D(dim=128, dim_mults=[1, 2, 4, 8], channels=9, out_dim=9, resnet_block_groups=1)
+    torch.manual_seed(0)
+    mine = Unet2D(dim=128, dim_mults=[1, 2, 4, 8], channels=9, out_dim=9, resnet_block_groups=1)
+    a, c = ref.state_dict(), mine.state_dict()
+    assert list(a.keys()) == list(c.keys()) and all(torch.equal(a[k], c[k]) for k in a)

@@ -21,7 +21,7 @@ SIGNATURES = {
     "wdno_pack_bfchw_f16": [P, P, I, I, I, I, I, I, P],
     "wdno_gn_finalize": [P, P, P, P, I, P, P, I, I, I, D, F, P],
     "wdno_gn_silu_add": [P, P, P, P, P, I, I, L64, P],
-    "wdno_chan_layernorm": [P, P, P, L64, I, F, P],
+    "wdno_chan_layernorm": [P, P, P, P, L64, I, F, P],
     "wdno_time_mlp": [P, P, P, P, P, P, P, I, I, I, F, P],
     "wdno_small_linear": [P, P, P, P, I, I, I, P],
     "wdno_softmax_attn": [P, P, P, P, P, L64, I, L64, L64, L64, L64, F, P],

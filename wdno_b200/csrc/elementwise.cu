@@ -114,7 +114,7 @@ __global__ void gn_silu_add_kernel(const __half* __restrict__ y, const float* __
 // LPV lanes cooperate on one voxel; each lane owns C/(8*LPV) 16-byte chunks.
 template <int LPV, int CPL>
 __global__ void chan_layernorm_kernel(const __half* __restrict__ x, const float* __restrict__ gamma,
-                                      __half* __restrict__ out, size_t nvox, float eps) {
+                                      const __half* __restrict__ resid, __half* __restrict__ out, size_t nvox, float eps) {
   constexpr int C = LPV * CPL * 8;
   const size_t gt = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
   const size_t vox = gt / LPV;
@@ -151,12 +151,15 @@ __global__ void chan_layernorm_kernel(const __half* __restrict__ x, const float*
 #pragma unroll
   for (int k = 0; k < CPL; ++k) {
     const int ch = (k * LPV + l) * 8;
-    uint4 ov;
+    uint4 ov, rv = make_uint4(0u, 0u, 0u, 0u);
+    if (resid != nullptr) rv = __ldg(reinterpret_cast<const uint4*>(resid + vox * C) + k * LPV + l);
     __half2* oh = reinterpret_cast<__half2*>(&ov);
+    const __half2* rh = reinterpret_cast<const __half2*>(&rv);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float g0 = __ldg(gamma + ch + 2 * j), g1 = __ldg(gamma + ch + 2 * j + 1);
-      oh[j] = __floats2half2_rn((f[k * 8 + 2 * j] - mean) * rstd * g0, (f[k * 8 + 2 * j + 1] - mean) * rstd * g1);
+      const float2 rr = __half22float2(rh[j]);
+      oh[j] = __floats2half2_rn((f[k * 8 + 2 * j] - mean) * rstd * g0 + rr.x, (f[k * 8 + 2 * j + 1] - mean) * rstd * g1 + rr.y);
     }
     reinterpret_cast<uint4*>(out + vox * C)[k * LPV + l] = ov;
   }
@@ -248,18 +251,19 @@ extern "C" int wdno_gn_silu_add(const void* y, const float* a, const float* c, c
   return check_launch("gn_silu_add");
 }
 
-extern "C" int wdno_chan_layernorm(const void* x, const float* gamma, void* out, int64_t nvox, int C, float eps,
-                                   void* stream) {
+extern "C" int wdno_chan_layernorm(const void* x, const float* gamma, const void* resid, void* out, int64_t nvox, int C,
+                                   float eps, void* stream) {
   if (!x || !gamma || !out || nvox < 1) return set_error(WDNO_E_INVALID, "chan_layernorm: bad arguments");
   const __half* xi = static_cast<const __half*>(x);
   __half* o = static_cast<__half*>(out);
+  const __half* rs = static_cast<const __half*>(resid);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int threads = 256;
 #define WDNO_LN(LPV, CPL)                                                                              \
   {                                                                                                    \
     const size_t total = static_cast<size_t>(nvox) * LPV;                                              \
     chan_layernorm_kernel<LPV, CPL><<<static_cast<unsigned>((total + threads - 1) / threads), threads, 0, st>>>( \
-        xi, gamma, o, static_cast<size_t>(nvox), eps);                                                 \
+        xi, gamma, rs, o, static_cast<size_t>(nvox), eps);                                                 \
   }
   switch (C) {
     case 64: WDNO_LN(8, 1); break;

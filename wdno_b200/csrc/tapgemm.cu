@@ -412,9 +412,23 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const wdno_tapgemm
                     static_cast<size_t>(y) * p.W + x;
           }
           const int n16 = p.N >> 4;
+          // residual row prefetch, 64 columns at a time, so the global loads overlap the TMEM reads
+          uint4 rpre[8];
+          const bool has_res = (p.resid != nullptr) && valid && (p.out_mode != 2);
+          const __half* res_row = static_cast<const __half*>(p.resid) + obase;
+          if (has_res) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              if (q * 8 < ci.n_valid) rpre[q] = __ldg(reinterpret_cast<const uint4*>(res_row + q * 8));
+          }
 #pragma unroll
           for (int c16 = 0; c16 < 8; ++c16) {
             if (c16 >= n16) break;
+            if (c16 == 4 && has_res) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q)
+                if (64 + q * 8 < ci.n_valid) rpre[q] = __ldg(reinterpret_cast<const uint4*>(res_row + 64 + q * 8));
+            }
             uint32_t r[16];
             ptx::tmem_ld16(tcol + static_cast<uint32_t>(c16 * 16), r);
             ptx::tmem_ld_wait();
@@ -449,8 +463,8 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const wdno_tapgemm
               for (int hb = 0; hb < 2; ++hb) {
                 if (ncol0 + hb * 8 >= ci.n_valid) continue;
                 const size_t off = obase + ncol0 + hb * 8;
-                if (p.resid != nullptr) {
-                  const uint4 rv = __ldg(reinterpret_cast<const uint4*>(static_cast<const __half*>(p.resid) + off));
+                if (has_res) {
+                  const uint4 rv = rpre[(c16 & 3) * 2 + hb];
                   const __half2* rh = reinterpret_cast<const __half2*>(&rv);
 #pragma unroll
                   for (int i = 0; i < 4; ++i) {

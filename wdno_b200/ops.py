@@ -48,11 +48,11 @@ def gn_silu_add(y, a, c, resid=None):
     return out
 
 
-def chan_layernorm(x, gamma, eps=1e-5):
+def chan_layernorm(x, gamma, eps=1e-5, resid=None):
     _chk(x, torch.float16, "x")
     Cc = x.shape[-1]
     out = torch.empty_like(x)
-    _lib.check(_lib.lib().wdno_chan_layernorm(_p(x), _p(gamma), _p(out), x.numel() // Cc, Cc, float(eps), _st()),
+    _lib.check(_lib.lib().wdno_chan_layernorm(_p(x), _p(gamma), _p(resid), _p(out), x.numel() // Cc, Cc, float(eps), _st()),
                "chan_layernorm")
     return out
 
