@@ -43,7 +43,8 @@ def test_tapgemm_against_torch_conv(case):
     # fp16 output rounding (2^-11 relative to the largest magnitude) dominates
     for k, v in r.items():
         if k.startswith("err"):
-            assert v < 1.5e-3, (r["name"], k, v)
+            for e in (v if isinstance(v, list) else [v]):
+                assert e < 1.5e-3, (r["name"], k, v)
 
 
 def test_elementwise_kernels():
