@@ -144,6 +144,7 @@ __device__ __forceinline__ void mma_role(const wdno_tapgemm_params& p, Bars* bar
             if (s >= nslot) { s -= nslot; ph ^= 1u; }
             ptx::mbar_wait(&bars->slab_full[s], ph);
           }
+          ptx::fence_proxy_async_smem();  // cp.async (generic proxy) slab writes -> tcgen05 (async proxy) reads
         }
         const wdno_tap* tp_ptr = s_taps + st.tap_begin;
         for (int kz = 0; kz < KD; ++kz) {
@@ -158,6 +159,7 @@ __device__ __forceinline__ void mma_role(const wdno_tapgemm_params& p, Bars* bar
             uint32_t sn = s0 + kz + ZT - 1, ph = sph;
             if (sn >= nslot) { sn -= nslot; ph ^= 1u; }
             ptx::mbar_wait(&bars->slab_full[sn], ph);
+            ptx::fence_proxy_async_smem();
           }
           for (int g = 0; g < groups_per_kz; ++g) {
             ptx::mbar_wait(&bars->b_full[bst], bph);
@@ -226,7 +228,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const wdno_tapgemm
   // ---------------------------------------------------------------- setup
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.NSLOT; ++i) {
-      ptx::mbar_init(&bars->slab_full[i], kProdWarps);
+      ptx::mbar_init(&bars->slab_full[i], kProdThreads);  // every producer thread arrives (directly or via cp.async)
       ptx::mbar_init(&bars->slab_empty[i], 1);
     }
     for (int i = 0; i < p.NBST; ++i) {
@@ -262,6 +264,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const wdno_tapgemm
     int Hs = p.H, Ws = p.W;
     if (p.src_mode == 1) { Hs = 2 * p.H; Ws = 2 * p.W; }
     if (p.src_mode == 2) { Hs = p.H >> 1; Ws = p.W >> 1; }
+    const bool any_act = (p.coef_a[0] != nullptr) || (p.coef_a[1] != nullptr);
     uint32_t slot = 0, sph = 0;
     for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
       const Work wk = decode_work(w, p.n_chunks, ptiles, zgroups, p.reuse);
@@ -292,50 +295,69 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const wdno_tapgemm
           const bool zok = (zi >= 0) && (zi < p.D);
           const __half* plane = src + ((static_cast<size_t>(wk.b) * p.D + (zok ? zi : 0)) * Hs * Ws) * csrc + chn;
           int s = s_first, yp = yp0, xp = xp0;
-          while (s < S) {
-            uint4 v[kLoadBatch];
-            bool ok[kLoadBatch];
-            int so[kLoadBatch];
-#pragma unroll
-            for (int k = 0; k < kLoadBatch; ++k) {
-              v[k] = make_uint4(0u, 0u, 0u, 0u);
-              ok[k] = false;
-              so[k] = s;
-              if (s < S) {
-                const int y = yp - p.py, x = xp - p.px;
-                if (zok && y >= 0 && y < p.H && x >= 0 && x < p.W) {
-                  int ys = y, xs = x;
-                  if (p.src_mode == 1) { ys = 2 * y + st.ph_y; xs = 2 * x + st.ph_x; }
-                  if (p.src_mode == 2) { ys = y >> 1; xs = x >> 1; }
-                  v[k] = __ldg(reinterpret_cast<const uint4*>(plane + (static_cast<size_t>(ys) * Ws + xs) * csrc));
-                  ok[k] = true;
-                }
-              }
+          if (!any_act) {
+            // identity prologue: asynchronous 16-byte copies (LDGSTS, zero-fill outside the tensor) -- no register
+            // staging, so a thread keeps every copy of the plane in flight and moves on to the next slot
+            const uint32_t dst_u32 = ptx::smem_u32(dst);
+            while (s < S) {
+              const int y = yp - p.py, x = xp - p.px;
+              const bool ok = zok && y >= 0 && y < p.H && x >= 0 && x < p.W;
+              int ys = y, xs = x;
+              if (p.src_mode == 1) { ys = 2 * y + st.ph_y; xs = 2 * x + st.ph_x; }
+              if (p.src_mode == 2) { ys = y >> 1; xs = x >> 1; }
+              const __half* ptr = ok ? plane + (static_cast<size_t>(ys) * Ws + xs) * csrc : plane;
+              ptx::cp_async16_zfill(dst_u32 + static_cast<uint32_t>(s) * 16u, ptr, ok ? 16u : 0u);
               s += SP;
               xp += step_x;
               yp += step_y;
               if (xp >= p.Wp) { xp -= p.Wp; ++yp; }
             }
+            ptx::cp_async_mbar_arrive_noinc(&bars->slab_full[slot]);
+          } else {
+            while (s < S) {
+              uint4 v[kLoadBatch];
+              bool ok[kLoadBatch];
+              int so[kLoadBatch];
 #pragma unroll
-            for (int k = 0; k < kLoadBatch; ++k) {
-              if (so[k] >= S) continue;
-              if (act && ok[k]) {
-                __half2* h = reinterpret_cast<__half2*>(&v[k]);
-                float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]);
-                float2 f2 = __half22float2(h[2]), f3 = __half22float2(h[3]);
-                f0.x = silu_f(fmaf(a0.x, f0.x, c0.x)); f0.y = silu_f(fmaf(a0.y, f0.y, c0.y));
-                f1.x = silu_f(fmaf(a0.z, f1.x, c0.z)); f1.y = silu_f(fmaf(a0.w, f1.y, c0.w));
-                f2.x = silu_f(fmaf(a1.x, f2.x, c1.x)); f2.y = silu_f(fmaf(a1.y, f2.y, c1.y));
-                f3.x = silu_f(fmaf(a1.z, f3.x, c1.z)); f3.y = silu_f(fmaf(a1.w, f3.y, c1.w));
-                h[0] = __float22half2_rn(f0); h[1] = __float22half2_rn(f1);
-                h[2] = __float22half2_rn(f2); h[3] = __float22half2_rn(f3);
+              for (int k = 0; k < kLoadBatch; ++k) {
+                v[k] = make_uint4(0u, 0u, 0u, 0u);
+                ok[k] = false;
+                so[k] = s;
+                if (s < S) {
+                  const int y = yp - p.py, x = xp - p.px;
+                  if (zok && y >= 0 && y < p.H && x >= 0 && x < p.W) {
+                    int ys = y, xs = x;
+                    if (p.src_mode == 1) { ys = 2 * y + st.ph_y; xs = 2 * x + st.ph_x; }
+                    if (p.src_mode == 2) { ys = y >> 1; xs = x >> 1; }
+                    v[k] = __ldg(reinterpret_cast<const uint4*>(plane + (static_cast<size_t>(ys) * Ws + xs) * csrc));
+                    ok[k] = true;
+                  }
+                }
+                s += SP;
+                xp += step_x;
+                yp += step_y;
+                if (xp >= p.Wp) { xp -= p.Wp; ++yp; }
               }
-              *reinterpret_cast<uint4*>(dst + static_cast<size_t>(so[k]) * 16) = v[k];
+#pragma unroll
+              for (int k = 0; k < kLoadBatch; ++k) {
+                if (so[k] >= S) continue;
+                if (act && ok[k]) {
+                  __half2* h = reinterpret_cast<__half2*>(&v[k]);
+                  float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]);
+                  float2 f2 = __half22float2(h[2]), f3 = __half22float2(h[3]);
+                  f0.x = silu_f(fmaf(a0.x, f0.x, c0.x)); f0.y = silu_f(fmaf(a0.y, f0.y, c0.y));
+                  f1.x = silu_f(fmaf(a0.z, f1.x, c0.z)); f1.y = silu_f(fmaf(a0.w, f1.y, c0.w));
+                  f2.x = silu_f(fmaf(a1.x, f2.x, c1.x)); f2.y = silu_f(fmaf(a1.y, f2.y, c1.y));
+                  f3.x = silu_f(fmaf(a1.z, f3.x, c1.z)); f3.y = silu_f(fmaf(a1.w, f3.y, c1.w));
+                  h[0] = __float22half2_rn(f0); h[1] = __float22half2_rn(f1);
+                  h[2] = __float22half2_rn(f2); h[3] = __float22half2_rn(f3);
+                }
+                *reinterpret_cast<uint4*>(dst + static_cast<size_t>(so[k]) * 16) = v[k];
+              }
             }
+            ptx::fence_proxy_async_smem();
+            ptx::mbar_arrive(&bars->slab_full[slot]);
           }
-          ptx::fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&bars->slab_full[slot]);
           if (++slot == static_cast<uint32_t>(p.NSLOT)) { slot = 0; sph ^= 1u; }
         }
       }

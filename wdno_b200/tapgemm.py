@@ -12,6 +12,7 @@ enqueues one kernel on the current torch CUDA stream.  Layer kinds (reference ca
   conv+up2   nn.Upsample(scale_factor=2, 'nearest') + Conv2d(3, padding=1)           (unet.py:35-39): kind='conv', up2=True
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -68,6 +69,9 @@ class TapGemm:
         assert self.KD % 2 == 1 and self.KH % 2 == 1 and self.KW % 2 == 1
         if n_tile is None:
             n_tile = 64 if self.cout >= 64 else _round_up(self.cout, 16)
+            big = int(os.environ.get("WDNO_NTILE_BIG", "1"))  # tuning knob: N=128 tiles for wide spatial convolutions
+            if big and self.cout % 128 == 0 and kind == "conv" and w.shape[2] * w.shape[3] * w.shape[4] > 1:
+                n_tile = 128
         self.N = int(n_tile)
         self.cout_pad = _round_up(self.cout, self.N)
         self.kc_override = kc

@@ -268,17 +268,25 @@ class Unet3DEngine:
         self.stats_slots += 2
         return p
 
+    def _out_plus_residual(self, weight, bias):
+        """to_out(o) + x as ONE GEMM: the residual stream x is appended as an extra K-set with identity weights
+        ([W | I] over the concatenated sources (o, x)); x*1.0 accumulates exactly in fp32, and the residual is read by
+        the deep asynchronous operand pipeline instead of the epilogue."""
+        w = weight.detach().float().cpu().reshape(weight.shape[0], -1)
+        c = w.shape[0]
+        return TapGemm(torch.cat((w, torch.eye(c)), dim=1), bias, src_channels=(w.shape[1], c), device=self.dev)
+
     def _attn_plan(self, res, temporal):
         attn = res.fn.fn.fn
         return dict(gamma=self._f32(res.fn.norm.gamma.reshape(-1)),
                     qkv=TapGemm(attn.to_qkv.weight, None, device=self.dev),
-                    out=TapGemm(attn.to_out.weight, None, device=self.dev), temporal=temporal)
+                    out=self._out_plus_residual(attn.to_out.weight, None), temporal=temporal)
 
     def _lin_attn_plan(self, res):
         attn = res.fn.fn
         return dict(gamma=self._f32(res.fn.norm.gamma.reshape(-1)),
                     qkv=TapGemm(attn.to_qkv.weight, None, device=self.dev),
-                    out=TapGemm(attn.to_out.weight, attn.to_out.bias, device=self.dev))
+                    out=self._out_plus_residual(attn.to_out.weight, attn.to_out.bias))
 
     def _rel_tables(self, n):
         """T5 relative-position bias [heads][n][n] (conv3d.py:74-112) and rotary cos/sin [n][16]."""
@@ -328,7 +336,7 @@ class Unet3DEngine:
         qkv = ap["qkv"](xn)
         o = ops.softmax_attn(qkv, B * H * W, D, H * W, D * H * W, 1, H * W, self.scale, bias=bias, rot=rot)
         self.launches += 4
-        return ap["out"](o, resid=x)
+        return ap["out"](o, x)
 
     def _mid_spatial_attn(self, ap, x):
         B, D, H, W, C = x.shape
@@ -336,7 +344,7 @@ class Unet3DEngine:
         qkv = ap["qkv"](xn)
         o = ops.softmax_attn(qkv, B * D, H * W, 1, H * W, 0, 1, self.scale)
         self.launches += 4
-        return ap["out"](o, resid=x)
+        return ap["out"](o, x)
 
     def _linear_attn(self, ap, x):
         B, D, H, W, C = x.shape
@@ -344,7 +352,7 @@ class Unet3DEngine:
         qkv = ap["qkv"](xn)
         o = ops.linear_attn(qkv, B * D, H * W, self.scale)
         self.launches += 4
-        return ap["out"](o, resid=x)
+        return ap["out"](o, x)
 
     # ------------------------------------------------------------ forward
     def forward(self, x, time, taps=None):
