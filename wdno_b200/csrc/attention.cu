@@ -271,6 +271,9 @@ extern "C" int wdno_softmax_attn(const void* qkv, void* out, const float* bias, 
                                  float scale, void* stream) {
   if (!qkv || !out || n_seq < 1 || n_tok < 1 || inner < 1) return set_error(WDNO_E_INVALID, "softmax_attn: bad arguments");
   if ((rot_cos == nullptr) != (rot_sin == nullptr)) return set_error(WDNO_E_INVALID, "softmax_attn: rotary tables must both be given");
+  if (n_tok <= 32)  // short sequences (temporal attention): tensor-core kernel
+    return launch_short_attn_mma(qkv, out, bias, rot_cos, rot_sin, n_seq, n_tok, inner, outerT, innerT, tokT, scale,
+                                 static_cast<cudaStream_t>(stream));
   SeqMap m{inner, outerT, innerT, tokT};
   int qt = ((n_tok + 31) / 32) * 32;
   if (qt > 128) qt = 128;
