@@ -71,7 +71,15 @@ __device__ __forceinline__ Work decode_work(int w, int n_chunks, int ptiles, int
   return k;
 }
 
-__device__ __forceinline__ float silu_f(float v) { return v / (1.0f + __expf(-v)); }
+// silu(v) = v * sigmoid(v) = 0.5 v (1 + tanh(v/2)): one MUFU op (tanh.approx.f32, rel. error 2^-11, i.e. the fp16 rounding
+// the value receives anyway) instead of ex2 + rcp + Newton steps -- the fused prologue recomputes halo positions, so its
+// transcendental count is ~2.5x that of a stand-alone pass and must stay off the critical path
+__device__ __forceinline__ float silu_f(float v) {
+  const float h = 0.5f * v;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
 
 // ------------------------------------------------------------------ MMA issue
 // All MMAs of one weight tile: ZT*PT accumulators x KS k-steps, fully unrolled, operands in registers.
@@ -253,7 +261,11 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const wdno_tapgemm
 
   if (warp >= kFirstProdWarp) {
     // ============================================================ A producers
-    // thread -> fixed 16-byte chunk c of positions s0, s0+SP, s0+2SP, ...; (yp, xp) advance without divisions
+    // thread -> fixed 16-byte chunk c of positions s_first, s_first+SP, ...; (yp, xp) advance without divisions.
+    // Every plane is fetched with asynchronous 16-byte copies (LDGSTS, zero fill outside the tensor).  Identity
+    // prologue: the copies signal the slot's mbarrier themselves, so a thread never waits for data.  GroupNorm+SiLU
+    // prologue: up to kAhead planes are kept in flight (cp.async groups); the oldest one is then transformed in
+    // place in shared memory (each thread touches only the chunks it copied) and published.
     const int ptid = threadIdx.x - kFirstProdWarp * 32;
     const int S = 128 * p.PT + p.maxshift;  // positions needed per plane
     const int c = ptid & (CH - 1);
@@ -265,101 +277,130 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const wdno_tapgemm
     if (p.src_mode == 1) { Hs = 2 * p.H; Ws = 2 * p.W; }
     if (p.src_mode == 2) { Hs = p.H >> 1; Ws = p.W >> 1; }
     const bool any_act = (p.coef_a[0] != nullptr) || (p.coef_a[1] != nullptr);
-    uint32_t slot = 0, sph = 0;
-    for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-      const Work wk = decode_work(w, p.n_chunks, ptiles, zgroups, p.reuse);
+
+    // cursor over the sequence of plane jobs (work item, K-set, plane) this CTA produces
+    struct Cursor {
+      int w, si, j, nset, set_begin;
+      uint32_t slot, ph;
+      int b, z0, yp0, xp0;
+    };
+    auto load_work = [&](Cursor& cu) {
+      if (cu.w >= n_work) return;
+      const Work wk = decode_work(cu.w, p.n_chunks, ptiles, zgroups, p.reuse);
       const wdno_nchunk ci = p.chunks[wk.nc0];  // with reuse every chunk shares chunk 0's K-sets
-      const int o0 = wk.pt * 128 * p.PT;
-      const int z0 = wk.zg * p.ZT;
-      const int q0 = o0 + s_first;
-      const int yp0 = q0 / p.Wp, xp0 = q0 - yp0 * p.Wp;
-      for (int si = 0; si < ci.set_count; ++si) {
-        const wdno_kset st = p.sets[ci.set_begin + si];
-        const __half* src = static_cast<const __half*>(p.src[st.src]);
-        const int csrc = p.src_c[st.src];
-        const int chn = st.ch_off + c * 8;
-        float4 a0, a1, c0, c1;
-        const bool act = p.coef_a[st.src] != nullptr;
-        if (act) {
-          const float* pa = p.coef_a[st.src] + static_cast<size_t>(wk.b) * csrc + chn;
-          const float* pc = p.coef_c[st.src] + static_cast<size_t>(wk.b) * csrc + chn;
-          a0 = __ldg(reinterpret_cast<const float4*>(pa));
-          a1 = __ldg(reinterpret_cast<const float4*>(pa + 4));
-          c0 = __ldg(reinterpret_cast<const float4*>(pc));
-          c1 = __ldg(reinterpret_cast<const float4*>(pc + 4));
+      cu.nset = ci.set_count;
+      cu.set_begin = ci.set_begin;
+      cu.b = wk.b;
+      cu.z0 = wk.zg * p.ZT;
+      const int q0 = wk.pt * 128 * p.PT + s_first;
+      cu.yp0 = q0 / p.Wp;
+      cu.xp0 = q0 - cu.yp0 * p.Wp;
+    };
+    auto advance = [&](Cursor& cu) {
+      if (++cu.slot == static_cast<uint32_t>(p.NSLOT)) { cu.slot = 0; cu.ph ^= 1u; }
+      if (++cu.j == P) {
+        cu.j = 0;
+        if (++cu.si == cu.nset) {
+          cu.si = 0;
+          cu.w += gridDim.x;
+          load_work(cu);
         }
-        for (int j = 0; j < P; ++j) {
-          ptx::mbar_wait(&bars->slab_empty[slot], sph ^ 1u);
-          uint8_t* dst = slab_base + static_cast<size_t>(slot) * slot_bytes + static_cast<size_t>(c) * lbo_a;
-          const int zi = z0 - p.pz + j;
-          const bool zok = (zi >= 0) && (zi < p.D);
-          const __half* plane = src + ((static_cast<size_t>(wk.b) * p.D + (zok ? zi : 0)) * Hs * Ws) * csrc + chn;
-          int s = s_first, yp = yp0, xp = xp0;
-          if (!any_act) {
-            // identity prologue: asynchronous 16-byte copies (LDGSTS, zero-fill outside the tensor) -- no register
-            // staging, so a thread keeps every copy of the plane in flight and moves on to the next slot
-            const uint32_t dst_u32 = ptx::smem_u32(dst);
-            while (s < S) {
-              const int y = yp - p.py, x = xp - p.px;
-              const bool ok = zok && y >= 0 && y < p.H && x >= 0 && x < p.W;
-              int ys = y, xs = x;
-              if (p.src_mode == 1) { ys = 2 * y + st.ph_y; xs = 2 * x + st.ph_x; }
-              if (p.src_mode == 2) { ys = y >> 1; xs = x >> 1; }
-              const __half* ptr = ok ? plane + (static_cast<size_t>(ys) * Ws + xs) * csrc : plane;
-              ptx::cp_async16_zfill(dst_u32 + static_cast<uint32_t>(s) * 16u, ptr, ok ? 16u : 0u);
-              s += SP;
-              xp += step_x;
-              yp += step_y;
-              if (xp >= p.Wp) { xp -= p.Wp; ++yp; }
-            }
-            ptx::cp_async_mbar_arrive_noinc(&bars->slab_full[slot]);
-          } else {
-            while (s < S) {
-              uint4 v[kLoadBatch];
-              bool ok[kLoadBatch];
-              int so[kLoadBatch];
-#pragma unroll
-              for (int k = 0; k < kLoadBatch; ++k) {
-                v[k] = make_uint4(0u, 0u, 0u, 0u);
-                ok[k] = false;
-                so[k] = s;
-                if (s < S) {
-                  const int y = yp - p.py, x = xp - p.px;
-                  if (zok && y >= 0 && y < p.H && x >= 0 && x < p.W) {
-                    int ys = y, xs = x;
-                    if (p.src_mode == 1) { ys = 2 * y + st.ph_y; xs = 2 * x + st.ph_x; }
-                    if (p.src_mode == 2) { ys = y >> 1; xs = x >> 1; }
-                    v[k] = __ldg(reinterpret_cast<const uint4*>(plane + (static_cast<size_t>(ys) * Ws + xs) * csrc));
-                    ok[k] = true;
-                  }
-                }
-                s += SP;
-                xp += step_x;
-                yp += step_y;
-                if (xp >= p.Wp) { xp -= p.Wp; ++yp; }
-              }
-#pragma unroll
-              for (int k = 0; k < kLoadBatch; ++k) {
-                if (so[k] >= S) continue;
-                if (act && ok[k]) {
-                  __half2* h = reinterpret_cast<__half2*>(&v[k]);
-                  float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]);
-                  float2 f2 = __half22float2(h[2]), f3 = __half22float2(h[3]);
-                  f0.x = silu_f(fmaf(a0.x, f0.x, c0.x)); f0.y = silu_f(fmaf(a0.y, f0.y, c0.y));
-                  f1.x = silu_f(fmaf(a0.z, f1.x, c0.z)); f1.y = silu_f(fmaf(a0.w, f1.y, c0.w));
-                  f2.x = silu_f(fmaf(a1.x, f2.x, c1.x)); f2.y = silu_f(fmaf(a1.y, f2.y, c1.y));
-                  f3.x = silu_f(fmaf(a1.z, f3.x, c1.z)); f3.y = silu_f(fmaf(a1.w, f3.y, c1.w));
-                  h[0] = __float22half2_rn(f0); h[1] = __float22half2_rn(f1);
-                  h[2] = __float22half2_rn(f2); h[3] = __float22half2_rn(f3);
-                }
-                *reinterpret_cast<uint4*>(dst + static_cast<size_t>(so[k]) * 16) = v[k];
-              }
-            }
-            ptx::fence_proxy_async_smem();
-            ptx::mbar_arrive(&bars->slab_full[slot]);
+      }
+    };
+    // issue the asynchronous copies of the cursor's plane (the slot must be free)
+    auto issue = [&](const Cursor& cu) {
+      const wdno_kset st = p.sets[cu.set_begin + cu.si];
+      const int csrc = p.src_c[st.src];
+      const int zi = cu.z0 - p.pz + cu.j;
+      const bool zok = (zi >= 0) && (zi < p.D);
+      const __half* plane = static_cast<const __half*>(p.src[st.src]) +
+                            ((static_cast<size_t>(cu.b) * p.D + (zok ? zi : 0)) * Hs * Ws) * csrc + st.ch_off + c * 8;
+      const uint32_t dst = ptx::smem_u32(slab_base) + cu.slot * slot_bytes + static_cast<uint32_t>(c) * lbo_a;
+      int yp = cu.yp0, xp = cu.xp0;
+      for (int s = s_first; s < S; s += SP) {
+        const int y = yp - p.py, x = xp - p.px;
+        const bool ok = zok && y >= 0 && y < p.H && x >= 0 && x < p.W;
+        int ys = y, xs = x;
+        if (p.src_mode == 1) { ys = 2 * y + st.ph_y; xs = 2 * x + st.ph_x; }
+        if (p.src_mode == 2) { ys = y >> 1; xs = x >> 1; }
+        const __half* ptr = ok ? plane + (static_cast<size_t>(ys) * Ws + xs) * csrc : plane;
+        ptx::cp_async16_zfill(dst + static_cast<uint32_t>(s) * 16u, ptr, ok ? 16u : 0u);
+        xp += step_x;
+        yp += step_y;
+        if (xp >= p.Wp) { xp -= p.Wp; ++yp; }
+      }
+    };
+    // in-place silu(a*x + c) on the chunks this thread copied (zero-filled positions stay zero)
+    auto transform = [&](const Cursor& cu) {
+      const wdno_kset st = p.sets[cu.set_begin + cu.si];
+      if (p.coef_a[st.src] == nullptr) return;
+      const int csrc = p.src_c[st.src];
+      const int chn = st.ch_off + c * 8;
+      const float* pa = p.coef_a[st.src] + static_cast<size_t>(cu.b) * csrc + chn;
+      const float* pc = p.coef_c[st.src] + static_cast<size_t>(cu.b) * csrc + chn;
+      const float4 a0 = __ldg(reinterpret_cast<const float4*>(pa)), a1 = __ldg(reinterpret_cast<const float4*>(pa + 4));
+      const float4 c0 = __ldg(reinterpret_cast<const float4*>(pc)), c1 = __ldg(reinterpret_cast<const float4*>(pc + 4));
+      const int zi = cu.z0 - p.pz + cu.j;
+      if (zi < 0 || zi >= p.D) return;
+      uint8_t* dst = slab_base + static_cast<size_t>(cu.slot) * slot_bytes + static_cast<size_t>(c) * lbo_a;
+      int yp = cu.yp0, xp = cu.xp0;
+      for (int s = s_first; s < S; s += SP) {
+        const int y = yp - p.py, x = xp - p.px;
+        if (y >= 0 && y < p.H && x >= 0 && x < p.W) {
+          uint4 v = *reinterpret_cast<const uint4*>(dst + static_cast<size_t>(s) * 16);
+          __half2* h = reinterpret_cast<__half2*>(&v);
+          float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]);
+          float2 f2 = __half22float2(h[2]), f3 = __half22float2(h[3]);
+          f0.x = silu_f(fmaf(a0.x, f0.x, c0.x)); f0.y = silu_f(fmaf(a0.y, f0.y, c0.y));
+          f1.x = silu_f(fmaf(a0.z, f1.x, c0.z)); f1.y = silu_f(fmaf(a0.w, f1.y, c0.w));
+          f2.x = silu_f(fmaf(a1.x, f2.x, c1.x)); f2.y = silu_f(fmaf(a1.y, f2.y, c1.y));
+          f3.x = silu_f(fmaf(a1.z, f3.x, c1.z)); f3.y = silu_f(fmaf(a1.w, f3.y, c1.w));
+          h[0] = __float22half2_rn(f0); h[1] = __float22half2_rn(f1);
+          h[2] = __float22half2_rn(f2); h[3] = __float22half2_rn(f3);
+          *reinterpret_cast<uint4*>(dst + static_cast<size_t>(s) * 16) = v;
+        }
+        xp += step_x;
+        yp += step_y;
+        if (xp >= p.Wp) { xp -= p.Wp; ++yp; }
+      }
+    };
+
+    Cursor iss;
+    iss.w = blockIdx.x; iss.si = 0; iss.j = 0; iss.slot = 0; iss.ph = 0; iss.nset = 0; iss.set_begin = 0;
+    iss.b = 0; iss.z0 = 0; iss.yp0 = 0; iss.xp0 = 0;
+    load_work(iss);
+    if (!any_act) {
+      while (iss.w < n_work) {
+        ptx::mbar_wait(&bars->slab_empty[iss.slot], iss.ph ^ 1u);
+        issue(iss);
+        ptx::cp_async_mbar_arrive_noinc(&bars->slab_full[iss.slot]);
+        advance(iss);
+      }
+    } else {
+      constexpr int kAhead = 3;
+      Cursor fin = iss;
+      int pending = 0;
+      while (true) {
+        while (iss.w < n_work && pending < kAhead) {
+          if (pending == 0) {
+            ptx::mbar_wait(&bars->slab_empty[iss.slot], iss.ph ^ 1u);
+          } else if (!ptx::mbar_try_wait(&bars->slab_empty[iss.slot], iss.ph ^ 1u)) {
+            break;
           }
-          if (++slot == static_cast<uint32_t>(p.NSLOT)) { slot = 0; sph ^= 1u; }
+          issue(iss);
+          ptx::cp_async_commit();
+          advance(iss);
+          ++pending;
         }
+        if (pending == 0) break;
+        if (pending >= 3) ptx::cp_async_wait<2>();
+        else if (pending == 2) ptx::cp_async_wait<1>();
+        else ptx::cp_async_wait<0>();
+        transform(fin);
+        ptx::fence_proxy_async_smem();
+        ptx::mbar_arrive(&bars->slab_full[fin.slot]);
+        advance(fin);
+        --pending;
       }
     }
   } else if (warp == kBWarp) {

@@ -249,7 +249,8 @@ class TapGemm:
             S_pad = S + ((rem - S) % 8)
             slot = CH * S_pad * 16
             tpk = {"conv": KH * KW, "down144": 4, "up144": 4, "unshuffle": 1}[self.kind]  # taps per kz group
-            divs = [d for d in range(tpk, 0, -1) if tpk % d == 0 and (d * btile(KC) <= 16384 or d == 1)]
+            stage_cap = int(os.environ.get("WDNO_BSTAGE", "16384"))
+            divs = [d for d in range(tpk, 0, -1) if tpk % d == 0 and (d * btile(KC) <= stage_cap or d == 1)]
             for nslot in range(min(12, want_slots), min_slots - 1, -1):
                 for tps in divs:
                     for nbst in (4, 3, 2):
@@ -258,6 +259,8 @@ class TapGemm:
             return None
 
         kcs = [self.kc_override] if self.kc_override else [64, 32, 16]
+        if os.environ.get("WDNO_KC"):  # tuning knobs (tools/sweep_tapgemm.py)
+            kcs = [int(os.environ["WDNO_KC"])]
         kcs = [k for k in kcs if ctot % k == 0 and not any(c % k for c in self.src_channels[:-1])]
         plan = None
         if is_1x1 and ncn > 1:
@@ -283,7 +286,7 @@ class TapGemm:
             P = ZT + KD - 1
             best = None
             for KC in kcs:
-                f = fit(KC, ZT, PT, P + 2, P)
+                f = fit(KC, ZT, PT, P + int(os.environ.get("WDNO_SLOT_EXTRA", "2")), P)
                 if not f:
                     continue
                 score = (min(f[1] - P, 2), KC)  # prefer a full ring (P+2 slots), then the larger KC
@@ -386,7 +389,8 @@ class TapGemm:
         _lib.check(L.wdno_tapgemm(C.byref(p), _lib.current_stream_ptr()), "tapgemm")
         if tm is not None:
             e1.record()
-            flops = 2.0 * B * D * H * W * self.cout * self.cin * self.w.shape[2] * self.w.shape[3] * self.w.shape[4]
+            # algorithmic FLOPs of the reference layer (identity K-sets that carry a fused residual are not counted)
+            flops = 2.0 * B * D * H * W * self.cout * getattr(self, "algo_cin", self.cin) * self.w.shape[2] * self.w.shape[3] * self.w.shape[4]
             if self.kind == "unshuffle":
                 flops *= 4
             tm.append((e0, e1, flops, (self.kind, self.cin, self.cout, self.KD, self.KH, self.KW, B, D, H, W)))

@@ -274,7 +274,9 @@ class Unet3DEngine:
         the deep asynchronous operand pipeline instead of the epilogue."""
         w = weight.detach().float().cpu().reshape(weight.shape[0], -1)
         c = w.shape[0]
-        return TapGemm(torch.cat((w, torch.eye(c)), dim=1), bias, src_channels=(w.shape[1], c), device=self.dev)
+        plan = TapGemm(torch.cat((w, torch.eye(c)), dim=1), bias, src_channels=(w.shape[1], c), device=self.dev)
+        plan.algo_cin = w.shape[1]
+        return plan
 
     def _attn_plan(self, res, temporal):
         attn = res.fn.fn.fn
