@@ -100,7 +100,7 @@ typedef struct {
   int32_t TPS;            /* weight tiles per bulk-copy stage */
   int32_t reuse;          /* 1: (1x1 layers) slabs of all K-sets stay resident while every N-chunk is computed */
   int32_t n_taps;         /* entries of taps[] (<= 384; copied to shared memory) */
-  int32_t pad_;
+  int32_t bias_len;       /* floats readable at bias (padded output channels, <= 1024; staged in shared memory) */
 } wdno_tapgemm_params;
 
 /* bytes of dynamic shared memory the plan needs, or <0 */

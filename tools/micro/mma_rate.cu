@@ -64,8 +64,8 @@ int main() {
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   const int iters = 2000;
   for (int swz : {0, 2, 4})
-  for (int N : {64, 128, 256})
-    for (int shift : {0, 1})
+  for (int N : {64, 128, 192, 256})
+    for (int shift : {0, 1, 3})
       for (int nacc : {2, 4}) {
         if ((N <= 64 ? 64 : N) * nacc > 512) continue;
         const int ksteps = 2;

@@ -18,6 +18,10 @@ NVCC_FLAGS = [
 ]
 
 
+if os.environ.get("WDNO_PROF"):  # debug: per-role stall counters in tapgemm (tools/prof_roles.py)
+    NVCC_FLAGS.append("-DWDNO_PROF")
+
+
 def _nvcc():
     nv = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nv):

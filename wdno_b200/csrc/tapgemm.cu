@@ -34,8 +34,27 @@ constexpr int kMaxSlots = 12;
 constexpr int kMaxBStages = 8;
 constexpr int kBarBytes = 512;
 constexpr int kMaxTaps = 384;             // tap table copied to shared memory (7x7x7 = 343)
-constexpr int kHdrBytes = kBarBytes + kMaxTaps * 8;
+constexpr int kStageRow = 144;             // epilogue staging: 128 B of fp16 columns + 16 B pad (row's global offset)
+constexpr int kStageWarp = 32 * kStageRow;
+constexpr int kStageBytes = kEpiWarps * kStageWarp;
+constexpr int kMaxBias = 1024;             // bias of the whole layer, staged in shared memory
+constexpr int kMaxChunks = 32;             // N-chunk descriptors staged in shared memory
+constexpr int kHdrBytes = kBarBytes + kMaxTaps * 8 + kStageBytes + kMaxBias * 4 + kMaxChunks * 40;
+static_assert(sizeof(wdno_nchunk) == 40, "wdno_nchunk layout");
 constexpr int kLoadBatch = 8;             // independent 16-byte loads in flight per producer thread
+
+#ifdef WDNO_PROF
+__device__ unsigned long long g_prof[32];
+// per-role stall accounting (debug builds only): g_prof[i] += cycles lane 0 of the role's first warp spent in region i
+#define PROF_DECL long long _pacc[6] = {0, 0, 0, 0, 0, 0}; const long long _pstart = clock64()
+#define PROF_REGION(i, ...) do { const long long _t = clock64(); __VA_ARGS__; _pacc[i] += clock64() - _t; } while (0)
+#define PROF_COMMIT(base, cond) do { if (cond) { for (int _i = 0; _i < 6; ++_i) atomicAdd(&g_prof[(base) + _i], static_cast<unsigned long long>(_pacc[_i])); \
+    atomicAdd(&g_prof[(base) + 6], static_cast<unsigned long long>(clock64() - _pstart)); } } while (0)
+#else
+#define PROF_DECL do {} while (0)
+#define PROF_REGION(i, ...) do { __VA_ARGS__; } while (0)
+#define PROF_COMMIT(base, cond) do {} while (0)
+#endif
 
 struct Bars {
   uint64_t slab_full[kMaxSlots];
@@ -109,7 +128,8 @@ __device__ __forceinline__ void issue_tile(uint32_t a_tap_lo, uint32_t s_kz, uin
 // The whole warp runs the warp-uniform control flow (waits, ring bookkeeping); one elected lane issues the MMAs of a
 // whole weight stage (TPS taps of one kz group) and the tcgen05.commit that frees it.  No divisions on this path.
 template <int ZT, int PT, int KS>
-__device__ __forceinline__ void mma_role(const wdno_tapgemm_params& p, Bars* bars, const wdno_tap* s_taps, uint32_t tmem_base,
+__device__ __forceinline__ void mma_role(const wdno_tapgemm_params& p, Bars* bars, const wdno_tap* s_taps,
+                                         const wdno_nchunk* s_chunks, uint32_t tmem_base,
                                          const uint8_t* slab_base, const uint8_t* b_base, int n_work, int ptiles, int zgroups) {
   constexpr int NACC = ZT * PT;
   const uint32_t N = static_cast<uint32_t>(p.N);
@@ -128,17 +148,18 @@ __device__ __forceinline__ void mma_role(const wdno_tapgemm_params& p, Bars* bar
   uint32_t s0 = 0, sph = 0;   // ring slot / phase of plane 0 of the current K-set
   uint32_t bst = 0, bph = 0;  // weight stage / phase
   uint32_t acnt = 0;          // accumulator-buffer use counter
+  PROF_DECL;
   for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
     const int nc0 = reuse ? 0 : (w % n_chunks);
     const int nc1 = reuse ? n_chunks : nc0 + 1;
     const uint32_t su = s0, suph = sph;  // ring position at the start of this work item
     for (int nc = nc0; nc < nc1; ++nc, ++acnt) {
-      const wdno_nchunk ci = p.chunks[nc];
+      const wdno_nchunk ci = s_chunks[nc];
       const bool first_pass = (nc == nc0), last_pass = (nc == nc1 - 1);
       if (reuse) { s0 = su; sph = suph; }
       const uint32_t buf = two_buf ? (acnt & 1u) : 0u;
       const uint32_t aph = two_buf ? ((acnt >> 1) & 1u) : (acnt & 1u);
-      ptx::mbar_wait(&bars->acc_empty[buf], aph ^ 1u);
+      PROF_REGION(0, ptx::mbar_wait(&bars->acc_empty[buf], aph ^ 1u));
       ptx::tc_fence_after();
       const uint32_t acc0 = tmem_base + buf * static_cast<uint32_t>(NACC) * npad;
       uint32_t accum = 0u;
@@ -150,7 +171,7 @@ __device__ __forceinline__ void mma_role(const wdno_tapgemm_params& p, Bars* bar
           for (int j = 0; j < ZT; ++j) {
             uint32_t s = s0 + j, ph = sph;
             if (s >= nslot) { s -= nslot; ph ^= 1u; }
-            ptx::mbar_wait(&bars->slab_full[s], ph);
+            PROF_REGION(1, ptx::mbar_wait(&bars->slab_full[s], ph));
           }
           ptx::fence_proxy_async_smem();  // cp.async (generic proxy) slab writes -> tcgen05 (async proxy) reads
         }
@@ -166,13 +187,13 @@ __device__ __forceinline__ void mma_role(const wdno_tapgemm_params& p, Bars* bar
             __syncwarp();
             uint32_t sn = s0 + kz + ZT - 1, ph = sph;
             if (sn >= nslot) { sn -= nslot; ph ^= 1u; }
-            ptx::mbar_wait(&bars->slab_full[sn], ph);
+            PROF_REGION(1, ptx::mbar_wait(&bars->slab_full[sn], ph));
             ptx::fence_proxy_async_smem();
           }
           for (int g = 0; g < groups_per_kz; ++g) {
-            ptx::mbar_wait(&bars->b_full[bst], bph);
+            PROF_REGION(2, ptx::mbar_wait(&bars->b_full[bst], bph));
             ptx::tc_fence_after();
-            if (ptx::elect_one()) {
+            PROF_REGION(3, if (ptx::elect_one()) {
               uint32_t b_lo = b_lo0 + bst * bstage_u;
               uint32_t af = accum;
 #pragma unroll 1
@@ -183,7 +204,7 @@ __device__ __forceinline__ void mma_role(const wdno_tapgemm_params& p, Bars* bar
                 b_lo += btile_u;
               }
               ptx::tc_commit(&bars->b_empty[bst]);
-            }
+            });
             __syncwarp();
             accum = 1u;
             tp_ptr += TPS;
@@ -207,12 +228,16 @@ __device__ __forceinline__ void mma_role(const wdno_tapgemm_params& p, Bars* bar
       __syncwarp();
     }
   }
+  PROF_COMMIT(0, (threadIdx.x & 31) == 0);
 }
 
 __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const wdno_tapgemm_params p) {
   extern __shared__ __align__(128) uint8_t smem[];
   Bars* bars = reinterpret_cast<Bars*>(smem);
   wdno_tap* s_taps = reinterpret_cast<wdno_tap*>(smem + kBarBytes);
+  uint8_t* stage_base = smem + kBarBytes + kMaxTaps * 8;
+  float* s_bias = reinterpret_cast<float*>(stage_base + kStageBytes);
+  wdno_nchunk* s_chunks = reinterpret_cast<wdno_nchunk*>(stage_base + kStageBytes + kMaxBias * 4);
   uint8_t* slab_base = smem + kHdrBytes;
   const int CH = p.KC >> 3;  // 16-byte chunks per position
   const uint32_t lbo_a = static_cast<uint32_t>(p.S_pad) * 16u;
@@ -250,6 +275,9 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const wdno_tapgemm
     ptx::fence_barrier_init();
   }
   for (int i = threadIdx.x; i < p.n_taps; i += blockDim.x) s_taps[i] = p.taps[i];
+  for (int i = threadIdx.x; i < p.n_chunks; i += blockDim.x) s_chunks[i] = p.chunks[i];
+  if (p.bias != nullptr)
+    for (int i = threadIdx.x; i < p.bias_len; i += blockDim.x) s_bias[i] = p.bias[i];
   if (warp == kMmaWarp) {
     ptx::tmem_alloc(&bars->tmem_base, 512);
     ptx::tmem_relinquish();
@@ -287,7 +315,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const wdno_tapgemm
     auto load_work = [&](Cursor& cu) {
       if (cu.w >= n_work) return;
       const Work wk = decode_work(cu.w, p.n_chunks, ptiles, zgroups, p.reuse);
-      const wdno_nchunk ci = p.chunks[wk.nc0];  // with reuse every chunk shares chunk 0's K-sets
+      const wdno_nchunk ci = s_chunks[wk.nc0];  // with reuse every chunk shares chunk 0's K-sets
       cu.nset = ci.set_count;
       cu.set_begin = ci.set_begin;
       cu.b = wk.b;
@@ -369,9 +397,10 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const wdno_tapgemm
     iss.w = blockIdx.x; iss.si = 0; iss.j = 0; iss.slot = 0; iss.ph = 0; iss.nset = 0; iss.set_begin = 0;
     iss.b = 0; iss.z0 = 0; iss.yp0 = 0; iss.xp0 = 0;
     load_work(iss);
+    PROF_DECL;
     if (!any_act) {
       while (iss.w < n_work) {
-        ptx::mbar_wait(&bars->slab_empty[iss.slot], iss.ph ^ 1u);
+        PROF_REGION(0, ptx::mbar_wait(&bars->slab_empty[iss.slot], iss.ph ^ 1u));
         issue(iss);
         ptx::cp_async_mbar_arrive_noinc(&bars->slab_full[iss.slot]);
         advance(iss);
@@ -383,38 +412,40 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const wdno_tapgemm
       while (true) {
         while (iss.w < n_work && pending < kAhead) {
           if (pending == 0) {
-            ptx::mbar_wait(&bars->slab_empty[iss.slot], iss.ph ^ 1u);
+            PROF_REGION(0, ptx::mbar_wait(&bars->slab_empty[iss.slot], iss.ph ^ 1u));
           } else if (!ptx::mbar_try_wait(&bars->slab_empty[iss.slot], iss.ph ^ 1u)) {
             break;
           }
-          issue(iss);
+          PROF_REGION(1, issue(iss));
           ptx::cp_async_commit();
           advance(iss);
           ++pending;
         }
         if (pending == 0) break;
-        if (pending >= 3) ptx::cp_async_wait<2>();
+        PROF_REGION(2, if (pending >= 3) ptx::cp_async_wait<2>();
         else if (pending == 2) ptx::cp_async_wait<1>();
-        else ptx::cp_async_wait<0>();
-        transform(fin);
+        else ptx::cp_async_wait<0>(););
+        PROF_REGION(3, transform(fin));
         ptx::fence_proxy_async_smem();
         ptx::mbar_arrive(&bars->slab_full[fin.slot]);
         advance(fin);
         --pending;
       }
     }
+    PROF_COMMIT(8, ptid == 0);
   } else if (warp == kBWarp) {
     // ============================================================ B (weight tile) producer
     // warp-uniform control flow, one elected lane issues the bulk copies (TPS tiles per stage)
     uint32_t bst = 0, bph = 0;
+    PROF_DECL;
     for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
       const Work wk = decode_work(w, p.n_chunks, ptiles, zgroups, p.reuse);
       for (int nc = wk.nc0; nc < wk.nc1; ++nc) {
-        const wdno_nchunk ci = p.chunks[nc];
+        const wdno_nchunk ci = s_chunks[nc];
         const uint8_t* wsrc = static_cast<const uint8_t*>(p.wpacked) + static_cast<size_t>(ci.w_tile_off) * btile_bytes;
         for (int i = 0; i < ci.n_tiles; i += p.TPS) {  // the plan guarantees TPS | taps of every kz group
           const uint32_t cnt = static_cast<uint32_t>(p.TPS);
-          ptx::mbar_wait(&bars->b_empty[bst], bph ^ 1u);
+          PROF_REGION(0, ptx::mbar_wait(&bars->b_empty[bst], bph ^ 1u));
           if (ptx::elect_one()) {
             ptx::mbar_arrive_expect_tx(&bars->b_full[bst], cnt * btile_bytes);
             ptx::bulk_g2s(b_base + static_cast<size_t>(bst) * bstage_bytes, wsrc + static_cast<size_t>(i) * btile_bytes,
@@ -425,13 +456,14 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const wdno_tapgemm
         }
       }
     }
+    PROF_COMMIT(16, lane == 0);
   } else if (warp == kMmaWarp) {
     // ============================================================ MMA issuer (templated on the accumulator shape)
     const int ks = p.KC >> 4;
 #define WDNO_MMA(ZT_, PT_) \
-    if (ks == 1) mma_role<ZT_, PT_, 1>(p, bars, s_taps, tmem_base, slab_base, b_base, n_work, ptiles, zgroups); \
-    else if (ks == 2) mma_role<ZT_, PT_, 2>(p, bars, s_taps, tmem_base, slab_base, b_base, n_work, ptiles, zgroups); \
-    else mma_role<ZT_, PT_, 4>(p, bars, s_taps, tmem_base, slab_base, b_base, n_work, ptiles, zgroups);
+    if (ks == 1) mma_role<ZT_, PT_, 1>(p, bars, s_taps, s_chunks, tmem_base, slab_base, b_base, n_work, ptiles, zgroups); \
+    else if (ks == 2) mma_role<ZT_, PT_, 2>(p, bars, s_taps, s_chunks, tmem_base, slab_base, b_base, n_work, ptiles, zgroups); \
+    else mma_role<ZT_, PT_, 4>(p, bars, s_taps, s_chunks, tmem_base, slab_base, b_base, n_work, ptiles, zgroups);
     if (p.ZT == 4) { WDNO_MMA(4, 1) }
     else if (p.ZT == 2) { WDNO_MMA(2, 1) }
     else if (p.PT == 4) { WDNO_MMA(1, 4) }
@@ -439,116 +471,166 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const wdno_tapgemm
 #undef WDNO_MMA
   } else {
     // ============================================================ epilogue warps 0..3
+    // fp16 outputs go through a per-warp staging tile (32 rows x 128 B, rows padded to 144 B; the pad holds the row's
+    // global offset) so that global stores are coalesced: 8 lanes write one row's 128 contiguous bytes.
     const int row = warp * 32 + lane;
     const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
     const int nblk = p.N >> 3;  // 8-column blocks, <= 16
+    const int n16 = p.N >> 4;
+    uint8_t* stage_w = stage_base + warp * kStageWarp;
+    uint8_t* stage_row = stage_w + lane * kStageRow;
+    const uint32_t wp_magic = 0xFFFFFFFFu / static_cast<uint32_t>(p.Wp) + 1u;  // exact o / Wp for o * Wp < 2^32
+    const long long plane_elems = static_cast<long long>(p.H) * p.W * p.out_c * ((p.out_mode == 1) ? 4 : 1);
+    const bool has_bias = p.bias != nullptr, has_stats = p.stats != nullptr;
     uint32_t acnt = 0;
+    PROF_DECL;
     for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
       const Work wk = decode_work(w, p.n_chunks, ptiles, zgroups, p.reuse);
       const int o0 = wk.pt * 128 * p.PT;
       const int z0 = wk.zg * p.ZT;
       for (int nc = wk.nc0; nc < wk.nc1; ++nc, ++acnt) {
-        const wdno_nchunk ci = p.chunks[nc];
+        const wdno_nchunk ci = s_chunks[nc];
         const uint32_t buf = (NBUF == 2) ? (acnt & 1u) : 0u;
         const uint32_t aph = (NBUF == 2) ? ((acnt >> 1) & 1u) : (acnt & 1u);
         float s1[16], s2[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
-        ptx::mbar_wait(&bars->acc_full[buf], aph);
+        const float* bias_s = s_bias + ci.out_ch_off;
+        PROF_REGION(0, ptx::mbar_wait(&bars->acc_full[buf], aph));
         ptx::tc_fence_after();
-        for (int a = 0; a < NACC; ++a) {
-          const int za = a / p.PT, pi = a - za * p.PT;
-          const int z = z0 + za;
+        int a = 0;
+        for (int pi = 0; pi < p.PT; ++pi) {
+          // row geometry: shared by the ZT planes of this position tile
           const int o = o0 + pi * 128 + row;
-          const int y = o / p.Wp;
+          const int y = static_cast<int>(__umulhi(static_cast<uint32_t>(o), wp_magic));
           const int x = o - y * p.Wp;
-          const bool valid = (z < p.D) && (y < p.H) && (x < p.W);
-          const uint32_t tcol = tmem_base + lane_base + buf * static_cast<uint32_t>(NACC * NPAD) + static_cast<uint32_t>(a * NPAD);
-          size_t obase = 0;
+          const bool valid_yx = (y < p.H) && (x < p.W);
+          long long rbase;
           if (p.out_mode == 0) {
-            obase = (((static_cast<size_t>(wk.b) * p.D + z) * p.H + y) * p.W + x) * p.out_c + ci.out_ch_off;
+            rbase = ((static_cast<long long>(wk.b) * p.D * p.H + y) * p.W + x) * p.out_c + ci.out_ch_off;
           } else if (p.out_mode == 1) {
-            obase = (((static_cast<size_t>(wk.b) * p.D + z) * (2 * p.H) + (2 * y + ci.ph_y)) * (2 * p.W) + (2 * x + ci.ph_x)) *
-                        p.out_c + ci.out_ch_off;
+            rbase = ((static_cast<long long>(wk.b) * p.D * (2 * p.H) + (2 * y + ci.ph_y)) * (2 * p.W) + (2 * x + ci.ph_x)) * p.out_c +
+                    ci.out_ch_off;
           } else {
-            obase = ((static_cast<size_t>(wk.b) * p.D + z) * p.out_c + ci.out_ch_off) * (static_cast<size_t>(p.H) * p.W) +
-                    static_cast<size_t>(y) * p.W + x;
+            rbase = (static_cast<long long>(wk.b) * p.D * p.out_c + ci.out_ch_off) * (static_cast<long long>(p.H) * p.W) +
+                    static_cast<long long>(y) * p.W + x;
           }
-          const int n16 = p.N >> 4;
-          // residual row prefetch, 64 columns at a time, so the global loads overlap the TMEM reads
-          uint4 rpre[8];
-          const bool has_res = (p.resid != nullptr) && valid && (p.out_mode != 2);
-          const __half* res_row = static_cast<const __half*>(p.resid) + obase;
-          if (has_res) {
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-              if (q * 8 < ci.n_valid) rpre[q] = __ldg(reinterpret_cast<const uint4*>(res_row + q * 8));
-          }
-#pragma unroll
-          for (int c16 = 0; c16 < 8; ++c16) {
-            if (c16 >= n16) break;
-            if (c16 == 4 && has_res) {
-#pragma unroll
-              for (int q = 0; q < 8; ++q)
-                if (64 + q * 8 < ci.n_valid) rpre[q] = __ldg(reinterpret_cast<const uint4*>(res_row + 64 + q * 8));
-            }
-            uint32_t r[16];
-            ptx::tmem_ld16(tcol + static_cast<uint32_t>(c16 * 16), r);
-            ptx::tmem_ld_wait();
-            if (!valid) continue;
-            float f[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(r[i]);
-            const int ncol0 = c16 * 16;
-            if (p.bias != nullptr) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i)
-                if (ncol0 + i < ci.n_valid) f[i] += __ldg(p.bias + ci.out_ch_off + ncol0 + i);
-            }
-            if (p.stats != nullptr) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                if (ncol0 + i < ci.n_valid) {
-                  s1[c16 * 2 + (i >> 3)] += f[i];
-                  s2[c16 * 2 + (i >> 3)] += f[i] * f[i];
-                }
-              }
-            }
+          for (int za = 0; za < p.ZT; ++za, ++a) {
+            const int z = z0 + za;
+            const bool valid = valid_yx && (z < p.D);
+            const uint32_t tcol = tmem_base + lane_base + buf * static_cast<uint32_t>(NACC * NPAD) +
+                                  static_cast<uint32_t>((za * p.PT + pi) * NPAD);
             if (p.out_mode == 2) {
+              // fp32 [B, D, C, H, W]: consecutive lanes are consecutive x -> already coalesced per channel
+              const long long obase = rbase + static_cast<long long>(z) * p.out_c * (static_cast<long long>(p.H) * p.W);
               float* o32 = static_cast<float*>(p.out);
               const size_t cs = static_cast<size_t>(p.H) * p.W;
+              for (int c16 = 0; c16 < n16; ++c16) {
+                uint32_t r[16];
+                ptx::tmem_ld16(tcol + static_cast<uint32_t>(c16 * 16), r);
+                ptx::tmem_ld_wait();
+                if (!valid) continue;
 #pragma unroll
-              for (int i = 0; i < 16; ++i)
-                if (ncol0 + i < ci.n_valid) o32[obase + (ncol0 + i) * cs] = f[i];
-            } else {
-              __half* o16 = static_cast<__half*>(p.out);
+                for (int i = 0; i < 16; ++i) {
+                  const int col = c16 * 16 + i;
+                  if (col < ci.n_valid) o32[obase + col * cs] = __uint_as_float(r[i]) + (has_bias ? bias_s[col] : 0.f);
+                }
+              }
+              continue;
+            }
+            const long long obase = rbase + static_cast<long long>(z) * plane_elems;
+            *reinterpret_cast<long long*>(stage_row + 128) = valid ? obase : -1ll;
 #pragma unroll
-              for (int hb = 0; hb < 2; ++hb) {
-                if (ncol0 + hb * 8 >= ci.n_valid) continue;
-                const size_t off = obase + ncol0 + hb * 8;
-                if (has_res) {
-                  const uint4 rv = rpre[(c16 & 3) * 2 + hb];
-                  const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+            for (int cg = 0; cg < 2; ++cg) {  // 64-column groups
+              if (cg * 4 >= n16) break;
 #pragma unroll
-                  for (int i = 0; i < 4; ++i) {
-                    const float2 rf = __half22float2(rh[i]);
-                    f[hb * 8 + 2 * i] += rf.x;
-                    f[hb * 8 + 2 * i + 1] += rf.y;
+              for (int c2 = 0; c2 < 2; ++c2) {  // 32 columns per TMEM round trip
+                const int c16a = cg * 4 + c2 * 2;
+                if (c16a >= n16) break;
+                uint32_t r[32];
+                if (c16a + 1 < n16) {
+                  ptx::tmem_ld32(tcol + static_cast<uint32_t>(c16a * 16), r);
+                } else {
+                  ptx::tmem_ld16(tcol + static_cast<uint32_t>(c16a * 16), *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
+#pragma unroll
+                  for (int i = 16; i < 32; ++i) r[i] = 0u;
+                }
+                ptx::tmem_ld_wait();
+                float f[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(r[i]);
+                if (has_bias) {
+#pragma unroll
+                  for (int q = 0; q < 8; ++q) {
+                    const float4 bv = *reinterpret_cast<const float4*>(bias_s + c16a * 16 + q * 4);
+                    f[q * 4 + 0] += bv.x; f[q * 4 + 1] += bv.y; f[q * 4 + 2] += bv.z; f[q * 4 + 3] += bv.w;
                   }
                 }
-                uint4 ov;
-                __half2* oh = reinterpret_cast<__half2*>(&ov);
+                if (has_stats && valid) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) oh[i] = __floats2half2_rn(f[hb * 8 + 2 * i], f[hb * 8 + 2 * i + 1]);
-                *reinterpret_cast<uint4*>(o16 + off) = ov;
+                  for (int i = 0; i < 32; ++i) {
+                    s1[c16a * 2 + (i >> 3)] += f[i];
+                    s2[c16a * 2 + (i >> 3)] = fmaf(f[i], f[i], s2[c16a * 2 + (i >> 3)]);
+                  }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  uint4 ov;
+                  __half2* oh = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) oh[i] = __floats2half2_rn(f[q * 8 + 2 * i], f[q * 8 + 2 * i + 1]);
+                  *reinterpret_cast<uint4*>(stage_row + (c2 * 4 + q) * 16) = ov;
+                }
               }
+              // coalesced phase: item = (row, 16-byte chunk); 8 consecutive lanes cover one row's 128 bytes
+              __syncwarp();
+              __half* o16 = static_cast<__half*>(p.out);
+              const __half* res16 = static_cast<const __half*>(p.resid);
+              const int ck = lane & 7;
+              const int colc = cg * 64 + ck * 8;
+              const bool col_ok = colc < ci.n_valid;
+              const uint8_t* srow = stage_w + (lane >> 3) * kStageRow;
+#pragma unroll
+              for (int hf = 0; hf < 2; ++hf) {  // 2 x 4 rows in flight per lane
+                const uint8_t* sr = srow + hf * 16 * kStageRow;
+                long long ob[4];
+                uint4 v[4];
+#pragma unroll
+                for (int it = 0; it < 4; ++it) {
+                  ob[it] = *reinterpret_cast<const long long*>(sr + it * 4 * kStageRow + 128);
+                  v[it] = *reinterpret_cast<const uint4*>(sr + it * 4 * kStageRow + ck * 16);
+                  if (!col_ok) ob[it] = -1ll;
+                }
+                if (res16 != nullptr) {
+                  uint4 rv[4];
+#pragma unroll
+                  for (int it = 0; it < 4; ++it)
+                    if (ob[it] >= 0) rv[it] = __ldg(reinterpret_cast<const uint4*>(res16 + ob[it] + colc));
+#pragma unroll
+                  for (int it = 0; it < 4; ++it) {
+                    if (ob[it] >= 0) {
+                      __half2* vh = reinterpret_cast<__half2*>(&v[it]);
+                      const __half2* rh = reinterpret_cast<const __half2*>(&rv[it]);
+#pragma unroll
+                      for (int i = 0; i < 4; ++i) {
+                        const float2 a2 = __half22float2(vh[i]), b2 = __half22float2(rh[i]);
+                        vh[i] = __floats2half2_rn(a2.x + b2.x, a2.y + b2.y);
+                      }
+                    }
+                  }
+                }
+#pragma unroll
+                for (int it = 0; it < 4; ++it)
+                  if (ob[it] >= 0) *reinterpret_cast<uint4*>(o16 + ob[it] + colc) = v[it];
+              }
+              __syncwarp();
             }
           }
         }
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&bars->acc_empty[buf]);
-        if (p.stats != nullptr) {
+        if (has_stats) {
           // 8-column blocks -> groups (cpg is a multiple of 8); warp-reduce, then one atomic pair per group
           float g1 = 0.f, g2 = 0.f;
           int cur_g = -1;
@@ -583,6 +665,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const wdno_tapgemm
         }
       }
     }
+    PROF_COMMIT(24, threadIdx.x == 0);
   }
 
   // ---------------------------------------------------------------- teardown
@@ -627,10 +710,23 @@ static int validate(const wdno_tapgemm_params* p) {
   if (p->src_mode == 2 && ((p->H & 1) || (p->W & 1))) return set_error(WDNO_E_INVALID, "tapgemm: up2 needs even H,W");
   if (smem_bytes_of(p) > 227 * 1024) return set_error(WDNO_E_INVALID, "tapgemm: shared-memory plan exceeds 227 KB");
   if (p->grid < 1) return set_error(WDNO_E_INVALID, "tapgemm: grid must be >= 1");
+  if (p->n_chunks > kMaxChunks) return set_error(WDNO_E_INVALID, "tapgemm: more than 32 N-chunks");
+  if (p->bias && (p->bias_len < 1 || p->bias_len > kMaxBias)) return set_error(WDNO_E_INVALID, "tapgemm: bias_len must be in [1,1024]");
   return WDNO_OK;
 }
 
 }  // namespace wdno
+
+#ifdef WDNO_PROF
+// debug builds: read (and clear) the per-role stall counters; not part of the product ABI
+extern "C" int wdno_tapgemm_prof_read(unsigned long long* out32_host) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out32_host, wdno::g_prof, sizeof(unsigned long long) * 32);
+  unsigned long long z[32] = {0};
+  cudaMemcpyToSymbol(wdno::g_prof, z, sizeof(z));
+  return 0;
+}
+#endif
 
 extern "C" int64_t wdno_tapgemm_smem_bytes(const wdno_tapgemm_params* p) {
   if (!p) return WDNO_E_INVALID;

@@ -20,7 +20,7 @@ from . import _lib
 from ._lib import KSet, NChunk, Tap, TapGemmParams
 
 _SMEM_LIMIT = 227 * 1024
-_BAR_BYTES = 512 + 384 * 8  # barriers + shared-memory tap table
+_BAR_BYTES = 512 + 384 * 8 + 4 * 32 * 144 + 1024 * 4 + 32 * 40  # barriers, tap table, epilogue staging, bias, N-chunk table
 
 
 def _device_bytes(ctypes_array, device):
@@ -374,6 +374,7 @@ class TapGemm:
         p.out = out.data_ptr()
         if self.bias is not None:
             p.bias = self.bias.data_ptr()
+            p.bias_len = self.bias.numel()
         if resid is not None:
             assert resid.dtype == torch.float16 and resid.is_contiguous() and resid.shape == out.shape
             p.resid = resid.data_ptr()
