@@ -101,6 +101,8 @@ typedef struct {
   int32_t reuse;          /* 1: (1x1 layers) slabs of all K-sets stay resident while every N-chunk is computed */
   int32_t n_taps;         /* entries of taps[] (<= 384; copied to shared memory) */
   int32_t bias_len;       /* floats readable at bias (padded output channels, <= 1024; staged in shared memory) */
+  int32_t n_sets;         /* entries of sets[] (<= 128; copied to shared memory) */
+  int32_t pad_;
 } wdno_tapgemm_params;
 
 /* bytes of dynamic shared memory the plan needs, or <0 */
@@ -140,6 +142,20 @@ int wdno_softmax_attn(const void* qkv, void* out, const float* bias /*[4][n][n] 
                       int64_t inner, int64_t outerT, int64_t innerT, int64_t tokT, float scale, void* stream);
 /* qkv fp16 [n_img][n_pos][384] -> out fp16 [n_img][n_pos][128] */
 int wdno_linear_attn(const void* qkv, void* out, int64_t n_img, int n_pos, float scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * fused attention blocks: Residual(PreNorm(dim, attention)) in one pass over the residual stream
+ * (LayerNorm, qkv projection, attention, output projection and the residual add never leave the SM).
+ * x, y: fp16 channels-last [n_img][n_pos][C] (C = 64, 128 or 256; x != y).  Weight operands are pre-packed
+ * in mma.sync fragment order by wdno_b200/attn_fused.py (pack_a_frags / pack_b_frags).
+ *   linattn_block: SpatialLinearAttention, reference conv3d.py:165-184,232-258.
+ *     wq_pack  fp16 B-fragments of W_q [128][C];  wkv_pack fp16 A-fragments [k|v][head][32][C];
+ *     wout fp32 [C][128]; bias fp32 [C] or NULL; work: wdno_linattn_work_bytes() bytes of scratch.
+ * ------------------------------------------------------------------------------------------ */
+int64_t wdno_linattn_work_bytes(int64_t n_img, int n_pos, int C);
+int wdno_linattn_block(const void* x, void* y, const float* gamma, const void* wq_pack, const void* wkv_pack,
+                       const float* wout, const float* bias, void* work, int64_t n_img, int n_pos, int C,
+                       float scale, float eps, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * diffusion step algebra on the fp32 state [B,F,C,H,W] (Burgers: F=1).

@@ -26,6 +26,7 @@ SIGNATURES = {
     "wdno_small_linear": [P, P, P, P, I, I, I, P],
     "wdno_softmax_attn": [P, P, P, P, P, L64, I, L64, L64, L64, L64, F, P],
     "wdno_linear_attn": [P, P, L64, I, F, P],
+    "wdno_linattn_block": [P, P, P, P, P, P, P, P, L64, I, I, F, F, P],
     "wdno_ddim_step": [P, P, P, P, P, P, I, I, I, I, I, I, I, P],
     "wdno_ddpm_step": [P, P, P, P, P, P, I, I, I, I, I, I, I, P],
     "wdno_apply_conditions": [P, P, I, I, I, I, I, I, P],
@@ -43,3 +44,5 @@ def bind(lib):
         fn = getattr(lib, name)
         fn.restype = C.c_int
         fn.argtypes = argtypes
+    lib.wdno_linattn_work_bytes.restype = C.c_int64
+    lib.wdno_linattn_work_bytes.argtypes = [L64, I, I]

@@ -1,0 +1,70 @@
+"""Host-side plans of the fused attention blocks (csrc/attn_fused.cu): weights re-packed once per parameter snapshot
+into mma.sync fragment order, plus the small per-call workspace.
+
+  LinAttnBlock   Residual(PreNorm(dim, SpatialLinearAttention(dim)))      conv3d.py:165-184, 232-258, 426-427, 459
+  TemporalBlock  Residual(PreNorm(dim, EinopsToAndFrom(Attention(dim))))  conv3d.py:262-353, 383, 397, 428, 460
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+
+def pack_b_frags(w):
+    """w [N, K] (out-features x in-features, N % 8 == 0, K % 32 == 0) -> fp16 [N/8, K/32, 32 lanes, 8]: the B fragments
+    (col-major k x n) of two consecutive k-steps of mma.m16n8k16 for one 8-wide n-tile, one 16-byte load per lane."""
+    N, K = w.shape
+    assert N % 8 == 0 and K % 32 == 0
+    r = w.reshape(N // 8, 8, K // 32, 2, 2, 4, 2)          # nt, g, kp, ks, reg(+0/+8), q, half
+    return r.permute(0, 2, 1, 5, 3, 4, 6).contiguous().reshape(N // 8, K // 32, 32, 8).to(torch.float16)
+
+
+def pack_a_frags(w):
+    """w [M, K] (M % 16 == 0, K % 16 == 0) -> fp16 [M/16, K/16, 32 lanes, 8]: the A fragment (row-major m x k) of one
+    k-step: a0=(g,2q) a1=(g+8,2q) a2=(g,2q+8) a3=(g+8,2q+8)."""
+    M, K = w.shape
+    assert M % 16 == 0 and K % 16 == 0
+    r = w.reshape(M // 16, 2, 8, K // 16, 2, 4, 2)         # mt, rh(+0/+8), g, ks, kh(+0/+8), q, half
+    return r.permute(0, 3, 2, 5, 4, 1, 6).contiguous().reshape(M // 16, K // 16, 32, 8).to(torch.float16)
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class LinAttnBlock:
+    """y = x + to_out(linear_attention(to_qkv(LayerNorm(x))))  on fp16 channels-last [B, D, H, W, C] (images = B*D)."""
+
+    def __init__(self, gamma, w_qkv, w_out, b_out, heads=4, dim_head=32, device="cuda"):
+        assert heads == 4 and dim_head == 32
+        dev = torch.device(device)
+        wq = w_qkv.detach().float().cpu().reshape(w_qkv.shape[0], -1)    # [384, C]
+        self.C = wq.shape[1]
+        assert wq.shape[0] == 384 and self.C in (64, 128, 256)
+        self.gamma = gamma.detach().float().reshape(-1).contiguous().to(dev)
+        self.wq = pack_b_frags(wq[:128]).to(dev)
+        # k / v: per (section, head) a [32, C] A operand
+        kv = wq[128:].reshape(2, 4, 32, self.C)
+        self.wkv = torch.stack([torch.stack([pack_a_frags(kv[s, h]) for h in range(4)]) for s in range(2)]).contiguous().to(dev)
+        self.wout = w_out.detach().float().cpu().reshape(w_out.shape[0], -1).contiguous().to(dev)   # [C, 128]
+        assert self.wout.shape == (self.C, 128)
+        self.bias = None if b_out is None else b_out.detach().float().contiguous().to(dev)
+        self.scale = dim_head ** -0.5
+        self._work = {}
+
+    def __call__(self, x, eps=1e-5):
+        assert x.dtype == torch.float16 and x.is_contiguous() and x.dim() == 5 and x.shape[-1] == self.C
+        B, D, H, W, _ = x.shape
+        n_img, n_pos = B * D, H * W
+        L = _lib.lib()
+        key = (n_img, n_pos)
+        if key not in self._work:
+            nbytes = L.wdno_linattn_work_bytes(n_img, n_pos, self.C)
+            assert nbytes > 0
+            self._work[key] = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+        y = torch.empty_like(x)
+        _lib.check(L.wdno_linattn_block(_p(x), _p(y), _p(self.gamma), _p(self.wq), _p(self.wkv), _p(self.wout), _p(self.bias),
+                                        _p(self._work[key]), n_img, n_pos, self.C, self.scale, float(eps),
+                                        _lib.current_stream_ptr()), "linattn_block")
+        return y

@@ -1,0 +1,417 @@
+// Fused attention blocks of the smoke U-Net: Residual(PreNorm(dim, attention)) in ONE pass over the residual stream.
+//
+//   linattn_block  -- SpatialLinearAttention block (reference conv3d.py:165-184, 232-258):
+//        y = x + to_out( ctx^T softmax_d(q) * scale ) ,  ctx = softmax_n(k) v^T ,  (q,k,v) = to_qkv(LayerNorm(x))
+//      la1: per image, per tile of 64 positions: LayerNorm -> k^T, v^T (tensor cores, weights as the A operand so the
+//           results are already the fragments of the next product) -> exp(k - running max) -> S += ek v^T ; one partial
+//           (max, sum, S) per (image, part, head) goes to a small workspace -- k and v never touch HBM;
+//      la_mid: per image: merge the partials, ctx = S / z, and fold to_out into it:  M = scale * W_out blockdiag(ctx^T)
+//           (C x 128), written in B-fragment order;
+//      la2: per tile of 128 positions: LayerNorm -> q (tensor cores) -> softmax over each head's 32 dims in registers
+//           -> y = q M^T + bias + x -> coalesced store.
+//   HBM traffic: x is read twice and y written once (3 x 2C bytes per voxel) instead of the ~21 x 2C bytes of the
+//   unfused LN / qkv GEMM / attention core / out GEMM chain.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "common.cuh"
+#include "mma_sync.cuh"
+
+namespace wdno {
+
+constexpr int kLaHeads = 4, kLaDh = 32, kLaHid = 128;
+constexpr int kLaPart = 64 + 32 * 32;  // floats per (image, part, head): max[32], sum[32], S[32][32]
+
+// ------------------------------------------------------------------ la1: context partials
+template <int C>
+__global__ void __launch_bounds__(256, 2) la1_kernel(const __half* __restrict__ x, const float* __restrict__ gamma,
+                                                  const uint4* __restrict__ wkv, float* __restrict__ part, int n, int split,
+                                                  float eps) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  __half* xn = reinterpret_cast<__half*>(smem_raw);  // [64][C + 8]
+  constexpr int XS = C + 8;
+  constexpr int KS = C / 16;
+  const int img = blockIdx.x / split, sp = blockIdx.x - img * split;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, q = lane & 3;
+  const int h = warp & 3, ph = warp >> 2;
+  const int tiles = (n + 63) >> 6;
+  const int t0 = (tiles * sp) / split, t1 = (tiles * (sp + 1)) / split;
+  const uint4* wk = wkv + static_cast<size_t>((0 * 4 + h) * 2) * KS * 32 + lane;
+  const uint4* wv = wkv + static_cast<size_t>((1 * 4 + h) * 2) * KS * 32 + lane;
+  const __half* ximg = x + static_cast<size_t>(img) * n * C;
+  const uint32_t xn_s = static_cast<uint32_t>(__cvta_generic_to_shared(xn));
+  // ldmatrix lane address of the B operand (activations): row = position, 8-column blocks along channels
+  const uint32_t b_off = static_cast<uint32_t>(((32 * ph + (lane & 7)) * XS + 8 * (lane >> 3)) * 2);
+
+  float S[2][4][4];
+  float mrun[4], z[4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) S[i][j][c] = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { mrun[i] = -INFINITY; z[i] = 0.f; }
+
+  for (int t = t0; t < t1; ++t) {
+    __syncthreads();
+    const int p0 = t * 64;
+    ln_tile<C, 64, 256>(ximg + static_cast<size_t>(p0) * C, min(64, n - p0), gamma, xn, eps);
+    __syncthreads();
+    // ---- k^T[d][p] = Wk_h xn^T
+    float acc[2][4][4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[i][j][c] = 0.f;
+#pragma unroll
+    for (int kp = 0; kp < C / 32; ++kp) {
+      uint32_t bf[4][4];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+        ldsm_x4(xn_s + b_off + static_cast<uint32_t>((nt * 8 * XS + kp * 32) * 2), bf[nt][0], bf[nt][1], bf[nt][2], bf[nt][3]);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const uint4 a0 = __ldg(wk + (mt * KS + 2 * kp) * 32), a1 = __ldg(wk + (mt * KS + 2 * kp + 1) * 32);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          mma16816(acc[mt][nt], a0.x, a0.y, a0.z, a0.w, bf[nt][0], bf[nt][1]);
+          mma16816(acc[mt][nt], a1.x, a1.y, a1.z, a1.w, bf[nt][2], bf[nt][3]);
+        }
+      }
+    }
+    // ---- running column max (over positions) per row d, rescale, ek = exp(k - max)
+    const int pbase = p0 + 32 * ph + 2 * q;
+    uint32_t ekA[2][2][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        float mx = -INFINITY;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+          for (int e = 0; e < 2; ++e)
+            if (pbase + 8 * nt + e < n) mx = fmaxf(mx, acc[mt][nt][2 * r + e]);
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+        const int ri = mt * 2 + r;
+        const float mnew = fmaxf(mrun[ri], mx);
+        const float sc = (mnew == -INFINITY) ? 1.0f : __expf(mrun[ri] - mnew);
+        mrun[ri] = mnew;
+        z[ri] *= sc;
+#pragma unroll
+        for (int ne = 0; ne < 4; ++ne) {
+          S[mt][ne][2 * r] *= sc;
+          S[mt][ne][2 * r + 1] *= sc;
+        }
+        float zs = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const float v = (pbase + 8 * nt + e < n) ? __expf(acc[mt][nt][2 * r + e] - mnew) : 0.f;
+            acc[mt][nt][2 * r + e] = v;
+            zs += v;
+          }
+        z[ri] += zs;
+      }
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk) {
+        ekA[mt][kk][0] = pack_h2(acc[mt][2 * kk][0], acc[mt][2 * kk][1]);
+        ekA[mt][kk][1] = pack_h2(acc[mt][2 * kk][2], acc[mt][2 * kk][3]);
+        ekA[mt][kk][2] = pack_h2(acc[mt][2 * kk + 1][0], acc[mt][2 * kk + 1][1]);
+        ekA[mt][kk][3] = pack_h2(acc[mt][2 * kk + 1][2], acc[mt][2 * kk + 1][3]);
+      }
+    }
+    // ---- v^T[e][p] = Wv_h xn^T
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[i][j][c] = 0.f;
+#pragma unroll
+    for (int kp = 0; kp < C / 32; ++kp) {
+      uint32_t bf[4][4];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+        ldsm_x4(xn_s + b_off + static_cast<uint32_t>((nt * 8 * XS + kp * 32) * 2), bf[nt][0], bf[nt][1], bf[nt][2], bf[nt][3]);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const uint4 a0 = __ldg(wv + (mt * KS + 2 * kp) * 32), a1 = __ldg(wv + (mt * KS + 2 * kp + 1) * 32);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          mma16816(acc[mt][nt], a0.x, a0.y, a0.z, a0.w, bf[nt][0], bf[nt][1]);
+          mma16816(acc[mt][nt], a1.x, a1.y, a1.z, a1.w, bf[nt][2], bf[nt][3]);
+        }
+      }
+    }
+    // ---- S[d][e] += sum_p ek[d][p] v^T[e][p]   (v^T accumulator fragments are the B fragments)
+#pragma unroll
+    for (int ne = 0; ne < 4; ++ne) {
+      const int me = ne >> 1, rr = 2 * (ne & 1);
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk) {
+        const uint32_t b0 = pack_h2(acc[me][2 * kk][rr], acc[me][2 * kk][rr + 1]);
+        const uint32_t b1 = pack_h2(acc[me][2 * kk + 1][rr], acc[me][2 * kk + 1][rr + 1]);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) mma16816(S[mt][ne], ekA[mt][kk], b0, b1);
+      }
+    }
+  }
+  // ---- partial of this (image, part = 2*sp + ph, head)
+  float* dst = part + (static_cast<size_t>(img * (split * 2) + sp * 2 + ph) * kLaHeads + h) * kLaPart;
+#pragma unroll
+  for (int ri = 0; ri < 4; ++ri) {
+    float zz = z[ri];
+    zz += __shfl_xor_sync(0xffffffffu, zz, 1);
+    zz += __shfl_xor_sync(0xffffffffu, zz, 2);
+    const int d = (ri >> 1) * 16 + g + 8 * (ri & 1);
+    if (q == 0) {
+      dst[d] = mrun[ri];
+      dst[32 + d] = zz;
+    }
+  }
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int ne = 0; ne < 4; ++ne)
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int d = mt * 16 + g + 8 * r;
+        *reinterpret_cast<float2*>(dst + 64 + d * 32 + ne * 8 + 2 * q) = make_float2(S[mt][ne][2 * r], S[mt][ne][2 * r + 1]);
+      }
+}
+
+// ------------------------------------------------------------------ la_mid: merge partials, fold to_out into the context
+// mpack[img]: M[c][j] = scale * sum_e Wout[c][32h + e] ctx_h[d][e]  (j = 32h + d) in B-fragment order
+// [c/8][j/32][lane][8 halves] (see mma_sync.cuh).
+__global__ void __launch_bounds__(256) la_mid_kernel(const float* __restrict__ part, const float* __restrict__ wout,
+                                                     __half* __restrict__ mpack, int C, int nparts, float scale) {
+  __shared__ float ctx[kLaHeads][kLaDh][kLaDh + 1];
+  const int img = blockIdx.x;
+  const int t = threadIdx.x & 127, chalf = threadIdx.x >> 7;
+  const int h = t >> 5, d = t & 31;
+  const float* pb = part + static_cast<size_t>(img) * nparts * kLaHeads * kLaPart + static_cast<size_t>(h) * kLaPart;
+  if (chalf == 0) {
+    float m = -INFINITY;
+    for (int i = 0; i < nparts; ++i) m = fmaxf(m, pb[static_cast<size_t>(i) * kLaHeads * kLaPart + d]);
+    float zt = 0.f;
+    for (int i = 0; i < nparts; ++i) {
+      const float* pi = pb + static_cast<size_t>(i) * kLaHeads * kLaPart;
+      zt += pi[32 + d] * __expf(pi[d] - m);
+    }
+    const float inv = scale / zt;
+    for (int e = 0; e < kLaDh; ++e) {
+      float s = 0.f;
+      for (int i = 0; i < nparts; ++i) {
+        const float* pi = pb + static_cast<size_t>(i) * kLaHeads * kLaPart;
+        s += pi[64 + d * 32 + e] * __expf(pi[d] - m);
+      }
+      ctx[h][d][e] = s * inv;
+    }
+  }
+  __syncthreads();
+  const int j = h * 32 + d;
+  const int ks = j >> 4, kk = j & 15;
+  const int reg = kk >> 3, qq = (kk & 7) >> 1, half = kk & 1;
+  __half* mp = mpack + static_cast<size_t>(img) * C * kLaHid;
+  const int c0 = chalf * (C / 2);
+  for (int c = c0; c < c0 + C / 2; ++c) {
+    const float* wr = wout + static_cast<size_t>(c) * kLaHid + h * 32;
+    float s = 0.f;
+#pragma unroll
+    for (int e = 0; e < kLaDh; ++e) s = fmaf(__ldg(wr + e), ctx[h][d][e], s);
+    const int nt = c >> 3, gg = c & 7;
+    mp[(static_cast<size_t>(nt * 4 + (ks >> 1)) * 32 + (gg * 4 + qq)) * 8 + ((ks & 1) * 2 + reg) * 2 + half] = __float2half_rn(s);
+  }
+}
+
+// ------------------------------------------------------------------ la2: q -> softmax_d -> y = q M^T + bias + x
+template <int C>
+__global__ void __launch_bounds__(256, 2) la2_kernel(const __half* __restrict__ x, __half* __restrict__ y,
+                                                  const float* __restrict__ gamma, const uint4* __restrict__ wq,
+                                                  const uint4* __restrict__ mpack, const float* __restrict__ bias, int n,
+                                                  int tiles, float eps) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  __half* xn = reinterpret_cast<__half*>(smem_raw);  // [128][C + 8]
+  constexpr int XS = C + 8;
+  const int img = blockIdx.x / tiles, tile = blockIdx.x - img * tiles;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, q = lane & 3;
+  const int p0 = tile * 128;
+  const int rows_valid = min(128, n - p0);
+  const __half* xt = x + (static_cast<size_t>(img) * n + p0) * C;
+  __half* yt = y + (static_cast<size_t>(img) * n + p0) * C;
+  ln_tile<C, 128, 256>(xt, rows_valid, gamma, xn, eps);
+  __syncthreads();
+  if (warp * 16 >= rows_valid) return;  // no barriers below
+  const uint32_t xn_s = static_cast<uint32_t>(__cvta_generic_to_shared(xn));
+  const uint32_t a_off = static_cast<uint32_t>(((16 * warp + (lane & 15)) * XS + 8 * (lane >> 4)) * 2);
+
+  // ---- q[16 rows][128] = xn Wq^T
+  float acc[16][4];
+#pragma unroll
+  for (int i = 0; i < 16; ++i)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[i][c] = 0.f;
+#pragma unroll
+  for (int kp = 0; kp < C / 32; ++kp) {
+    uint32_t a0[4], a1[4];
+    ldsm_x4(xn_s + a_off + static_cast<uint32_t>(kp * 32 * 2), a0[0], a0[1], a0[2], a0[3]);
+    ldsm_x4(xn_s + a_off + static_cast<uint32_t>((kp * 32 + 16) * 2), a1[0], a1[1], a1[2], a1[3]);
+#pragma unroll
+    for (int nt = 0; nt < 16; ++nt) {
+      const uint4 b = __ldg(wq + (nt * (C / 32) + kp) * 32 + lane);
+      mma16816(acc[nt], a0, b.x, b.y);
+      mma16816(acc[nt], a1, b.z, b.w);
+    }
+  }
+  // ---- softmax over each head's 32 dims (rows g and g+8 of this warp's 16); scale is folded into M
+  uint32_t aq[8][4];
+#pragma unroll
+  for (int hh = 0; hh < 4; ++hh) {
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) mx = fmaxf(mx, fmaxf(acc[4 * hh + j][2 * r], acc[4 * hh + j][2 * r + 1]));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      float sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float e0 = __expf(acc[4 * hh + j][2 * r] - mx), e1 = __expf(acc[4 * hh + j][2 * r + 1] - mx);
+        acc[4 * hh + j][2 * r] = e0;
+        acc[4 * hh + j][2 * r + 1] = e1;
+        sum += e0 + e1;
+      }
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+      const float inv = 1.0f / sum;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        acc[4 * hh + j][2 * r] *= inv;
+        acc[4 * hh + j][2 * r + 1] *= inv;
+      }
+    }
+#pragma unroll
+    for (int k2 = 0; k2 < 2; ++k2) {
+      const int ks = 2 * hh + k2;
+      aq[ks][0] = pack_h2(acc[2 * ks][0], acc[2 * ks][1]);
+      aq[ks][1] = pack_h2(acc[2 * ks][2], acc[2 * ks][3]);
+      aq[ks][2] = pack_h2(acc[2 * ks + 1][0], acc[2 * ks + 1][1]);
+      aq[ks][3] = pack_h2(acc[2 * ks + 1][2], acc[2 * ks + 1][3]);
+    }
+  }
+  // ---- y = q M^T + bias, 64 output channels at a time, written over this warp's own (dead) xn rows
+  const uint4* mp = mpack + static_cast<size_t>(img) * (C / 8) * 4 * 32 + lane;
+  __syncwarp();
+#pragma unroll 1
+  for (int cc = 0; cc < C / 64; ++cc) {
+    float yacc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) yacc[i][c] = 0.f;
+#pragma unroll
+    for (int kp = 0; kp < 4; ++kp) {
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const uint4 b = __ldg(mp + ((cc * 8 + nt) * 4 + kp) * 32);
+        mma16816(yacc[nt], aq[2 * kp], b.x, b.y);
+        mma16816(yacc[nt], aq[2 * kp + 1], b.z, b.w);
+      }
+    }
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const int c = cc * 64 + nt * 8 + 2 * q;
+      const float b0 = bias ? __ldg(bias + c) : 0.f, b1 = bias ? __ldg(bias + c + 1) : 0.f;
+      *reinterpret_cast<uint32_t*>(xn + (16 * warp + g) * XS + c) = pack_h2(yacc[nt][0] + b0, yacc[nt][1] + b1);
+      *reinterpret_cast<uint32_t*>(xn + (16 * warp + g + 8) * XS + c) = pack_h2(yacc[nt][2] + b0, yacc[nt][3] + b1);
+    }
+  }
+  __syncwarp();
+  // ---- + residual, coalesced store of this warp's 16 rows
+  constexpr int CPR = C / 8;  // 16-byte chunks per row
+#pragma unroll
+  for (int it = 0; it < 16 * CPR / 32; ++it) {
+    const int idx = it * 32 + lane;
+    const int r = idx / CPR, ch = idx - r * CPR;
+    const int row = 16 * warp + r;
+    if (row < rows_valid) {
+      uint4 v = *reinterpret_cast<const uint4*>(xn + row * XS + ch * 8);
+      const uint4 rv = __ldg(reinterpret_cast<const uint4*>(xt + static_cast<size_t>(row) * C) + ch);
+      __half2* vh = reinterpret_cast<__half2*>(&v);
+      const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 a2 = __half22float2(vh[i]), b2 = __half22float2(rh[i]);
+        vh[i] = __floats2half2_rn(a2.x + b2.x, a2.y + b2.y);
+      }
+      *(reinterpret_cast<uint4*>(yt + static_cast<size_t>(row) * C) + ch) = v;
+    }
+  }
+}
+
+static int la_split(int n_pos) { return ((n_pos + 63) / 64 >= 16) ? 2 : 1; }
+
+template <int C>
+static int launch_linattn(const __half* x, __half* y, const float* gamma, const uint4* wq, const uint4* wkv,
+                          const float* wout, const float* bias, void* work, int n_img, int n_pos, float scale, float eps,
+                          cudaStream_t st) {
+  const int split = la_split(n_pos);
+  const int nparts = split * 2;
+  float* part = static_cast<float*>(work);
+  __half* mpack = reinterpret_cast<__half*>(part + static_cast<size_t>(n_img) * nparts * kLaHeads * kLaPart);
+  const int smem1 = 64 * (C + 8) * 2, smem2 = 128 * (C + 8) * 2;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(la2_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
+    if (e != cudaSuccess) return set_cuda_error(e, "linattn_block: cudaFuncSetAttribute");
+    configured = true;
+  }
+  la1_kernel<C><<<n_img * split, 256, smem1, st>>>(x, gamma, wkv, part, n_pos, split, eps);
+  la_mid_kernel<<<n_img, 256, 0, st>>>(part, wout, mpack, C, nparts, scale);
+  const int tiles = (n_pos + 127) / 128;
+  la2_kernel<C><<<n_img * tiles, 256, smem2, st>>>(x, y, gamma, wq, reinterpret_cast<const uint4*>(mpack), bias, n_pos, tiles,
+                                                   eps);
+  return check_launch("linattn_block");
+}
+
+}  // namespace wdno
+
+using namespace wdno;
+
+extern "C" int64_t wdno_linattn_work_bytes(int64_t n_img, int n_pos, int C) {
+  if (n_img < 1 || n_pos < 1 || C < 1) return WDNO_E_INVALID;
+  const int nparts = la_split(n_pos) * 2;
+  return n_img * nparts * kLaHeads * kLaPart * 4 + n_img * static_cast<int64_t>(C) * kLaHid * 2;
+}
+
+extern "C" int wdno_linattn_block(const void* x, void* y, const float* gamma, const void* wq_pack, const void* wkv_pack,
+                                  const float* wout, const float* bias, void* work, int64_t n_img, int n_pos, int C,
+                                  float scale, float eps, void* stream) {
+  if (!x || !y || !gamma || !wq_pack || !wkv_pack || !wout || !work || n_img < 1 || n_pos < 1)
+    return set_error(WDNO_E_INVALID, "linattn_block: bad arguments");
+  if (n_img > (1 << 20)) return set_error(WDNO_E_INVALID, "linattn_block: too many images");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const __half* xi = static_cast<const __half*>(x);
+  __half* yo = static_cast<__half*>(y);
+  const uint4* wq = static_cast<const uint4*>(wq_pack);
+  const uint4* wkv = static_cast<const uint4*>(wkv_pack);
+  const int ni = static_cast<int>(n_img);
+  switch (C) {
+    case 64: return launch_linattn<64>(xi, yo, gamma, wq, wkv, wout, bias, work, ni, n_pos, scale, eps, st);
+    case 128: return launch_linattn<128>(xi, yo, gamma, wq, wkv, wout, bias, work, ni, n_pos, scale, eps, st);
+    case 256: return launch_linattn<256>(xi, yo, gamma, wq, wkv, wout, bias, work, ni, n_pos, scale, eps, st);
+    default: return set_error(WDNO_E_INVALID, "linattn_block: C must be 64, 128 or 256");
+  }
+}

@@ -39,7 +39,9 @@ constexpr int kStageWarp = 32 * kStageRow;
 constexpr int kStageBytes = kEpiWarps * kStageWarp;
 constexpr int kMaxBias = 1024;             // bias of the whole layer, staged in shared memory
 constexpr int kMaxChunks = 32;             // N-chunk descriptors staged in shared memory
-constexpr int kHdrBytes = kBarBytes + kMaxTaps * 8 + kStageBytes + kMaxBias * 4 + kMaxChunks * 40;
+constexpr int kMaxSets = 128;              // K-set descriptors staged in shared memory
+constexpr int kHdrBytes = kBarBytes + kMaxTaps * 8 + kStageBytes + kMaxBias * 4 + kMaxChunks * 40 + kMaxSets * 24;
+static_assert(sizeof(wdno_kset) == 24, "wdno_kset layout");
 static_assert(sizeof(wdno_nchunk) == 40, "wdno_nchunk layout");
 constexpr int kLoadBatch = 8;             // independent 16-byte loads in flight per producer thread
 
@@ -100,6 +102,13 @@ __device__ __forceinline__ float silu_f(float v) {
   return fmaf(h, t, h);
 }
 
+// h = v / 2 -> silu(v) = h + h * tanh(h)
+__device__ __forceinline__ float silu_half(float h) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
+
 // ------------------------------------------------------------------ MMA issue
 // All MMAs of one weight tile: ZT*PT accumulators x KS k-steps, fully unrolled, operands in registers.
 template <int ZT, int PT, int KS>
@@ -129,7 +138,7 @@ __device__ __forceinline__ void issue_tile(uint32_t a_tap_lo, uint32_t s_kz, uin
 // whole weight stage (TPS taps of one kz group) and the tcgen05.commit that frees it.  No divisions on this path.
 template <int ZT, int PT, int KS>
 __device__ __forceinline__ void mma_role(const wdno_tapgemm_params& p, Bars* bars, const wdno_tap* s_taps,
-                                         const wdno_nchunk* s_chunks, uint32_t tmem_base,
+                                         const wdno_nchunk* s_chunks, const wdno_kset* s_sets, uint32_t tmem_base,
                                          const uint8_t* slab_base, const uint8_t* b_base, int n_work, int ptiles, int zgroups) {
   constexpr int NACC = ZT * PT;
   const uint32_t N = static_cast<uint32_t>(p.N);
@@ -164,7 +173,7 @@ __device__ __forceinline__ void mma_role(const wdno_tapgemm_params& p, Bars* bar
       const uint32_t acc0 = tmem_base + buf * static_cast<uint32_t>(NACC) * npad;
       uint32_t accum = 0u;
       for (int si = 0; si < ci.set_count; ++si) {
-        const wdno_kset st = p.sets[ci.set_begin + si];
+        const wdno_kset st = s_sets[ci.set_begin + si];
         const int groups_per_kz = (st.tap_count / KD) / TPS;
         if (first_pass) {
 #pragma unroll
@@ -238,6 +247,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const wdno_tapgemm
   uint8_t* stage_base = smem + kBarBytes + kMaxTaps * 8;
   float* s_bias = reinterpret_cast<float*>(stage_base + kStageBytes);
   wdno_nchunk* s_chunks = reinterpret_cast<wdno_nchunk*>(stage_base + kStageBytes + kMaxBias * 4);
+  wdno_kset* s_sets = reinterpret_cast<wdno_kset*>(stage_base + kStageBytes + kMaxBias * 4 + kMaxChunks * 40);
   uint8_t* slab_base = smem + kHdrBytes;
   const int CH = p.KC >> 3;  // 16-byte chunks per position
   const uint32_t lbo_a = static_cast<uint32_t>(p.S_pad) * 16u;
@@ -276,6 +286,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const wdno_tapgemm
   }
   for (int i = threadIdx.x; i < p.n_taps; i += blockDim.x) s_taps[i] = p.taps[i];
   for (int i = threadIdx.x; i < p.n_chunks; i += blockDim.x) s_chunks[i] = p.chunks[i];
+  for (int i = threadIdx.x; i < p.n_sets; i += blockDim.x) s_sets[i] = p.sets[i];
   if (p.bias != nullptr)
     for (int i = threadIdx.x; i < p.bias_len; i += blockDim.x) s_bias[i] = p.bias[i];
   if (warp == kMmaWarp) {
@@ -289,28 +300,46 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const wdno_tapgemm
 
   if (warp >= kFirstProdWarp) {
     // ============================================================ A producers
-    // thread -> fixed 16-byte chunk c of positions s_first, s_first+SP, ...; (yp, xp) advance without divisions.
+    // thread -> fixed 16-byte chunk c of positions s_first, s_first+SP, ... of every plane.  The source offset of each of
+    // the thread's positions depends only on the work item's position tile, so it is computed once per work item
+    // (kIt cached offsets; longer slabs recompute the tail) and reused by all planes / K-sets of the item.
     // Every plane is fetched with asynchronous 16-byte copies (LDGSTS, zero fill outside the tensor).  Identity
     // prologue: the copies signal the slot's mbarrier themselves, so a thread never waits for data.  GroupNorm+SiLU
     // prologue: up to kAhead planes are kept in flight (cp.async groups); the oldest one is then transformed in
-    // place in shared memory (each thread touches only the chunks it copied) and published.
+    // place in shared memory (each thread touches only the chunks it copied; kIt independent chains) and published.
+    constexpr int kIt = 8;
+    constexpr int kSkip = -2, kZero = -1;  // offset codes: beyond the slab / outside the tensor (zero fill)
     const int ptid = threadIdx.x - kFirstProdWarp * 32;
     const int S = 128 * p.PT + p.maxshift;  // positions needed per plane
     const int c = ptid & (CH - 1);
     const int ch_shift = (CH == 8) ? 3 : (CH == 4) ? 2 : 1;
     const int s_first = ptid >> ch_shift;
     const int SP = kProdThreads >> ch_shift;  // positions covered per sweep of all producer threads
-    const int step_y = SP / p.Wp, step_x = SP - step_y * p.Wp;
+    const int n_it = (S - s_first + SP - 1) / SP;  // this thread's positions per plane
+    const uint32_t wp_magic = 0xFFFFFFFFu / static_cast<uint32_t>(p.Wp) + 1u;  // exact q / Wp for q * Wp < 2^32
     int Hs = p.H, Ws = p.W;
     if (p.src_mode == 1) { Hs = 2 * p.H; Ws = 2 * p.W; }
     if (p.src_mode == 2) { Hs = p.H >> 1; Ws = p.W >> 1; }
     const bool any_act = (p.coef_a[0] != nullptr) || (p.coef_a[1] != nullptr);
 
+    // source position (ys * Ws + xs, without the space-to-depth phase) of slab position index i, or a code
+    auto src_pos = [&](int q0, int i) -> int {
+      if (i >= n_it) return kSkip;
+      const int q = q0 + s_first + i * SP;
+      const int yp = static_cast<int>(__umulhi(static_cast<uint32_t>(q), wp_magic));
+      const int y = yp - p.py, x = q - yp * p.Wp - p.px;
+      if (y < 0 || y >= p.H || x < 0 || x >= p.W) return kZero;
+      if (p.src_mode == 1) return 2 * y * Ws + 2 * x;
+      if (p.src_mode == 2) return (y >> 1) * Ws + (x >> 1);
+      return y * Ws + x;
+    };
+
     // cursor over the sequence of plane jobs (work item, K-set, plane) this CTA produces
     struct Cursor {
       int w, si, j, nset, set_begin;
       uint32_t slot, ph;
-      int b, z0, yp0, xp0;
+      int b, z0, q0;
+      int off[kIt];
     };
     auto load_work = [&](Cursor& cu) {
       if (cu.w >= n_work) return;
@@ -320,9 +349,9 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const wdno_tapgemm
       cu.set_begin = ci.set_begin;
       cu.b = wk.b;
       cu.z0 = wk.zg * p.ZT;
-      const int q0 = wk.pt * 128 * p.PT + s_first;
-      cu.yp0 = q0 / p.Wp;
-      cu.xp0 = q0 - cu.yp0 * p.Wp;
+      cu.q0 = wk.pt * 128 * p.PT;
+#pragma unroll
+      for (int i = 0; i < kIt; ++i) cu.off[i] = src_pos(cu.q0, i);
     };
     auto advance = [&](Cursor& cu) {
       if (++cu.slot == static_cast<uint32_t>(p.NSLOT)) { cu.slot = 0; cu.ph ^= 1u; }
@@ -337,65 +366,86 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const wdno_tapgemm
     };
     // issue the asynchronous copies of the cursor's plane (the slot must be free)
     auto issue = [&](const Cursor& cu) {
-      const wdno_kset st = p.sets[cu.set_begin + cu.si];
+      const wdno_kset st = s_sets[cu.set_begin + cu.si];
       const int csrc = p.src_c[st.src];
       const int zi = cu.z0 - p.pz + cu.j;
       const bool zok = (zi >= 0) && (zi < p.D);
       const __half* plane = static_cast<const __half*>(p.src[st.src]) +
-                            ((static_cast<size_t>(cu.b) * p.D + (zok ? zi : 0)) * Hs * Ws) * csrc + st.ch_off + c * 8;
-      const uint32_t dst = ptx::smem_u32(slab_base) + cu.slot * slot_bytes + static_cast<uint32_t>(c) * lbo_a;
-      int yp = cu.yp0, xp = cu.xp0;
-      for (int s = s_first; s < S; s += SP) {
-        const int y = yp - p.py, x = xp - p.px;
-        const bool ok = zok && y >= 0 && y < p.H && x >= 0 && x < p.W;
-        int ys = y, xs = x;
-        if (p.src_mode == 1) { ys = 2 * y + st.ph_y; xs = 2 * x + st.ph_x; }
-        if (p.src_mode == 2) { ys = y >> 1; xs = x >> 1; }
-        const __half* ptr = ok ? plane + (static_cast<size_t>(ys) * Ws + xs) * csrc : plane;
-        ptx::cp_async16_zfill(dst + static_cast<uint32_t>(s) * 16u, ptr, ok ? 16u : 0u);
-        xp += step_x;
-        yp += step_y;
-        if (xp >= p.Wp) { xp -= p.Wp; ++yp; }
+                            ((static_cast<size_t>(cu.b) * p.D + (zok ? zi : 0)) * Hs * Ws + (st.ph_y * Ws + st.ph_x)) * csrc +
+                            st.ch_off + c * 8;
+      const uint32_t dst = ptx::smem_u32(slab_base) + cu.slot * slot_bytes + static_cast<uint32_t>(c) * lbo_a +
+                           static_cast<uint32_t>(s_first) * 16u;
+#pragma unroll
+      for (int i = 0; i < kIt; ++i) {
+        const int o = cu.off[i];
+        if (o != kSkip) {
+          const bool ok = zok && (o >= 0);
+          ptx::cp_async16_zfill(dst + static_cast<uint32_t>(i * SP) * 16u, ok ? plane + static_cast<size_t>(o) * csrc : plane,
+                                ok ? 16u : 0u);
+        }
+      }
+      for (int i = kIt; i < n_it; ++i) {  // long slabs (2-D layers with PT = 4): offsets recomputed
+        const int o = src_pos(cu.q0, i);
+        const bool ok = zok && (o >= 0);
+        ptx::cp_async16_zfill(dst + static_cast<uint32_t>(i * SP) * 16u, ok ? plane + static_cast<size_t>(o) * csrc : plane,
+                              ok ? 16u : 0u);
       }
     };
     // in-place silu(a*x + c) on the chunks this thread copied (zero-filled positions stay zero)
     auto transform = [&](const Cursor& cu) {
-      const wdno_kset st = p.sets[cu.set_begin + cu.si];
+      const wdno_kset st = s_sets[cu.set_begin + cu.si];
       if (p.coef_a[st.src] == nullptr) return;
+      const int zi = cu.z0 - p.pz + cu.j;
+      if (zi < 0 || zi >= p.D) return;
       const int csrc = p.src_c[st.src];
       const int chn = st.ch_off + c * 8;
       const float* pa = p.coef_a[st.src] + static_cast<size_t>(cu.b) * csrc + chn;
       const float* pc = p.coef_c[st.src] + static_cast<size_t>(cu.b) * csrc + chn;
-      const float4 a0 = __ldg(reinterpret_cast<const float4*>(pa)), a1 = __ldg(reinterpret_cast<const float4*>(pa + 4));
-      const float4 c0 = __ldg(reinterpret_cast<const float4*>(pc)), c1 = __ldg(reinterpret_cast<const float4*>(pc + 4));
-      const int zi = cu.z0 - p.pz + cu.j;
-      if (zi < 0 || zi >= p.D) return;
-      uint8_t* dst = slab_base + static_cast<size_t>(cu.slot) * slot_bytes + static_cast<size_t>(c) * lbo_a;
-      int yp = cu.yp0, xp = cu.xp0;
-      for (int s = s_first; s < S; s += SP) {
-        const int y = yp - p.py, x = xp - p.px;
-        if (y >= 0 && y < p.H && x >= 0 && x < p.W) {
-          uint4 v = *reinterpret_cast<const uint4*>(dst + static_cast<size_t>(s) * 16);
-          __half2* h = reinterpret_cast<__half2*>(&v);
-          float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]);
-          float2 f2 = __half22float2(h[2]), f3 = __half22float2(h[3]);
-          f0.x = silu_f(fmaf(a0.x, f0.x, c0.x)); f0.y = silu_f(fmaf(a0.y, f0.y, c0.y));
-          f1.x = silu_f(fmaf(a0.z, f1.x, c0.z)); f1.y = silu_f(fmaf(a0.w, f1.y, c0.w));
-          f2.x = silu_f(fmaf(a1.x, f2.x, c1.x)); f2.y = silu_f(fmaf(a1.y, f2.y, c1.y));
-          f3.x = silu_f(fmaf(a1.z, f3.x, c1.z)); f3.y = silu_f(fmaf(a1.w, f3.y, c1.w));
-          h[0] = __float22half2_rn(f0); h[1] = __float22half2_rn(f1);
-          h[2] = __float22half2_rn(f2); h[3] = __float22half2_rn(f3);
-          *reinterpret_cast<uint4*>(dst + static_cast<size_t>(s) * 16) = v;
+      // silu(v) = h + h * tanh(h) with h = v / 2 = (a/2) x + c/2
+      float4 a0 = __ldg(reinterpret_cast<const float4*>(pa)), a1 = __ldg(reinterpret_cast<const float4*>(pa + 4));
+      float4 c0 = __ldg(reinterpret_cast<const float4*>(pc)), c1 = __ldg(reinterpret_cast<const float4*>(pc + 4));
+      a0.x *= 0.5f; a0.y *= 0.5f; a0.z *= 0.5f; a0.w *= 0.5f; a1.x *= 0.5f; a1.y *= 0.5f; a1.z *= 0.5f; a1.w *= 0.5f;
+      c0.x *= 0.5f; c0.y *= 0.5f; c0.z *= 0.5f; c0.w *= 0.5f; c1.x *= 0.5f; c1.y *= 0.5f; c1.z *= 0.5f; c1.w *= 0.5f;
+      uint8_t* dst = slab_base + static_cast<size_t>(cu.slot) * slot_bytes + static_cast<size_t>(c) * lbo_a +
+                     static_cast<size_t>(s_first) * 16;
+      auto act8 = [&](uint4& v) {
+        __half2* h = reinterpret_cast<__half2*>(&v);
+        float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]);
+        float2 f2 = __half22float2(h[2]), f3 = __half22float2(h[3]);
+        f0.x = silu_half(fmaf(a0.x, f0.x, c0.x)); f0.y = silu_half(fmaf(a0.y, f0.y, c0.y));
+        f1.x = silu_half(fmaf(a0.z, f1.x, c0.z)); f1.y = silu_half(fmaf(a0.w, f1.y, c0.w));
+        f2.x = silu_half(fmaf(a1.x, f2.x, c1.x)); f2.y = silu_half(fmaf(a1.y, f2.y, c1.y));
+        f3.x = silu_half(fmaf(a1.z, f3.x, c1.z)); f3.y = silu_half(fmaf(a1.w, f3.y, c1.w));
+        h[0] = __float22half2_rn(f0); h[1] = __float22half2_rn(f1);
+        h[2] = __float22half2_rn(f2); h[3] = __float22half2_rn(f3);
+      };
+#pragma unroll
+      for (int i0 = 0; i0 < kIt; i0 += 4) {  // 4 independent load -> math -> store chains in flight
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (cu.off[i0 + u] >= 0) v[u] = *reinterpret_cast<const uint4*>(dst + static_cast<size_t>((i0 + u) * SP) * 16);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (cu.off[i0 + u] >= 0) act8(v[u]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (cu.off[i0 + u] >= 0) *reinterpret_cast<uint4*>(dst + static_cast<size_t>((i0 + u) * SP) * 16) = v[u];
+      }
+      for (int i = kIt; i < n_it; ++i) {
+        if (src_pos(cu.q0, i) >= 0) {
+          uint4 v = *reinterpret_cast<const uint4*>(dst + static_cast<size_t>(i * SP) * 16);
+          act8(v);
+          *reinterpret_cast<uint4*>(dst + static_cast<size_t>(i * SP) * 16) = v;
         }
-        xp += step_x;
-        yp += step_y;
-        if (xp >= p.Wp) { xp -= p.Wp; ++yp; }
       }
     };
 
     Cursor iss;
     iss.w = blockIdx.x; iss.si = 0; iss.j = 0; iss.slot = 0; iss.ph = 0; iss.nset = 0; iss.set_begin = 0;
-    iss.b = 0; iss.z0 = 0; iss.yp0 = 0; iss.xp0 = 0;
+    iss.b = 0; iss.z0 = 0; iss.q0 = 0;
+#pragma unroll
+    for (int i = 0; i < kIt; ++i) iss.off[i] = kSkip;
     load_work(iss);
     PROF_DECL;
     if (!any_act) {
@@ -461,9 +511,9 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const wdno_tapgemm
     // ============================================================ MMA issuer (templated on the accumulator shape)
     const int ks = p.KC >> 4;
 #define WDNO_MMA(ZT_, PT_) \
-    if (ks == 1) mma_role<ZT_, PT_, 1>(p, bars, s_taps, s_chunks, tmem_base, slab_base, b_base, n_work, ptiles, zgroups); \
-    else if (ks == 2) mma_role<ZT_, PT_, 2>(p, bars, s_taps, s_chunks, tmem_base, slab_base, b_base, n_work, ptiles, zgroups); \
-    else mma_role<ZT_, PT_, 4>(p, bars, s_taps, s_chunks, tmem_base, slab_base, b_base, n_work, ptiles, zgroups);
+    if (ks == 1) mma_role<ZT_, PT_, 1>(p, bars, s_taps, s_chunks, s_sets, tmem_base, slab_base, b_base, n_work, ptiles, zgroups); \
+    else if (ks == 2) mma_role<ZT_, PT_, 2>(p, bars, s_taps, s_chunks, s_sets, tmem_base, slab_base, b_base, n_work, ptiles, zgroups); \
+    else mma_role<ZT_, PT_, 4>(p, bars, s_taps, s_chunks, s_sets, tmem_base, slab_base, b_base, n_work, ptiles, zgroups);
     if (p.ZT == 4) { WDNO_MMA(4, 1) }
     else if (p.ZT == 2) { WDNO_MMA(2, 1) }
     else if (p.PT == 4) { WDNO_MMA(1, 4) }
@@ -711,6 +761,7 @@ static int validate(const wdno_tapgemm_params* p) {
   if (smem_bytes_of(p) > 227 * 1024) return set_error(WDNO_E_INVALID, "tapgemm: shared-memory plan exceeds 227 KB");
   if (p->grid < 1) return set_error(WDNO_E_INVALID, "tapgemm: grid must be >= 1");
   if (p->n_chunks > kMaxChunks) return set_error(WDNO_E_INVALID, "tapgemm: more than 32 N-chunks");
+  if (p->n_sets < 1 || p->n_sets > kMaxSets) return set_error(WDNO_E_INVALID, "tapgemm: n_sets must be in [1,128]");
   if (p->bias && (p->bias_len < 1 || p->bias_len > kMaxBias)) return set_error(WDNO_E_INVALID, "tapgemm: bias_len must be in [1,1024]");
   return WDNO_OK;
 }

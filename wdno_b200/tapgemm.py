@@ -20,7 +20,7 @@ from . import _lib
 from ._lib import KSet, NChunk, Tap, TapGemmParams
 
 _SMEM_LIMIT = 227 * 1024
-_BAR_BYTES = 512 + 384 * 8 + 4 * 32 * 144 + 1024 * 4 + 32 * 40  # barriers, tap table, epilogue staging, bias, N-chunk table
+_BAR_BYTES = 512 + 384 * 8 + 4 * 32 * 144 + 1024 * 4 + 32 * 40 + 128 * 24  # barriers, tap table, epilogue staging, bias, N-chunk / K-set tables
 
 
 def _device_bytes(ctypes_array, device):
@@ -219,7 +219,7 @@ class TapGemm:
             wpacked=wpacked.to(torch.float16).to(self.device),
             sets=_device_bytes(sets_c, self.device),
             chunks=_device_bytes(chunks_c, self.device),
-            taps_kyx=taps, n_chunks=len(chunks),
+            taps_kyx=taps, n_chunks=len(chunks), n_sets=len(sets),
             taps_dev={},  # Wp -> device tap table
         )
         self._packed[KC] = pk
@@ -321,6 +321,7 @@ class TapGemm:
         p.NSLOT, p.NBST, p.S_pad = NSLOT, NBST, S_pad
         p.TPS, p.reuse = TPS, reuse
         p.n_taps = len(pk["taps_kyx"])
+        p.n_sets = pk["n_sets"]
         p.grid = max(1, min(n_work, sms))
         self._launch[key] = p
         return p

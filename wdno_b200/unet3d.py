@@ -17,6 +17,7 @@ import torch
 from torch import nn
 
 from . import ops
+from .attn_fused import LinAttnBlock
 from .tapgemm import TapGemm
 
 
@@ -286,9 +287,7 @@ class Unet3DEngine:
 
     def _lin_attn_plan(self, res):
         attn = res.fn.fn
-        return dict(gamma=self._f32(res.fn.norm.gamma.reshape(-1)),
-                    qkv=TapGemm(attn.to_qkv.weight, None, device=self.dev),
-                    out=self._out_plus_residual(attn.to_out.weight, attn.to_out.bias))
+        return LinAttnBlock(res.fn.norm.gamma, attn.to_qkv.weight, attn.to_out.weight, attn.to_out.bias, device=self.dev)
 
     def _rel_tables(self, n):
         """T5 relative-position bias [heads][n][n] (conv3d.py:74-112) and rotary cos/sin [n][16]."""
@@ -349,12 +348,8 @@ class Unet3DEngine:
         return ap["out"](o, x)
 
     def _linear_attn(self, ap, x):
-        B, D, H, W, C = x.shape
-        xn = ops.chan_layernorm(x, ap["gamma"])
-        qkv = ap["qkv"](xn)
-        o = ops.linear_attn(qkv, B * D, H * W, self.scale)
-        self.launches += 4
-        return ap["out"](o, x)
+        self.launches += 3
+        return ap(x)
 
     # ------------------------------------------------------------ forward
     def forward(self, x, time, taps=None):
