@@ -151,8 +151,16 @@ int wdno_linear_attn(const void* qkv, void* out, int64_t n_img, int n_pos, float
  *   linattn_block: SpatialLinearAttention, reference conv3d.py:165-184,232-258.
  *     wq_pack  fp16 B-fragments of W_q [128][C];  wkv_pack fp16 A-fragments [k|v][head][32][C];
  *     wout fp32 [C][128]; bias fp32 [C] or NULL; work: wdno_linattn_work_bytes() bytes of scratch.
- * ------------------------------------------------------------------------------------------ */
+ *   tattn_block: temporal Attention over the frame axis (n_frames <= 32 tokens per pixel; rotary on q,k; T5 relative
+ *     position bias), reference conv3d.py:74-112,165-184,262-353,383.  x,y: [n_samples][n_frames][hw][C], hw even.
+ *     wqk_pack fp16 B-fragments of W_qk [256][C]; wv_pack fp16 A-fragments [head][32][C]; wout_pack fp16 B-fragments of
+ *     W_out [C][128]; bias fp32 [4][n_frames][n_frames] or NULL; rot_cos/rot_sin fp32 [n_frames][16] or both NULL.
+ */
 int64_t wdno_linattn_work_bytes(int64_t n_img, int n_pos, int C);
+int wdno_tattn_block(const void* x, void* y, const float* gamma, const void* wqk_pack, const void* wv_pack,
+                     const void* wout_pack, const float* bias, const float* rot_cos, const float* rot_sin,
+                     int64_t n_samples, int n_frames, int64_t hw, int C, float scale, float eps, void* stream);
+/* ------------------------------------------------------------------------------------------ */
 int wdno_linattn_block(const void* x, void* y, const float* gamma, const void* wq_pack, const void* wkv_pack,
                        const float* wout, const float* bias, void* work, int64_t n_img, int n_pos, int C,
                        float scale, float eps, void* stream);

@@ -68,3 +68,37 @@ class LinAttnBlock:
                                         _p(self._work[key]), n_img, n_pos, self.C, self.scale, float(eps),
                                         _lib.current_stream_ptr()), "linattn_block")
         return y
+
+
+class TemporalBlock:
+    """y = x + to_out(softmax(q k^T + rel_pos_bias) v)  along the frame axis of fp16 channels-last [B, D, H, W, C],
+    q/k rotary-embedded; (q, k, v) = to_qkv(LayerNorm(x)).  D <= 32, H*W even."""
+
+    def __init__(self, gamma, w_qkv, w_out, heads=4, dim_head=32, device="cuda"):
+        assert heads == 4 and dim_head == 32
+        dev = torch.device(device)
+        wq = w_qkv.detach().float().cpu().reshape(w_qkv.shape[0], -1)    # [384, C]
+        self.C = wq.shape[1]
+        assert wq.shape[0] == 384 and self.C in (64, 128, 256)
+        self.gamma = gamma.detach().float().reshape(-1).contiguous().to(dev)
+        self.wqk = pack_b_frags(wq[:256]).to(dev)                                             # q | k as B operands
+        self.wv = torch.stack([pack_a_frags(wq[256 + 32 * h: 288 + 32 * h]) for h in range(4)]).contiguous().to(dev)
+        wo = w_out.detach().float().cpu().reshape(w_out.shape[0], -1)    # [C, 128]
+        assert wo.shape == (self.C, 128)
+        self.wo = pack_b_frags(wo).to(dev)
+        self.scale = dim_head ** -0.5
+
+    def __call__(self, x, bias=None, rot=None, eps=1e-5):
+        """bias fp32 [4, D, D] or None; rot = (cos, sin) fp32 [D, 16] or None."""
+        assert x.dtype == torch.float16 and x.is_contiguous() and x.dim() == 5 and x.shape[-1] == self.C
+        B, D, H, W, _ = x.shape
+        y = torch.empty_like(x)
+        rc, rs = (rot if rot is not None else (None, None))
+        if bias is not None:
+            assert bias.dtype == torch.float32 and bias.is_contiguous() and tuple(bias.shape) == (4, D, D)
+        if rc is not None:
+            assert rc.dtype == torch.float32 and rc.is_contiguous() and tuple(rc.shape) == (D, 16) and tuple(rs.shape) == (D, 16)
+        _lib.check(_lib.lib().wdno_tattn_block(_p(x), _p(y), _p(self.gamma), _p(self.wqk), _p(self.wv), _p(self.wo), _p(bias),
+                                               _p(rc), _p(rs), B, D, H * W, self.C, self.scale, float(eps),
+                                               _lib.current_stream_ptr()), "tattn_block")
+        return y

@@ -361,6 +361,371 @@ __global__ void __launch_bounds__(256, 2) la2_kernel(const __half* __restrict__ 
   }
 }
 
+// ================================================================== temporal attention block
+// Residual(PreNorm(dim, EinopsToAndFrom('b c f h w', 'b (h w) f c', Attention(dim, heads=4, dim_head=32, rotary))))
+// reference conv3d.py:165-184, 262-353 (focus_present_mask all False), 74-112 (T5 relative position bias).
+// One sequence = the n <= 24..32 frames of one pixel.  A block of 8 warps works on two adjacent pixels at a time:
+//   LayerNorm -> shared xn[2][32][C+8] (rows >= n stay zero);
+//   warp (s, h): Q = xn Wq_h^T (scale, rotary), K = xn Wk_h^T (rotary), V^T = Wv_h xn^T -- all three land directly in
+//   the register fragments the next products need -- S = Q K^T + bias -> softmax -> O = P V -> shared obuf[s][32][128];
+//   warp (s, c4): Y[:, c4*C/4 ...] = O Wout^T -> shared (over xn) -> + x -> coalesced store.
+constexpr int kTaRows = 32;
+
+template <int C>
+__global__ void __launch_bounds__(256, 2) tattn_kernel(const __half* __restrict__ x, __half* __restrict__ y,
+                                                        const float* __restrict__ gamma, const uint4* __restrict__ wqk,
+                                                        const uint4* __restrict__ wv, const uint4* __restrict__ wo,
+                                                        const float* __restrict__ bias, const float* __restrict__ rot_cos,
+                                                        const float* __restrict__ rot_sin, long long n_pix, long long hw,
+                                                        int n, float scale, float eps) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  constexpr int XS = C + 8, OS = kLaHid + 8, KS = C / 16;
+  __half* xn = reinterpret_cast<__half*>(smem_raw);                       // [2][32][XS]
+  __half* obuf = xn + 2 * kTaRows * XS;                                    // [2][32][OS]
+  float* sbias = reinterpret_cast<float*>(obuf + 2 * kTaRows * OS);        // [4][32][32], -inf for keys >= n
+  float* scs = sbias + 4 * 32 * 32;                                        // [32][16] cos, [32][16] sin
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, q = lane & 3;
+  const int s = warp >> 2, h = warp & 3;
+
+  for (int i = tid; i < 2 * kTaRows * XS / 8; i += 256) reinterpret_cast<uint4*>(xn)[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = tid; i < 4 * 32 * 32; i += 256) {
+    const int hh = i >> 10, r = (i >> 5) & 31, c = i & 31;
+    float b = 0.f;
+    if (c >= n) b = -INFINITY;
+    else if (r < n && bias != nullptr) b = __ldg(bias + (static_cast<size_t>(hh) * n + r) * n + c);
+    sbias[i] = b;
+  }
+  for (int i = tid; i < 32 * 16; i += 256) {
+    const int f = i >> 4;
+    scs[i] = (rot_cos != nullptr && f < n) ? __ldg(rot_cos + f * 16 + (i & 15)) : 1.0f;
+    scs[512 + i] = (rot_sin != nullptr && f < n) ? __ldg(rot_sin + f * 16 + (i & 15)) : 0.0f;
+  }
+
+  const uint32_t xn_s = static_cast<uint32_t>(__cvta_generic_to_shared(xn + s * kTaRows * XS));
+  const uint32_t ob_s = static_cast<uint32_t>(__cvta_generic_to_shared(obuf + s * kTaRows * OS));
+  const uint32_t a_off = static_cast<uint32_t>((((lane & 15)) * XS + 8 * (lane >> 4)) * 2);   // A operand rows = tokens
+  const uint32_t b_off = static_cast<uint32_t>((((lane & 7)) * XS + 8 * (lane >> 3)) * 2);    // B operand rows = tokens
+  const uint32_t oa_off = static_cast<uint32_t>((((lane & 15)) * OS + 8 * (lane >> 4)) * 2);
+  constexpr int LP = C / 8, RPP = 256 / LP, ROWS = 2 * 24;
+  constexpr int PASSES = (2 * kTaRows + RPP - 1) / RPP;  // enough for n <= 32
+  const long long n_pairs = (n_pix + 1) >> 1;
+
+  for (long long pr = blockIdx.x; pr < n_pairs; pr += gridDim.x) {
+    const long long pix0 = pr * 2;
+    const long long bimg = pix0 / hw, pin = pix0 - bimg * hw;  // both pixels of a pair lie in one sample when hw is even
+    const __half* xb = x + (static_cast<size_t>(bimg) * n * hw + pin) * C;
+    __half* yb = y + (static_cast<size_t>(bimg) * n * hw + pin) * C;
+    const int nseq = (pix0 + 1 < n_pix) ? 2 : 1;
+    __syncthreads();  // previous iteration's staging reads are done (also orders the table setup)
+    // ---- LayerNorm of 2 x n tokens: row rr = 2 f + s
+    {
+      const int l = tid % LP, r0 = tid / LP;
+      float gm[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) gm[j] = __ldg(gamma + l * 8 + j);
+      uint4 raw[PASSES];
+#pragma unroll
+      for (int ps = 0; ps < PASSES; ++ps) {
+        const int rr = r0 + ps * RPP;
+        const int f = rr >> 1, ss = rr & 1;
+        raw[ps] = make_uint4(0u, 0u, 0u, 0u);
+        if (f < n && ss < nseq) raw[ps] = __ldg(reinterpret_cast<const uint4*>(xb + (static_cast<size_t>(f) * hw + ss) * C) + l);
+      }
+#pragma unroll
+      for (int ps = 0; ps < PASSES; ++ps) {
+        const int rr = r0 + ps * RPP;
+        const int f = rr >> 1, ss = rr & 1;
+        const __half2* hh = reinterpret_cast<const __half2*>(&raw[ps]);
+        float fv[8];
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 t = __half22float2(hh[j]);
+          fv[2 * j] = t.x;
+          fv[2 * j + 1] = t.y;
+          sum += t.x + t.y;
+        }
+#pragma unroll
+        for (int sh = LP / 2; sh > 0; sh >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, sh);
+        const float mean = sum * (1.0f / C);
+        float sq = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          fv[j] -= mean;
+          sq = fmaf(fv[j], fv[j], sq);
+        }
+#pragma unroll
+        for (int sh = LP / 2; sh > 0; sh >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, sh);
+        const float rstd = rsqrtf(sq * (1.0f / C) + eps);
+        if (f < n) {
+          uint4 ov;
+          uint32_t* o = reinterpret_cast<uint32_t*>(&ov);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) o[j] = pack_h2(fv[2 * j] * rstd * gm[2 * j], fv[2 * j + 1] * rstd * gm[2 * j + 1]);
+          if (ss >= nseq) ov = make_uint4(0u, 0u, 0u, 0u);
+          *reinterpret_cast<uint4*>(xn + (ss * kTaRows + f) * XS + l * 8) = ov;
+        }
+      }
+    }
+    __syncthreads();
+
+    // ================= attention core of (sequence s, head h)
+    {
+      // ---- Q (scaled, rotated) -> A fragments ; K (rotated) -> B fragments
+      uint32_t qa[2][2][4], kb[4][2][2];
+#pragma unroll
+      for (int sec = 0; sec < 2; ++sec) {
+        float acc[2][4][4];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[i][j][c] = 0.f;
+        const uint4* wb = wqk + static_cast<size_t>((sec * 16 + 4 * h) * (C / 32)) * 32 + lane;
+#pragma unroll
+        for (int kp = 0; kp < C / 32; ++kp) {
+          uint32_t a0[2][4], a1[2][4];
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) {
+            ldsm_x4(xn_s + a_off + static_cast<uint32_t>((mt * 16 * XS + kp * 32) * 2), a0[mt][0], a0[mt][1], a0[mt][2], a0[mt][3]);
+            ldsm_x4(xn_s + a_off + static_cast<uint32_t>((mt * 16 * XS + kp * 32 + 16) * 2), a1[mt][0], a1[mt][1], a1[mt][2], a1[mt][3]);
+          }
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) {
+            const uint4 b = __ldg(wb + (nt * (C / 32) + kp) * 32);
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+              mma16816(acc[mt][nt], a0[mt], b.x, b.y);
+              mma16816(acc[mt][nt], a1[mt], b.z, b.w);
+            }
+          }
+        }
+        const float sc = (sec == 0) ? scale : 1.0f;
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            const int f = 16 * mt + g + 8 * r;
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+              const float cs = scs[f * 16 + 4 * nt + q], sn = scs[512 + f * 16 + 4 * nt + q];
+              const float x0 = acc[mt][nt][2 * r] * sc, x1 = acc[mt][nt][2 * r + 1] * sc;
+              acc[mt][nt][2 * r] = x0 * cs - x1 * sn;
+              acc[mt][nt][2 * r + 1] = x1 * cs + x0 * sn;
+            }
+          }
+        if (sec == 0) {
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+              qa[mt][ks][0] = pack_h2(acc[mt][2 * ks][0], acc[mt][2 * ks][1]);
+              qa[mt][ks][1] = pack_h2(acc[mt][2 * ks][2], acc[mt][2 * ks][3]);
+              qa[mt][ks][2] = pack_h2(acc[mt][2 * ks + 1][0], acc[mt][2 * ks + 1][1]);
+              qa[mt][ks][3] = pack_h2(acc[mt][2 * ks + 1][2], acc[mt][2 * ks + 1][3]);
+            }
+        } else {
+          // key tile j (keys 8j..8j+7) = rows g + 8 (j & 1) of m-tile j >> 1
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+              const int rr = 2 * (j & 1);
+              kb[j][ks][0] = pack_h2(acc[j >> 1][2 * ks][rr], acc[j >> 1][2 * ks][rr + 1]);
+              kb[j][ks][1] = pack_h2(acc[j >> 1][2 * ks + 1][rr], acc[j >> 1][2 * ks + 1][rr + 1]);
+            }
+        }
+      }
+      // ---- S = Q K^T + bias (keys >= n masked by the table), softmax over keys
+      float sfr[2][4][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) sfr[mt][j][c] = 0.f;
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) mma16816(sfr[mt][j], qa[mt][ks], kb[j][ks][0], kb[j][ks][1]);
+        }
+      uint32_t pa[2][2][4];
+      float inv[2][2];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const float* brow = sbias + (h * 32 + 16 * mt + g + 8 * r) * 32 + 2 * q;
+          float mx = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 bv = *reinterpret_cast<const float2*>(brow + 8 * j);
+            sfr[mt][j][2 * r] += bv.x;
+            sfr[mt][j][2 * r + 1] += bv.y;
+            mx = fmaxf(mx, fmaxf(sfr[mt][j][2 * r], sfr[mt][j][2 * r + 1]));
+          }
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+          float sum = 0.f;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float p0 = __expf(sfr[mt][j][2 * r] - mx), p1 = __expf(sfr[mt][j][2 * r + 1] - mx);
+            sfr[mt][j][2 * r] = p0;
+            sfr[mt][j][2 * r + 1] = p1;
+            sum += p0 + p1;
+          }
+          sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+          sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+          inv[mt][r] = 1.0f / sum;
+        }
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+          pa[mt][kk][0] = pack_h2(sfr[mt][2 * kk][0], sfr[mt][2 * kk][1]);
+          pa[mt][kk][1] = pack_h2(sfr[mt][2 * kk][2], sfr[mt][2 * kk][3]);
+          pa[mt][kk][2] = pack_h2(sfr[mt][2 * kk + 1][0], sfr[mt][2 * kk + 1][1]);
+          pa[mt][kk][3] = pack_h2(sfr[mt][2 * kk + 1][2], sfr[mt][2 * kk + 1][3]);
+        }
+      }
+      // ---- V^T[d][key] = Wv_h xn^T  (its accumulator fragments are the B fragments of P V)
+      float vt[2][4][4];
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) vt[i][j][c] = 0.f;
+      {
+        const uint4* wa = wv + static_cast<size_t>(h * 2) * KS * 32 + lane;
+#pragma unroll
+        for (int kp = 0; kp < C / 32; ++kp) {
+          uint32_t bf[4][4];
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt)
+            ldsm_x4(xn_s + b_off + static_cast<uint32_t>((nt * 8 * XS + kp * 32) * 2), bf[nt][0], bf[nt][1], bf[nt][2], bf[nt][3]);
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) {
+            const uint4 a0 = __ldg(wa + (mt * KS + 2 * kp) * 32), a1 = __ldg(wa + (mt * KS + 2 * kp + 1) * 32);
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+              mma16816(vt[mt][nt], a0.x, a0.y, a0.z, a0.w, bf[nt][0], bf[nt][1]);
+              mma16816(vt[mt][nt], a1.x, a1.y, a1.z, a1.w, bf[nt][2], bf[nt][3]);
+            }
+          }
+        }
+      }
+      // ---- O = P V, normalised -> obuf[s][token][32 h + d]
+      float ofr[2][4][4];
+#pragma unroll
+      for (int nd = 0; nd < 4; ++nd) {
+        const int me = nd >> 1, rr = 2 * (nd & 1);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) ofr[mt][nd][c] = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+          const uint32_t b0 = pack_h2(vt[me][2 * kk][rr], vt[me][2 * kk][rr + 1]);
+          const uint32_t b1 = pack_h2(vt[me][2 * kk + 1][rr], vt[me][2 * kk + 1][rr + 1]);
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) mma16816(ofr[mt][nd], pa[mt][kk], b0, b1);
+        }
+      }
+      __half* ob = obuf + s * kTaRows * OS + h * 32;
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nd = 0; nd < 4; ++nd)
+#pragma unroll
+          for (int r = 0; r < 2; ++r)
+            *reinterpret_cast<uint32_t*>(ob + (16 * mt + g + 8 * r) * OS + 8 * nd + 2 * q) =
+                pack_h2(ofr[mt][nd][2 * r] * inv[mt][r], ofr[mt][nd][2 * r + 1] * inv[mt][r]);
+    }
+    __syncthreads();
+
+    // ================= output projection: warp (s, c4 = h) -> channels [c4*C/4, (c4+1)*C/4)
+    {
+      constexpr int NT = C / 32;  // n-tiles per warp
+      float yacc[2][NT][4];
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) yacc[i][j][c] = 0.f;
+      const uint4* wb = wo + static_cast<size_t>(h * NT) * 4 * 32 + lane;
+#pragma unroll
+      for (int kp = 0; kp < 4; ++kp) {
+        uint32_t a0[2][4], a1[2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          ldsm_x4(ob_s + oa_off + static_cast<uint32_t>((mt * 16 * OS + kp * 32) * 2), a0[mt][0], a0[mt][1], a0[mt][2], a0[mt][3]);
+          ldsm_x4(ob_s + oa_off + static_cast<uint32_t>((mt * 16 * OS + kp * 32 + 16) * 2), a1[mt][0], a1[mt][1], a1[mt][2], a1[mt][3]);
+        }
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          const uint4 b = __ldg(wb + (nt * 4 + kp) * 32);
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) {
+            mma16816(yacc[mt][nt], a0[mt], b.x, b.y);
+            mma16816(yacc[mt][nt], a1[mt], b.z, b.w);
+          }
+        }
+      }
+      // Y -> xn rows (all warps are past their last xn read: barrier above); rows >= n stay zero
+      __half* xs = xn + s * kTaRows * XS + h * (C / 4);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const int f = 16 * mt + g + 8 * r;
+          if (f < n) {
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+              *reinterpret_cast<uint32_t*>(xs + f * XS + 8 * nt + 2 * q) = pack_h2(yacc[mt][nt][2 * r], yacc[mt][nt][2 * r + 1]);
+          }
+        }
+    }
+    __syncthreads();
+    // ---- y = Y + x, coalesced: item = (f, s, 16-byte chunk)
+    for (int idx = tid; idx < n * 2 * LP; idx += 256) {
+      const int l = idx % LP, rr = idx / LP;
+      const int f = rr >> 1, ss = rr & 1;
+      if (ss < nseq) {
+        uint4 v = *reinterpret_cast<const uint4*>(xn + (ss * kTaRows + f) * XS + l * 8);
+        const size_t off = (static_cast<size_t>(f) * hw + ss) * C;
+        const uint4 rv = __ldg(reinterpret_cast<const uint4*>(xb + off) + l);
+        __half2* vh = reinterpret_cast<__half2*>(&v);
+        const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 a2 = __half22float2(vh[i]), b2 = __half22float2(rh[i]);
+          vh[i] = __floats2half2_rn(a2.x + b2.x, a2.y + b2.y);
+        }
+        *(reinterpret_cast<uint4*>(yb + off) + l) = v;
+      }
+    }
+  }
+  (void)ROWS;
+}
+
+template <int C>
+static int launch_tattn(const __half* x, __half* y, const float* gamma, const uint4* wqk, const uint4* wv, const uint4* wo,
+                        const float* bias, const float* rot_cos, const float* rot_sin, long long n_pix, long long hw, int n,
+                        float scale, float eps, cudaStream_t st) {
+  const int smem = (2 * kTaRows * (C + 8) + 2 * kTaRows * (kLaHid + 8)) * 2 + (4 * 32 * 32 + 2 * 32 * 16) * 4;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(tattn_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return set_cuda_error(e, "tattn_block: cudaFuncSetAttribute");
+    configured = true;
+  }
+  const long long n_pairs = (n_pix + 1) / 2;
+  const long long cap = static_cast<long long>(num_sms()) * 2 * 4;
+  const unsigned grid = static_cast<unsigned>(n_pairs < cap ? n_pairs : cap);
+  tattn_kernel<C><<<grid, 256, smem, st>>>(x, y, gamma, wqk, wv, wo, bias, rot_cos, rot_sin, n_pix, hw, n, scale, eps);
+  return check_launch("tattn_block");
+}
+
 static int la_split(int n_pos) { return ((n_pos + 63) / 64 >= 16) ? 2 : 1; }
 
 template <int C>
@@ -389,6 +754,29 @@ static int launch_linattn(const __half* x, __half* y, const float* gamma, const 
 }  // namespace wdno
 
 using namespace wdno;
+
+extern "C" int wdno_tattn_block(const void* x, void* y, const float* gamma, const void* wqk_pack, const void* wv_pack,
+                                const void* wout_pack, const float* bias, const float* rot_cos, const float* rot_sin,
+                                int64_t n_samples, int n_frames, int64_t hw, int C, float scale, float eps, void* stream) {
+  if (!x || !y || !gamma || !wqk_pack || !wv_pack || !wout_pack || n_samples < 1 || hw < 1)
+    return set_error(WDNO_E_INVALID, "tattn_block: bad arguments");
+  if (n_frames < 1 || n_frames > 32) return set_error(WDNO_E_INVALID, "tattn_block: frames must be in [1,32]");
+  if (hw & 1) return set_error(WDNO_E_INVALID, "tattn_block: H*W must be even");
+  if ((rot_cos == nullptr) != (rot_sin == nullptr)) return set_error(WDNO_E_INVALID, "tattn_block: rotary tables must both be given");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const __half* xi = static_cast<const __half*>(x);
+  __half* yo = static_cast<__half*>(y);
+  const uint4* a = static_cast<const uint4*>(wqk_pack);
+  const uint4* b = static_cast<const uint4*>(wv_pack);
+  const uint4* c = static_cast<const uint4*>(wout_pack);
+  const long long npix = n_samples * hw;
+  switch (C) {
+    case 64: return launch_tattn<64>(xi, yo, gamma, a, b, c, bias, rot_cos, rot_sin, npix, hw, n_frames, scale, eps, st);
+    case 128: return launch_tattn<128>(xi, yo, gamma, a, b, c, bias, rot_cos, rot_sin, npix, hw, n_frames, scale, eps, st);
+    case 256: return launch_tattn<256>(xi, yo, gamma, a, b, c, bias, rot_cos, rot_sin, npix, hw, n_frames, scale, eps, st);
+    default: return set_error(WDNO_E_INVALID, "tattn_block: C must be 64, 128 or 256");
+  }
+}
 
 extern "C" int64_t wdno_linattn_work_bytes(int64_t n_img, int n_pos, int C) {
   if (n_img < 1 || n_pos < 1 || C < 1) return WDNO_E_INVALID;

@@ -17,7 +17,7 @@ import torch
 from torch import nn
 
 from . import ops
-from .attn_fused import LinAttnBlock
+from .attn_fused import LinAttnBlock, TemporalBlock
 from .tapgemm import TapGemm
 
 
@@ -281,6 +281,8 @@ class Unet3DEngine:
 
     def _attn_plan(self, res, temporal):
         attn = res.fn.fn.fn
+        if temporal:
+            return TemporalBlock(res.fn.norm.gamma, attn.to_qkv.weight, attn.to_out.weight, device=self.dev)
         return dict(gamma=self._f32(res.fn.norm.gamma.reshape(-1)),
                     qkv=TapGemm(attn.to_qkv.weight, None, device=self.dev),
                     out=self._out_plus_residual(attn.to_out.weight, None), temporal=temporal)
@@ -331,13 +333,9 @@ class Unet3DEngine:
         return p.res(src0, src1, resid=h)
 
     def _temporal_attn(self, ap, x):
-        B, D, H, W, C = x.shape
-        bias, rot = self._rel_tables(D)
-        xn = ops.chan_layernorm(x, ap["gamma"])
-        qkv = ap["qkv"](xn)
-        o = ops.softmax_attn(qkv, B * H * W, D, H * W, D * H * W, 1, H * W, self.scale, bias=bias, rot=rot)
-        self.launches += 4
-        return ap["out"](o, x)
+        bias, rot = self._rel_tables(x.shape[1])
+        self.launches += 1
+        return ap(x, bias=bias, rot=rot)
 
     def _mid_spatial_attn(self, ap, x):
         B, D, H, W, C = x.shape
