@@ -22,12 +22,22 @@
 namespace wdno {
 
 constexpr int kLaHeads = 4, kLaDh = 32, kLaHid = 128;
+
+// weight fragments: shared memory (staged once per block) when WS, else read-only global loads
+template <bool WS>
+__device__ __forceinline__ uint4 ldw(const uint4* p) {
+  if constexpr (WS) return *p;
+  else return __ldg(p);
+}
+__device__ __forceinline__ void stage_weights(uint4* dst, const uint4* __restrict__ src, int n_u4, int tid, int nthreads) {
+  for (int i = tid; i < n_u4; i += nthreads) dst[i] = __ldg(src + i);
+}
 constexpr int kLaPart = 64 + 32 * 32;  // floats per (image, part, head): max[32], sum[32], S[32][32]
 
 // ------------------------------------------------------------------ la1: context partials
-template <int C>
+template <int C, bool WS>
 __global__ void __launch_bounds__(256, 2) la1_kernel(const __half* __restrict__ x, const float* __restrict__ gamma,
-                                                  const uint4* __restrict__ wkv, float* __restrict__ part, int n, int split,
+                                                  const uint4* wkv, float* __restrict__ part, int n, int split,
                                                   float eps) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __half* xn = reinterpret_cast<__half*>(smem_raw);  // [64][C + 8]
@@ -39,6 +49,11 @@ __global__ void __launch_bounds__(256, 2) la1_kernel(const __half* __restrict__ 
   const int h = warp & 3, ph = warp >> 2;
   const int tiles = (n + 63) >> 6;
   const int t0 = (tiles * sp) / split, t1 = (tiles * (sp + 1)) / split;
+  if constexpr (WS) {
+    uint4* wsm = reinterpret_cast<uint4*>(smem_raw + 64 * XS * 2);
+    stage_weights(wsm, wkv, 2 * 4 * 2 * KS * 32, threadIdx.x, 256);
+    wkv = wsm;  // visible after the first barrier of the tile loop
+  }
   const uint4* wk = wkv + static_cast<size_t>((0 * 4 + h) * 2) * KS * 32 + lane;
   const uint4* wv = wkv + static_cast<size_t>((1 * 4 + h) * 2) * KS * 32 + lane;
   const __half* ximg = x + static_cast<size_t>(img) * n * C;
@@ -78,7 +93,7 @@ __global__ void __launch_bounds__(256, 2) la1_kernel(const __half* __restrict__ 
         ldsm_x4(xn_s + b_off + static_cast<uint32_t>((nt * 8 * XS + kp * 32) * 2), bf[nt][0], bf[nt][1], bf[nt][2], bf[nt][3]);
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {
-        const uint4 a0 = __ldg(wk + (mt * KS + 2 * kp) * 32), a1 = __ldg(wk + (mt * KS + 2 * kp + 1) * 32);
+        const uint4 a0 = ldw<WS>(wk + (mt * KS + 2 * kp) * 32), a1 = ldw<WS>(wk + (mt * KS + 2 * kp + 1) * 32);
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
           mma16816(acc[mt][nt], a0.x, a0.y, a0.z, a0.w, bf[nt][0], bf[nt][1]);
@@ -145,7 +160,7 @@ __global__ void __launch_bounds__(256, 2) la1_kernel(const __half* __restrict__ 
         ldsm_x4(xn_s + b_off + static_cast<uint32_t>((nt * 8 * XS + kp * 32) * 2), bf[nt][0], bf[nt][1], bf[nt][2], bf[nt][3]);
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {
-        const uint4 a0 = __ldg(wv + (mt * KS + 2 * kp) * 32), a1 = __ldg(wv + (mt * KS + 2 * kp + 1) * 32);
+        const uint4 a0 = ldw<WS>(wv + (mt * KS + 2 * kp) * 32), a1 = ldw<WS>(wv + (mt * KS + 2 * kp + 1) * 32);
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
           mma16816(acc[mt][nt], a0.x, a0.y, a0.z, a0.w, bf[nt][0], bf[nt][1]);
@@ -196,167 +211,280 @@ __global__ void __launch_bounds__(256, 2) la1_kernel(const __half* __restrict__ 
 __global__ void __launch_bounds__(256) la_mid_kernel(const float* __restrict__ part, const float* __restrict__ wout,
                                                      __half* __restrict__ mpack, int C, int nparts, float scale) {
   __shared__ float ctx[kLaHeads][kLaDh][kLaDh + 1];
+  __shared__ float wts[4][kLaHid];  // per part: exp(m_i - m) * scale / z  for (h, d)
   const int img = blockIdx.x;
-  const int t = threadIdx.x & 127, chalf = threadIdx.x >> 7;
-  const int h = t >> 5, d = t & 31;
-  const float* pb = part + static_cast<size_t>(img) * nparts * kLaHeads * kLaPart + static_cast<size_t>(h) * kLaPart;
-  if (chalf == 0) {
+  const float* pimg = part + static_cast<size_t>(img) * nparts * kLaHeads * kLaPart;
+  if (threadIdx.x < kLaHid) {
+    const int h = threadIdx.x >> 5, d = threadIdx.x & 31;
+    const float* pb = pimg + static_cast<size_t>(h) * kLaPart;
+    float mi[4], zi[4];
     float m = -INFINITY;
-    for (int i = 0; i < nparts; ++i) m = fmaxf(m, pb[static_cast<size_t>(i) * kLaHeads * kLaPart + d]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      mi[i] = -INFINITY;
+      zi[i] = 0.f;
+      if (i < nparts) {
+        mi[i] = pb[static_cast<size_t>(i) * kLaHeads * kLaPart + d];
+        zi[i] = pb[static_cast<size_t>(i) * kLaHeads * kLaPart + 32 + d];
+      }
+      m = fmaxf(m, mi[i]);
+    }
     float zt = 0.f;
-    for (int i = 0; i < nparts; ++i) {
-      const float* pi = pb + static_cast<size_t>(i) * kLaHeads * kLaPart;
-      zt += pi[32 + d] * __expf(pi[d] - m);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      mi[i] = (i < nparts) ? __expf(mi[i] - m) : 0.f;
+      zt = fmaf(zi[i], mi[i], zt);
     }
     const float inv = scale / zt;
-    for (int e = 0; e < kLaDh; ++e) {
-      float s = 0.f;
-      for (int i = 0; i < nparts; ++i) {
-        const float* pi = pb + static_cast<size_t>(i) * kLaHeads * kLaPart;
-        s += pi[64 + d * 32 + e] * __expf(pi[d] - m);
-      }
-      ctx[h][d][e] = s * inv;
-    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) wts[i][threadIdx.x] = mi[i] * inv;
   }
   __syncthreads();
+  // ctx[h][d][e] = sum_i S_i[h][d][e] * w_i[h][d]   (coalesced over e)
+  for (int idx = threadIdx.x; idx < kLaHeads * 32 * 32; idx += 256) {
+    const int h = idx >> 10, d = (idx >> 5) & 31, e = idx & 31;
+    float sacc = 0.f;
+    for (int i = 0; i < nparts; ++i)
+      sacc = fmaf(pimg[(static_cast<size_t>(i) * kLaHeads + h) * kLaPart + 64 + d * 32 + e], wts[i][h * 32 + d], sacc);
+    ctx[h][d][e] = sacc;
+  }
+  __syncthreads();
+  const int t = threadIdx.x & 127, chalf = threadIdx.x >> 7;
+  const int h = t >> 5, d = t & 31;
+  float cr[kLaDh];
+#pragma unroll
+  for (int e = 0; e < kLaDh; ++e) cr[e] = ctx[h][d][e];
   const int j = h * 32 + d;
   const int ks = j >> 4, kk = j & 15;
   const int reg = kk >> 3, qq = (kk & 7) >> 1, half = kk & 1;
   __half* mp = mpack + static_cast<size_t>(img) * C * kLaHid;
   const int c0 = chalf * (C / 2);
+#pragma unroll 2
   for (int c = c0; c < c0 + C / 2; ++c) {
-    const float* wr = wout + static_cast<size_t>(c) * kLaHid + h * 32;
-    float s = 0.f;
+    const float4* wr = reinterpret_cast<const float4*>(wout + static_cast<size_t>(c) * kLaHid + h * 32);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-    for (int e = 0; e < kLaDh; ++e) s = fmaf(__ldg(wr + e), ctx[h][d][e], s);
+    for (int e4 = 0; e4 < 8; ++e4) {
+      const float4 w4 = __ldg(wr + e4);
+      s0 = fmaf(w4.x, cr[4 * e4], s0);
+      s1 = fmaf(w4.y, cr[4 * e4 + 1], s1);
+      s2 = fmaf(w4.z, cr[4 * e4 + 2], s2);
+      s3 = fmaf(w4.w, cr[4 * e4 + 3], s3);
+    }
     const int nt = c >> 3, gg = c & 7;
-    mp[(static_cast<size_t>(nt * 4 + (ks >> 1)) * 32 + (gg * 4 + qq)) * 8 + ((ks & 1) * 2 + reg) * 2 + half] = __float2half_rn(s);
+    mp[(static_cast<size_t>(nt * 4 + (ks >> 1)) * 32 + (gg * 4 + qq)) * 8 + ((ks & 1) * 2 + reg) * 2 + half] =
+        __float2half_rn((s0 + s1) + (s2 + s3));
   }
 }
 
 // ------------------------------------------------------------------ la2: q -> softmax_d -> y = q M^T + bias + x
-template <int C>
+// Persistent blocks walk over (image, 128-position tile) items; the raw x tile of the NEXT item is fetched with cp.async
+// into the other half of a double buffer while the current one is normalised and multiplied, and also serves the
+// residual add (x is read from HBM exactly once here).
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int C, bool WS>
 __global__ void __launch_bounds__(256, 2) la2_kernel(const __half* __restrict__ x, __half* __restrict__ y,
-                                                  const float* __restrict__ gamma, const uint4* __restrict__ wq,
+                                                  const float* __restrict__ gamma, const uint4* wq,
                                                   const uint4* __restrict__ mpack, const float* __restrict__ bias, int n,
-                                                  int tiles, float eps) {
+                                                  int tiles, int n_items, float eps) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  __half* xn = reinterpret_cast<__half*>(smem_raw);  // [128][C + 8]
   constexpr int XS = C + 8;
-  const int img = blockIdx.x / tiles, tile = blockIdx.x - img * tiles;
+  constexpr int LP = C / 8, RPP = 256 / LP, PASSES = 128 / RPP;
+  __half* xn = reinterpret_cast<__half*>(smem_raw);             // [128][C + 8]
+  __half* raw = xn + 128 * XS;                                  // [2][128][C]
+  uint4* wsm = reinterpret_cast<uint4*>(raw + 2 * 128 * C);     // WS: Wq fragments, then the image's M fragments
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, q = lane & 3;
-  const int p0 = tile * 128;
-  const int rows_valid = min(128, n - p0);
-  const __half* xt = x + (static_cast<size_t>(img) * n + p0) * C;
-  __half* yt = y + (static_cast<size_t>(img) * n + p0) * C;
-  ln_tile<C, 128, 256>(xt, rows_valid, gamma, xn, eps);
-  __syncthreads();
-  if (warp * 16 >= rows_valid) return;  // no barriers below
+  const int ln_l = threadIdx.x % LP, ln_r0 = threadIdx.x / LP;
+  constexpr int n_wq = 16 * (C / 32) * 32, n_m = (C / 8) * 4 * 32;
+  if constexpr (WS) {
+    stage_weights(wsm, wq, n_wq, threadIdx.x, 256);
+    wq = wsm;
+  }
+  float gm[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) gm[j] = __ldg(gamma + ln_l * 8 + j);
+  const uint32_t raw_s = static_cast<uint32_t>(__cvta_generic_to_shared(raw));
+  auto fetch = [&](int item, int buf) {
+    const int img = item / tiles, tile = item - img * tiles;
+    const int p0 = tile * 128;
+    const int rows_valid = min(128, n - p0);
+    const __half* xt = x + (static_cast<size_t>(img) * n + p0) * C;
+#pragma unroll
+    for (int ps = 0; ps < PASSES; ++ps) {
+      const int r = ln_r0 + ps * RPP;
+      const bool ok = r < rows_valid;
+      cp_async16(raw_s + static_cast<uint32_t>(((buf * 128 + r) * C + ln_l * 8) * 2), ok ? xt + static_cast<size_t>(r) * C + ln_l * 8 : xt,
+                 ok ? 16u : 0u);
+    }
+    cp_async_commit_group();
+  };
   const uint32_t xn_s = static_cast<uint32_t>(__cvta_generic_to_shared(xn));
   const uint32_t a_off = static_cast<uint32_t>(((16 * warp + (lane & 15)) * XS + 8 * (lane >> 4)) * 2);
+  int cur_img = -1;
+  int buf = 0;
+  if (static_cast<int>(blockIdx.x) < n_items) fetch(blockIdx.x, 0);
 
-  // ---- q[16 rows][128] = xn Wq^T
-  float acc[16][4];
-#pragma unroll
-  for (int i = 0; i < 16; ++i)
-#pragma unroll
-    for (int c = 0; c < 4; ++c) acc[i][c] = 0.f;
-#pragma unroll
-  for (int kp = 0; kp < C / 32; ++kp) {
-    uint32_t a0[4], a1[4];
-    ldsm_x4(xn_s + a_off + static_cast<uint32_t>(kp * 32 * 2), a0[0], a0[1], a0[2], a0[3]);
-    ldsm_x4(xn_s + a_off + static_cast<uint32_t>((kp * 32 + 16) * 2), a1[0], a1[1], a1[2], a1[3]);
-#pragma unroll
-    for (int nt = 0; nt < 16; ++nt) {
-      const uint4 b = __ldg(wq + (nt * (C / 32) + kp) * 32 + lane);
-      mma16816(acc[nt], a0, b.x, b.y);
-      mma16816(acc[nt], a1, b.z, b.w);
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x, buf ^= 1) {
+    const int img = item / tiles, tile = item - img * tiles;
+    const int p0 = tile * 128;
+    const int rows_valid = min(128, n - p0);
+    __half* yt = y + (static_cast<size_t>(img) * n + p0) * C;
+    const __half* rawb = raw + buf * 128 * C;
+    cp_async_wait_group<0>();
+    __syncthreads();  // raw[buf] landed for everyone; all warps are done with the previous item (xn, raw[buf^1], M)
+    if (item + static_cast<int>(gridDim.x) < n_items) fetch(item + gridDim.x, buf ^ 1);
+    const uint4* mp_img = mpack + static_cast<size_t>(img) * n_m;
+    if constexpr (WS) {
+      if (img != cur_img) stage_weights(wsm + n_wq, mp_img, n_m, threadIdx.x, 256);
+      mp_img = wsm + n_wq;
     }
-  }
-  // ---- softmax over each head's 32 dims (rows g and g+8 of this warp's 16); scale is folded into M
-  uint32_t aq[8][4];
+    cur_img = img;
+    // ---- LayerNorm raw[buf] -> xn
 #pragma unroll
-  for (int hh = 0; hh < 4; ++hh) {
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      float mx = -INFINITY;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) mx = fmaxf(mx, fmaxf(acc[4 * hh + j][2 * r], acc[4 * hh + j][2 * r + 1]));
-      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    for (int ps = 0; ps < PASSES; ++ps) {
+      const int r = ln_r0 + ps * RPP;
+      const uint4 rv = *reinterpret_cast<const uint4*>(rawb + r * C + ln_l * 8);
+      const __half2* h = reinterpret_cast<const __half2*>(&rv);
+      float f[8];
       float sum = 0.f;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float e0 = __expf(acc[4 * hh + j][2 * r] - mx), e1 = __expf(acc[4 * hh + j][2 * r + 1] - mx);
-        acc[4 * hh + j][2 * r] = e0;
-        acc[4 * hh + j][2 * r + 1] = e1;
-        sum += e0 + e1;
+        const float2 t = __half22float2(h[j]);
+        f[2 * j] = t.x;
+        f[2 * j + 1] = t.y;
+        sum += t.x + t.y;
       }
-      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-      const float inv = 1.0f / sum;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        acc[4 * hh + j][2 * r] *= inv;
-        acc[4 * hh + j][2 * r + 1] *= inv;
+      for (int sh = LP / 2; sh > 0; sh >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, sh);
+      const float mean = sum * (1.0f / C);
+      float sq = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        f[j] -= mean;
+        sq = fmaf(f[j], f[j], sq);
+      }
+#pragma unroll
+      for (int sh = LP / 2; sh > 0; sh >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, sh);
+      const float rstd = rsqrtf(sq * (1.0f / C) + eps);
+      uint4 ov;
+      uint32_t* o = reinterpret_cast<uint32_t*>(&ov);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[j] = pack_h2(f[2 * j] * rstd * gm[2 * j], f[2 * j + 1] * rstd * gm[2 * j + 1]);
+      if (r >= rows_valid) ov = make_uint4(0u, 0u, 0u, 0u);
+      *reinterpret_cast<uint4*>(xn + r * XS + ln_l * 8) = ov;
+    }
+    __syncthreads();
+    if (warp * 16 >= rows_valid) continue;  // warp-uniform; the barriers above are reached by every warp each item
+
+    // ---- q[16 rows][128] = xn Wq^T
+    float acc[16][4];
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[i][c] = 0.f;
+#pragma unroll
+    for (int kp = 0; kp < C / 32; ++kp) {
+      uint32_t a0[4], a1[4];
+      ldsm_x4(xn_s + a_off + static_cast<uint32_t>(kp * 32 * 2), a0[0], a0[1], a0[2], a0[3]);
+      ldsm_x4(xn_s + a_off + static_cast<uint32_t>((kp * 32 + 16) * 2), a1[0], a1[1], a1[2], a1[3]);
+#pragma unroll
+      for (int nt = 0; nt < 16; ++nt) {
+        const uint4 b = ldw<WS>(wq + (nt * (C / 32) + kp) * 32 + lane);
+        mma16816(acc[nt], a0, b.x, b.y);
+        mma16816(acc[nt], a1, b.z, b.w);
       }
     }
+    // ---- softmax over each head's 32 dims (rows g and g+8 of this warp's 16); scale is folded into M
+    uint32_t aq[8][4];
 #pragma unroll
-    for (int k2 = 0; k2 < 2; ++k2) {
-      const int ks = 2 * hh + k2;
-      aq[ks][0] = pack_h2(acc[2 * ks][0], acc[2 * ks][1]);
-      aq[ks][1] = pack_h2(acc[2 * ks][2], acc[2 * ks][3]);
-      aq[ks][2] = pack_h2(acc[2 * ks + 1][0], acc[2 * ks + 1][1]);
-      aq[ks][3] = pack_h2(acc[2 * ks + 1][2], acc[2 * ks + 1][3]);
+    for (int hh = 0; hh < 4; ++hh) {
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        float mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) mx = fmaxf(mx, fmaxf(acc[4 * hh + j][2 * r], acc[4 * hh + j][2 * r + 1]));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float e0 = __expf(acc[4 * hh + j][2 * r] - mx), e1 = __expf(acc[4 * hh + j][2 * r + 1] - mx);
+          acc[4 * hh + j][2 * r] = e0;
+          acc[4 * hh + j][2 * r + 1] = e1;
+          sum += e0 + e1;
+        }
+        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+        const float inv = 1.0f / sum;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          acc[4 * hh + j][2 * r] *= inv;
+          acc[4 * hh + j][2 * r + 1] *= inv;
+        }
+      }
+#pragma unroll
+      for (int k2 = 0; k2 < 2; ++k2) {
+        const int ks = 2 * hh + k2;
+        aq[ks][0] = pack_h2(acc[2 * ks][0], acc[2 * ks][1]);
+        aq[ks][1] = pack_h2(acc[2 * ks][2], acc[2 * ks][3]);
+        aq[ks][2] = pack_h2(acc[2 * ks + 1][0], acc[2 * ks + 1][1]);
+        aq[ks][3] = pack_h2(acc[2 * ks + 1][2], acc[2 * ks + 1][3]);
+      }
     }
-  }
-  // ---- y = q M^T + bias, 64 output channels at a time, written over this warp's own (dead) xn rows
-  const uint4* mp = mpack + static_cast<size_t>(img) * (C / 8) * 4 * 32 + lane;
-  __syncwarp();
+    // ---- y = q M^T + bias, 64 output channels at a time, written over this warp's own (dead) xn rows
+    const uint4* mp = mp_img + lane;
+    __syncwarp();
 #pragma unroll 1
-  for (int cc = 0; cc < C / 64; ++cc) {
-    float yacc[8][4];
+    for (int cc = 0; cc < C / 64; ++cc) {
+      float yacc[8][4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < 8; ++i)
 #pragma unroll
-      for (int c = 0; c < 4; ++c) yacc[i][c] = 0.f;
+        for (int c = 0; c < 4; ++c) yacc[i][c] = 0.f;
 #pragma unroll
-    for (int kp = 0; kp < 4; ++kp) {
+      for (int kp = 0; kp < 4; ++kp) {
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          const uint4 b = ldw<WS>(mp + ((cc * 8 + nt) * 4 + kp) * 32);
+          mma16816(yacc[nt], aq[2 * kp], b.x, b.y);
+          mma16816(yacc[nt], aq[2 * kp + 1], b.z, b.w);
+        }
+      }
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
-        const uint4 b = __ldg(mp + ((cc * 8 + nt) * 4 + kp) * 32);
-        mma16816(yacc[nt], aq[2 * kp], b.x, b.y);
-        mma16816(yacc[nt], aq[2 * kp + 1], b.z, b.w);
+        const int c = cc * 64 + nt * 8 + 2 * q;
+        const float b0 = bias ? __ldg(bias + c) : 0.f, b1 = bias ? __ldg(bias + c + 1) : 0.f;
+        *reinterpret_cast<uint32_t*>(xn + (16 * warp + g) * XS + c) = pack_h2(yacc[nt][0] + b0, yacc[nt][1] + b1);
+        *reinterpret_cast<uint32_t*>(xn + (16 * warp + g + 8) * XS + c) = pack_h2(yacc[nt][2] + b0, yacc[nt][3] + b1);
       }
     }
+    __syncwarp();
+    // ---- + residual (from the raw tile in shared memory), coalesced store of this warp's 16 rows
+    constexpr int CPR = C / 8;  // 16-byte chunks per row
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      const int c = cc * 64 + nt * 8 + 2 * q;
-      const float b0 = bias ? __ldg(bias + c) : 0.f, b1 = bias ? __ldg(bias + c + 1) : 0.f;
-      *reinterpret_cast<uint32_t*>(xn + (16 * warp + g) * XS + c) = pack_h2(yacc[nt][0] + b0, yacc[nt][1] + b1);
-      *reinterpret_cast<uint32_t*>(xn + (16 * warp + g + 8) * XS + c) = pack_h2(yacc[nt][2] + b0, yacc[nt][3] + b1);
-    }
-  }
-  __syncwarp();
-  // ---- + residual, coalesced store of this warp's 16 rows
-  constexpr int CPR = C / 8;  // 16-byte chunks per row
+    for (int it = 0; it < 16 * CPR / 32; ++it) {
+      const int idx = it * 32 + lane;
+      const int r = idx / CPR, ch = idx - r * CPR;
+      const int row = 16 * warp + r;
+      if (row < rows_valid) {
+        uint4 v = *reinterpret_cast<const uint4*>(xn + row * XS + ch * 8);
+        const uint4 rv = *reinterpret_cast<const uint4*>(rawb + row * C + ch * 8);
+        __half2* vh = reinterpret_cast<__half2*>(&v);
+        const __half2* rh = reinterpret_cast<const __half2*>(&rv);
 #pragma unroll
-  for (int it = 0; it < 16 * CPR / 32; ++it) {
-    const int idx = it * 32 + lane;
-    const int r = idx / CPR, ch = idx - r * CPR;
-    const int row = 16 * warp + r;
-    if (row < rows_valid) {
-      uint4 v = *reinterpret_cast<const uint4*>(xn + row * XS + ch * 8);
-      const uint4 rv = __ldg(reinterpret_cast<const uint4*>(xt + static_cast<size_t>(row) * C) + ch);
-      __half2* vh = reinterpret_cast<__half2*>(&v);
-      const __half2* rh = reinterpret_cast<const __half2*>(&rv);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float2 a2 = __half22float2(vh[i]), b2 = __half22float2(rh[i]);
-        vh[i] = __floats2half2_rn(a2.x + b2.x, a2.y + b2.y);
+        for (int i = 0; i < 4; ++i) {
+          const float2 a2 = __half22float2(vh[i]), b2 = __half22float2(rh[i]);
+          vh[i] = __floats2half2_rn(a2.x + b2.x, a2.y + b2.y);
+        }
+        *(reinterpret_cast<uint4*>(yt + static_cast<size_t>(row) * C) + ch) = v;
       }
-      *(reinterpret_cast<uint4*>(yt + static_cast<size_t>(row) * C) + ch) = v;
     }
   }
 }
@@ -371,10 +499,10 @@ __global__ void __launch_bounds__(256, 2) la2_kernel(const __half* __restrict__ 
 //   warp (s, c4): Y[:, c4*C/4 ...] = O Wout^T -> shared (over xn) -> + x -> coalesced store.
 constexpr int kTaRows = 32;
 
-template <int C>
+template <int C, bool WS>
 __global__ void __launch_bounds__(256, 2) tattn_kernel(const __half* __restrict__ x, __half* __restrict__ y,
-                                                        const float* __restrict__ gamma, const uint4* __restrict__ wqk,
-                                                        const uint4* __restrict__ wv, const uint4* __restrict__ wo,
+                                                        const float* __restrict__ gamma, const uint4* wqk,
+                                                        const uint4* wv, const uint4* wo,
                                                         const float* __restrict__ bias, const float* __restrict__ rot_cos,
                                                         const float* __restrict__ rot_sin, long long n_pix, long long hw,
                                                         int n, float scale, float eps) {
@@ -382,8 +510,11 @@ __global__ void __launch_bounds__(256, 2) tattn_kernel(const __half* __restrict_
   constexpr int XS = C + 8, OS = kLaHid + 8, KS = C / 16;
   __half* xn = reinterpret_cast<__half*>(smem_raw);                       // [2][32][XS]
   __half* obuf = xn + 2 * kTaRows * XS;                                    // [2][32][OS]
-  float* sbias = reinterpret_cast<float*>(obuf + 2 * kTaRows * OS);        // [4][32][32], -inf for keys >= n
-  float* scs = sbias + 4 * 32 * 32;                                        // [32][16] cos, [32][16] sin
+  // bias rows are 40 floats apart and (cos, sin) rows 20 float2 apart: the 8 rows a warp touches per load then fall
+  // into distinct banks
+  constexpr int BS = 40, RS = 20;
+  float* sbias = reinterpret_cast<float*>(obuf + 2 * kTaRows * OS);        // [4][32][BS], -inf for keys >= n
+  float2* scs = reinterpret_cast<float2*>(sbias + 4 * 32 * BS);            // [32][RS] (cos, sin)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, q = lane & 3;
   const int s = warp >> 2, h = warp & 3;
@@ -394,14 +525,24 @@ __global__ void __launch_bounds__(256, 2) tattn_kernel(const __half* __restrict_
     float b = 0.f;
     if (c >= n) b = -INFINITY;
     else if (r < n && bias != nullptr) b = __ldg(bias + (static_cast<size_t>(hh) * n + r) * n + c);
-    sbias[i] = b;
+    sbias[(hh * 32 + r) * BS + c] = b;
   }
   for (int i = tid; i < 32 * 16; i += 256) {
     const int f = i >> 4;
-    scs[i] = (rot_cos != nullptr && f < n) ? __ldg(rot_cos + f * 16 + (i & 15)) : 1.0f;
-    scs[512 + i] = (rot_sin != nullptr && f < n) ? __ldg(rot_sin + f * 16 + (i & 15)) : 0.0f;
+    scs[f * RS + (i & 15)] = make_float2((rot_cos != nullptr && f < n) ? __ldg(rot_cos + f * 16 + (i & 15)) : 1.0f,
+                                         (rot_sin != nullptr && f < n) ? __ldg(rot_sin + f * 16 + (i & 15)) : 0.0f);
   }
 
+  if constexpr (WS) {
+    uint4* wsm = reinterpret_cast<uint4*>(scs + 32 * RS);
+    constexpr int n_qk = 32 * (C / 32) * 32, n_v = 4 * 2 * KS * 32, n_o = (C / 8) * 4 * 32;
+    stage_weights(wsm, wqk, n_qk, tid, 256);
+    stage_weights(wsm + n_qk, wv, n_v, tid, 256);
+    stage_weights(wsm + n_qk + n_v, wo, n_o, tid, 256);
+    wqk = wsm;
+    wv = wsm + n_qk;
+    wo = wsm + n_qk + n_v;
+  }
   const uint32_t xn_s = static_cast<uint32_t>(__cvta_generic_to_shared(xn + s * kTaRows * XS));
   const uint32_t ob_s = static_cast<uint32_t>(__cvta_generic_to_shared(obuf + s * kTaRows * OS));
   const uint32_t a_off = static_cast<uint32_t>((((lane & 15)) * XS + 8 * (lane >> 4)) * 2);   // A operand rows = tokens
@@ -410,6 +551,27 @@ __global__ void __launch_bounds__(256, 2) tattn_kernel(const __half* __restrict_
   constexpr int LP = C / 8, RPP = 256 / LP, ROWS = 2 * 24;
   constexpr int PASSES = (2 * kTaRows + RPP - 1) / RPP;  // enough for n <= 32
   const long long n_pairs = (n_pix + 1) >> 1;
+
+  // raw x of the NEXT pair is fetched into registers while the current pair is being computed
+  const int ln_l = tid % LP, ln_r0 = tid / LP;
+  float gm[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) gm[j] = __ldg(gamma + ln_l * 8 + j);
+  uint4 raw[PASSES];
+  auto fetch = [&](long long pr) {
+    const long long pix0 = pr * 2;
+    const long long bimg = pix0 / hw, pin = pix0 - bimg * hw;
+    const __half* xb = x + (static_cast<size_t>(bimg) * n * hw + pin) * C;
+    const int nseq = (pix0 + 1 < n_pix) ? 2 : 1;
+#pragma unroll
+    for (int ps = 0; ps < PASSES; ++ps) {
+      const int rr = ln_r0 + ps * RPP;
+      const int f = rr >> 1, ss = rr & 1;
+      raw[ps] = make_uint4(0u, 0u, 0u, 0u);
+      if (f < n && ss < nseq) raw[ps] = __ldg(reinterpret_cast<const uint4*>(xb + (static_cast<size_t>(f) * hw + ss) * C) + ln_l);
+    }
+  };
+  if (blockIdx.x < n_pairs) fetch(blockIdx.x);
 
   for (long long pr = blockIdx.x; pr < n_pairs; pr += gridDim.x) {
     const long long pix0 = pr * 2;
@@ -420,21 +582,9 @@ __global__ void __launch_bounds__(256, 2) tattn_kernel(const __half* __restrict_
     __syncthreads();  // previous iteration's staging reads are done (also orders the table setup)
     // ---- LayerNorm of 2 x n tokens: row rr = 2 f + s
     {
-      const int l = tid % LP, r0 = tid / LP;
-      float gm[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) gm[j] = __ldg(gamma + l * 8 + j);
-      uint4 raw[PASSES];
 #pragma unroll
       for (int ps = 0; ps < PASSES; ++ps) {
-        const int rr = r0 + ps * RPP;
-        const int f = rr >> 1, ss = rr & 1;
-        raw[ps] = make_uint4(0u, 0u, 0u, 0u);
-        if (f < n && ss < nseq) raw[ps] = __ldg(reinterpret_cast<const uint4*>(xb + (static_cast<size_t>(f) * hw + ss) * C) + l);
-      }
-#pragma unroll
-      for (int ps = 0; ps < PASSES; ++ps) {
-        const int rr = r0 + ps * RPP;
+        const int rr = ln_r0 + ps * RPP;
         const int f = rr >> 1, ss = rr & 1;
         const __half2* hh = reinterpret_cast<const __half2*>(&raw[ps]);
         float fv[8];
@@ -464,11 +614,12 @@ __global__ void __launch_bounds__(256, 2) tattn_kernel(const __half* __restrict_
 #pragma unroll
           for (int j = 0; j < 4; ++j) o[j] = pack_h2(fv[2 * j] * rstd * gm[2 * j], fv[2 * j + 1] * rstd * gm[2 * j + 1]);
           if (ss >= nseq) ov = make_uint4(0u, 0u, 0u, 0u);
-          *reinterpret_cast<uint4*>(xn + (ss * kTaRows + f) * XS + l * 8) = ov;
+          *reinterpret_cast<uint4*>(xn + (ss * kTaRows + f) * XS + ln_l * 8) = ov;
         }
       }
     }
     __syncthreads();
+    if (pr + gridDim.x < n_pairs) fetch(pr + gridDim.x);
 
     // ================= attention core of (sequence s, head h)
     {
@@ -494,7 +645,7 @@ __global__ void __launch_bounds__(256, 2) tattn_kernel(const __half* __restrict_
           }
 #pragma unroll
           for (int nt = 0; nt < 4; ++nt) {
-            const uint4 b = __ldg(wb + (nt * (C / 32) + kp) * 32);
+            const uint4 b = ldw<WS>(wb + (nt * (C / 32) + kp) * 32);
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt) {
               mma16816(acc[mt][nt], a0[mt], b.x, b.y);
@@ -510,10 +661,10 @@ __global__ void __launch_bounds__(256, 2) tattn_kernel(const __half* __restrict_
             const int f = 16 * mt + g + 8 * r;
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt) {
-              const float cs = scs[f * 16 + 4 * nt + q], sn = scs[512 + f * 16 + 4 * nt + q];
+              const float2 cs = scs[f * RS + 4 * nt + q];
               const float x0 = acc[mt][nt][2 * r] * sc, x1 = acc[mt][nt][2 * r + 1] * sc;
-              acc[mt][nt][2 * r] = x0 * cs - x1 * sn;
-              acc[mt][nt][2 * r + 1] = x1 * cs + x0 * sn;
+              acc[mt][nt][2 * r] = x0 * cs.x - x1 * cs.y;
+              acc[mt][nt][2 * r + 1] = x1 * cs.x + x0 * cs.y;
             }
           }
         if (sec == 0) {
@@ -555,7 +706,7 @@ __global__ void __launch_bounds__(256, 2) tattn_kernel(const __half* __restrict_
       for (int mt = 0; mt < 2; ++mt) {
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
-          const float* brow = sbias + (h * 32 + 16 * mt + g + 8 * r) * 32 + 2 * q;
+          const float* brow = sbias + (h * 32 + 16 * mt + g + 8 * r) * BS + 2 * q;
           float mx = -INFINITY;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -604,7 +755,7 @@ __global__ void __launch_bounds__(256, 2) tattn_kernel(const __half* __restrict_
             ldsm_x4(xn_s + b_off + static_cast<uint32_t>((nt * 8 * XS + kp * 32) * 2), bf[nt][0], bf[nt][1], bf[nt][2], bf[nt][3]);
 #pragma unroll
           for (int mt = 0; mt < 2; ++mt) {
-            const uint4 a0 = __ldg(wa + (mt * KS + 2 * kp) * 32), a1 = __ldg(wa + (mt * KS + 2 * kp + 1) * 32);
+            const uint4 a0 = ldw<WS>(wa + (mt * KS + 2 * kp) * 32), a1 = ldw<WS>(wa + (mt * KS + 2 * kp + 1) * 32);
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt) {
               mma16816(vt[mt][nt], a0.x, a0.y, a0.z, a0.w, bf[nt][0], bf[nt][1]);
@@ -663,7 +814,7 @@ __global__ void __launch_bounds__(256, 2) tattn_kernel(const __half* __restrict_
         }
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) {
-          const uint4 b = __ldg(wb + (nt * 4 + kp) * 32);
+          const uint4 b = ldw<WS>(wb + (nt * 4 + kp) * 32);
 #pragma unroll
           for (int mt = 0; mt < 2; ++mt) {
             mma16816(yacc[mt][nt], a0[mt], b.x, b.y);
@@ -712,17 +863,19 @@ template <int C>
 static int launch_tattn(const __half* x, __half* y, const float* gamma, const uint4* wqk, const uint4* wv, const uint4* wo,
                         const float* bias, const float* rot_cos, const float* rot_sin, long long n_pix, long long hw, int n,
                         float scale, float eps, cudaStream_t st) {
-  const int smem = (2 * kTaRows * (C + 8) + 2 * kTaRows * (kLaHid + 8)) * 2 + (4 * 32 * 32 + 2 * 32 * 16) * 4;
+  constexpr bool WS = false;  // weight fragments come through L1 (staging them in shared memory measured the same: both share one data path)
+  const int wbytes = WS ? (32 * (C / 32) + 4 * 2 * (C / 16) + (C / 8) * 4) * 32 * 16 : 0;
+  const int smem = (2 * kTaRows * (C + 8) + 2 * kTaRows * (kLaHid + 8)) * 2 + (4 * 32 * 40 + 2 * 32 * 20) * 4 + wbytes;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tattn_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(tattn_kernel<C, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return set_cuda_error(e, "tattn_block: cudaFuncSetAttribute");
     configured = true;
   }
   const long long n_pairs = (n_pix + 1) / 2;
   const long long cap = static_cast<long long>(num_sms()) * 2 * 4;
   const unsigned grid = static_cast<unsigned>(n_pairs < cap ? n_pairs : cap);
-  tattn_kernel<C><<<grid, 256, smem, st>>>(x, y, gamma, wqk, wv, wo, bias, rot_cos, rot_sin, n_pix, hw, n, scale, eps);
+  tattn_kernel<C, WS><<<grid, 256, smem, st>>>(x, y, gamma, wqk, wv, wo, bias, rot_cos, rot_sin, n_pix, hw, n, scale, eps);
   return check_launch("tattn_block");
 }
 
@@ -736,18 +889,24 @@ static int launch_linattn(const __half* x, __half* y, const float* gamma, const 
   const int nparts = split * 2;
   float* part = static_cast<float*>(work);
   __half* mpack = reinterpret_cast<__half*>(part + static_cast<size_t>(n_img) * nparts * kLaHeads * kLaPart);
-  const int smem1 = 64 * (C + 8) * 2, smem2 = 128 * (C + 8) * 2;
+  constexpr bool WS1 = (C <= 128);  // la1: K/V weight fragments staged in shared memory while two blocks still fit per SM
+  constexpr bool WS2 = (C == 64);   // la2: Wq and the image's M fragments in shared memory
+  const int smem1 = 64 * (C + 8) * 2 + (WS1 ? 2 * 4 * 2 * (C / 16) * 32 * 16 : 0);
+  const int smem2 = 128 * (C + 8) * 2 + 2 * 128 * C * 2 + (WS2 ? (16 * (C / 32) + (C / 8) * 4) * 32 * 16 : 0);
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(la2_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
+    cudaError_t e = cudaFuncSetAttribute(la2_kernel<C, WS2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(la1_kernel<C, WS1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
     if (e != cudaSuccess) return set_cuda_error(e, "linattn_block: cudaFuncSetAttribute");
     configured = true;
   }
-  la1_kernel<C><<<n_img * split, 256, smem1, st>>>(x, gamma, wkv, part, n_pos, split, eps);
+  la1_kernel<C, WS1><<<n_img * split, 256, smem1, st>>>(x, gamma, wkv, part, n_pos, split, eps);
   la_mid_kernel<<<n_img, 256, 0, st>>>(part, wout, mpack, C, nparts, scale);
   const int tiles = (n_pos + 127) / 128;
-  la2_kernel<C><<<n_img * tiles, 256, smem2, st>>>(x, y, gamma, wq, reinterpret_cast<const uint4*>(mpack), bias, n_pos, tiles,
-                                                   eps);
+  const int n_items = n_img * tiles;
+  const int cap = num_sms() * 2;
+  la2_kernel<C, WS2><<<n_items < cap ? n_items : cap, 256, smem2, st>>>(x, y, gamma, wq, reinterpret_cast<const uint4*>(mpack),
+                                                                        bias, n_pos, tiles, n_items, eps);
   return check_launch("linattn_block");
 }
 

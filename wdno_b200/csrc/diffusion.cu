@@ -37,6 +37,36 @@ __device__ __forceinline__ float apply_conditions(const CondProgram& cp, float v
   return v;
 }
 
+// 4 consecutive x of one row (W % 4 == 0): the (f, c, y) box tests are shared, only the x range is per element
+__device__ __forceinline__ void apply_conditions4(const CondProgram& cp, float (&v)[4], int b, int f, int c, int y, int x0) {
+#pragma unroll 1
+  for (int k = 0; k < cp.n; ++k) {
+    const wdno_cond_op& o = cp.op[k];
+    if (f >= o.f0 && f < o.f1 && c >= o.c0 && c < o.c1 && y >= o.y0 && y < o.y1 && x0 + 3 >= o.x0 && x0 < o.x1) {
+      const float* row = (o.src == nullptr) ? nullptr : o.src + (b * o.sb + (f - o.of) * o.sf + (c - o.oc) * o.sc + (y - o.oy) * o.sy);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int x = x0 + j;
+        if (x >= o.x0 && x < o.x1) v[j] = (row == nullptr) ? 0.f : row[(x - o.ox) * o.sx];
+      }
+    }
+  }
+}
+
+// 32-bit decode of a float4 index (total < 2^31)
+__device__ __forceinline__ void decode4(unsigned i4, const StateDims& d, int& b, int& f, int& c, int& y, int& x) {
+  const unsigned w4 = static_cast<unsigned>(d.W) >> 2;
+  unsigned r = i4 / w4;
+  x = static_cast<int>(i4 - r * w4) * 4;
+  unsigned r2 = r / d.H;
+  y = static_cast<int>(r - r2 * d.H);
+  r = r2 / d.C;
+  c = static_cast<int>(r2 - r * d.C);
+  r2 = r / d.F;
+  f = static_cast<int>(r - r2 * d.F);
+  b = static_cast<int>(r2);
+}
+
 __device__ __forceinline__ void decode(size_t i, const StateDims& d, int& b, int& f, int& c, int& y, int& x) {
   x = static_cast<int>(i % d.W);
   size_t r = i / d.W;
@@ -82,6 +112,56 @@ __global__ void ddim_step_kernel(float* __restrict__ x, const float* __restrict_
     }
     x[i] = v;
   }
+}
+
+// float4 variant of the two step kernels (W % 4 == 0, 16-byte aligned tensors, total < 2^31): same per-element arithmetic
+template <bool DDPM>
+__global__ void __launch_bounds__(256) step4_kernel(float* __restrict__ x, const float* __restrict__ eps,
+                                                    const float* __restrict__ noise, const float* __restrict__ g,
+                                                    const float* __restrict__ coef, CondProgram cp, StateDims d, unsigned total4,
+                                                    int cond_mode) {
+  const float sr = coef[0], srm1 = coef[1], k2 = coef[2], k3 = coef[3], k4 = coef[4];
+  const bool last = !DDPM && coef[5] != 0.f;
+  const float gs = coef[6];
+  const bool do_cond = DDPM ? (cond_mode != 0) : (cond_mode == 2 || (cond_mode == 1 && !last));
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += gridDim.x * blockDim.x) {
+    const float4 xv4 = reinterpret_cast<const float4*>(x)[i];
+    const float4 e4 = __ldg(reinterpret_cast<const float4*>(eps) + i);
+    float4 n4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = n4;
+    if (noise != nullptr) n4 = __ldg(reinterpret_cast<const float4*>(noise) + i);
+    if (g != nullptr) g4 = __ldg(reinterpret_cast<const float4*>(g) + i);
+    const float xa[4] = {xv4.x, xv4.y, xv4.z, xv4.w}, ea[4] = {e4.x, e4.y, e4.z, e4.w};
+    const float na[4] = {n4.x, n4.y, n4.z, n4.w}, ga[4] = {g4.x, g4.y, g4.z, g4.w};
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float e = ea[j];
+      if (g != nullptr) e = __fadd_rn(e, __fmul_rn(gs, ga[j]));
+      const float srx = __fmul_rn(sr, xa[j]);
+      const float x0 = clamp1(__fsub_rn(srx, __fmul_rn(srm1, e)));
+      if (DDPM) {
+        v[j] = __fadd_rn(__fmul_rn(k2, x0), __fmul_rn(k3, xa[j]));
+        if (noise != nullptr && k4 != 0.f) v[j] = __fadd_rn(v[j], __fmul_rn(k4, na[j]));
+      } else if (last) {
+        v[j] = x0;
+      } else {
+        const float e2 = __fdiv_rn(__fsub_rn(srx, x0), srm1);
+        v[j] = __fadd_rn(__fmul_rn(x0, k2), __fmul_rn(k3, e2));
+        if (noise != nullptr) v[j] = __fadd_rn(v[j], __fmul_rn(k4, na[j]));
+      }
+    }
+    if (do_cond) {
+      int b, f, c, y, xx;
+      decode4(i, d, b, f, c, y, xx);
+      apply_conditions4(cp, v, b, f, c, y, xx);
+    }
+    reinterpret_cast<float4*>(x)[i] = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
+static bool vec4_ok(const void* a, const void* b, const void* c, const void* d, int W, size_t total) {
+  auto al = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  return (W % 4 == 0) && total < (1ull << 31) && al(a) && al(b) && al(c) && al(d);
 }
 
 // coef: [0] sqrt_recip  [1] sqrt_recipm1  [2] posterior_mean_coef1  [3] posterior_mean_coef2
@@ -205,8 +285,12 @@ extern "C" int wdno_ddim_step(float* x, const float* eps, const float* noise, co
   if (rc) return rc;
   StateDims d{B, F, C, H, W};
   const size_t total = static_cast<size_t>(B) * F * C * H * W;
-  ddim_step_kernel<<<ew_grid(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, eps, noise, guidance, coef_dev, cp, d,
-                                                                                  total, cond_mode);
+  if (vec4_ok(x, eps, noise, guidance, W, total))
+    step4_kernel<false><<<ew_grid(total / 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, eps, noise, guidance, coef_dev, cp, d,
+                                                                                        static_cast<unsigned>(total / 4), cond_mode);
+  else
+    ddim_step_kernel<<<ew_grid(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, eps, noise, guidance, coef_dev, cp, d,
+                                                                                    total, cond_mode);
   return check_launch("ddim_step");
 }
 
@@ -219,8 +303,12 @@ extern "C" int wdno_ddpm_step(float* x, const float* eps, const float* noise, co
   if (rc) return rc;
   StateDims d{B, F, C, H, W};
   const size_t total = static_cast<size_t>(B) * F * C * H * W;
-  ddpm_step_kernel<<<ew_grid(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, eps, noise, guidance, coef_dev, cp, d,
-                                                                                  total, cond_mode);
+  if (vec4_ok(x, eps, noise, guidance, W, total))
+    step4_kernel<true><<<ew_grid(total / 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, eps, noise, guidance, coef_dev, cp, d,
+                                                                                       static_cast<unsigned>(total / 4), cond_mode);
+  else
+    ddpm_step_kernel<<<ew_grid(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, eps, noise, guidance, coef_dev, cp, d,
+                                                                                    total, cond_mode);
   return check_launch("ddpm_step");
 }
 
