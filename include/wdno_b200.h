@@ -102,7 +102,8 @@ typedef struct {
   int32_t n_taps;         /* entries of taps[] (<= 384; copied to shared memory) */
   int32_t bias_len;       /* floats readable at bias (padded output channels, <= 1024; staged in shared memory) */
   int32_t n_sets;         /* entries of sets[] (<= 128; copied to shared memory) */
-  int32_t pad_;
+  int32_t zstack;         /* 1: weight tiles hold the KD depth taps of one in-plane tap stacked along N ([kz][64] rows);
+                             taps[] lists in-plane taps only; one MMA per input plane updates up to 4 output planes */
 } wdno_tapgemm_params;
 
 /* bytes of dynamic shared memory the plan needs, or <0 */

@@ -30,13 +30,14 @@ def emulate(plan, src0, src1=None, coef0=None, coef1=None, resid=None, groups=8,
     else:
         H, W = Hs, Ws
     p = plan._plan(B, D, H, W)
-    pk = plan._packed[p.KC]
+    pk = plan._packed[(p.KC, bool(p.zstack))]
     chunks = _table(pk["chunks"], NChunk)
     sets = _table(pk["sets"], KSet)
     taps = _table(pk["taps_dev"][p.Wp], Tap)
     wpk = pk["wpacked"].float().numpy()
     KC, N = p.KC, p.N
-    tile_elems = N * KC
+    rows = N * (p.KD if p.zstack else 1)   # rows of one weight tile (kz-stacked tiles hold [kz][N])
+    tile_elems = rows * KC
     srcs = [src0.float().numpy(), None if src1 is None else src1.float().numpy()]
     coefs = [coef0, coef1]
     NACC = p.ZT * p.PT
@@ -93,9 +94,16 @@ def emulate(plan, src0, src1=None, coef0=None, coef1=None, resid=None, groups=8,
                             slabs[j] = np.where(ok[:, None], v, 0.0)
                         for t in range(st.tap_count):
                             tp = taps[st.tap_begin + t]
-                            tile = wpk[tile_i * tile_elems:(tile_i + 1) * tile_elems].reshape(KC // 8, N, 8)
-                            wmat = tile.transpose(1, 0, 2).reshape(N, KC)  # [N, KC]
+                            tile = wpk[tile_i * tile_elems:(tile_i + 1) * tile_elems].reshape(KC // 8, rows, 8)
+                            wmat = tile.transpose(1, 0, 2).reshape(rows, KC)  # [rows, KC]
                             tile_i += 1
+                            if p.zstack:
+                                # mma_role_zstack: input plane j feeds output plane o = j - kz through rows [kz*N, (kz+1)*N)
+                                for j in range(P):
+                                    a_rows = slabs[j, tp.shift: tp.shift + 128].astype(np.float64)
+                                    for kz in range(max(0, j - (p.ZT - 1)), min(p.KD - 1, j) + 1):
+                                        acc[j - kz] += a_rows @ wmat[kz * N:(kz + 1) * N].T.astype(np.float64)
+                                continue
                             for za in range(p.ZT):
                                 for pi in range(p.PT):
                                     a_rows = slabs[tp.kz + za, tp.shift + pi * 128: tp.shift + pi * 128 + 128]

@@ -240,6 +240,115 @@ __device__ __forceinline__ void mma_role(const wdno_tapgemm_params& p, Bars* bar
   PROF_COMMIT(0, (threadIdx.x & 31) == 0);
 }
 
+// ------------------------------------------------------------------ kz-stacked MMA issue (p.zstack)
+// For 64-wide N-chunks of a KD x KH x KW convolution an N = 64 MMA is shared-memory-bandwidth bound (A and B are both
+// re-read per MMA: 48 cycles instead of 32).  Here the weight tile of one in-plane tap holds all KD depth taps stacked
+// along N ([kz][64] rows), and the ZT = 4 accumulators sit in TMEM in DESCENDING plane order, so that for input plane j
+// ONE MMA with N = 64 * (number of valid kz) updates every output plane that plane contributes to (o = j - kz):
+// A is read once for up to 4 taps.  All P = ZT + KD - 1 planes of a K-set stay resident; they are acquired plane by
+// plane during the first in-plane tap and released plane by plane during the last one.
+template <int KS, int KD>
+__device__ __forceinline__ void mma_role_zstack(const wdno_tapgemm_params& p, Bars* bars, const wdno_tap* s_taps,
+                                                const wdno_nchunk* s_chunks, const wdno_kset* s_sets, uint32_t tmem_base,
+                                                const uint8_t* slab_base, const uint8_t* b_base, int n_work) {
+  constexpr int ZT = 4;
+  constexpr int P = ZT + KD - 1;
+  constexpr uint64_t kDescHi = static_cast<uint64_t>(8u | (1u << 14)) << 32;  // SBO = 128 B, descriptor version 1
+  constexpr uint32_t rows = 64u * KD;  // rows of one stacked weight tile
+  const int TPS = p.TPS, n_chunks = p.n_chunks;
+  const uint32_t nslot = static_cast<uint32_t>(p.NSLOT), nbst = static_cast<uint32_t>(p.NBST);
+  const uint32_t S_pad = static_cast<uint32_t>(p.S_pad);
+  const uint32_t slot_u = (static_cast<uint32_t>(p.KC >> 3) * S_pad * 16u) >> 4;
+  const uint32_t btile_u = (rows * static_cast<uint32_t>(p.KC) * 2u) >> 4, bstage_u = btile_u * static_cast<uint32_t>(TPS);
+  const uint32_t a_lo0 = (ptx::smem_u32(slab_base) >> 4) + (S_pad << 16);  // start | LBO = S_pad*16 B
+  const uint32_t b_lo0 = (ptx::smem_u32(b_base) >> 4) + (rows << 16);      // start | LBO = rows*16 B
+  const uint32_t a_kstep = 2u * S_pad;
+  constexpr uint32_t b_kstep = 2u * rows;
+  const uint32_t id1 = ptx::make_idesc_f16(64, 0), id2 = ptx::make_idesc_f16(128, 0), id3 = ptx::make_idesc_f16(192, 0),
+                 id4 = ptx::make_idesc_f16(256, 0);
+  uint32_t s0 = 0, sph = 0, bst = 0, bph = 0, acnt = 0;
+  PROF_DECL;
+  // all MMAs of in-plane tap (a_tap, b_tap) for planes [j0, j1): compile-time kz ranges, one MMA per (plane, k-step)
+  auto issue = [&](uint32_t a_tap, uint32_t b_tap, uint32_t acc0, int j0, int j1, bool init, bool release) {
+    uint32_t sj = s0;
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+      constexpr int dummy = 0;
+      (void)dummy;
+      const int kz_lo = (j - (ZT - 1) > 0) ? j - (ZT - 1) : 0;
+      const int kz_hi = (j < KD - 1) ? j : KD - 1;
+      const int nkz = kz_hi - kz_lo + 1;
+      const int o_hi = j - kz_lo;
+      if (j >= j0 && j < j1) {
+        const uint32_t a_lo = a_tap + sj * slot_u;
+        const uint32_t b_lo = b_tap + static_cast<uint32_t>(kz_lo) * 64u;
+        const uint32_t dcol = acc0 + static_cast<uint32_t>(ZT - 1 - o_hi) * 64u;
+        const uint32_t idn = (nkz == 1) ? id1 : (nkz == 2) ? id2 : (nkz == 3) ? id3 : id4;
+        if (init) {
+          // very first k-step of the work item: one N = 64 MMA per (plane, kz); output plane o is first touched by
+          // plane j = o through kz = 0, which therefore clears the accumulator
+#pragma unroll
+          for (int kz = kz_lo; kz <= kz_hi; ++kz)
+            ptx::tc_mma_f16(acc0 + static_cast<uint32_t>(ZT - 1 - (j - kz)) * 64u, kDescHi | a_lo,
+                            kDescHi | (b_tap + static_cast<uint32_t>(kz) * 64u), id1, (kz == 0) ? 0u : 1u);
+        }
+#pragma unroll
+        for (int k = 0; k < KS; ++k) {
+          if (k == 0 && init) continue;
+          ptx::tc_mma_f16(dcol, kDescHi | (a_lo + static_cast<uint32_t>(k) * a_kstep),
+                          kDescHi | (b_lo + static_cast<uint32_t>(k) * b_kstep), idn, 1u);
+        }
+        if (release) ptx::tc_commit(&bars->slab_empty[sj]);
+      }
+      if (++sj == nslot) sj = 0;
+    }
+  };
+  for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++acnt) {
+    const wdno_nchunk ci = s_chunks[w % n_chunks];
+    const uint32_t buf = acnt & 1u, aph = (acnt >> 1) & 1u;
+    PROF_REGION(0, ptx::mbar_wait(&bars->acc_empty[buf], aph ^ 1u));
+    ptx::tc_fence_after();
+    const uint32_t acc0 = tmem_base + buf * 256u;
+    for (int si = 0; si < ci.set_count; ++si) {
+      const wdno_kset st = s_sets[ci.set_begin + si];
+      const int T = st.tap_count;  // in-plane taps
+      const wdno_tap* tp_ptr = s_taps + st.tap_begin;
+      int t = 0;
+      for (int gi = 0; gi < T / TPS; ++gi) {
+        PROF_REGION(2, ptx::mbar_wait(&bars->b_full[bst], bph));
+        ptx::tc_fence_after();
+        for (int i = 0; i < TPS; ++i, ++t) {
+          const uint32_t a_tap = a_lo0 + static_cast<uint32_t>(tp_ptr[t].shift);
+          const uint32_t b_tap = b_lo0 + bst * bstage_u + static_cast<uint32_t>(i) * btile_u;
+          const bool last_t = (t == T - 1);
+          if (t == 0) {
+            // acquire the K-set's planes one by one so the MMAs start as soon as the first plane has landed
+            for (int j = 0; j < P; ++j) {
+              uint32_t sj = s0 + j, ph = sph;
+              if (sj >= nslot) { sj -= nslot; ph ^= 1u; }
+              PROF_REGION(1, ptx::mbar_wait(&bars->slab_full[sj], ph));
+              ptx::fence_proxy_async_smem();  // cp.async (generic proxy) slab writes -> tcgen05 (async proxy) reads
+              PROF_REGION(3, if (ptx::elect_one()) issue(a_tap, b_tap, acc0, j, j + 1, si == 0, last_t));
+              __syncwarp();
+            }
+          } else {
+            PROF_REGION(3, if (ptx::elect_one()) issue(a_tap, b_tap, acc0, 0, P, false, last_t));
+            __syncwarp();
+          }
+        }
+        if (ptx::elect_one()) ptx::tc_commit(&bars->b_empty[bst]);
+        __syncwarp();
+        if (++bst == nbst) { bst = 0; bph ^= 1u; }
+      }
+      s0 += static_cast<uint32_t>(P);
+      if (s0 >= nslot) { s0 -= nslot; sph ^= 1u; }
+    }
+    if (ptx::elect_one()) ptx::tc_commit(&bars->acc_full[buf]);
+    __syncwarp();
+  }
+  PROF_COMMIT(0, (threadIdx.x & 31) == 0);
+}
+
 __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const wdno_tapgemm_params p) {
   extern __shared__ __align__(128) uint8_t smem[];
   Bars* bars = reinterpret_cast<Bars*>(smem);
@@ -253,7 +362,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const wdno_tapgemm
   const uint32_t lbo_a = static_cast<uint32_t>(p.S_pad) * 16u;
   const uint32_t slot_bytes = static_cast<uint32_t>(CH) * lbo_a;
   uint8_t* b_base = slab_base + ((static_cast<size_t>(p.NSLOT) * slot_bytes + 127) & ~static_cast<size_t>(127));
-  const uint32_t btile_bytes = static_cast<uint32_t>(p.N) * static_cast<uint32_t>(p.KC) * 2u;
+  const uint32_t btile_bytes = static_cast<uint32_t>(p.N) * static_cast<uint32_t>(p.KC) * 2u * (p.zstack ? p.KD : 1);
   const uint32_t bstage_bytes = btile_bytes * static_cast<uint32_t>(p.TPS);
 
   const int warp = threadIdx.x >> 5;
@@ -510,14 +619,25 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const wdno_tapgemm
   } else if (warp == kMmaWarp) {
     // ============================================================ MMA issuer (templated on the accumulator shape)
     const int ks = p.KC >> 4;
+    if (p.zstack) {
+#define WDNO_ZS(KS_, KD_) mma_role_zstack<KS_, KD_>(p, bars, s_taps, s_chunks, s_sets, tmem_base, slab_base, b_base, n_work)
+      if (p.KD == 3) {
+        if (ks == 1) WDNO_ZS(1, 3); else if (ks == 2) WDNO_ZS(2, 3); else WDNO_ZS(4, 3);
+      } else {
+        if (ks == 1) WDNO_ZS(1, 7); else if (ks == 2) WDNO_ZS(2, 7); else WDNO_ZS(4, 7);
+      }
+#undef WDNO_ZS
+    } else
 #define WDNO_MMA(ZT_, PT_) \
     if (ks == 1) mma_role<ZT_, PT_, 1>(p, bars, s_taps, s_chunks, s_sets, tmem_base, slab_base, b_base, n_work, ptiles, zgroups); \
     else if (ks == 2) mma_role<ZT_, PT_, 2>(p, bars, s_taps, s_chunks, s_sets, tmem_base, slab_base, b_base, n_work, ptiles, zgroups); \
     else mma_role<ZT_, PT_, 4>(p, bars, s_taps, s_chunks, s_sets, tmem_base, slab_base, b_base, n_work, ptiles, zgroups);
-    if (p.ZT == 4) { WDNO_MMA(4, 1) }
-    else if (p.ZT == 2) { WDNO_MMA(2, 1) }
-    else if (p.PT == 4) { WDNO_MMA(1, 4) }
-    else { WDNO_MMA(1, 1) }
+    {
+      if (p.ZT == 4) { WDNO_MMA(4, 1) }
+      else if (p.ZT == 2) { WDNO_MMA(2, 1) }
+      else if (p.PT == 4) { WDNO_MMA(1, 4) }
+      else { WDNO_MMA(1, 1) }
+    }
 #undef WDNO_MMA
   } else {
     // ============================================================ epilogue warps 0..3
@@ -569,7 +689,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const wdno_tapgemm
             const int z = z0 + za;
             const bool valid = valid_yx && (z < p.D);
             const uint32_t tcol = tmem_base + lane_base + buf * static_cast<uint32_t>(NACC * NPAD) +
-                                  static_cast<uint32_t>((za * p.PT + pi) * NPAD);
+                                  static_cast<uint32_t>((p.zstack ? (p.ZT - 1 - za) : (za * p.PT + pi)) * NPAD);
             if (p.out_mode == 2) {
               // fp32 [B, D, C, H, W]: consecutive lanes are consecutive x -> already coalesced per channel
               const long long obase = rbase + static_cast<long long>(z) * p.out_c * (static_cast<long long>(p.H) * p.W);
@@ -731,7 +851,7 @@ static int64_t smem_bytes_of(const wdno_tapgemm_params* p) {
   const int64_t CH = p->KC / 8;
   const int64_t slot = CH * p->S_pad * 16;
   const int64_t slabs = (p->NSLOT * slot + 127) & ~static_cast<int64_t>(127);
-  const int64_t bt = static_cast<int64_t>(p->N) * p->KC * 2;
+  const int64_t bt = static_cast<int64_t>(p->N) * p->KC * 2 * (p->zstack ? p->KD : 1);
   return kHdrBytes + slabs + static_cast<int64_t>(p->NBST) * p->TPS * bt;
 }
 
@@ -760,6 +880,8 @@ static int validate(const wdno_tapgemm_params* p) {
   if (p->src_mode == 2 && ((p->H & 1) || (p->W & 1))) return set_error(WDNO_E_INVALID, "tapgemm: up2 needs even H,W");
   if (smem_bytes_of(p) > 227 * 1024) return set_error(WDNO_E_INVALID, "tapgemm: shared-memory plan exceeds 227 KB");
   if (p->grid < 1) return set_error(WDNO_E_INVALID, "tapgemm: grid must be >= 1");
+  if (p->zstack && (p->ZT != 4 || p->PT != 1 || p->N != 64 || (p->KD != 3 && p->KD != 7) || p->reuse || p->NSLOT < p->ZT + p->KD - 1))
+    return set_error(WDNO_E_INVALID, "tapgemm: zstack needs ZT=4, PT=1, N=64, KD in {3,7}, no slab reuse and NSLOT >= ZT+KD-1");
   if (p->n_chunks > kMaxChunks) return set_error(WDNO_E_INVALID, "tapgemm: more than 32 N-chunks");
   if (p->n_sets < 1 || p->n_sets > kMaxSets) return set_error(WDNO_E_INVALID, "tapgemm: n_sets must be in [1,128]");
   if (p->bias && (p->bias_len < 1 || p->bias_len > kMaxBias)) return set_error(WDNO_E_INVALID, "tapgemm: bias_len must be in [1,1024]");

@@ -87,9 +87,9 @@ class TapGemm:
         """total channels of the (concatenated) sources"""
         return sum(self.src_channels)
 
-    def _pack(self, KC):
-        if KC in self._packed:
-            return self._packed[KC]
+    def _pack(self, KC, zstack=False):
+        if (KC, zstack) in self._packed:
+            return self._packed[(KC, zstack)]
         N, kind = self.N, self.kind
         w = self.w
         ctot = self._virtual_cin()
@@ -119,7 +119,24 @@ class TapGemm:
             out[: wfull.shape[0], : wfull.shape[1]] = wfull
             return out
 
-        if kind == "conv":
+        if kind == "conv" and zstack:
+            # kz-stacked tiles: one tile per (N-chunk, K-set, in-plane tap) with rows [kz][N] (csrc/tapgemm.cu, mma_role_zstack)
+            wp = padded_w(w)
+            KD, KH, KW = self.KD, self.KH, self.KW
+            T = KH * KW
+            for ky in range(KH):
+                for kx in range(KW):
+                    taps.append((0, ky, kx))
+            for ck in range(nck):
+                s_, ch = src_of(ck)
+                sets.append(dict(src=s_, ch_off=ch, ph_y=0, ph_x=0, tap_begin=0, tap_count=T))
+            # [NC, N, nck, KC/8, 8, KD, T] -> [NC, nck, T, KC/8, KD, N, 8]
+            wr = wp.reshape(ncn, N, nck, KC // 8, 8, KD, T).permute(0, 2, 6, 3, 5, 1, 4).contiguous()
+            wpacked = wr.reshape(-1)
+            for cn in range(ncn):
+                chunks.append(dict(out_ch_off=cn * N, n_valid=min(N, self.cout - cn * N), ph_y=0, ph_x=0,
+                                   set_begin=0, set_count=nck, n_tiles=nck * T, w_tile_off=cn * nck * T))
+        elif kind == "conv":
             wp = padded_w(w)
             KD, KH, KW = self.KD, self.KH, self.KW
             tap_list = [(kz, ky, kx) for kz in range(KD) for ky in range(KH) for kx in range(KW)]
@@ -222,7 +239,7 @@ class TapGemm:
             taps_kyx=taps, n_chunks=len(chunks), n_sets=len(sets),
             taps_dev={},  # Wp -> device tap table
         )
-        self._packed[KC] = pk
+        self._packed[(KC, zstack)] = pk
         return pk
 
     # ------------------------------------------------------------------ geometry / smem plan
@@ -277,26 +294,67 @@ class TapGemm:
                         break
                 if plan:
                     break
-        if plan is None:
-            ZT = 4 if D >= 4 else (2 if D >= 2 else 1)
-            PT = 4 if ZT == 1 else 1
-            if self.N > 64:
-                while ZT * PT * 128 > 512:
-                    PT = max(1, PT - 1)
+        zstack = 0
+        if (plan is None and self.kind == "conv" and KD in (3, 7) and self.N == 64 and D >= 4 and not self.up2
+                and int(os.environ.get("WDNO_ZSTACK", "1"))):
+            # kz-stacked MMAs (N = 64..256 per input plane): all P planes of a K-set resident, >= 3 weight stages
+            ZT, PT = 4, 1
             P = ZT + KD - 1
+            T = KH * KW
             best = None
             for KC in kcs:
-                f = fit(KC, ZT, PT, P + int(os.environ.get("WDNO_SLOT_EXTRA", "2")), P)
-                if not f:
-                    continue
-                score = (min(f[1] - P, 2), KC)  # prefer a full ring (P+2 slots), then the larger KC
-                if best is None or score > best[0]:
-                    best = (score, (KC, ZT, PT, 0) + f)
+                CH = KC // 8
+                S = 128 + maxshift
+                S_pad = S + (({8: 1, 4: 2, 2: 4}[CH] - S) % 8)
+                slot = CH * S_pad * 16
+                tile = KD * self.N * KC * 2
+                for nbst in (4, 3, 2):
+                    room = _SMEM_LIMIT - _BAR_BYTES - nbst * tile
+                    nslot = min(12, 2 * P, room // slot if room > 0 else 0)
+                    while nslot >= P and _BAR_BYTES + _round_up(nslot * slot, 128) + nbst * tile > _SMEM_LIMIT:
+                        nslot -= 1
+                    if nslot < P:
+                        continue
+                    score = (nbst >= 3, 1.5 * min(nslot - P, 4) + nbst, KC)
+                    if best is None or score > best[0]:
+                        best = (score, (KC, ZT, PT, 0, S_pad, nslot, nbst, 1))
+            if best is not None:
+                plan = best[1]
+                zstack = 1
+        if plan is None:
+            # accumulator shape: pick the plane-group depth ZT whose work-item count balances best over the persistent
+            # CTAs (estimated makespan = waves x (MMA cycles + per-item operand/pipeline overhead)); PT = 4 only for 2-D
+            sms_ = (torch.cuda.get_device_properties(self.device).multi_processor_count
+                    if self.device.type == "cuda" else 148)
+            zts = [z for z in (4, 2, 1) if z <= D] or [1]
+            if os.environ.get("WDNO_ZT"):
+                zts = [int(os.environ["WDNO_ZT"])]
+            ntaps = {"conv": KD * KH * KW, "down144": 16, "up144": 4, "unshuffle": 4}[self.kind]
+            mma_cyc = 48 if self.N <= 64 else self.N // 2  # N <= 64 is shared-memory-bandwidth bound (tools/micro/mma_rate)
+            best = None
+            for ZT in zts:
+                PT = 4 if (ZT == 1 and D == 1) else 1
+                if self.N > 64:
+                    while ZT * PT * 128 > 512:
+                        PT = max(1, PT - 1)
+                P = ZT + KD - 1
+                for KC in kcs:
+                    f = fit(KC, ZT, PT, P + int(os.environ.get("WDNO_SLOT_EXTRA", "2")), P)
+                    if not f:
+                        continue
+                    ptiles_ = (H * Wp + 128 * PT - 1) // (128 * PT)
+                    items = B * ((D + ZT - 1) // ZT) * ptiles_ * ncn
+                    waves = (items + sms_ - 1) // sms_
+                    per_item = ZT * PT * ntaps * (ctot // 16) * mma_cyc + 3000 + P * (ctot // KC) * 800 * PT
+                    est = waves * per_item
+                    score = (-est, min(f[1] - P, 2), KC)  # then prefer a full ring (P+2 slots) and the larger KC
+                    if best is None or score > best[0]:
+                        best = (score, (KC, ZT, PT, 0) + f)
             if best is None:
                 raise ValueError(f"tapgemm: no shared-memory plan for grid {(B, D, H, W)} taps {(KD, KH, KW)}")
             plan = best[1]
         KC, ZT, PT, reuse, S_pad, NSLOT, NBST, TPS = plan
-        pk = self._pack(KC)
+        pk = self._pack(KC, bool(zstack))
         if Wp not in pk["taps_dev"]:
             tl = pk["taps_kyx"]
             taps_c = (Tap * len(tl))(*[Tap(kz, ky * Wp + kx) for (kz, ky, kx) in tl])
@@ -322,6 +380,7 @@ class TapGemm:
         p.TPS, p.reuse = TPS, reuse
         p.n_taps = len(pk["taps_kyx"])
         p.n_sets = pk["n_sets"]
+        p.zstack = zstack
         p.grid = max(1, min(n_work, sms))
         self._launch[key] = p
         return p
