@@ -28,8 +28,11 @@ constexpr int kProdWarps = 8;
 constexpr int kMmaWarp = kEpiWarps;       // warp 4
 constexpr int kBWarp = kEpiWarps + 1;     // warp 5
 constexpr int kFirstProdWarp = kEpiWarps + 2;
-constexpr int kThreads = (kEpiWarps + 2 + kProdWarps) * 32;
+constexpr int kLoadWarps = 2;              // act mode only: dedicated cp.async issuers feeding the transforming producers
+constexpr int kFirstLoadWarp = kFirstProdWarp + kProdWarps;
+constexpr int kThreads = (kEpiWarps + 2 + kProdWarps + kLoadWarps) * 32;
 constexpr int kProdThreads = kProdWarps * 32;
+constexpr int kLoadThreads = kLoadWarps * 32;
 constexpr int kMaxSlots = 12;
 constexpr int kMaxBStages = 8;
 constexpr int kBarBytes = 512;
@@ -61,6 +64,7 @@ __device__ unsigned long long g_prof[32];
 struct Bars {
   uint64_t slab_full[kMaxSlots];
   uint64_t slab_empty[kMaxSlots];
+  uint64_t raw_full[kMaxSlots];
   uint64_t b_full[kMaxBStages];
   uint64_t b_empty[kMaxBStages];
   uint64_t acc_full[2];
@@ -382,6 +386,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const wdno_tapgemm
     for (int i = 0; i < p.NSLOT; ++i) {
       ptx::mbar_init(&bars->slab_full[i], kProdThreads);  // every producer thread arrives (directly or via cp.async)
       ptx::mbar_init(&bars->slab_empty[i], 1);
+      ptx::mbar_init(&bars->raw_full[i], kLoadThreads);  // the loader threads' copies arrive by themselves
     }
     for (int i = 0; i < p.NBST; ++i) {
       ptx::mbar_init(&bars->b_full[i], 1);
@@ -407,7 +412,63 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const wdno_tapgemm
   ptx::tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
 
-  if (warp >= kFirstProdWarp) {
+  if (warp >= kFirstLoadWarp) {
+    // ============================================================ A loaders (GroupNorm+SiLU prologue only)
+    // With a fused activation the 8 producer warps spend their time transforming; these two warps run ahead of them
+    // and only issue the asynchronous copies of every plane (same slab layout), so copy latency, address arithmetic
+    // and the transform overlap instead of alternating in one thread.
+    const bool any_act = (p.coef_a[0] != nullptr) || (p.coef_a[1] != nullptr);
+    if (any_act) {
+      const int ltid = threadIdx.x - kFirstLoadWarp * 32;
+      const int S = 128 * p.PT + p.maxshift;
+      const int P = p.ZT + p.KD - 1;
+      const int c = ltid & (CH - 1);
+      const int ch_shift = (CH == 8) ? 3 : (CH == 4) ? 2 : 1;
+      const int s_first = ltid >> ch_shift;
+      const int SP = kLoadThreads >> ch_shift;
+      const int step_y = SP / p.Wp, step_x = SP - step_y * p.Wp;
+      const uint32_t wp_magic = 0xFFFFFFFFu / static_cast<uint32_t>(p.Wp) + 1u;
+      int Hs = p.H, Ws = p.W;
+      if (p.src_mode == 1) { Hs = 2 * p.H; Ws = 2 * p.W; }
+      if (p.src_mode == 2) { Hs = p.H >> 1; Ws = p.W >> 1; }
+      uint32_t slot = 0, ph = 0;
+      for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+        const Work wk = decode_work(w, p.n_chunks, ptiles, zgroups, p.reuse);
+        const wdno_nchunk ci = s_chunks[wk.nc0];
+        const int q0 = wk.pt * 128 * p.PT + s_first;
+        const int yp0 = static_cast<int>(__umulhi(static_cast<uint32_t>(q0), wp_magic));
+        const int xp0 = q0 - yp0 * p.Wp;
+        for (int si = 0; si < ci.set_count; ++si) {
+          const wdno_kset st = s_sets[ci.set_begin + si];
+          const int csrc = p.src_c[st.src];
+          for (int j = 0; j < P; ++j) {
+            const int zi = wk.zg * p.ZT - p.pz + j;
+            const bool zok = (zi >= 0) && (zi < p.D);
+            const __half* plane = static_cast<const __half*>(p.src[st.src]) +
+                                  ((static_cast<size_t>(wk.b) * p.D + (zok ? zi : 0)) * Hs * Ws + (st.ph_y * Ws + st.ph_x)) * csrc +
+                                  st.ch_off + c * 8;
+            const uint32_t dst = ptx::smem_u32(slab_base) + slot * slot_bytes + static_cast<uint32_t>(c) * lbo_a;
+            ptx::mbar_wait(&bars->slab_empty[slot], ph ^ 1u);
+            int yp = yp0, xp = xp0;
+            for (int sq = s_first; sq < S; sq += SP) {
+              const int y = yp - p.py, x = xp - p.px;
+              const bool ok = zok && y >= 0 && y < p.H && x >= 0 && x < p.W;
+              int so = y * Ws + x;
+              if (p.src_mode == 1) so = 2 * y * Ws + 2 * x;
+              if (p.src_mode == 2) so = (y >> 1) * Ws + (x >> 1);
+              ptx::cp_async16_zfill(dst + static_cast<uint32_t>(sq) * 16u, ok ? plane + static_cast<size_t>(so) * csrc : plane,
+                                    ok ? 16u : 0u);
+              xp += step_x;
+              yp += step_y;
+              if (xp >= p.Wp) { xp -= p.Wp; ++yp; }
+            }
+            ptx::cp_async_mbar_arrive_noinc(&bars->raw_full[slot]);
+            if (++slot == static_cast<uint32_t>(p.NSLOT)) { slot = 0; ph ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp >= kFirstProdWarp) {
     // ============================================================ A producers
     // thread -> fixed 16-byte chunk c of positions s_first, s_first+SP, ... of every plane.  The source offset of each of
     // the thread's positions depends only on the work item's position tile, so it is computed once per work item
@@ -565,30 +626,13 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const wdno_tapgemm
         advance(iss);
       }
     } else {
-      constexpr int kAhead = 3;
-      Cursor fin = iss;
-      int pending = 0;
-      while (true) {
-        while (iss.w < n_work && pending < kAhead) {
-          if (pending == 0) {
-            PROF_REGION(0, ptx::mbar_wait(&bars->slab_empty[iss.slot], iss.ph ^ 1u));
-          } else if (!ptx::mbar_try_wait(&bars->slab_empty[iss.slot], iss.ph ^ 1u)) {
-            break;
-          }
-          PROF_REGION(1, issue(iss));
-          ptx::cp_async_commit();
-          advance(iss);
-          ++pending;
-        }
-        if (pending == 0) break;
-        PROF_REGION(2, if (pending >= 3) ptx::cp_async_wait<2>();
-        else if (pending == 2) ptx::cp_async_wait<1>();
-        else ptx::cp_async_wait<0>(););
-        PROF_REGION(3, transform(fin));
+      // the loader warps fill the slot; transform it in place (each thread its own chunks) and publish
+      while (iss.w < n_work) {
+        PROF_REGION(0, ptx::mbar_wait(&bars->raw_full[iss.slot], iss.ph));
+        PROF_REGION(3, transform(iss));
         ptx::fence_proxy_async_smem();
-        ptx::mbar_arrive(&bars->slab_full[fin.slot]);
-        advance(fin);
-        --pending;
+        ptx::mbar_arrive(&bars->slab_full[iss.slot]);
+        advance(iss);
       }
     }
     PROF_COMMIT(8, ptid == 0);
