@@ -266,7 +266,7 @@ class TapGemm:
             S_pad = S + ((rem - S) % 8)
             slot = CH * S_pad * 16
             tpk = {"conv": KH * KW, "down144": 4, "up144": 4, "unshuffle": 1}[self.kind]  # taps per kz group
-            stage_cap = int(os.environ.get("WDNO_BSTAGE", "16384"))
+            stage_cap = int(os.environ.get("WDNO_BSTAGE", "49152"))  # several taps per issue block (fewer, larger MMA bursts)
             divs = [d for d in range(tpk, 0, -1) if tpk % d == 0 and (d * btile(KC) <= stage_cap or d == 1)]
             for nslot in range(min(12, want_slots), min_slots - 1, -1):
                 for tps in divs:
@@ -308,16 +308,19 @@ class TapGemm:
                 S_pad = S + (({8: 1, 4: 2, 2: 4}[CH] - S) % 8)
                 slot = CH * S_pad * 16
                 tile = KD * self.N * KC * 2
-                for nbst in (4, 3, 2):
-                    room = _SMEM_LIMIT - _BAR_BYTES - nbst * tile
-                    nslot = min(12, 2 * P, room // slot if room > 0 else 0)
-                    while nslot >= P and _BAR_BYTES + _round_up(nslot * slot, 128) + nbst * tile > _SMEM_LIMIT:
-                        nslot -= 1
-                    if nslot < P:
-                        continue
-                    score = (nbst >= 3, 1.5 * min(nslot - P, 4) + nbst, KC)
-                    if best is None or score > best[0]:
-                        best = (score, (KC, ZT, PT, 0, S_pad, nslot, nbst, 1))
+                stage_cap = int(os.environ.get("WDNO_ZSTAGE", "40960"))
+                for tps in [d for d in range(T, 0, -1) if T % d == 0 and (d * tile <= stage_cap or d == 1)][:2]:
+                    for nbst in (4, 3, 2):
+                        room = _SMEM_LIMIT - _BAR_BYTES - nbst * tps * tile
+                        nslot = min(12, 2 * P, room // slot if room > 0 else 0)
+                        while nslot >= P and _BAR_BYTES + _round_up(nslot * slot, 128) + nbst * tps * tile > _SMEM_LIMIT:
+                            nslot -= 1
+                        if nslot < P:
+                            continue
+                        # >= 3 taps of weights in flight, then slabs ahead of the MMAs, then fewer / larger issue blocks
+                        score = (min(nbst * tps, 6) >= 3 and nslot > P, KC, 1.5 * min(nslot - P, 4) + min(nbst * tps, 6) + 0.5 * tps)
+                        if best is None or score > best[0]:
+                            best = (score, (KC, ZT, PT, 0, S_pad, nslot, nbst, tps))
             if best is not None:
                 plan = best[1]
                 zstack = 1
