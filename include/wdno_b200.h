@@ -76,7 +76,7 @@ typedef struct {
   /* tap grid == output grid (before depth-to-space) */
   int32_t B, D, H, W;
   int32_t KD, pz, py, px; /* input plane for tap kz is z + kz - pz; padded position = (y+py, x+px) */
-  int32_t Wp;             /* padded row width (W + KW - 1) */
+  int32_t Wp;             /* padded row width: W + KW/2 (the zero run between rows is shared by both neighbours) */
   int32_t maxshift;       /* largest tap shift */
   int32_t ZT, PT;         /* accumulators per unit: ZT planes x PT 128-position tiles (ZT*PT <= 4) */
   int32_t KC;             /* channels per K-set: 16, 32 or 64 */

@@ -251,7 +251,9 @@ class TapGemm:
         if key in self._launch:
             return self._launch[key]
         KD, KH, KW = self.KD, self.KH, self.KW
-        Wp = W + KW - 1
+        # padded row width: ONE shared run of KW//2 zero columns per row -- the left pad of row y+1 doubles as the right
+        # pad of row y (positions are linearised, so x + kx simply runs into the next row's pad)
+        Wp = W + KW // 2
         maxshift = (KH - 1) * Wp + (KW - 1)
         ctot = self._virtual_cin()
         ncn = self.cout_pad // self.N
