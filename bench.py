@@ -52,7 +52,7 @@ class ClockSampler:
                     self.rows.append([c.strip() for c in o.split(",")])
             except Exception:
                 pass
-            self.stop.wait(0.2)
+            self.stop.wait(0.02)
 
     def __enter__(self):
         self.th.start()
@@ -217,9 +217,18 @@ def main():
         n_tg = len(recs) // n_prof
         peak_tf, hbm, psrc = peaks()
         achieved = tg_flops / (tg_ms * 1e-3) / 1e12
+        # DRAM bytes of the same launches from the committed ncu capture (profiles/, tools/gpu_prof_final.sh)
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "r1_tapgemm_traffic.json")
+        if os.path.exists(tp):
+            td = json.load(open(tp))
+            if td.get("launches") == n_tg:
+                traffic = td["dram_bytes_total"]
         roof = {"bound": "tensor", "kernel": "wdno::tapgemm_kernel (all %d launches of one step)" % n_tg,
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                "peak_source": f"{psrc} bf16 sustained (fp16 operands run at the bf16 rate)", "traffic": None,
+                "peak_source": f"{psrc} bf16 sustained (fp16 operands run at the bf16 rate)", "traffic": traffic,
+                "traffic_note": "dram__bytes_read+write summed over the same launches of one step (ncu, profiles/r1_tapgemm_traffic.json); "
+                                "algorithmic activation+weight bytes of those layers: see DESIGN.md section 4.1",
                 "kernel_ms_per_step": tg_ms, "kernel_share_of_step": tg_ms / (ms / K),
                 "algorithmic_gflop_per_step": tg_flops / 1e9}
 

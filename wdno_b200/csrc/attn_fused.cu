@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(256) la_mid_kernel(const float* __restrict__ p
   const int j = h * 32 + d;
   const int ks = j >> 4, kk = j & 15;
   const int reg = kk >> 3, qq = (kk & 7) >> 1, half = kk & 1;
-  __half* mp = mpack + static_cast<size_t>(img) * C * kLaHid;
+  extern __shared__ __align__(16) __half msm[];  // the image's M in fragment order, then copied out coalesced
   const int c0 = chalf * (C / 2);
 #pragma unroll 2
   for (int c = c0; c < c0 + C / 2; ++c) {
@@ -272,9 +272,11 @@ __global__ void __launch_bounds__(256) la_mid_kernel(const float* __restrict__ p
       s3 = fmaf(w4.w, cr[4 * e4 + 3], s3);
     }
     const int nt = c >> 3, gg = c & 7;
-    mp[(static_cast<size_t>(nt * 4 + (ks >> 1)) * 32 + (gg * 4 + qq)) * 8 + ((ks & 1) * 2 + reg) * 2 + half] =
-        __float2half_rn((s0 + s1) + (s2 + s3));
+    msm[((nt * 4 + (ks >> 1)) * 32 + (gg * 4 + qq)) * 8 + ((ks & 1) * 2 + reg) * 2 + half] = __float2half_rn((s0 + s1) + (s2 + s3));
   }
+  __syncthreads();
+  uint4* dst = reinterpret_cast<uint4*>(mpack + static_cast<size_t>(img) * C * kLaHid);
+  for (int i = threadIdx.x; i < C * kLaHid / 8; i += 256) dst[i] = reinterpret_cast<const uint4*>(msm)[i];
 }
 
 // ------------------------------------------------------------------ la2: q -> softmax_d -> y = q M^T + bias + x
@@ -896,12 +898,13 @@ static int launch_linattn(const __half* x, __half* y, const float* gamma, const 
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(la2_kernel<C, WS2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(la_mid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * kLaHid * 2);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(la1_kernel<C, WS1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
     if (e != cudaSuccess) return set_cuda_error(e, "linattn_block: cudaFuncSetAttribute");
     configured = true;
   }
   la1_kernel<C, WS1><<<n_img * split, 256, smem1, st>>>(x, gamma, wkv, part, n_pos, split, eps);
-  la_mid_kernel<<<n_img, 256, 0, st>>>(part, wout, mpack, C, nparts, scale);
+  la_mid_kernel<<<n_img, 256, C * kLaHid * 2, st>>>(part, wout, mpack, C, nparts, scale);
   const int tiles = (n_pos + 127) / 128;
   const int n_items = n_img * tiles;
   const int cap = num_sms() * 2;
