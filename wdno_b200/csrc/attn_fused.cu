@@ -40,6 +40,7 @@ __global__ void __launch_bounds__(256, 2) la1_kernel(const __half* __restrict__ 
                                                   const uint4* wkv, float* __restrict__ part, int n, int split,
                                                   float eps) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
+  pdl_trigger();
   __half* xn = reinterpret_cast<__half*>(smem_raw);  // [64][C + 8]
   constexpr int XS = C + 8;
   constexpr int KS = C / 16;
@@ -72,6 +73,7 @@ __global__ void __launch_bounds__(256, 2) la1_kernel(const __half* __restrict__ 
 #pragma unroll
   for (int i = 0; i < 4; ++i) { mrun[i] = -INFINITY; z[i] = 0.f; }
 
+  pdl_wait();  // weights above are plan constants; x is the predecessor's output
   for (int t = t0; t < t1; ++t) {
     __syncthreads();
     const int p0 = t * 64;
@@ -212,6 +214,8 @@ __global__ void __launch_bounds__(256) la_mid_kernel(const float* __restrict__ p
                                                      __half* __restrict__ mpack, int C, int nparts, float scale) {
   __shared__ float ctx[kLaHeads][kLaDh][kLaDh + 1];
   __shared__ float wts[4][kLaHid];  // per part: exp(m_i - m) * scale / z  for (h, d)
+  pdl_trigger();
+  pdl_wait();
   const int img = blockIdx.x;
   const float* pimg = part + static_cast<size_t>(img) * nparts * kLaHeads * kLaPart;
   if (threadIdx.x < kLaHid) {
@@ -305,6 +309,7 @@ __global__ void __launch_bounds__(256, 2) la2_kernel(const __half* __restrict__ 
   const int g = lane >> 2, q = lane & 3;
   const int ln_l = threadIdx.x % LP, ln_r0 = threadIdx.x / LP;
   constexpr int n_wq = 16 * (C / 32) * 32, n_m = (C / 8) * 4 * 32;
+  pdl_trigger();
   if constexpr (WS) {
     stage_weights(wsm, wq, n_wq, threadIdx.x, 256);
     wq = wsm;
@@ -331,6 +336,7 @@ __global__ void __launch_bounds__(256, 2) la2_kernel(const __half* __restrict__ 
   const uint32_t a_off = static_cast<uint32_t>(((16 * warp + (lane & 15)) * XS + 8 * (lane >> 4)) * 2);
   int cur_img = -1;
   int buf = 0;
+  pdl_wait();  // Wq / gamma are plan constants; x and the per-image M come from predecessors
   if (static_cast<int>(blockIdx.x) < n_items) fetch(blockIdx.x, 0);
 
   for (int item = blockIdx.x; item < n_items; item += gridDim.x, buf ^= 1) {
@@ -520,6 +526,7 @@ __global__ void __launch_bounds__(256, 2) tattn_kernel(const __half* __restrict_
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, q = lane & 3;
   const int s = warp >> 2, h = warp & 3;
+  pdl_trigger();
 
   for (int i = tid; i < 2 * kTaRows * XS / 8; i += 256) reinterpret_cast<uint4*>(xn)[i] = make_uint4(0u, 0u, 0u, 0u);
   for (int i = tid; i < 4 * 32 * 32; i += 256) {
@@ -573,6 +580,7 @@ __global__ void __launch_bounds__(256, 2) tattn_kernel(const __half* __restrict_
       if (f < n && ss < nseq) raw[ps] = __ldg(reinterpret_cast<const uint4*>(xb + (static_cast<size_t>(f) * hw + ss) * C) + ln_l);
     }
   };
+  pdl_wait();  // tables / weights above are plan constants; x is the predecessor's output
   if (blockIdx.x < n_pairs) fetch(blockIdx.x);
 
   for (long long pr = blockIdx.x; pr < n_pairs; pr += gridDim.x) {
@@ -877,7 +885,8 @@ static int launch_tattn(const __half* x, __half* y, const float* gamma, const ui
   const long long n_pairs = (n_pix + 1) / 2;
   const long long cap = static_cast<long long>(num_sms()) * 2 * 4;
   const unsigned grid = static_cast<unsigned>(n_pairs < cap ? n_pairs : cap);
-  tattn_kernel<C, WS><<<grid, 256, smem, st>>>(x, y, gamma, wqk, wv, wo, bias, rot_cos, rot_sin, n_pix, hw, n, scale, eps);
+  launch_pdl(tattn_kernel<C, WS>, dim3(grid), dim3(256), static_cast<size_t>(smem), st, x, y, gamma, wqk, wv, wo, bias, rot_cos,
+             rot_sin, n_pix, hw, n, scale, eps);
   return check_launch("tattn_block");
 }
 
@@ -903,13 +912,15 @@ static int launch_linattn(const __half* x, __half* y, const float* gamma, const 
     if (e != cudaSuccess) return set_cuda_error(e, "linattn_block: cudaFuncSetAttribute");
     configured = true;
   }
-  la1_kernel<C, WS1><<<n_img * split, 256, smem1, st>>>(x, gamma, wkv, part, n_pos, split, eps);
-  la_mid_kernel<<<n_img, 256, C * kLaHid * 2, st>>>(part, wout, mpack, C, nparts, scale);
+  launch_pdl(la1_kernel<C, WS1>, dim3(n_img * split), dim3(256), static_cast<size_t>(smem1), st, x, gamma, wkv, part, n_pos, split,
+             eps);
+  launch_pdl(la_mid_kernel, dim3(n_img), dim3(256), static_cast<size_t>(C * kLaHid * 2), st, static_cast<const float*>(part), wout,
+             mpack, C, nparts, scale);
   const int tiles = (n_pos + 127) / 128;
   const int n_items = n_img * tiles;
   const int cap = num_sms() * 2;
-  la2_kernel<C, WS2><<<n_items < cap ? n_items : cap, 256, smem2, st>>>(x, y, gamma, wq, reinterpret_cast<const uint4*>(mpack),
-                                                                        bias, n_pos, tiles, n_items, eps);
+  launch_pdl(la2_kernel<C, WS2>, dim3(n_items < cap ? n_items : cap), dim3(256), static_cast<size_t>(smem2), st, x, y, gamma, wq,
+             reinterpret_cast<const uint4*>(mpack), bias, n_pos, tiles, n_items, eps);
   return check_launch("linattn_block");
 }
 

@@ -17,4 +17,28 @@ int launch_short_attn_mma(const void* qkv, void* out, const float* bias, const f
                           long long n_seq, int n_tok, long long inner, long long outerT, long long innerT, long long tokT,
                           float scale, cudaStream_t st);
 
+// ---- programmatic dependent launch (PDL): a kernel launched through launch_pdl may start (run its prologue) while
+// the previous kernel of the stream drains; it must execute pdl_wait() before touching anything a predecessor wrote.
+// Every kernel calls pdl_trigger() first so that its successor can be scheduled as early as resources allow.
+bool pdl_enabled();  // WDNO_PDL=1 turns it on (default: plain stream order; measured neutral in round 1)
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 }  // namespace wdno

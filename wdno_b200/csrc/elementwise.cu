@@ -39,6 +39,8 @@ __global__ void gn_finalize_kernel(const double* __restrict__ stats, const float
                                    const float* __restrict__ beta, const float* __restrict__ ss, int ss_stride,
                                    float* __restrict__ a, float* __restrict__ c, int B, int C, int G, double count,
                                    float eps) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * C) return;
   const int b = i / C, ch = i - b * C;
@@ -67,6 +69,8 @@ __global__ void gn_finalize_kernel(const double* __restrict__ stats, const float
 __global__ void __launch_bounds__(256) gn_silu_add_fast_kernel(const __half* __restrict__ y, const float* __restrict__ a,
                                                                const float* __restrict__ c, const __half* __restrict__ r,
                                                                __half* __restrict__ out, int C, unsigned chunks_per_sample) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.y;
   const int cpv = C >> 3;
   const int ch = static_cast<int>(threadIdx.x % cpv) * 8;
@@ -290,7 +294,7 @@ extern "C" int wdno_gn_finalize(const double* stats, const float* gamma, const f
   if (!stats || !gamma || !beta || !a || !c || B < 1 || C < 1 || G < 1 || (C % G) || count <= 0)
     return set_error(WDNO_E_INVALID, "gn_finalize: bad arguments");
   const int n = B * C;
-  gn_finalize_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(stats, gamma, beta, scale_shift,
+  launch_pdl(gn_finalize_kernel, dim3((n + 255) / 256), dim3(256), 0, static_cast<cudaStream_t>(stream), stats, gamma, beta, scale_shift,
                                                                                     ss_stride, a, c, B, C, G, count, eps);
   return check_launch("gn_finalize");
 }
@@ -305,9 +309,8 @@ extern "C" int wdno_gn_silu_add(const void* y, const float* a, const float* c, c
     const size_t want = (cps + 511) / 512;  // two chunks per thread per pass
     const size_t cap = std::max<size_t>(1, static_cast<size_t>(num_sms()) * 16 / B);
     dim3 grid2(static_cast<unsigned>(std::min(want, cap)), static_cast<unsigned>(B));
-    gn_silu_add_fast_kernel<<<grid2, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const __half*>(y), a, c, static_cast<const __half*>(resid), static_cast<__half*>(out), C,
-        static_cast<unsigned>(cps));
+    launch_pdl(gn_silu_add_fast_kernel, grid2, dim3(256), 0, static_cast<cudaStream_t>(stream), static_cast<const __half*>(y), a, c,
+               static_cast<const __half*>(resid), static_cast<__half*>(out), C, static_cast<unsigned>(cps));
     return check_launch("gn_silu_add");
   }
   const int grid = static_cast<int>(std::min<size_t>((chunks + 255) / 256, static_cast<size_t>(num_sms()) * 16));

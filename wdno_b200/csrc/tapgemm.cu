@@ -355,6 +355,7 @@ __device__ __forceinline__ void mma_role_zstack(const wdno_tapgemm_params& p, Ba
 
 __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const wdno_tapgemm_params p) {
   extern __shared__ __align__(128) uint8_t smem[];
+  pdl_trigger();
   Bars* bars = reinterpret_cast<Bars*>(smem);
   wdno_tap* s_taps = reinterpret_cast<wdno_tap*>(smem + kBarBytes);
   uint8_t* stage_base = smem + kBarBytes + kMaxTaps * 8;
@@ -411,6 +412,9 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const wdno_tapgemm
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
+  // everything above touched only plan constants (tables, bias) and on-chip state; activations, GroupNorm
+  // coefficients, statistics and outputs are the predecessors' business from here on
+  pdl_wait();
 
   if (warp >= kFirstLoadWarp) {
     // ============================================================ A loaders (GroupNorm+SiLU prologue only)
@@ -960,6 +964,8 @@ extern "C" int wdno_tapgemm(const wdno_tapgemm_params* p, void* stream) {
     if (e != cudaSuccess) return wdno::set_cuda_error(e, "tapgemm: cudaFuncSetAttribute");
     configured = 227 * 1024;
   }
-  wdno::tapgemm_kernel<<<p->grid, wdno::kThreads, smem, static_cast<cudaStream_t>(stream)>>>(*p);
+  cudaError_t le = wdno::launch_pdl(wdno::tapgemm_kernel, dim3(p->grid), dim3(wdno::kThreads), static_cast<size_t>(smem),
+                                    static_cast<cudaStream_t>(stream), *p);
+  if (le != cudaSuccess) return wdno::set_cuda_error(le, "tapgemm: launch");
   return wdno::check_launch("tapgemm");
 }
