@@ -116,6 +116,21 @@ def _install_shims():
         mod("multiprocess", Process=_Dummy)
 
 
+def install_wavelet_shims():
+    """Give the absent wavelet packages WORKING, differentiable stand-ins (oracle/wavelets_torch.py) so the reference's
+    own glue code (inference_2d.py guidance_fn / InferencePipeline, eval_ddpm_burgers.py helpers) runs unchanged."""
+    from . import wavelets_torch as wt
+    _install_shims()
+    for name, attrs in (("pywt", dict(Wavelet=wt.Wavelet)),
+                        ("ptwt", dict(wavedec3=wt.wavedec3, waverec3=wt.waverec3)),
+                        ("pytorch_wavelets", dict(DWTForward=wt.DWTForward, DWTInverse=wt.DWTInverse,
+                                                  DWT1DForward=wt.DWT1DForward, DWT1DInverse=wt.DWT1DInverse))):
+        m = sys.modules[name]
+        if getattr(m, "__file__", None) is None:  # only our shim modules, never a real installation
+            for k, v in attrs.items():
+                setattr(m, k, v)
+
+
 def _import_from(path, name, patch=None):
     """exec a reference source file as module `name` (optionally patching its text in memory)."""
     with open(path, "r") as f:
@@ -154,6 +169,25 @@ def smoke():
         ns.wave_trans_2d_error = repr(e)
     _cache["smoke"] = ns
     return ns
+
+
+def smoke_inference():
+    """-> the reference's smoke/inference_2d.py (guidance_fn, InferencePipeline) as a module.  Its imports of the dataset
+    classes and of the PhiFlow solver (`ddpm.data_2d`, `dataset.evaluate_solver`: never used by guidance_fn /
+    run_model) are dropped from the text in memory; everything else is the file as it is."""
+    if "smoke_inference" in _cache:
+        return _cache["smoke_inference"]
+    smoke()
+    install_wavelet_shims()
+    sroot = os.path.join(REF_ROOT, "smoke")
+
+    def patch(src):
+        src = src.split("if __name__")[0]
+        src = src.replace("from ddpm.data_2d import Smoke, Smoke_wave", "")
+        return src.replace("from dataset.evaluate_solver import *", "")
+    m = _import_from(os.path.join(sroot, "inference_2d.py"), "ref_inference_2d", patch=patch)
+    _cache["smoke_inference"] = m
+    return m
 
 
 def burgers():

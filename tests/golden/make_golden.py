@@ -26,8 +26,8 @@ def checksum(sd):
     return float(sum(v.double().abs().sum() for v in sd.values()))
 
 
-def sub(t):
-    return t.reshape(-1)[::STRIDE].clone()
+def sub(t, stride=STRIDE):
+    return t.reshape(-1)[::stride].clone()
 
 
 def smoke_fixture():
@@ -82,7 +82,186 @@ def burgers_fixture():
     print("burgers", out["weights_checksum"], out["y_norm"], out["sample_norm"])
 
 
+def pipeline_args(control, super_model):
+    """argparse namespace of inference_2d.py reduced to what guidance_fn / InferencePipeline read"""
+    import types
+    return types.SimpleNamespace(is_wavelet=True, wave_type="bior1.3", pad_mode="zero", is_condition_control=control,
+                                 is_condition_pad=True, is_super_model=super_model, upsample=1 if super_model else 0,
+                                 image_size=64, device="cpu", w_energy=0.5, w_init=0.1)
+
+
+def pipeline_inputs(gen, B, nt, n):
+    """physical fields [B,nt,6,n,n] (rho, v1, v2, c1, c2, smoke-out), O(1).  The pipeline strides them down to the base
+    resolution: control mode [B,256,6,64,64] -> ::8 in time; simulation mode [B,32,6,128,128] -> ::2 in space"""
+    return 0.5 * torch.randn(B, nt, 6, n, n, generator=gen)
+
+
+def smoke_guided_fixture():
+    """rows f-1 / C5: the REAL reference guidance_fn + InferencePipeline.run_model (base model, control NOT conditioned,
+    design_guidance='standard', standard_fixed_ratio=100, w_init=0.1: scripts/smoke/inf_base_control.sh) with the
+    wavelet packages replaced by oracle/wavelets_torch.py"""
+    s = ref_loader.smoke()
+    inf = ref_loader.smoke_inference()
+    torch.manual_seed(0)
+    m = s.Unet3D_with_Conv3D(dim=64, dim_mults=(1, 2, 4), channels=42).eval()
+    shape, ori_shape = [18, 34, 34], [32, 64, 64]
+    rescaler = torch.linspace(0.5, 3.0, 42).reshape(1, 1, 42, 1, 1)
+    S = 3
+    gd = s.GaussianDiffusion(m, rescaler, False, True, True, False, "bior1.3", "zero", shape, ori_shape, image_size=40,
+                             frames=24, timesteps=1000, sampling_timesteps=S, ddim_sampling_eta=1.0,
+                             standard_fixed_ratio=100.0)
+    args = pipeline_args(False, False)
+    gen = torch.Generator().manual_seed(21)
+    state = pipeline_inputs(gen, 1, 256, 64)
+    # single gradient evaluation on a fixed point
+    xg = torch.randn(1, 24, 42, 40, 40, generator=gen).clamp(-1, 1).requires_grad_()
+    init_u = state[:, 0, 0]
+    g = inf.guidance_fn(xg, args, shape, ori_shape, rescaler, w_energy=0.5, w_init=0.1, init_u=init_u)
+    # the closure of load_model (needs checkpoints there), restated
+    design_fn = lambda x, low=None, init=None, init_u=None: inf.guidance_fn(
+        x, args, shape, ori_shape, rescaler, w_energy=args.w_energy, w_init=args.w_init, low=low, init=init, init_u=init_u)
+    pipe = inf.InferencePipeline([gd], args=dict(design_fn=design_fn, design_guidance="standard"), RESCALER=rescaler,
+                                 results_path="/tmp/wdno_golden_results", args_general=args)
+    with patched_randn(NoiseTape(31)), torch.no_grad():
+        out = pipe.run_model(state)
+    res = dict(weights_checksum=checksum(m.state_dict()), state_checksum=float(state.double().abs().sum()),
+               grad_sub=sub(g, 23), grad_norm=float(g.norm()), out_sub=sub(out, 23), out_norm=float(out.norm()),
+               out_shape=tuple(out.shape), stride=23, steps=S, tape_seed=31, input_seed=21)
+    torch.save(res, os.path.join(HERE, "smoke_guided_pipeline.pt"))
+    print("smoke_guided", res["grad_norm"], res["out_norm"], res["out_shape"])
+
+
+def smoke_cascade_fixture():
+    """rows f-2 / C4: the REAL InferencePipeline.run_model with [base, super] models (is_condition_control=True,
+    upsample=1, 'space'): base DDIM -> nearest x2 coefficients -> 82-channel model on [1,24,82,80,80] -> inverse
+    transforms at both resolutions.  Guidance active in both (w_init=0.1, ratio 100)."""
+    s = ref_loader.smoke()
+    inf = ref_loader.smoke_inference()
+    torch.manual_seed(0)
+    mb = s.Unet3D_with_Conv3D(dim=64, dim_mults=(1, 2, 4), channels=42).eval()
+    torch.manual_seed(0)
+    ms = s.Unet3D_with_Conv3D(dim=64, dim_mults=(1, 2, 4), channels=82).eval()
+    shape, ori_shape = [[18, 34, 34], [18, 66, 66]], [[32, 64, 64], [32, 128, 128]]
+    rescaler = torch.linspace(0.5, 3.0, 82).reshape(1, 1, 82, 1, 1)
+    S = 2
+    kw = dict(image_size=40, frames=24, timesteps=1000, sampling_timesteps=S, ddim_sampling_eta=1.0,
+              standard_fixed_ratio=100.0)
+    gb = s.GaussianDiffusion(mb, rescaler[:, :, 40:], True, True, True, False, "bior1.3", "zero", shape[0], ori_shape[0], **kw)
+    gs = s.GaussianDiffusion(ms, rescaler, True, True, True, True, "bior1.3", "zero", shape, ori_shape, **kw)
+    args = pipeline_args(True, True)
+
+    def design_fn(x, low=None, init=None, init_u=None):  # load_model's closure (inference_2d.py:82-91)
+        import math
+        if low is not None:
+            up = int(math.log2(low.shape[-1] / 40))
+            return inf.guidance_fn(x, args, shape[up], ori_shape[up], rescaler, w_energy=args.w_energy,
+                                   w_init=args.w_init, low=low, init=init, init_u=init_u)
+        return inf.guidance_fn(x, args, shape[0], ori_shape[0], rescaler[:, :, 40:], w_energy=args.w_energy,
+                               w_init=args.w_init, low=low, init=init, init_u=init_u)
+    pipe = inf.InferencePipeline([gb, gs], args=dict(design_fn=design_fn, design_guidance="standard"),
+                                 RESCALER=rescaler, results_path="/tmp/wdno_golden_results", args_general=args)
+    gen = torch.Generator().manual_seed(22)
+    state = pipeline_inputs(gen, 1, 32, 128)
+    with patched_randn(NoiseTape(32)), torch.no_grad():
+        outs = pipe.run_model(state)
+    res = dict(weights_checksum=checksum(mb.state_dict()), super_weights_checksum=checksum(ms.state_dict()),
+               state_checksum=float(state.double().abs().sum()), stride=23, steps=S, tape_seed=32, input_seed=22,
+               out_sub=[sub(o, 23) for o in outs], out_norm=[float(o.norm()) for o in outs],
+               out_shape=[tuple(o.shape) for o in outs])
+    torch.save(res, os.path.join(HERE, "smoke_cascade_pipeline.pt"))
+    print("smoke_cascade", res["out_norm"], res["out_shape"])
+
+
+def burgers_ref_guidance_loss():
+    """burgers/ddpm_burgers/test_util.py::ddpm_guidance_loss, exec'd from the reference source text alone (the module
+    itself imports the dataset / trainer / solver stack)"""
+    import re
+    src = open(os.path.join(ref_loader.REF_ROOT, "burgers", "ddpm_burgers", "test_util.py")).read()
+    m = re.search(r"^def ddpm_guidance_loss\(.*?(?=^# Loading dataset)", src, re.S | re.M)
+    ns = {"torch": torch}
+    exec(m.group(0), ns)
+    return ns["ddpm_guidance_loss"]
+
+
+def burgers_cascade_fixture():
+    """rows f-1/f-2, Burgers: guided base DDIM (nablaJ through the inverse 2-D bior2.4 'periodization' transform,
+    J_scheduler='cosine') -> coefficient up-sampling -> 17-channel super model on 128x128 with `low` -> inverse
+    transforms, assembled from the REAL reference pieces (GaussianDiffusion, Unet2D, wave_trans.tensor_to_coef[_super],
+    wavelet_utils.upsample_coef, model_utils.get_nablaJ/get_scheduler, test_util.ddpm_guidance_loss) in the order of
+    eval_ddpm_burgers.py:108-143,151-193,279-338; targets / conditions are synthetic tensors instead of dataset rows."""
+    import types
+    b = ref_loader.burgers()
+    ref_loader.install_wavelet_shims()
+    from oracle import wavelets_torch as wt
+    gloss = burgers_ref_guidance_loss()
+    mu = b.model_utils
+    args = types.SimpleNamespace(is_wavelet=True, pad_mode="periodization", wave_type="bior2.4", is_super_model=True,
+                                 upsample_x=1, upsample_t=1, is_condition_f=True, is_condition_u0=True)
+    torch.manual_seed(0)
+    mb = b.Unet2D(dim=64, dim_mults=[1, 2, 4, 8], channels=9, out_dim=9, resnet_block_groups=1).eval()
+    torch.manual_seed(0)
+    ms = b.Unet2D(dim=64, dim_mults=[1, 2, 4, 8], channels=17, out_dim=17, resnet_block_groups=1).eval()
+    S = 3
+    R = torch.linspace(0.5, 2.0, 17).reshape(1, 17, 1, 1)
+    Rb = R[:, 8:17]
+    kw = dict(is_wavelet=True, pad_mode="periodization", wave_type="bior2.4", timesteps=1000, sampling_timesteps=S,
+              ddim_sampling_eta=0.5, is_condition_u0=True, is_condition_f=True)
+    gb = b.GaussianDiffusion(mb, seq_length=(64, 64), padded_shape=[41, 60], ori_shape=[81, 120], loss_layer_weight=Rb, **kw)
+    gs = b.GaussianDiffusion(ms, seq_length=(128, 128), padded_shape=[[81, 120]], ori_shape=[[161, 240]],
+                             is_super_model=True, upsample_t=1, upsample_x=1, loss_layer_weight=R, **kw)
+    gen = torch.Generator().manual_seed(23)
+    B = 2
+    u_t = [torch.randn(B, 81, 120, generator=gen), torch.randn(B, 161, 240, generator=gen)]
+    u_c = [torch.randn(B, 64, 64, generator=gen), torch.randn(B, 128, 128, generator=gen)]
+    fs = [torch.randn(B, 4, 64, 64, generator=gen), torch.randn(B, 4, 128, 128, generator=gen)]
+    wu, wf = 5.0, 0.01
+
+    def loss_fn_of(u_target, shape, ori_shape, Rk, is_super):
+        def loss_fn(x):
+            x = x[:, :8] * Rk[:, :8] if is_super else x * Rk
+            Yl, Yh = b.wave_trans.tensor_to_coef(x, shape)
+            u_f = wt.DWTInverse(mode="periodization", wave="bior2.4")((Yl, Yh))[:, :, :ori_shape[-2], :ori_shape[-1]]
+            return gloss(u_target[:, :ori_shape[-2], :ori_shape[-1]], u_f[:, 0], u_f[:, 1, :ori_shape[-2] - 1],
+                         wu=wu if not is_super else 0, wf=wf if not is_super else 0, condition_f=True)
+        return loss_fn
+
+    def fields(x, shape, ori_shape, sup):
+        Yl, Yh = (b.wave_trans.tensor_to_coef_super if sup else b.wave_trans.tensor_to_coef)(x, shape)
+        u_f = wt.DWTInverse(mode="periodization", wave="bior2.4")((Yl, Yh))[:, :, :ori_shape[-2], :ori_shape[-1]]
+        return x[:, :, :shape[-2], :shape[-1]][:, :8], u_f[:, 0], u_f[:, 1, :ori_shape[-2] - 1]
+    # fixed-point gradient
+    xg = torch.randn(B, 9, 64, 64, generator=gen).clamp(-1, 1)
+    g = mu.get_nablaJ(loss_fn_of(u_t[0], [41, 60], [81, 120], Rb, False))(xg.clone())
+    sched = mu.get_scheduler("cosine")
+    with patched_randn(NoiseTape(33)), torch.no_grad():
+        x = gb.sample(batch_size=B, J_scheduler=sched, u_init=u_c[0][:, :32] / Rb.squeeze()[-1],
+                      u_final=u_c[0][:, -32:] / Rb.squeeze()[-1], f=fs[0] / Rb[:, 4:8], x_gt=None,
+                      nablaJ=mu.get_nablaJ(loss_fn_of(u_t[0], [41, 60], [81, 120], Rb, False))) * Rb
+        c0, u0, f0 = fields(x, [41, 60], [81, 120], False)
+        low = b.wavelet_utils.upsample_coef(c0, [81, 120])
+        low = torch.nn.functional.pad(low, (0, 128 - low.shape[-1], 0, 128 - low.shape[-2]), "constant", 0) / R[:, 8:16]
+        x1 = gs.sample(batch_size=B, N_upsample=1, J_scheduler=sched, low=low, u_init=u_c[1][:, :64] / R.squeeze()[-1],
+                       u_final=u_c[1][:, -64:] / R.squeeze()[-1], f=fs[1] / R[:, 4:8], x_gt=None,
+                       nablaJ=mu.get_nablaJ(loss_fn_of(u_t[1], [81, 120], [161, 240], R, True))) * R
+        c1, u1, f1 = fields(x1, [81, 120], [161, 240], True)
+    res = dict(base_checksum=checksum(mb.state_dict()), super_checksum=checksum(ms.state_dict()), input_seed=23,
+               tape_seed=33, steps=S, eta=0.5, wu=wu, wf=wf, grad=g.clone(), stride=5,
+               levels=[dict(coef=sub(c, 5), u=sub(u, 5), f=sub(f, 5), shapes=(tuple(c.shape), tuple(u.shape), tuple(f.shape)),
+                            u_norm=float(u.norm())) for c, u, f in ((c0, u0, f0), (c1, u1, f1))])
+    torch.save(res, os.path.join(HERE, "burgers_cascade.pt"))
+    print("burgers_cascade", float(g.norm()), [l["u_norm"] for l in res["levels"]], [l["shapes"] for l in res["levels"]])
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "burgers_cascade":
+        burgers_cascade_fixture()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "guided":
+        smoke_guided_fixture()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "cascade":
+        smoke_cascade_fixture()
+        sys.exit(0)
     if len(sys.argv) < 2 or sys.argv[1] == "smoke":
         smoke_fixture()
     if len(sys.argv) < 2 or sys.argv[1] == "burgers":

@@ -335,12 +335,13 @@ extern "C" int wdno_chan_layernorm(const void* x, const float* gamma, const void
         xi, gamma, rs, o, static_cast<size_t>(nvox), eps);                                                 \
   }
   switch (C) {
+    case 32: WDNO_LN(4, 1); break;
     case 64: WDNO_LN(8, 1); break;
     case 128: WDNO_LN(16, 1); break;
     case 256: WDNO_LN(32, 1); break;
     case 512: WDNO_LN(32, 2); break;
     case 1024: WDNO_LN(32, 4); break;
-    default: return set_error(WDNO_E_INVALID, "chan_layernorm: C must be 64/128/256/512/1024");
+    default: return set_error(WDNO_E_INVALID, "chan_layernorm: C must be 32/64/128/256/512/1024");
   }
 #undef WDNO_LN
   return check_launch("chan_layernorm");
