@@ -104,6 +104,11 @@ typedef struct {
   int32_t n_sets;         /* entries of sets[] (<= 128; copied to shared memory) */
   int32_t zstack;         /* 1: weight tiles hold the KD depth taps of one in-plane tap stacked along N ([kz][64] rows);
                              taps[] lists in-plane taps only; one MMA per input plane updates up to 4 output planes */
+  int32_t strips;         /* >= 1.  > 1: every plane is cut into `strips` column strips of W tap-grid columns each; a strip is
+                             a work-item dimension of its own, its slab carries real neighbour columns as halo
+                             (Wp = W + 2*px) instead of the shared zero run.  Keeps the haloed slab small for wide planes
+                             with large in-plane kernels (7x7 on 80x80).  Only src_mode 0, out_mode 0/2. */
+  int32_t Wfull;          /* row width of the source / output tensors (== W when strips == 1) */
 } wdno_tapgemm_params;
 
 /* bytes of dynamic shared memory the plan needs, or <0 */

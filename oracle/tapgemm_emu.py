@@ -30,6 +30,7 @@ def emulate(plan, src0, src1=None, coef0=None, coef1=None, resid=None, groups=8,
     else:
         H, W = Hs, Ws
     p = plan._plan(B, D, H, W)
+    Wfull, W = W, p.W            # p.W: tap-grid columns of one strip (== Wfull when p.strips == 1)
     pk = plan._packed[(p.KC, bool(p.zstack))]
     chunks = _table(pk["chunks"], NChunk)
     sets = _table(pk["sets"], KSet)
@@ -46,17 +47,18 @@ def emulate(plan, src0, src1=None, coef0=None, coef1=None, resid=None, groups=8,
     positions = H * p.Wp
     ptiles = (positions + 128 * p.PT - 1) // (128 * p.PT)
     zgroups = (D + p.ZT - 1) // p.ZT
-    Ho, Wo = (2 * H, 2 * W) if plan.kind == "up144" else (H, W)
+    Ho, Wo = (2 * H, 2 * Wfull) if plan.kind == "up144" else (H, Wfull)
     cout = plan.cout
     if out_fp32_bfchw:
-        out = np.zeros((B, D, cout, H, W), np.float32)
+        out = np.zeros((B, D, cout, H, Wfull), np.float32)
     else:
         out = np.zeros((B, D, Ho, Wo, cout), np.float32)
     stats = np.zeros((B, groups, 2), np.float64)
     bias = None if plan.bias is None else plan.bias.cpu().numpy()
     res = None if resid is None else resid.float().numpy()
     cpg = max(1, cout // groups)
-    for b in range(B):
+    for bs in range(B * p.strips):
+        b, xs0 = bs // p.strips, (bs % p.strips) * W
         for zg in range(zgroups):
             for pt in range(ptiles):
                 for nc in range(p.n_chunks):
@@ -75,8 +77,8 @@ def emulate(plan, src0, src1=None, coef0=None, coef1=None, resid=None, groups=8,
                                 continue
                             q = o0 + np.arange(S)
                             yp, xp = q // p.Wp, q % p.Wp
-                            y, x = yp - p.py, xp - p.px
-                            ok = (y >= 0) & (y < H) & (x >= 0) & (x < W)
+                            y, x = yp - p.py, xp - p.px + xs0
+                            ok = (y >= 0) & (y < H) & (x >= 0) & (x < Wfull)
                             ys, xs = y.copy(), x.copy()
                             if p.src_mode == 1:
                                 ys, xs = 2 * y + st.ph_y, 2 * x + st.ph_x
@@ -117,8 +119,9 @@ def emulate(plan, src0, src1=None, coef0=None, coef1=None, resid=None, groups=8,
                             continue
                         for r in range(128):
                             o = o0 + pi * 128 + r
-                            y, x = o // p.Wp, o % p.Wp
-                            if y >= H or x >= W:
+                            y, xl = o // p.Wp, o % p.Wp
+                            x = xl + xs0
+                            if y >= H or xl >= W or x >= Wfull:
                                 continue
                             v = acc[a, r, :ci.n_valid].astype(np.float32)
                             ch = slice(ci.out_ch_off, ci.out_ch_off + ci.n_valid)

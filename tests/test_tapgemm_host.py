@@ -107,3 +107,36 @@ def test_fused_affine_silu_on_load():
     act = F.silu(x * a[:, :, None, None, None] + c[:, :, None, None, None]).half().float()
     ref = F.conv3d(act, w, padding=1)
     assert torch.allclose(uncl(out), ref, atol=2e-3, rtol=1e-3)
+
+
+def test_column_strips_7x7_and_3x3(monkeypatch):
+    """strip mode (p.strips > 1): every plane cut into column strips with real neighbour columns as halo -- forced here
+    on small grids (the planner only picks it for wide planes whose kz-stacked plan does not fit otherwise), for the
+    generic and the kz-stacked issue schemes, including a width that the strips do not divide."""
+    torch.manual_seed(6)
+    for (cin, cout, k, B, D, H, W, strips, ntile) in ((16, 64, 7, 1, 4, 5, 11, 2, None), (16, 16, 3, 2, 2, 4, 9, 3, 16),
+                                                      (32, 64, 3, 1, 5, 6, 8, 2, None)):
+        x = torch.randn(B, cin, D, H, W).half().float()
+        w = (torch.randn(cout, cin, k, k, k) * 0.05).half().float()
+        bias = torch.randn(cout)
+        monkeypatch.setenv("WDNO_FORCE_STRIPS", str(strips))
+        plan = TapGemm(w, bias, device="cpu", n_tile=ntile, kc=16)
+        p = plan._plan(B, D, H, W)
+        assert p.strips == strips and p.Wfull == W and p.W == (W + strips - 1) // strips and p.Wp == p.W + 2 * (k // 2)
+        out, stats = emulate(plan, cl(x), want_stats=True, groups=2)
+        ref = F.conv3d(x, w, bias, padding=k // 2)
+        assert torch.allclose(uncl(out), ref, atol=3e-4, rtol=1e-4), (cin, cout, k)
+        rs = ref.reshape(B, 2, -1)
+        assert torch.allclose(stats[:, :, 0].float(), rs.sum(-1), atol=2e-2)
+        monkeypatch.delenv("WDNO_FORCE_STRIPS")
+
+
+def test_planner_picks_strips_for_the_super_resolution_stem():
+    """82(->96 padded) -> 64 channels, 7x7x7 on 24x80x80 (config C4): without strips the kz-stacked plan does not fit
+    227 KB and the layer falls back to unstacked N = 64 MMAs (measured 261 TFLOP/s); with strips it fits"""
+    w = torch.zeros(64, 82, 7, 7, 7)
+    plan = TapGemm(w, None, src_channels=(96,), device="cpu")
+    p = plan._plan(1, 24, 80, 80)
+    assert p.zstack == 1 and p.strips == 2 and p.W == 40 and p.Wp == 46 and p.Wfull == 80
+    p40 = TapGemm(torch.zeros(64, 42, 7, 7, 7), None, src_channels=(48,), device="cpu")._plan(1, 24, 40, 40)
+    assert p40.zstack == 1 and p40.strips == 1 and p40.Wp == 43

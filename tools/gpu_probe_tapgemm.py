@@ -217,13 +217,46 @@ def run_case(i):
         errs.append(relerr(uncl(out), F.conv3d(torch.cat([x0, x1], 1), w[:, :, None, None, None], b) + r))
         res["errs"] = errs
         res["err"] = max(errs)
+    elif i == 13:
+        res["name"] = "column strips: 7x7x7 82(96)->64 at 24x80x80 (planner-chosen), forced strips on 3x3x3 64->64 24x40x44 + stats, fp32 out"
+        x = torch.zeros(1, 96, 24, 80, 80, device=dev)
+        x[:, :82] = rnd(1, 82, 24, 80, 80)
+        w, b = rnd(64, 82, 7, 7, 7, scale=0.01), rnd(64)
+        plan = TapGemm(w, b, src_channels=(96,), device=dev)
+        out = plan(cl(x))
+        pl = plan._plan(1, 24, 80, 80)
+        res["strips"], res["zstack"] = int(pl.strips), int(pl.zstack)
+        ref = F.conv3d(x[:, :82], w, b, padding=3)
+        errs = [relerr(uncl(out), ref)]
+        if pl.strips < 2 or not pl.zstack:
+            errs.append(1.0)  # the planner must choose strips + the stacked scheme here
+        os.environ["WDNO_FORCE_STRIPS"] = "3"
+        try:
+            x = rnd(2, 64, 24, 40, 44)
+            w, b = rnd(64, 64, 3, 3, 3, scale=0.03), rnd(64)
+            plan = TapGemm(w, b, device=dev)
+            stats = torch.zeros(2, 8, 2, dtype=torch.float64, device=dev)
+            out = plan(cl(x), stats=stats, groups=8)
+            ref = F.conv3d(x, w, b, padding=1)
+            errs.append(relerr(uncl(out), ref))
+            rs = ref.reshape(2, 8, -1).double()
+            errs.append(relerr(stats[:, :, 1], (rs ** 2).sum(-1)))
+            w2, b2 = rnd(42, 64, 3, 3, 3, scale=0.03), rnd(42)
+            plan2 = TapGemm(w2, b2, device=dev)
+            out2 = plan2(cl(x), out_fp32_bfchw=True)
+            errs.append(relerr(out2.permute(0, 2, 1, 3, 4), F.conv3d(x, w2, b2, padding=1)))
+            res["forced_strips"] = int(plan._plan(2, 24, 40, 44).strips)
+        finally:
+            del os.environ["WDNO_FORCE_STRIPS"]
+        res["errs"] = errs
+        res["err"] = max(errs)
     else:
         return None
     torch.cuda.synchronize()
     return res
 
 
-NCASES = 13
+NCASES = 14
 
 
 def main():

@@ -34,9 +34,23 @@ from wdno_b200 import _abi  # noqa: E402
 for n in list(_abi.SIGNATURES) + ["wdno_tapgemm"]:
     setattr(L, n, Wrap(n, getattr(L, n)))
 
-B = int(os.environ.get("B", str(B_PER_GPU)))
-m, gd = build_engine(250)
-x = torch.randn((B,) + SHAPE, device="cuda")
+CONFIG = os.environ.get("CONFIG", "C3")   # C3 (default) | C4 (82-ch super model, 80x80) | C2 (Burgers Unet2D, batch 256)
+if CONFIG == "C2":
+    from wdno_b200.unet2d import Unet2D
+    B = int(os.environ.get("B", "256"))
+    torch.manual_seed(0)
+    m = Unet2D(dim=128, dim_mults=[1, 2, 4, 8], channels=9, out_dim=9, resnet_block_groups=1).cuda().eval()
+    x = torch.randn(B, 9, 64, 64, device="cuda")
+elif CONFIG == "C4":
+    from wdno_b200.unet3d import Unet3D_with_Conv3D
+    B = int(os.environ.get("B", str(B_PER_GPU)))
+    torch.manual_seed(0)
+    m = Unet3D_with_Conv3D(dim=64, dim_mults=(1, 2, 4), channels=82).cuda().eval()
+    x = torch.randn(B, 24, 82, 80, 80, device="cuda")
+else:
+    B = int(os.environ.get("B", str(B_PER_GPU)))
+    m, gd = build_engine(250)
+    x = torch.randn((B,) + SHAPE, device="cuda")
 t = torch.full((B,), 500, device="cuda")
 with torch.no_grad():
     for _ in range(3):
@@ -53,6 +67,6 @@ for name, e0, e1 in recs:
     d[0] += 1
     d[1] += e0.elapsed_time(e1)
 tot = sum(v[1] for v in agg.values()) / n
-print(f"sum of launches {tot:.3f} ms / forward")
+print(f"[{CONFIG}] batch {B}: sum of launches {tot:.3f} ms / forward")
 for k, (c, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     print(f"{k:28s} x{c // n:3d} {ms / n:8.3f} ms  {100 * ms / n / tot:5.1f}%")

@@ -76,9 +76,11 @@ static_assert(sizeof(Bars) <= kBarBytes, "barrier block too large");
 // work item w -> (b, zg, pt) and the N-chunk range it covers
 struct Work {
   int b, zg, pt, nc0, nc1;
+  int xs0;  // first tensor column of the work item's column strip (0 unless p.strips > 1)
 };
 
-__device__ __forceinline__ Work decode_work(int w, int n_chunks, int ptiles, int zgroups, int reuse) {
+__device__ __forceinline__ Work decode_work(int w, int n_chunks, int ptiles, int zgroups, int reuse, int strips = 1,
+                                            int strip_w = 0) {
   Work k;
   int r = w;
   if (reuse) {
@@ -92,7 +94,13 @@ __device__ __forceinline__ Work decode_work(int w, int n_chunks, int ptiles, int
   k.pt = r % ptiles;
   r /= ptiles;
   k.zg = r % zgroups;
-  k.b = r / zgroups;
+  r /= zgroups;
+  k.b = r;
+  k.xs0 = 0;
+  if (strips > 1) {
+    k.b = r / strips;
+    k.xs0 = (r - k.b * strips) * strip_w;
+  }
   return k;
 }
 
@@ -380,7 +388,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const wdno_tapgemm
   const int positions = p.H * p.Wp;
   const int ptiles = (positions + 128 * p.PT - 1) / (128 * p.PT);
   const int zgroups = (p.D + p.ZT - 1) / p.ZT;
-  const int n_work = p.B * zgroups * ptiles * (p.reuse ? 1 : p.n_chunks);
+  const int n_work = p.B * p.strips * zgroups * ptiles * (p.reuse ? 1 : p.n_chunks);
 
   // ---------------------------------------------------------------- setup
   if (threadIdx.x == 0) {
@@ -432,12 +440,12 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const wdno_tapgemm
       const int SP = kLoadThreads >> ch_shift;
       const int step_y = SP / p.Wp, step_x = SP - step_y * p.Wp;
       const uint32_t wp_magic = 0xFFFFFFFFu / static_cast<uint32_t>(p.Wp) + 1u;
-      int Hs = p.H, Ws = p.W;
-      if (p.src_mode == 1) { Hs = 2 * p.H; Ws = 2 * p.W; }
-      if (p.src_mode == 2) { Hs = p.H >> 1; Ws = p.W >> 1; }
+      int Hs = p.H, Ws = p.Wfull;
+      if (p.src_mode == 1) { Hs = 2 * p.H; Ws = 2 * p.Wfull; }
+      if (p.src_mode == 2) { Hs = p.H >> 1; Ws = p.Wfull >> 1; }
       uint32_t slot = 0, ph = 0;
       for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-        const Work wk = decode_work(w, p.n_chunks, ptiles, zgroups, p.reuse);
+        const Work wk = decode_work(w, p.n_chunks, ptiles, zgroups, p.reuse, p.strips, p.W);
         const wdno_nchunk ci = s_chunks[wk.nc0];
         const int q0 = wk.pt * 128 * p.PT + s_first;
         const int yp0 = static_cast<int>(__umulhi(static_cast<uint32_t>(q0), wp_magic));
@@ -455,8 +463,8 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const wdno_tapgemm
             ptx::mbar_wait(&bars->slab_empty[slot], ph ^ 1u);
             int yp = yp0, xp = xp0;
             for (int sq = s_first; sq < S; sq += SP) {
-              const int y = yp - p.py, x = xp - p.px;
-              const bool ok = zok && y >= 0 && y < p.H && x >= 0 && x < p.W;
+              const int y = yp - p.py, x = xp - p.px + wk.xs0;
+              const bool ok = zok && y >= 0 && y < p.H && x >= 0 && x < p.Wfull;
               int so = y * Ws + x;
               if (p.src_mode == 1) so = 2 * y * Ws + 2 * x;
               if (p.src_mode == 2) so = (y >> 1) * Ws + (x >> 1);
@@ -491,18 +499,19 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const wdno_tapgemm
     const int SP = kProdThreads >> ch_shift;  // positions covered per sweep of all producer threads
     const int n_it = (S - s_first + SP - 1) / SP;  // this thread's positions per plane
     const uint32_t wp_magic = 0xFFFFFFFFu / static_cast<uint32_t>(p.Wp) + 1u;  // exact q / Wp for q * Wp < 2^32
-    int Hs = p.H, Ws = p.W;
-    if (p.src_mode == 1) { Hs = 2 * p.H; Ws = 2 * p.W; }
-    if (p.src_mode == 2) { Hs = p.H >> 1; Ws = p.W >> 1; }
+    int Hs = p.H, Ws = p.Wfull;
+    if (p.src_mode == 1) { Hs = 2 * p.H; Ws = 2 * p.Wfull; }
+    if (p.src_mode == 2) { Hs = p.H >> 1; Ws = p.Wfull >> 1; }
     const bool any_act = (p.coef_a[0] != nullptr) || (p.coef_a[1] != nullptr);
 
     // source position (ys * Ws + xs, without the space-to-depth phase) of slab position index i, or a code
-    auto src_pos = [&](int q0, int i) -> int {
+    // (xs0: first tensor column of the work item's column strip; the strip's halo columns are real neighbours)
+    auto src_pos = [&](int q0, int xs0, int i) -> int {
       if (i >= n_it) return kSkip;
       const int q = q0 + s_first + i * SP;
       const int yp = static_cast<int>(__umulhi(static_cast<uint32_t>(q), wp_magic));
-      const int y = yp - p.py, x = q - yp * p.Wp - p.px;
-      if (y < 0 || y >= p.H || x < 0 || x >= p.W) return kZero;
+      const int y = yp - p.py, x = q - yp * p.Wp - p.px + xs0;
+      if (y < 0 || y >= p.H || x < 0 || x >= p.Wfull) return kZero;
       if (p.src_mode == 1) return 2 * y * Ws + 2 * x;
       if (p.src_mode == 2) return (y >> 1) * Ws + (x >> 1);
       return y * Ws + x;
@@ -512,20 +521,21 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const wdno_tapgemm
     struct Cursor {
       int w, si, j, nset, set_begin;
       uint32_t slot, ph;
-      int b, z0, q0;
+      int b, z0, q0, xs0;
       int off[kIt];
     };
     auto load_work = [&](Cursor& cu) {
       if (cu.w >= n_work) return;
-      const Work wk = decode_work(cu.w, p.n_chunks, ptiles, zgroups, p.reuse);
+      const Work wk = decode_work(cu.w, p.n_chunks, ptiles, zgroups, p.reuse, p.strips, p.W);
       const wdno_nchunk ci = s_chunks[wk.nc0];  // with reuse every chunk shares chunk 0's K-sets
       cu.nset = ci.set_count;
       cu.set_begin = ci.set_begin;
       cu.b = wk.b;
       cu.z0 = wk.zg * p.ZT;
       cu.q0 = wk.pt * 128 * p.PT;
+      cu.xs0 = wk.xs0;
 #pragma unroll
-      for (int i = 0; i < kIt; ++i) cu.off[i] = src_pos(cu.q0, i);
+      for (int i = 0; i < kIt; ++i) cu.off[i] = src_pos(cu.q0, cu.xs0, i);
     };
     auto advance = [&](Cursor& cu) {
       if (++cu.slot == static_cast<uint32_t>(p.NSLOT)) { cu.slot = 0; cu.ph ^= 1u; }
@@ -559,7 +569,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const wdno_tapgemm
         }
       }
       for (int i = kIt; i < n_it; ++i) {  // long slabs (2-D layers with PT = 4): offsets recomputed
-        const int o = src_pos(cu.q0, i);
+        const int o = src_pos(cu.q0, cu.xs0, i);
         const bool ok = zok && (o >= 0);
         ptx::cp_async16_zfill(dst + static_cast<uint32_t>(i * SP) * 16u, ok ? plane + static_cast<size_t>(o) * csrc : plane,
                               ok ? 16u : 0u);
@@ -607,7 +617,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const wdno_tapgemm
           if (cu.off[i0 + u] >= 0) *reinterpret_cast<uint4*>(dst + static_cast<size_t>((i0 + u) * SP) * 16) = v[u];
       }
       for (int i = kIt; i < n_it; ++i) {
-        if (src_pos(cu.q0, i) >= 0) {
+        if (src_pos(cu.q0, cu.xs0, i) >= 0) {
           uint4 v = *reinterpret_cast<const uint4*>(dst + static_cast<size_t>(i * SP) * 16);
           act8(v);
           *reinterpret_cast<uint4*>(dst + static_cast<size_t>(i * SP) * 16) = v;
@@ -698,12 +708,12 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const wdno_tapgemm
     uint8_t* stage_w = stage_base + warp * kStageWarp;
     uint8_t* stage_row = stage_w + lane * kStageRow;
     const uint32_t wp_magic = 0xFFFFFFFFu / static_cast<uint32_t>(p.Wp) + 1u;  // exact o / Wp for o * Wp < 2^32
-    const long long plane_elems = static_cast<long long>(p.H) * p.W * p.out_c * ((p.out_mode == 1) ? 4 : 1);
+    const long long plane_elems = static_cast<long long>(p.H) * p.Wfull * p.out_c * ((p.out_mode == 1) ? 4 : 1);
     const bool has_bias = p.bias != nullptr, has_stats = p.stats != nullptr;
     uint32_t acnt = 0;
     PROF_DECL;
     for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-      const Work wk = decode_work(w, p.n_chunks, ptiles, zgroups, p.reuse);
+      const Work wk = decode_work(w, p.n_chunks, ptiles, zgroups, p.reuse, p.strips, p.W);
       const int o0 = wk.pt * 128 * p.PT;
       const int z0 = wk.zg * p.ZT;
       for (int nc = wk.nc0; nc < wk.nc1; ++nc, ++acnt) {
@@ -721,17 +731,18 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const wdno_tapgemm
           // row geometry: shared by the ZT planes of this position tile
           const int o = o0 + pi * 128 + row;
           const int y = static_cast<int>(__umulhi(static_cast<uint32_t>(o), wp_magic));
-          const int x = o - y * p.Wp;
-          const bool valid_yx = (y < p.H) && (x < p.W);
+          const int xl = o - y * p.Wp;   // column inside the strip's tap grid
+          const int x = xl + wk.xs0;     // tensor column
+          const bool valid_yx = (y < p.H) && (xl < p.W) && (x < p.Wfull);
           long long rbase;
           if (p.out_mode == 0) {
-            rbase = ((static_cast<long long>(wk.b) * p.D * p.H + y) * p.W + x) * p.out_c + ci.out_ch_off;
+            rbase = ((static_cast<long long>(wk.b) * p.D * p.H + y) * p.Wfull + x) * p.out_c + ci.out_ch_off;
           } else if (p.out_mode == 1) {
-            rbase = ((static_cast<long long>(wk.b) * p.D * (2 * p.H) + (2 * y + ci.ph_y)) * (2 * p.W) + (2 * x + ci.ph_x)) * p.out_c +
+            rbase = ((static_cast<long long>(wk.b) * p.D * (2 * p.H) + (2 * y + ci.ph_y)) * (2 * p.Wfull) + (2 * x + ci.ph_x)) * p.out_c +
                     ci.out_ch_off;
           } else {
-            rbase = (static_cast<long long>(wk.b) * p.D * p.out_c + ci.out_ch_off) * (static_cast<long long>(p.H) * p.W) +
-                    static_cast<long long>(y) * p.W + x;
+            rbase = (static_cast<long long>(wk.b) * p.D * p.out_c + ci.out_ch_off) * (static_cast<long long>(p.H) * p.Wfull) +
+                    static_cast<long long>(y) * p.Wfull + x;
           }
           for (int za = 0; za < p.ZT; ++za, ++a) {
             const int z = z0 + za;
@@ -740,9 +751,9 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const wdno_tapgemm
                                   static_cast<uint32_t>((p.zstack ? (p.ZT - 1 - za) : (za * p.PT + pi)) * NPAD);
             if (p.out_mode == 2) {
               // fp32 [B, D, C, H, W]: consecutive lanes are consecutive x -> already coalesced per channel
-              const long long obase = rbase + static_cast<long long>(z) * p.out_c * (static_cast<long long>(p.H) * p.W);
+              const long long obase = rbase + static_cast<long long>(z) * p.out_c * (static_cast<long long>(p.H) * p.Wfull);
               float* o32 = static_cast<float*>(p.out);
-              const size_t cs = static_cast<size_t>(p.H) * p.W;
+              const size_t cs = static_cast<size_t>(p.H) * p.Wfull;
               for (int c16 = 0; c16 < n16; ++c16) {
                 uint32_t r[16];
                 ptx::tmem_ld16(tcol + static_cast<uint32_t>(c16 * 16), r);
@@ -926,6 +937,11 @@ static int validate(const wdno_tapgemm_params* p) {
   if (p->out_mode != 2 && (p->out_c % 8)) return set_error(WDNO_E_INVALID, "tapgemm: fp16 output channels must be a multiple of 8");
   if (p->stats && (p->cpg % 8 || p->cpg < 8)) return set_error(WDNO_E_INVALID, "tapgemm: cpg must be a multiple of 8");
   if (p->src_mode == 2 && ((p->H & 1) || (p->W & 1))) return set_error(WDNO_E_INVALID, "tapgemm: up2 needs even H,W");
+  if (p->strips < 1 || p->Wfull < 1) return set_error(WDNO_E_INVALID, "tapgemm: strips / Wfull must be >= 1");
+  if (p->strips == 1 && p->Wfull != p->W) return set_error(WDNO_E_INVALID, "tapgemm: Wfull must equal W without strips");
+  if (p->strips > 1 && (p->src_mode != 0 || p->out_mode == 1 || p->Wp != p->W + 2 * p->px ||
+                        static_cast<int64_t>(p->W) * p->strips < p->Wfull || static_cast<int64_t>(p->W) * (p->strips - 1) >= p->Wfull))
+    return set_error(WDNO_E_INVALID, "tapgemm: strips need src_mode 0, out_mode 0/2, Wp = W + 2*px and strips*W covering Wfull");
   if (smem_bytes_of(p) > 227 * 1024) return set_error(WDNO_E_INVALID, "tapgemm: shared-memory plan exceeds 227 KB");
   if (p->grid < 1) return set_error(WDNO_E_INVALID, "tapgemm: grid must be >= 1");
   if (p->zstack && (p->ZT != 4 || p->PT != 1 || p->N != 64 || (p->KD != 3 && p->KD != 7) || p->reuse || p->NSLOT < p->ZT + p->KD - 1))

@@ -250,10 +250,40 @@ class TapGemm:
         key = (B, D, H, W)
         if key in self._launch:
             return self._launch[key]
+        # Column strips: a wide plane with a large in-plane kernel (7x7 on 80x80) needs a haloed slab of
+        # 128 + (KH-1)*Wp + KW-1 positions per 128 outputs -- too big for the kz-stacked plan's ZT+KD-1 resident planes.
+        # Cutting the plane into strips of ~40 columns (each a work-item dimension with real neighbour columns as halo)
+        # shrinks Wp and brings the stacked plan back (measured on the 82->64 7^3 stem at 80x80: 261 -> see DESIGN.md).
+        cands = [1]
+        if (self.kind == "conv" and not self.up2 and self.KD in (3, 7) and self.N == 64 and D >= 4 and self.KH * self.KW > 9
+                and int(os.environ.get("WDNO_STRIPS", "1"))):
+            cands += [s_ for s_ in (2, 3, 4) if (W + s_ - 1) // s_ >= 32]
+        if os.environ.get("WDNO_FORCE_STRIPS"):
+            cands = [int(os.environ["WDNO_FORCE_STRIPS"])]
+        chosen = None
+        for strips in cands:
+            p = self._plan_strips(B, D, H, W, strips)
+            if chosen is None:
+                chosen = p
+            if p is not None and (p.zstack or os.environ.get("WDNO_FORCE_STRIPS")):
+                chosen = p
+                break
+        if chosen is None:
+            raise ValueError(f"tapgemm: no shared-memory plan for grid {(B, D, H, W)} taps {(self.KD, self.KH, self.KW)}")
+        self._launch[key] = chosen
+        return chosen
+
+    def _plan_strips(self, B, D, H, Wfull, strips):
         KD, KH, KW = self.KD, self.KH, self.KW
-        # padded row width: ONE shared run of KW//2 zero columns per row -- the left pad of row y+1 doubles as the right
-        # pad of row y (positions are linearised, so x + kx simply runs into the next row's pad)
-        Wp = W + KW // 2
+        if strips == 1:
+            # padded row width: ONE shared run of KW//2 zero columns per row -- the left pad of row y+1 doubles as the
+            # right pad of row y (positions are linearised, so x + kx simply runs into the next row's pad)
+            W = Wfull
+            Wp = W + KW // 2
+        else:
+            # strip of W tap-grid columns with real neighbour columns on both sides
+            W = (Wfull + strips - 1) // strips
+            Wp = W + 2 * (KW // 2)
         maxshift = (KH - 1) * Wp + (KW - 1)
         ctot = self._virtual_cin()
         ncn = self.cout_pad // self.N
@@ -348,7 +378,7 @@ class TapGemm:
                     if not f:
                         continue
                     ptiles_ = (H * Wp + 128 * PT - 1) // (128 * PT)
-                    items = B * ((D + ZT - 1) // ZT) * ptiles_ * ncn
+                    items = B * strips * ((D + ZT - 1) // ZT) * ptiles_ * ncn
                     waves = (items + sms_ - 1) // sms_
                     per_item = ZT * PT * ntaps * (ctot // 16) * mma_cyc + 3000 + P * (ctot // KC) * 800 * PT
                     est = waves * per_item
@@ -356,7 +386,7 @@ class TapGemm:
                     if best is None or score > best[0]:
                         best = (score, (KC, ZT, PT, 0) + f)
             if best is None:
-                raise ValueError(f"tapgemm: no shared-memory plan for grid {(B, D, H, W)} taps {(KD, KH, KW)}")
+                return None
             plan = best[1]
         KC, ZT, PT, reuse, S_pad, NSLOT, NBST, TPS = plan
         pk = self._pack(KC, bool(zstack))
@@ -368,12 +398,13 @@ class TapGemm:
         positions = H * Wp
         ptiles = (positions + 128 * PT - 1) // (128 * PT)
         zgroups = (D + ZT - 1) // ZT
-        n_work = B * zgroups * ptiles * (1 if reuse else pk["n_chunks"])
+        n_work = B * strips * zgroups * ptiles * (1 if reuse else pk["n_chunks"])
         sms = (torch.cuda.get_device_properties(self.device).multi_processor_count
                if self.device.type == "cuda" else 148)
         p = TapGemmParams()
         p.src_mode = {"conv": 2 if self.up2 else 0, "down144": 1, "unshuffle": 1, "up144": 0}[self.kind]
         p.B, p.D, p.H, p.W = B, D, H, W
+        p.strips, p.Wfull = strips, Wfull
         p.KD, p.pz, p.py, p.px = KD, KD // 2, KH // 2, KW // 2
         p.Wp, p.maxshift = Wp, maxshift
         p.ZT, p.PT, p.KC, p.N, p.n_chunks = ZT, PT, KC, self.N, pk["n_chunks"]
@@ -387,7 +418,6 @@ class TapGemm:
         p.n_sets = pk["n_sets"]
         p.zstack = zstack
         p.grid = max(1, min(n_work, sms))
-        self._launch[key] = p
         return p
 
     # ------------------------------------------------------------------ launch
