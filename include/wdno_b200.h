@@ -109,6 +109,10 @@ typedef struct {
                              (Wp = W + 2*px) instead of the shared zero run.  Keeps the haloed slab small for wide planes
                              with large in-plane kernels (7x7 on 80x80).  Only src_mode 0, out_mode 0/2. */
   int32_t Wfull;          /* row width of the source / output tensors (== W when strips == 1) */
+  int32_t fold;           /* 1: the D planes of a "sample" are D independent samples of a 2-D layer folded into the depth
+                             axis (KD == 1 only) so that ZT of them share every weight tile: GroupNorm coefficients and
+                             statistics are indexed by b*D + z instead of b */
+  int32_t reserved0;
 } wdno_tapgemm_params;
 
 /* bytes of dynamic shared memory the plan needs, or <0 */

@@ -31,6 +31,9 @@ def emulate(plan, src0, src1=None, coef0=None, coef1=None, resid=None, groups=8,
         H, W = Hs, Ws
     p = plan._plan(B, D, H, W)
     Wfull, W = W, p.W            # p.W: tap-grid columns of one strip (== Wfull when p.strips == 1)
+    B_log, D_log = B, D
+    B, D = p.B, p.D              # batch folded into depth planes for 2-D layers (p.fold): B*D unchanged
+    assert B * D == B_log * D_log and (p.fold or (B, D) == (B_log, D_log))
     pk = plan._packed[(p.KC, bool(p.zstack))]
     chunks = _table(pk["chunks"], NChunk)
     sets = _table(pk["sets"], KSet)
@@ -39,7 +42,8 @@ def emulate(plan, src0, src1=None, coef0=None, coef1=None, resid=None, groups=8,
     KC, N = p.KC, p.N
     rows = N * (p.KD if p.zstack else 1)   # rows of one weight tile (kz-stacked tiles hold [kz][N])
     tile_elems = rows * KC
-    srcs = [src0.float().numpy(), None if src1 is None else src1.float().numpy()]
+    fold5 = lambda t: None if t is None else t.float().numpy().reshape((B, D) + tuple(t.shape[2:]))
+    srcs = [fold5(src0), fold5(src1)]
     coefs = [coef0, coef1]
     NACC = p.ZT * p.PT
     P = p.ZT + p.KD - 1
@@ -53,9 +57,9 @@ def emulate(plan, src0, src1=None, coef0=None, coef1=None, resid=None, groups=8,
         out = np.zeros((B, D, cout, H, Wfull), np.float32)
     else:
         out = np.zeros((B, D, Ho, Wo, cout), np.float32)
-    stats = np.zeros((B, groups, 2), np.float64)
+    stats = np.zeros((B_log, groups, 2), np.float64)
     bias = None if plan.bias is None else plan.bias.cpu().numpy()
-    res = None if resid is None else resid.float().numpy()
+    res = fold5(resid)
     cpg = max(1, cout // groups)
     for bs in range(B * p.strips):
         b, xs0 = bs // p.strips, (bs % p.strips) * W
@@ -88,8 +92,9 @@ def emulate(plan, src0, src1=None, coef0=None, coef1=None, resid=None, groups=8,
                             v = src[b, zi, ysc, xsc, st.ch_off:st.ch_off + KC]
                             if coefs[st.src] is not None:
                                 a, c = coefs[st.src]
-                                a = a[b, st.ch_off:st.ch_off + KC].numpy()
-                                c = c[b, st.ch_off:st.ch_off + KC].numpy()
+                                smp = b * D + zi if p.fold else b
+                                a = a[smp, st.ch_off:st.ch_off + KC].numpy()
+                                c = c[smp, st.ch_off:st.ch_off + KC].numpy()
                                 t = a * v + c
                                 v = t / (1.0 + np.exp(-t))
                                 v = v.astype(np.float16).astype(np.float32)
@@ -130,8 +135,9 @@ def emulate(plan, src0, src1=None, coef0=None, coef1=None, resid=None, groups=8,
                             if want_stats:
                                 for k in range(ci.n_valid):
                                     g = (ci.out_ch_off + k) // cpg
-                                    stats[b, g, 0] += v[k]
-                                    stats[b, g, 1] += float(v[k]) ** 2
+                                    smp = b * D + z if p.fold else b
+                                    stats[smp, g, 0] += v[k]
+                                    stats[smp, g, 1] += float(v[k]) ** 2
                             if out_fp32_bfchw:
                                 out[b, z, ch, y, x] = v
                             elif plan.kind == "up144":
@@ -143,4 +149,5 @@ def emulate(plan, src0, src1=None, coef0=None, coef1=None, resid=None, groups=8,
                                 if res is not None:
                                     v = v + res[b, z, y, x, ch]
                                 out[b, z, y, x, ch] = v
+    out = out.reshape((B_log, D_log) + out.shape[2:])
     return torch.from_numpy(out), torch.from_numpy(stats)

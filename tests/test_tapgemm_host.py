@@ -140,3 +140,32 @@ def test_planner_picks_strips_for_the_super_resolution_stem():
     assert p.zstack == 1 and p.strips == 2 and p.W == 40 and p.Wp == 46 and p.Wfull == 80
     p40 = TapGemm(torch.zeros(64, 42, 7, 7, 7), None, src_channels=(48,), device="cpu")._plan(1, 24, 40, 40)
     assert p40.zstack == 1 and p40.strips == 1 and p40.Wp == 43
+
+
+def test_batch_folding_of_2d_layers(monkeypatch):
+    """2-D layers (D == 1): samples folded into depth planes so that ZT of them share each weight tile; GroupNorm
+    coefficients and statistics stay per sample (p.fold)"""
+    torch.manual_seed(7)
+    monkeypatch.setenv("WDNO_FOLD", "force")
+    B, H, W = 8, 8, 8
+    x = torch.randn(B, 32, 1, H, W).half().float()
+    a, c = torch.randn(B, 32), torch.randn(B, 32)
+    w = (torch.randn(128, 32, 3, 3) * 0.1).half().float()
+    bias = torch.randn(128)
+    plan = TapGemm(w, bias, device="cpu")
+    p = plan._plan(B, 1, H, W)
+    assert p.fold == 1 and p.B * p.D == B and p.D == 4 and p.ZT in (4, 2, 1)
+    out, stats = emulate(plan, cl(x), coef0=(a, c), want_stats=True, groups=4)
+    act = F.silu(x * a[:, :, None, None, None] + c[:, :, None, None, None]).half().float()
+    ref = F.conv2d(act[:, :, 0], w, bias, padding=1)
+    assert out.shape == (B, 1, H, W, 128)
+    assert torch.allclose(uncl(out)[:, :, 0], ref, atol=3e-3, rtol=1e-3)
+    rs = ref.reshape(B, 4, -1)
+    assert torch.allclose(stats[:, :, 0].float(), rs.sum(-1), atol=5e-2, rtol=1e-3)
+    assert torch.allclose(stats[:, :, 1].float(), (rs ** 2).sum(-1), rtol=2e-3)
+    # the planner's own choice: folds the weight-heavy low-resolution layer, leaves the 64x64 layer alone
+    monkeypatch.setenv("WDNO_FOLD", "1")
+    heavy = TapGemm(torch.zeros(1024, 1024, 3, 3), None, device="cpu")._plan(256, 1, 8, 8)
+    assert heavy.fold == 1 and heavy.ZT == 4
+    light = TapGemm(torch.zeros(128, 128, 3, 3), None, device="cpu")._plan(256, 1, 64, 64)
+    print("light plan", light.fold, light.ZT, light.PT)

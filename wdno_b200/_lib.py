@@ -41,6 +41,7 @@ class TapGemmParams(C.Structure):
         ("NSLOT", C.c_int32), ("NBST", C.c_int32), ("S_pad", C.c_int32), ("grid", C.c_int32),
         ("TPS", C.c_int32), ("reuse", C.c_int32), ("n_taps", C.c_int32), ("bias_len", C.c_int32),
         ("n_sets", C.c_int32), ("zstack", C.c_int32), ("strips", C.c_int32), ("Wfull", C.c_int32),
+        ("fold", C.c_int32), ("reserved0", C.c_int32),
     ]
 
 

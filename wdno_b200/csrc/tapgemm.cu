@@ -583,8 +583,9 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const wdno_tapgemm
       if (zi < 0 || zi >= p.D) return;
       const int csrc = p.src_c[st.src];
       const int chn = st.ch_off + c * 8;
-      const float* pa = p.coef_a[st.src] + static_cast<size_t>(cu.b) * csrc + chn;
-      const float* pc = p.coef_c[st.src] + static_cast<size_t>(cu.b) * csrc + chn;
+      const size_t sample = p.fold ? static_cast<size_t>(cu.b) * p.D + zi : static_cast<size_t>(cu.b);
+      const float* pa = p.coef_a[st.src] + sample * csrc + chn;
+      const float* pc = p.coef_c[st.src] + sample * csrc + chn;
       // silu(v) = h + h * tanh(h) with h = v / 2 = (a/2) x + c/2
       float4 a0 = __ldg(reinterpret_cast<const float4*>(pa)), a1 = __ldg(reinterpret_cast<const float4*>(pa + 4));
       float4 c0 = __ldg(reinterpret_cast<const float4*>(pc)), c1 = __ldg(reinterpret_cast<const float4*>(pc + 4));
@@ -723,6 +724,42 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const wdno_tapgemm
         float s1[16], s2[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
+        // GroupNorm partial sums of `sample`: 8-column blocks -> groups (cpg is a multiple of 8); warp-reduce, then one
+        // atomic pair per group; the per-lane sums are cleared (batch-folded 2-D layers flush once per plane)
+        auto flush_stats = [&](size_t sample) {
+          float g1 = 0.f, g2 = 0.f;
+          int cur_g = -1;
+#pragma unroll
+          for (int blk = 0; blk < 16; ++blk) {
+            if (blk >= nblk || blk * 8 >= ci.n_valid) break;
+            const int gi = (ci.out_ch_off + blk * 8) / p.cpg;
+            if (gi != cur_g) {
+              if (cur_g >= 0 && lane == 0) {
+                double* sp = p.stats + (sample * p.G + cur_g) * 2;
+                atomicAdd(sp, static_cast<double>(g1));
+                atomicAdd(sp + 1, static_cast<double>(g2));
+              }
+              g1 = 0.f;
+              g2 = 0.f;
+              cur_g = gi;
+            }
+            float a1 = s1[blk], a2 = s2[blk];
+            s1[blk] = 0.f;
+            s2[blk] = 0.f;
+#pragma unroll
+            for (int sh = 16; sh > 0; sh >>= 1) {
+              a1 += __shfl_xor_sync(0xffffffffu, a1, sh);
+              a2 += __shfl_xor_sync(0xffffffffu, a2, sh);
+            }
+            g1 += a1;
+            g2 += a2;
+          }
+          if (cur_g >= 0 && lane == 0) {
+            double* sp = p.stats + (sample * p.G + cur_g) * 2;
+            atomicAdd(sp, static_cast<double>(g1));
+            atomicAdd(sp + 1, static_cast<double>(g2));
+          }
+        };
         const float* bias_s = s_bias + ci.out_ch_off;
         PROF_REGION(0, ptx::mbar_wait(&bars->acc_full[buf], aph));
         ptx::tc_fence_after();
@@ -854,44 +891,14 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const wdno_tapgemm
               }
               __syncwarp();
             }
+            // batch folded into depth (2-D layers): every plane is a sample of its own
+            if (has_stats && p.fold && z < p.D) flush_stats(static_cast<size_t>(wk.b) * p.D + z);
           }
         }
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&bars->acc_empty[buf]);
-        if (has_stats) {
-          // 8-column blocks -> groups (cpg is a multiple of 8); warp-reduce, then one atomic pair per group
-          float g1 = 0.f, g2 = 0.f;
-          int cur_g = -1;
-#pragma unroll
-          for (int blk = 0; blk < 16; ++blk) {
-            if (blk >= nblk || blk * 8 >= ci.n_valid) break;
-            const int gi = (ci.out_ch_off + blk * 8) / p.cpg;
-            if (gi != cur_g) {
-              if (cur_g >= 0 && lane == 0) {
-                double* sp = p.stats + (static_cast<size_t>(wk.b) * p.G + cur_g) * 2;
-                atomicAdd(sp, static_cast<double>(g1));
-                atomicAdd(sp + 1, static_cast<double>(g2));
-              }
-              g1 = 0.f;
-              g2 = 0.f;
-              cur_g = gi;
-            }
-            float a1 = s1[blk], a2 = s2[blk];
-#pragma unroll
-            for (int sh = 16; sh > 0; sh >>= 1) {
-              a1 += __shfl_xor_sync(0xffffffffu, a1, sh);
-              a2 += __shfl_xor_sync(0xffffffffu, a2, sh);
-            }
-            g1 += a1;
-            g2 += a2;
-          }
-          if (cur_g >= 0 && lane == 0) {
-            double* sp = p.stats + (static_cast<size_t>(wk.b) * p.G + cur_g) * 2;
-            atomicAdd(sp, static_cast<double>(g1));
-            atomicAdd(sp + 1, static_cast<double>(g2));
-          }
-        }
+        if (has_stats && !p.fold) flush_stats(static_cast<size_t>(wk.b));
       }
     }
     PROF_COMMIT(24, threadIdx.x == 0);
@@ -937,6 +944,7 @@ static int validate(const wdno_tapgemm_params* p) {
   if (p->out_mode != 2 && (p->out_c % 8)) return set_error(WDNO_E_INVALID, "tapgemm: fp16 output channels must be a multiple of 8");
   if (p->stats && (p->cpg % 8 || p->cpg < 8)) return set_error(WDNO_E_INVALID, "tapgemm: cpg must be a multiple of 8");
   if (p->src_mode == 2 && ((p->H & 1) || (p->W & 1))) return set_error(WDNO_E_INVALID, "tapgemm: up2 needs even H,W");
+  if (p->fold && p->KD != 1) return set_error(WDNO_E_INVALID, "tapgemm: batch folding needs KD == 1");
   if (p->strips < 1 || p->Wfull < 1) return set_error(WDNO_E_INVALID, "tapgemm: strips / Wfull must be >= 1");
   if (p->strips == 1 && p->Wfull != p->W) return set_error(WDNO_E_INVALID, "tapgemm: Wfull must equal W without strips");
   if (p->strips > 1 && (p->src_mode != 0 || p->out_mode == 1 || p->Wp != p->W + 2 * p->px ||

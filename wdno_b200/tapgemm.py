@@ -268,13 +268,36 @@ class TapGemm:
             if p is not None and (p.zstack or os.environ.get("WDNO_FORCE_STRIPS")):
                 chosen = p
                 break
+        # Batch folding (2-D layers, D == 1): 4 (or 2) samples become the depth planes of one "sample" so that ZT of them
+        # share every weight tile -- at 8x8 / 16x16 resolution with 512..1024 channels a work item otherwise streams
+        # megabytes of weights from L2 for one 128-position tile (measured 194 TFLOP/s on 1024->1024 3x3 at 8x8).
+        if (D == 1 and self.KD == 1 and chosen is not None and not chosen.zstack
+                and os.environ.get("WDNO_FOLD", "1") != "0"):
+            est0 = self._last_est
+            force = os.environ.get("WDNO_FOLD") == "force"
+            for f in (4, 2):
+                if B % f:
+                    continue
+                pf = self._plan_strips(B // f, f, H, W, 1, fold=True)
+                if pf is None:
+                    break
+                if chosen.reuse:
+                    # A-stationary 1x1 plans carry no estimate: more planes per item = fewer weight re-streams
+                    take = bool(pf.reuse) and pf.ZT > chosen.ZT
+                else:
+                    take = est0 is not None and self._last_est is not None and self._last_est < 0.8 * est0  # clear wins only
+                if take or force:
+                    chosen = pf
+                break
         if chosen is None:
             raise ValueError(f"tapgemm: no shared-memory plan for grid {(B, D, H, W)} taps {(self.KD, self.KH, self.KW)}")
         self._launch[key] = chosen
         return chosen
 
-    def _plan_strips(self, B, D, H, Wfull, strips):
+    def _plan_strips(self, B, D, H, Wfull, strips, fold=False):
         KD, KH, KW = self.KD, self.KH, self.KW
+        self._last_est = None
+        two_d = fold or D == 1
         if strips == 1:
             # padded row width: ONE shared run of KW//2 zero columns per row -- the left pad of row y+1 doubles as the
             # right pad of row y (positions are linearised, so x + kx simply runs into the next row's pad)
@@ -300,11 +323,15 @@ class TapGemm:
             tpk = {"conv": KH * KW, "down144": 4, "up144": 4, "unshuffle": 1}[self.kind]  # taps per kz group
             stage_cap = int(os.environ.get("WDNO_BSTAGE", "49152"))  # several taps per issue block (fewer, larger MMA bursts)
             divs = [d for d in range(tpk, 0, -1) if tpk % d == 0 and (d * btile(KC) <= stage_cap or d == 1)]
-            for nslot in range(min(12, want_slots), min_slots - 1, -1):
-                for tps in divs:
-                    for nbst in (4, 3, 2):
-                        if _BAR_BYTES + _round_up(nslot * slot, 128) + nbst * tps * btile(KC) <= _SMEM_LIMIT:
-                            return S_pad, nslot, nbst, tps
+            # 2-D layers are weight-stream heavy: keep >= 3 weight stages in flight before spending shared memory on
+            # slab slots beyond the minimum; 3-D layers (tuned on the smoke U-Net): slots first
+            top = min(12, want_slots)
+            for min_b, low in (((3, min(top, min_slots + 1)), (2, min_slots)) if two_d else ((2, min_slots),)):
+                for nslot in range(top, low - 1, -1):
+                    for tps in divs:
+                        for nbst in (4, 3, 2):
+                            if nbst >= min_b and _BAR_BYTES + _round_up(nslot * slot, 128) + nbst * tps * btile(KC) <= _SMEM_LIMIT:
+                                return S_pad, nslot, nbst, tps
             return None
 
         kcs = [self.kc_override] if self.kc_override else [64, 32, 16]
@@ -367,8 +394,9 @@ class TapGemm:
             ntaps = {"conv": KD * KH * KW, "down144": 16, "up144": 4, "unshuffle": 4}[self.kind]
             mma_cyc = 48 if self.N <= 64 else self.N // 2  # N <= 64 is shared-memory-bandwidth bound (tools/micro/mma_rate)
             best = None
-            for ZT in zts:
-                PT = 4 if (ZT == 1 and D == 1) else 1
+            for ZT, PT in [(z, pt) for z in zts for pt in ((4, 1) if (z == 1 and D == 1) else (1,))]:
+                # D == 1: four position tiles per item (PT = 4) unless the plane is so small that they would mostly be
+                # padding (8x8 planes: 72 positions) -- the estimate below decides
                 if self.N > 64:
                     while ZT * PT * 128 > 512:
                         PT = max(1, PT - 1)
@@ -380,7 +408,11 @@ class TapGemm:
                     ptiles_ = (H * Wp + 128 * PT - 1) // (128 * PT)
                     items = B * strips * ((D + ZT - 1) // ZT) * ptiles_ * ncn
                     waves = (items + sms_ - 1) // sms_
-                    per_item = ZT * PT * ntaps * (ctot // 16) * mma_cyc + 3000 + P * (ctot // KC) * 800 * PT
+                    mma_part = ZT * PT * ntaps * (ctot // 16) * mma_cyc
+                    if two_d:
+                        # weight tiles of one item stream from L2 at ~10 B/cycle/SM (measured on the 8x8 Burgers layers)
+                        mma_part = max(mma_part, ntaps * ctot * self.N * 2 // 10)
+                    per_item = mma_part + 3000 + P * (ctot // KC) * 800 * PT
                     est = waves * per_item
                     score = (-est, min(f[1] - P, 2), KC)  # then prefer a full ring (P+2 slots) and the larger KC
                     if best is None or score > best[0]:
@@ -388,6 +420,7 @@ class TapGemm:
             if best is None:
                 return None
             plan = best[1]
+            self._last_est = -best[0][0]
         KC, ZT, PT, reuse, S_pad, NSLOT, NBST, TPS = plan
         pk = self._pack(KC, bool(zstack))
         if Wp not in pk["taps_dev"]:
@@ -405,6 +438,7 @@ class TapGemm:
         p.src_mode = {"conv": 2 if self.up2 else 0, "down144": 1, "unshuffle": 1, "up144": 0}[self.kind]
         p.B, p.D, p.H, p.W = B, D, H, W
         p.strips, p.Wfull = strips, Wfull
+        p.fold = 1 if fold else 0
         p.KD, p.pz, p.py, p.px = KD, KD // 2, KH // 2, KW // 2
         p.Wp, p.maxshift = Wp, maxshift
         p.ZT, p.PT, p.KC, p.N, p.n_chunks = ZT, PT, KC, self.N, pk["n_chunks"]
@@ -434,7 +468,7 @@ class TapGemm:
             H, W = Hs * 2, Ws * 2
         else:
             H, W = Hs, Ws
-        p0 = self._plan(B, D, H, W)
+        p0 = self._plan(B, D, H, W)   # may fold the batch of a 2-D layer into depth planes (p.B * p.D == B * D)
         p = TapGemmParams.from_buffer_copy(p0)
         assert C0 == self.src_channels[0], (C0, self.src_channels)
         p.src[0] = src0.data_ptr()
