@@ -119,6 +119,17 @@ typedef struct {
 int64_t wdno_tapgemm_smem_bytes(const wdno_tapgemm_params* p);
 int wdno_tapgemm(const wdno_tapgemm_params* p, void* stream);
 
+/* Plain 1x1 convolution / Linear (no fused GroupNorm prologue or statistics): the HBM-bound layers -- ResnetBlock.res_conv
+ * (conv3d.py:216 ; unet.py:162), attention to_qkv / to_out (conv3d.py:291-292 ; unet.py:190-192,233-234) and the final
+ * 1x1 convolution (conv3d.py:471 ; unet.py:369).
+ *   out[m][n] = sum_k concat(src0[m][0..c0), src1[m][0..c1))[k] * w[n][k] + bias[n] (+ resid[m][n])
+ * src*: fp16 channels-last [M][c*] (c0, c1 multiples of 32; src1 may be NULL with c1 = 0); w: fp16 [npad][c0+c1], rows
+ * >= cout zero, npad a multiple of 64; bias: fp32 [npad] or NULL; resid: fp16 [M][cout] or NULL.
+ * out_mode 0: fp16 [M][cout] (cout % 8 == 0);  out_mode 2: fp32 planar [M/hw][cout][hw] -- the reference's
+ * [B,F,C,H,W] layout with hw = H*W (no residual). */
+int wdno_conv1x1(const void* src0, int c0, const void* src1, int c1, const void* w, int npad, const float* bias,
+                 const void* resid, void* out, int64_t M, int cout, int out_mode, int64_t hw, void* stream);
+
 
 /* ------------------------------------------------------------------------------------------
  * U-Net helper kernels (HBM-bound).  reference: conv3d.py:139-151,165-174,189-230,405-410 ;

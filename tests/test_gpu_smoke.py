@@ -36,7 +36,7 @@ def test_library_loads_on_sm100():
     assert L.wdno_device_cc() == 100
 
 
-@pytest.mark.parametrize("case", list(range(10)) + [12, 13])
+@pytest.mark.parametrize("case", list(range(10)) + [12, 13, 14])
 def test_tapgemm_against_torch_conv(case):
     import gpu_probe_tapgemm as probe
     r = probe.run_case(case)

@@ -250,13 +250,32 @@ def run_case(i):
             del os.environ["WDNO_FORCE_STRIPS"]
         res["errs"] = errs
         res["err"] = max(errs)
+    elif i == 14:
+        res["name"] = "conv1x1 kernel edge cases: ragged M, concat sources, bias+resid, masked N (72, 42), planar fp32 with odd planes"
+        errs = []
+        x0, x1 = rnd(3, 64, 5, 7, 9), rnd(3, 96, 5, 7, 9)           # M = 945 (not a multiple of 128)
+        w, b, r = rnd(72, 160, scale=0.1), rnd(72), rnd(3, 72, 5, 7, 9)
+        plan = TapGemm(w, b, src_channels=(64, 96), device=dev)
+        assert plan._c1 is not None
+        out = plan(cl(x0), cl(x1), resid=cl(r))
+        errs.append(relerr(uncl(out), F.conv3d(torch.cat([x0, x1], 1), w[:, :, None, None, None], b) + r))
+        w2, b2 = rnd(42, 64, scale=0.1), rnd(42)
+        plan2 = TapGemm(w2, b2, device=dev)
+        out2 = plan2(cl(x0), out_fp32_bfchw=True)                    # HW = 63: every tile straddles planes
+        errs.append(relerr(out2.permute(0, 2, 1, 3, 4), F.conv3d(x0, w2[:, :, None, None, None], b2)))
+        x3 = rnd(2, 1536, 1, 8, 8)
+        w3 = rnd(1024, 1536, scale=0.03)
+        plan3 = TapGemm(w3, None, device=dev)
+        errs.append(relerr(uncl(plan3(cl(x3))), F.conv3d(x3, w3[:, :, None, None, None])))
+        res["errs"] = errs
+        res["err"] = max(errs)
     else:
         return None
     torch.cuda.synchronize()
     return res
 
 
-NCASES = 14
+NCASES = 15
 
 
 def main():

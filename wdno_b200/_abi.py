@@ -24,6 +24,7 @@ SIGNATURES = {
     "wdno_chan_layernorm": [P, P, P, P, L64, I, F, P],
     "wdno_time_mlp": [P, P, P, P, P, P, P, I, I, I, F, P],
     "wdno_small_linear": [P, P, P, P, I, I, I, P],
+    "wdno_conv1x1": [P, I, P, I, P, I, P, P, P, L64, I, I, L64, P],
     "wdno_softmax_attn": [P, P, P, P, P, L64, I, L64, L64, L64, L64, F, P],
     "wdno_linear_attn": [P, P, L64, I, F, P],
     "wdno_linattn_block": [P, P, P, P, P, P, P, P, L64, I, I, F, F, P],

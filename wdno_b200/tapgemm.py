@@ -81,6 +81,21 @@ class TapGemm:
             self.bias = b.to(self.device)
         self._packed = {}   # KC -> dict(wpacked, chunks, sets, taps, n_chunks, tables kept alive)
         self._launch = {}   # geometry key -> (params, keepalive)
+        # plain 1x1 layers (no fused GroupNorm prologue / statistics) run on the HBM-bound mma.sync kernel csrc/conv1x1.cu
+        self._c1 = None
+        if (kind == "conv" and (self.KD, self.KH, self.KW) == (1, 1, 1) and len(self.src_channels) <= 2
+                and all(c % 32 == 0 for c in self.src_channels) and os.environ.get("WDNO_CONV1X1", "1") != "0"
+                and self.device.type == "cuda"):
+            ctot = sum(self.src_channels)
+            npad = _round_up(self.cout, 64)
+            w1 = torch.zeros(npad, ctot, dtype=torch.float32)
+            w1[: self.cout, : self.cin] = w[:, :, 0, 0, 0]
+            b1 = None
+            if bias is not None:
+                b1 = torch.zeros(npad, dtype=torch.float32)
+                b1[: self.cout] = bias.detach().float().cpu()
+                b1 = b1.to(self.device)
+            self._c1 = dict(w=w1.to(torch.float16).to(self.device), bias=b1, npad=npad)
 
     # ------------------------------------------------------------------ packing
     def _virtual_cin(self):
@@ -468,6 +483,8 @@ class TapGemm:
             H, W = Hs * 2, Ws * 2
         else:
             H, W = Hs, Ws
+        if self._c1 is not None and coef0 is None and coef1 is None and stats is None:
+            return self._call_1x1(L, src0, src1, out, resid, out_fp32_bfchw)
         p0 = self._plan(B, D, H, W)   # may fold the batch of a 2-D layer into depth planes (p.B * p.D == B * D)
         p = TapGemmParams.from_buffer_copy(p0)
         assert C0 == self.src_channels[0], (C0, self.src_channels)
@@ -524,6 +541,41 @@ class TapGemm:
             if self.kind == "unshuffle":
                 flops *= 4
             tm.append((e0, e1, flops, (self.kind, self.cin, self.cout, self.KD, self.KH, self.KW, B, D, H, W)))
+        return out
+
+    def _call_1x1(self, L, src0, src1, out, resid, out_fp32_bfchw):
+        B, D, H, W, C0 = src0.shape
+        c1 = self._c1
+        assert C0 == self.src_channels[0], (C0, self.src_channels)
+        if src1 is not None:
+            assert src1.dtype == torch.float16 and src1.is_contiguous() and src1.shape[:4] == src0.shape[:4]
+            assert src1.shape[4] == self.src_channels[1]
+        else:
+            assert len(self.src_channels) == 1
+        if out_fp32_bfchw:
+            assert resid is None
+            if out is None:
+                out = torch.empty((B, D, self.cout, H, W), dtype=torch.float32, device=src0.device)
+            assert out.dtype == torch.float32 and out.is_contiguous() and out.shape == (B, D, self.cout, H, W)
+        else:
+            if out is None:
+                out = torch.empty((B, D, H, W, self.cout), dtype=torch.float16, device=src0.device)
+            assert out.dtype == torch.float16 and out.is_contiguous() and out.shape == (B, D, H, W, self.cout)
+            if resid is not None:
+                assert resid.dtype == torch.float16 and resid.is_contiguous() and resid.shape == out.shape
+        tm = TapGemm.timing
+        if tm is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        _lib.check(L.wdno_conv1x1(src0.data_ptr(), C0, src1.data_ptr() if src1 is not None else None,
+                                  src1.shape[4] if src1 is not None else 0, c1["w"].data_ptr(), c1["npad"],
+                                  c1["bias"].data_ptr() if c1["bias"] is not None else None,
+                                  resid.data_ptr() if resid is not None else None, out.data_ptr(), B * D * H * W, self.cout,
+                                  2 if out_fp32_bfchw else 0, H * W, _lib.current_stream_ptr()), "conv1x1")
+        if tm is not None:
+            e1.record()
+            flops = 2.0 * B * D * H * W * self.cout * getattr(self, "algo_cin", self.cin)
+            tm.append((e0, e1, flops, ("conv1x1", self.cin, self.cout, 1, 1, 1, B, D, H, W)))
         return out
 
     # bench.py sets this to a list to collect (start event, end event, algorithmic FLOPs, shape) per launch
