@@ -263,20 +263,41 @@ __global__ void __launch_bounds__(256) la_mid_kernel(const float* __restrict__ p
   const int reg = kk >> 3, qq = (kk & 7) >> 1, half = kk & 1;
   extern __shared__ __align__(16) __half msm[];  // the image's M in fragment order, then copied out coalesced
   const int c0 = chalf * (C / 2);
-#pragma unroll 2
-  for (int c = c0; c < c0 + C / 2; ++c) {
-    const float4* wr = reinterpret_cast<const float4*>(wout + static_cast<size_t>(c) * kLaHid + h * 32);
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  // W_out rows reach the lanes through a per-warp staging tile: the warp (fixed head h) loads the 32 weights of 8 channels
+  // with coalesced 128-byte requests (lane = e), every lane then reads them back as broadcast LDS.128 -- the previous
+  // version issued 8 dependent uniform-address LDG.128 per channel and was latency bound (35..94 us per launch).
+  __shared__ __align__(16) float wstage[8][8][32];
+  float(*ws)[32] = wstage[threadIdx.x >> 5];
+  const int lane = threadIdx.x & 31;
+  const float* wbase = wout + static_cast<size_t>(c0) * kLaHid + h * 32 + lane;
+  float nxt[8];
 #pragma unroll
-    for (int e4 = 0; e4 < 8; ++e4) {
-      const float4 w4 = __ldg(wr + e4);
-      s0 = fmaf(w4.x, cr[4 * e4], s0);
-      s1 = fmaf(w4.y, cr[4 * e4 + 1], s1);
-      s2 = fmaf(w4.z, cr[4 * e4 + 2], s2);
-      s3 = fmaf(w4.w, cr[4 * e4 + 3], s3);
+  for (int cc = 0; cc < 8; ++cc) nxt[cc] = __ldg(wbase + static_cast<size_t>(cc) * kLaHid);
+  for (int cg = 0; cg < C / 2; cg += 8) {
+    __syncwarp();
+#pragma unroll
+    for (int cc = 0; cc < 8; ++cc) ws[cc][lane] = nxt[cc];
+    __syncwarp();
+    if (cg + 8 < C / 2) {
+#pragma unroll
+      for (int cc = 0; cc < 8; ++cc) nxt[cc] = __ldg(wbase + static_cast<size_t>(cg + 8 + cc) * kLaHid);
     }
-    const int nt = c >> 3, gg = c & 7;
-    msm[((nt * 4 + (ks >> 1)) * 32 + (gg * 4 + qq)) * 8 + ((ks & 1) * 2 + reg) * 2 + half] = __float2half_rn((s0 + s1) + (s2 + s3));
+#pragma unroll
+    for (int cc = 0; cc < 8; ++cc) {
+      const int c = c0 + cg + cc;
+      const float4* wr = reinterpret_cast<const float4*>(ws[cc]);
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+      for (int e4 = 0; e4 < 8; ++e4) {
+        const float4 w4 = wr[e4];
+        s0 = fmaf(w4.x, cr[4 * e4], s0);
+        s1 = fmaf(w4.y, cr[4 * e4 + 1], s1);
+        s2 = fmaf(w4.z, cr[4 * e4 + 2], s2);
+        s3 = fmaf(w4.w, cr[4 * e4 + 3], s3);
+      }
+      const int nt = c >> 3, gg = c & 7;
+      msm[((nt * 4 + (ks >> 1)) * 32 + (gg * 4 + qq)) * 8 + ((ks & 1) * 2 + reg) * 2 + half] = __float2half_rn((s0 + s1) + (s2 + s3));
+    }
   }
   __syncthreads();
   uint4* dst = reinterpret_cast<uint4*>(mpack + static_cast<size_t>(img) * C * kLaHid);
