@@ -210,27 +210,39 @@ def main():
             run.noise.normal_()
             run.step_eager(True)
         torch.cuda.synchronize()
-        recs = TapGemm.timing
+        recs_all = TapGemm.timing
         TapGemm.timing = None
+        # the dominant kernel is the tcgen05 tap-GEMM; the plain 1x1 layers run on the HBM-bound conv1x1 kernel (reported beside it)
+        recs = [r for r in recs_all if r[3][0] != "conv1x1"]
+        recs1 = [r for r in recs_all if r[3][0] == "conv1x1"]
         tg_ms = sum(a.elapsed_time(b) for a, b, _, _ in recs) / n_prof
         tg_flops = sum(f for _, _, f, _ in recs) / n_prof
         n_tg = len(recs) // n_prof
+        c1_ms = sum(a.elapsed_time(b) for a, b, _, _ in recs1) / n_prof
+        c1_flops = sum(f for _, _, f, _ in recs1) / n_prof
         peak_tf, hbm, psrc = peaks()
         achieved = tg_flops / (tg_ms * 1e-3) / 1e12
-        # DRAM bytes of the same launches from the committed ncu capture (profiles/, tools/gpu_prof_final.sh)
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "r1_tapgemm_traffic.json")
+        # DRAM bytes of the same launches from the committed ncu capture (profiles/, tools/gpu_prof_r1d.sh)
+        traffic, traffic1 = None, None
+        tp = os.path.join(ROOT, "profiles", "r1d_tapgemm_traffic.json")
         if os.path.exists(tp):
             td = json.load(open(tp))
-            if td.get("launches") == n_tg:
-                traffic = td["dram_bytes_total"]
+            if td.get("tapgemm", {}).get("launches") == n_tg:
+                traffic = td["tapgemm"]["dram_bytes_total"]
+            if td.get("conv1x1", {}).get("launches") == len(recs1) // n_prof:
+                traffic1 = td["conv1x1"]["dram_bytes_total"]
         roof = {"bound": "tensor", "kernel": "wdno::tapgemm_kernel (all %d launches of one step)" % n_tg,
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                 "peak_source": f"{psrc} bf16 sustained (fp16 operands run at the bf16 rate)", "traffic": traffic,
-                "traffic_note": "dram__bytes_read+write summed over the same launches of one step (ncu, profiles/r1_tapgemm_traffic.json); "
+                "traffic_note": "dram__bytes_read+write summed over the same launches of one step (ncu, profiles/r1d_tapgemm_traffic.json); "
                                 "algorithmic activation+weight bytes of those layers: see DESIGN.md section 4.1",
                 "kernel_ms_per_step": tg_ms, "kernel_share_of_step": tg_ms / (ms / K),
-                "algorithmic_gflop_per_step": tg_flops / 1e9}
+                "algorithmic_gflop_per_step": tg_flops / 1e9,
+                "conv1x1": {"kernel": "wdno::conv1x1_kernel (%d launches per step, HBM-bound)" % (len(recs1) // n_prof),
+                            "ms_per_step": c1_ms, "algorithmic_gflop_per_step": c1_flops / 1e9,
+                            "dram_traffic_bytes": traffic1,
+                            "achieved_GBps": (traffic1 / (c1_ms * 1e-3) / 1e9) if traffic1 and c1_ms > 0 else None,
+                            "peak_GBps": hbm}}
 
         # ---------------- end to end through the public API: host buffers in, host result out
         Ke = K

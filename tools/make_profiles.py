@@ -57,18 +57,52 @@ def ncu_raw(rep, dst, title):
                 f.write(f"| {h} | {u} | {v} |\n")
 
 
+def traffic_summary(src, dst):
+    """per-launch DRAM bytes of the tap-GEMM / conv1x1 launches of one step -> json (bench.py reads the totals)"""
+    import json
+    lines = [l for l in open(src) if not l.startswith("==")]
+    per = collections.OrderedDict()
+    for r in csv.DictReader(lines):
+        k = (r["ID"], re.sub(r"\(.*", "", r["Kernel Name"]))
+        v = float(r["Metric Value"].replace(",", ""))
+        u = r["Metric Unit"]
+        if r["Metric Name"] == "gpu__time_duration.sum":
+            v = v / 1e3 if u == "ns" else v * 1e3 if u == "ms" else v
+            per.setdefault(k, {})["us"] = v
+        elif r["Metric Name"].startswith("dram__bytes"):
+            mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
+            per.setdefault(k, {})["read" if "read" in r["Metric Name"] else "write"] = v * mult
+    out = {"what": "DRAM traffic of the tap-GEMM and conv1x1 launches of one Unet3D forward (C3, batch 16): ncu --metrics "
+                   "dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none (tools/gpu_prof_r1d.sh)"}
+    for tag in ("tapgemm", "conv1x1"):
+        rows = [(k, v) for k, v in per.items() if tag in k[1]]
+        out[tag] = {"launches": len(rows), "dram_bytes_read": sum(v.get("read", 0) for _, v in rows),
+                    "dram_bytes_write": sum(v.get("write", 0) for _, v in rows),
+                    "dram_bytes_total": sum(v.get("read", 0) + v.get("write", 0) for _, v in rows),
+                    "sum_duration_us_cold": sum(v.get("us", 0) for _, v in rows),
+                    "per_launch": [{"id": int(k[0]), "us": round(v.get("us", 0), 2), "read_MB": round(v.get("read", 0) / 1e6, 2),
+                                    "write_MB": round(v.get("write", 0) / 1e6, 2)} for k, v in rows]}
+    json.dump(out, open(dst, "w"), indent=1)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    t = os.path.join(GO, f"tapgemm_traffic_{TAG}.csv")
+    if os.path.exists(t):
+        traffic_summary(t, os.path.join(OUT, f"{TAG}_tapgemm_traffic.json"))
     s = os.path.join(GO, f"launches_{TAG}_step.csv")
     if os.path.exists(s):
         launch_summary(s, os.path.join(OUT, f"{TAG}_launches_step.csv"), os.path.join(OUT, f"{TAG}_launches_step.md"),
                        f"{TAG}: per-kernel split of one DDIM step (C3, batch 16)")
-    for name, title in (("prof_tapgemm_c64_v4", "tap-GEMM, 3x3x3 64->64 conv, B=16 24x40x40 (dominant kernel)"),
-                        ("prof_tapgemm_c64_final", "tap-GEMM, 3x3x3 64->64 conv, B=16 24x40x40 (dominant kernel), end of round")):
-        rep = os.path.join(GO, name + ".ncu-rep")
+    for name, title in (("prof_tapgemm_c64", "tap-GEMM, 3x3x3 64->64 conv, B=16 24x40x40 (dominant kernel)"),
+                        ("prof_conv1x1", "conv1x1 kernel, 128->64 res_conv at B=16 24x40x40 (HBM-bound)"),
+                        ("prof_tapgemm_stem_strips", "tap-GEMM, 7x7x7 82(96)->64 stem of the super-resolution model in "
+                                                     "column-strip mode, B=4 24x80x80")):
+        rep = os.path.join(GO, f"{name}_{TAG}.ncu-rep")
         if os.path.exists(rep):
             ncu_raw(rep, os.path.join(OUT, f"{TAG}_{name}.md"), title)
-    for extra in ("bench_r1_mid.json", "tapgemm_breakdown.json", "probe_tapgemm.log"):
+    for extra in ("tapgemm_breakdown_C3.json", "tapgemm_breakdown_C2.json", "tapgemm_breakdown_C4.json", "bench_configs.jsonl",
+                  "step_profile_C3.txt", "step_profile_C2.txt", "step_profile_C4.txt"):
         p = os.path.join(GO, extra)
         if os.path.exists(p):
             open(os.path.join(OUT, f"{TAG}_{extra}"), "w").write(open(p).read())
