@@ -12,6 +12,7 @@
 //   HBM traffic: x is read twice and y written once (3 x 2C bytes per voxel) instead of the ~21 x 2C bytes of the
 //   unfused LN / qkv GEMM / attention core / out GEMM chain.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -890,10 +891,346 @@ __global__ void __launch_bounds__(256, 2) tattn_kernel(const __half* __restrict_
   (void)ROWS;
 }
 
+// ------------------------------------------------------------------ temporal attention, one WARP per pixel (C = 64)
+// The block-per-pixel-pair kernel above synchronises its 8 warps four times per pair (LayerNorm tile shared by the head
+// warps, per-head outputs gathered for the output projection) and runs at ~0.27 IPC per scheduler on the full-resolution
+// level.  Here a warp owns a pixel end to end -- LayerNorm of its 24 tokens into a private tile, the four heads one after
+// the other, and the output projection accumulated head by head straight from the P.V accumulator fragments (they ARE
+// the A fragments of  Y += O_h Wout[:, 32h:32h+32]^T ) -- so there is no block-level barrier after the table setup and no
+// O round trip through shared memory; 3 CTAs x 4 warps per SM.
+template <int C>
+__global__ void __launch_bounds__(128, 3) tattn_warp_kernel(const __half* __restrict__ x, __half* __restrict__ y,
+                                                             const float* __restrict__ gamma, const uint4* __restrict__ wqk,
+                                                             const uint4* __restrict__ wv, const uint4* __restrict__ wo,
+                                                             const float* __restrict__ bias, const float* __restrict__ rot_cos,
+                                                             const float* __restrict__ rot_sin, long long n_pix, long long hw,
+                                                             int n, float scale, float eps) {
+  static_assert(C == 64, "one-warp-per-pixel temporal attention is specialised for C = 64");
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  constexpr int XS = C + 8, KS = C / 16, LP = C / 8;
+  constexpr int BS = 40, RS = 20;
+  __half* xn_all = reinterpret_cast<__half*>(smem_raw);                  // [4 warps][32][XS]
+  float* sbias = reinterpret_cast<float*>(xn_all + 4 * kTaRows * XS);      // [4][32][BS], -inf for keys >= n
+  float2* scs = reinterpret_cast<float2*>(sbias + 4 * 32 * BS);            // [32][RS] (cos, sin)
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, q = lane & 3;
+  pdl_trigger();
+  for (int i = tid; i < 4 * kTaRows * XS / 8; i += 128) reinterpret_cast<uint4*>(xn_all)[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = tid; i < 4 * 32 * 32; i += 128) {
+    const int hh = i >> 10, r = (i >> 5) & 31, c = i & 31;
+    float b = 0.f;
+    if (c >= n) b = -INFINITY;
+    else if (r < n && bias != nullptr) b = __ldg(bias + (static_cast<size_t>(hh) * n + r) * n + c);
+    sbias[(hh * 32 + r) * BS + c] = b;
+  }
+  for (int i = tid; i < 32 * 16; i += 128) {
+    const int f = i >> 4;
+    scs[f * RS + (i & 15)] = make_float2((rot_cos != nullptr && f < n) ? __ldg(rot_cos + f * 16 + (i & 15)) : 1.0f,
+                                         (rot_sin != nullptr && f < n) ? __ldg(rot_sin + f * 16 + (i & 15)) : 0.0f);
+  }
+  __syncthreads();
+  __half* xn = xn_all + warp * kTaRows * XS;
+  const uint32_t xn_s = static_cast<uint32_t>(__cvta_generic_to_shared(xn));
+  const uint32_t a_off = static_cast<uint32_t>((((lane & 15)) * XS + 8 * (lane >> 4)) * 2);   // A operand rows = tokens
+  const uint32_t b_off = static_cast<uint32_t>((((lane & 7)) * XS + 8 * (lane >> 3)) * 2);    // B operand rows = tokens
+  const int ln_l = lane & 7, ln_r = lane >> 3;   // LayerNorm: 8 lanes per token row, 4 rows per pass
+  float gm[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) gm[j] = __ldg(gamma + ln_l * 8 + j);
+  pdl_wait();
+
+  for (long long pix = static_cast<long long>(blockIdx.x) * 4 + warp; pix < n_pix; pix += static_cast<long long>(gridDim.x) * 4) {
+    const long long bimg = pix / hw, pin = pix - bimg * hw;
+    const __half* xb = x + (static_cast<size_t>(bimg) * n * hw + pin) * C;
+    __half* yb = y + (static_cast<size_t>(bimg) * n * hw + pin) * C;
+    // ---- LayerNorm of the pixel's n tokens -> xn rows 0..n-1 (rows >= n stay zero)
+    {
+      uint4 raw[8];
+#pragma unroll
+      for (int ps = 0; ps < 8; ++ps) {
+        const int f = ln_r + 4 * ps;
+        raw[ps] = make_uint4(0u, 0u, 0u, 0u);
+        if (f < n) raw[ps] = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<size_t>(f) * hw * C) + ln_l);
+      }
+      __syncwarp();  // the previous pixel's staged output has been read
+#pragma unroll
+      for (int ps = 0; ps < 8; ++ps) {
+        const int f = ln_r + 4 * ps;
+        const __half2* hh = reinterpret_cast<const __half2*>(&raw[ps]);
+        float fv[8];
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 t = __half22float2(hh[j]);
+          fv[2 * j] = t.x;
+          fv[2 * j + 1] = t.y;
+          sum += t.x + t.y;
+        }
+#pragma unroll
+        for (int sh = LP / 2; sh > 0; sh >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, sh);
+        const float mean = sum * (1.0f / C);
+        float sq = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          fv[j] -= mean;
+          sq = fmaf(fv[j], fv[j], sq);
+        }
+#pragma unroll
+        for (int sh = LP / 2; sh > 0; sh >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, sh);
+        const float rstd = rsqrtf(sq * (1.0f / C) + eps);
+        if (f < n) {
+          uint4 ov;
+          uint32_t* o = reinterpret_cast<uint32_t*>(&ov);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) o[j] = pack_h2(fv[2 * j] * rstd * gm[2 * j], fv[2 * j + 1] * rstd * gm[2 * j + 1]);
+          *reinterpret_cast<uint4*>(xn + f * XS + ln_l * 8) = ov;
+        }
+      }
+    }
+    __syncwarp();
+
+    float yacc[2][C / 8][4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < C / 8; ++j)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) yacc[i][j][c] = 0.f;
+
+#pragma unroll 1
+    for (int h = 0; h < 4; ++h) {
+      // ---- Q (scaled, rotated) -> A fragments ; K (rotated) -> B fragments
+      uint32_t qa[2][2][4], kb[4][2][2];
+#pragma unroll
+      for (int sec = 0; sec < 2; ++sec) {
+        float acc[2][4][4];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[i][j][c] = 0.f;
+        const uint4* wb = wqk + static_cast<size_t>((sec * 16 + 4 * h) * (C / 32)) * 32 + lane;
+#pragma unroll
+        for (int kp = 0; kp < C / 32; ++kp) {
+          uint32_t a0[2][4], a1[2][4];
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) {
+            ldsm_x4(xn_s + a_off + static_cast<uint32_t>((mt * 16 * XS + kp * 32) * 2), a0[mt][0], a0[mt][1], a0[mt][2], a0[mt][3]);
+            ldsm_x4(xn_s + a_off + static_cast<uint32_t>((mt * 16 * XS + kp * 32 + 16) * 2), a1[mt][0], a1[mt][1], a1[mt][2], a1[mt][3]);
+          }
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) {
+            const uint4 b = __ldg(wb + (nt * (C / 32) + kp) * 32);
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+              mma16816(acc[mt][nt], a0[mt], b.x, b.y);
+              mma16816(acc[mt][nt], a1[mt], b.z, b.w);
+            }
+          }
+        }
+        const float sc = (sec == 0) ? scale : 1.0f;
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            const int f = 16 * mt + g + 8 * r;
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+              const float2 cs = scs[f * RS + 4 * nt + q];
+              const float x0 = acc[mt][nt][2 * r] * sc, x1 = acc[mt][nt][2 * r + 1] * sc;
+              acc[mt][nt][2 * r] = x0 * cs.x - x1 * cs.y;
+              acc[mt][nt][2 * r + 1] = x1 * cs.x + x0 * cs.y;
+            }
+          }
+        if (sec == 0) {
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+              qa[mt][ks][0] = pack_h2(acc[mt][2 * ks][0], acc[mt][2 * ks][1]);
+              qa[mt][ks][1] = pack_h2(acc[mt][2 * ks][2], acc[mt][2 * ks][3]);
+              qa[mt][ks][2] = pack_h2(acc[mt][2 * ks + 1][0], acc[mt][2 * ks + 1][1]);
+              qa[mt][ks][3] = pack_h2(acc[mt][2 * ks + 1][2], acc[mt][2 * ks + 1][3]);
+            }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+              const int rr = 2 * (j & 1);
+              kb[j][ks][0] = pack_h2(acc[j >> 1][2 * ks][rr], acc[j >> 1][2 * ks][rr + 1]);
+              kb[j][ks][1] = pack_h2(acc[j >> 1][2 * ks + 1][rr], acc[j >> 1][2 * ks + 1][rr + 1]);
+            }
+        }
+      }
+      // ---- S = Q K^T + bias (keys >= n masked by the table), softmax over keys
+      float sfr[2][4][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) sfr[mt][j][c] = 0.f;
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) mma16816(sfr[mt][j], qa[mt][ks], kb[j][ks][0], kb[j][ks][1]);
+        }
+      uint32_t pa[2][2][4];
+      float inv[2][2];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const float* brow = sbias + (h * 32 + 16 * mt + g + 8 * r) * BS + 2 * q;
+          float mx = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 bv = *reinterpret_cast<const float2*>(brow + 8 * j);
+            sfr[mt][j][2 * r] += bv.x;
+            sfr[mt][j][2 * r + 1] += bv.y;
+            mx = fmaxf(mx, fmaxf(sfr[mt][j][2 * r], sfr[mt][j][2 * r + 1]));
+          }
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+          float sum = 0.f;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float p0 = __expf(sfr[mt][j][2 * r] - mx), p1 = __expf(sfr[mt][j][2 * r + 1] - mx);
+            sfr[mt][j][2 * r] = p0;
+            sfr[mt][j][2 * r + 1] = p1;
+            sum += p0 + p1;
+          }
+          sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+          sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+          inv[mt][r] = 1.0f / sum;
+        }
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+          pa[mt][kk][0] = pack_h2(sfr[mt][2 * kk][0], sfr[mt][2 * kk][1]);
+          pa[mt][kk][1] = pack_h2(sfr[mt][2 * kk][2], sfr[mt][2 * kk][3]);
+          pa[mt][kk][2] = pack_h2(sfr[mt][2 * kk + 1][0], sfr[mt][2 * kk + 1][1]);
+          pa[mt][kk][3] = pack_h2(sfr[mt][2 * kk + 1][2], sfr[mt][2 * kk + 1][3]);
+        }
+      }
+      // ---- V^T[d][key] = Wv_h xn^T  (its accumulator fragments are the B fragments of P V)
+      float vt[2][4][4];
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) vt[i][j][c] = 0.f;
+      {
+        const uint4* wa = wv + static_cast<size_t>(h * 2) * KS * 32 + lane;
+#pragma unroll
+        for (int kp = 0; kp < C / 32; ++kp) {
+          uint32_t bf[4][4];
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt)
+            ldsm_x4(xn_s + b_off + static_cast<uint32_t>((nt * 8 * XS + kp * 32) * 2), bf[nt][0], bf[nt][1], bf[nt][2], bf[nt][3]);
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) {
+            const uint4 a0 = __ldg(wa + (mt * KS + 2 * kp) * 32), a1 = __ldg(wa + (mt * KS + 2 * kp + 1) * 32);
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+              mma16816(vt[mt][nt], a0.x, a0.y, a0.z, a0.w, bf[nt][0], bf[nt][1]);
+              mma16816(vt[mt][nt], a1.x, a1.y, a1.z, a1.w, bf[nt][2], bf[nt][3]);
+            }
+          }
+        }
+      }
+      // ---- O = P V ; normalised O fragments are the A fragments of the head's slice of the output projection
+      uint32_t oa[2][2][4];
+#pragma unroll
+      for (int nd = 0; nd < 4; ++nd) {
+        const int me = nd >> 1, rr = 2 * (nd & 1);
+        float ofr[2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) ofr[mt][c] = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+          const uint32_t b0 = pack_h2(vt[me][2 * kk][rr], vt[me][2 * kk][rr + 1]);
+          const uint32_t b1 = pack_h2(vt[me][2 * kk + 1][rr], vt[me][2 * kk + 1][rr + 1]);
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) mma16816(ofr[mt], pa[mt][kk], b0, b1);
+        }
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          // n-tile nd covers d = 8 nd .. 8 nd + 7: k-step nd >> 1, low (a0, a1) or high (a2, a3) half
+          oa[mt][nd >> 1][2 * (nd & 1)] = pack_h2(ofr[mt][0] * inv[mt][0], ofr[mt][1] * inv[mt][0]);
+          oa[mt][nd >> 1][2 * (nd & 1) + 1] = pack_h2(ofr[mt][2] * inv[mt][1], ofr[mt][3] * inv[mt][1]);
+        }
+      }
+      // ---- Y += O_h Wout[:, 32 h : 32 h + 32]^T
+      {
+        const uint4* wb = wo + static_cast<size_t>(h) * 32 + lane;
+#pragma unroll
+        for (int nt = 0; nt < C / 8; ++nt) {
+          const uint4 b = __ldg(wb + nt * 4 * 32);
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) {
+            mma16816(yacc[mt][nt], oa[mt][0], b.x, b.y);
+            mma16816(yacc[mt][nt], oa[mt][1], b.z, b.w);
+          }
+        }
+      }
+    }
+    // ---- Y -> the warp's tile (its LayerNorm rows are dead), then y = Y + x with coalesced 16-byte accesses
+    __syncwarp();
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int f = 16 * mt + g + 8 * r;
+        if (f < n) {
+#pragma unroll
+          for (int nt = 0; nt < C / 8; ++nt)
+            *reinterpret_cast<uint32_t*>(xn + f * XS + 8 * nt + 2 * q) = pack_h2(yacc[mt][nt][2 * r], yacc[mt][nt][2 * r + 1]);
+        }
+      }
+    __syncwarp();
+    for (int idx = lane; idx < n * LP; idx += 32) {
+      const int f = idx / LP, l = idx - f * LP;
+      uint4 v = *reinterpret_cast<const uint4*>(xn + f * XS + l * 8);
+      const size_t off = static_cast<size_t>(f) * hw * C;
+      const uint4 rv = __ldg(reinterpret_cast<const uint4*>(xb + off) + l);
+      __half2* vh = reinterpret_cast<__half2*>(&v);
+      const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 a2 = __half22float2(vh[i]), b2 = __half22float2(rh[i]);
+        vh[i] = __floats2half2_rn(a2.x + b2.x, a2.y + b2.y);
+      }
+      *(reinterpret_cast<uint4*>(yb + off) + l) = v;
+    }
+  }
+}
+
 template <int C>
 static int launch_tattn(const __half* x, __half* y, const float* gamma, const uint4* wqk, const uint4* wv, const uint4* wo,
                         const float* bias, const float* rot_cos, const float* rot_sin, long long n_pix, long long hw, int n,
                         float scale, float eps, cudaStream_t st) {
+  if constexpr (C == 64) {
+    // one warp per pixel (no block barriers, O never leaves registers); WDNO_TATTN_WARP=0 selects the pair kernel
+    static const bool use_warp = [] { const char* e = getenv("WDNO_TATTN_WARP"); return !(e && e[0] == '0'); }();
+    if (use_warp) {
+      const int smem_w = 4 * kTaRows * (C + 8) * 2 + (4 * 32 * 40 + 2 * 32 * 20) * 4;
+      static bool configured_w = false;
+      if (!configured_w) {
+        cudaError_t e = cudaFuncSetAttribute(tattn_warp_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_w);
+        if (e != cudaSuccess) return set_cuda_error(e, "tattn_block: cudaFuncSetAttribute");
+        configured_w = true;
+      }
+      const long long want = (n_pix + 3) / 4;
+      const long long capw = static_cast<long long>(num_sms()) * 3;
+      const unsigned gridw = static_cast<unsigned>(want < capw ? want : capw);
+      launch_pdl(tattn_warp_kernel<C>, dim3(gridw), dim3(128), static_cast<size_t>(smem_w), st, x, y, gamma, wqk, wv, wo, bias,
+                 rot_cos, rot_sin, n_pix, hw, n, scale, eps);
+      return check_launch("tattn_block");
+    }
+  }
   constexpr bool WS = false;  // weight fragments come through L1 (staging them in shared memory measured the same: both share one data path)
   const int wbytes = WS ? (32 * (C / 32) + 4 * 2 * (C / 16) + (C / 8) * 4) * 32 * 16 : 0;
   const int smem = (2 * kTaRows * (C + 8) + 2 * kTaRows * (kLaHid + 8)) * 2 + (4 * 32 * 40 + 2 * 32 * 20) * 4 + wbytes;
