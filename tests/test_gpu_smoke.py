@@ -124,6 +124,14 @@ def test_attention_cores():
     q, k, v = [u.reshape(B * 3, H2 * W2, 4, 32).transpose(1, 2) for u in tok.chunk(3, -1)]
     out2 = (((q * scale) @ k.transpose(-1, -2)).softmax(-1) @ v).transpose(1, 2).reshape(B, 3, H2, W2, 128)
     assert rel_l2(got2.float().cpu(), out2) < 2e-3
+    # the tensor-core online-softmax path (32 < n <= 512): super-resolution mid attention (n = 400), Burgers (n = 64), ragged n
+    for (hh, ww) in ((20, 20), (8, 8), (7, 5), (16, 32)):
+        qx = torch.randn(B, 2, hh, ww, 384, device=dev).half()
+        gx = ops.softmax_attn(qx, B * 2, hh * ww, 1, hh * ww, 0, 1, scale)
+        tk = qx.float().reshape(B * 2, hh * ww, 384).cpu()
+        q_, k_, v_ = [u.reshape(B * 2, hh * ww, 4, 32).transpose(1, 2) for u in tk.chunk(3, -1)]
+        ox = (((q_ * scale) @ k_.transpose(-1, -2)).softmax(-1) @ v_).transpose(1, 2).reshape(B, 2, hh, ww, 128)
+        assert rel_l2(gx.float().cpu(), ox) < 2e-3, (hh, ww)
     # linear attention
     got3 = ops.linear_attn(qkv2, B * 3, H2 * W2, scale)
     q, k, v = [u.reshape(B * 3, H2 * W2, 4, 32).permute(0, 2, 3, 1) for u in tok.chunk(3, -1)]  # b h d n

@@ -274,6 +274,8 @@ extern "C" int wdno_softmax_attn(const void* qkv, void* out, const float* bias, 
   if (n_tok <= 32)  // short sequences (temporal attention): tensor-core kernel
     return launch_short_attn_mma(qkv, out, bias, rot_cos, rot_sin, n_seq, n_tok, inner, outerT, innerT, tokT, scale,
                                  static_cast<cudaStream_t>(stream));
+  if (n_tok <= 512 && bias == nullptr && rot_cos == nullptr)  // mid-level spatial attention: tensor-core online softmax
+    return launch_flash_attn_mma(qkv, out, n_seq, n_tok, inner, outerT, innerT, tokT, scale, static_cast<cudaStream_t>(stream));
   SeqMap m{inner, outerT, innerT, tokT};
   int qt = ((n_tok + 31) / 32) * 32;
   if (qt > 128) qt = 128;

@@ -17,6 +17,10 @@ int launch_short_attn_mma(const void* qkv, void* out, const float* bias, const f
                           long long n_seq, int n_tok, long long inner, long long outerT, long long innerT, long long tokT,
                           float scale, cudaStream_t st);
 
+// attention_mma.cu: tensor-core softmax attention for 32 < n <= 512 tokens without bias / rotary
+int launch_flash_attn_mma(const void* qkv, void* out, long long n_seq, int n_tok, long long inner, long long outerT,
+                          long long innerT, long long tokT, float scale, cudaStream_t st);
+
 // ---- programmatic dependent launch (PDL): a kernel launched through launch_pdl may start (run its prologue) while
 // the previous kernel of the stream drains; it must execute pdl_wait() before touching anything a predecessor wrote.
 // Every kernel calls pdl_trigger() first so that its successor can be scheduled as early as resources allow.
