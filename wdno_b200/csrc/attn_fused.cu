@@ -519,6 +519,201 @@ __global__ void __launch_bounds__(256, 2) la2_kernel(const __half* __restrict__ 
   }
 }
 
+// ------------------------------------------------------------------ la2, one WARP per 16-position tile
+// Same arithmetic as la2_kernel, but a warp owns its 16 rows end to end (private cp.async double buffer, private
+// LayerNorm tile, weights through L1), so there is no block-level barrier at all: the block kernel synchronised 8 warps
+// twice per 128-position item and ran at ~0.27 IPC per scheduler.
+template <int C>
+__global__ void __launch_bounds__(128, 4) la2_warp_kernel(const __half* __restrict__ x, __half* __restrict__ y,
+                                                          const float* __restrict__ gamma, const uint4* __restrict__ wq,
+                                                          const uint4* __restrict__ mpack, const float* __restrict__ bias, int n,
+                                                          int tiles, int n_items, float eps) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  constexpr int XS = C + 8;
+  constexpr int LP = C / 8, RPP = 32 / LP, PASSES = 16 / RPP;
+  constexpr int n_m = (C / 8) * 4 * 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, q = lane & 3;
+  __half* xn = reinterpret_cast<__half*>(smem_raw) + warp * (16 * XS + 2 * 16 * C);   // [16][C + 8]
+  __half* raw = xn + 16 * XS;                                                          // [2][16][C]
+  const int ln_l = lane % LP, ln_r0 = lane / LP;
+  pdl_trigger();
+  float gm[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) gm[j] = __ldg(gamma + ln_l * 8 + j);
+  const uint32_t raw_s = static_cast<uint32_t>(__cvta_generic_to_shared(raw));
+  auto fetch = [&](int item, int buf) {
+    const int img = item / tiles, tile = item - img * tiles;
+    const int p0 = tile * 16;
+    const int rows_valid = min(16, n - p0);
+    const __half* xt = x + (static_cast<size_t>(img) * n + p0) * C;
+#pragma unroll
+    for (int ps = 0; ps < PASSES; ++ps) {
+      const int r = ln_r0 + ps * RPP;
+      const bool ok = r < rows_valid;
+      cp_async16(raw_s + static_cast<uint32_t>(((buf * 16 + r) * C + ln_l * 8) * 2), ok ? xt + static_cast<size_t>(r) * C + ln_l * 8 : xt,
+                 ok ? 16u : 0u);
+    }
+    cp_async_commit_group();
+  };
+  const uint32_t xn_s = static_cast<uint32_t>(__cvta_generic_to_shared(xn));
+  const uint32_t a_off = static_cast<uint32_t>((((lane & 15)) * XS + 8 * (lane >> 4)) * 2);
+  const int w0 = blockIdx.x * 4 + warp, wstride = gridDim.x * 4;
+  int buf = 0;
+  pdl_wait();
+  if (w0 < n_items) fetch(w0, 0);
+  for (int item = w0; item < n_items; item += wstride, buf ^= 1) {
+    const int img = item / tiles, tile = item - img * tiles;
+    const int p0 = tile * 16;
+    const int rows_valid = min(16, n - p0);
+    __half* yt = y + (static_cast<size_t>(img) * n + p0) * C;
+    const __half* rawb = raw + buf * 16 * C;
+    cp_async_wait_group<0>();
+    __syncwarp();  // raw[buf] landed for the whole warp; the previous item's reads of xn / raw[buf^1] are done
+    if (item + wstride < n_items) fetch(item + wstride, buf ^ 1);
+    const uint4* mp_img = mpack + static_cast<size_t>(img) * n_m;
+    // ---- LayerNorm raw[buf] -> xn
+#pragma unroll
+    for (int ps = 0; ps < PASSES; ++ps) {
+      const int r = ln_r0 + ps * RPP;
+      const uint4 rv = *reinterpret_cast<const uint4*>(rawb + r * C + ln_l * 8);
+      const __half2* h = reinterpret_cast<const __half2*>(&rv);
+      float f[8];
+      float sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 t = __half22float2(h[j]);
+        f[2 * j] = t.x;
+        f[2 * j + 1] = t.y;
+        sum += t.x + t.y;
+      }
+#pragma unroll
+      for (int sh = LP / 2; sh > 0; sh >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, sh);
+      const float mean = sum * (1.0f / C);
+      float sq = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        f[j] -= mean;
+        sq = fmaf(f[j], f[j], sq);
+      }
+#pragma unroll
+      for (int sh = LP / 2; sh > 0; sh >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, sh);
+      const float rstd = rsqrtf(sq * (1.0f / C) + eps);
+      uint4 ov;
+      uint32_t* o = reinterpret_cast<uint32_t*>(&ov);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[j] = pack_h2(f[2 * j] * rstd * gm[2 * j], f[2 * j + 1] * rstd * gm[2 * j + 1]);
+      if (r >= rows_valid) ov = make_uint4(0u, 0u, 0u, 0u);
+      *reinterpret_cast<uint4*>(xn + r * XS + ln_l * 8) = ov;
+    }
+    __syncwarp();
+
+    // ---- q[16 rows][128] = xn Wq^T
+    float acc[16][4];
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[i][c] = 0.f;
+#pragma unroll
+    for (int kp = 0; kp < C / 32; ++kp) {
+      uint32_t a0[4], a1[4];
+      ldsm_x4(xn_s + a_off + static_cast<uint32_t>(kp * 32 * 2), a0[0], a0[1], a0[2], a0[3]);
+      ldsm_x4(xn_s + a_off + static_cast<uint32_t>((kp * 32 + 16) * 2), a1[0], a1[1], a1[2], a1[3]);
+#pragma unroll
+      for (int nt = 0; nt < 16; ++nt) {
+        const uint4 b = __ldg(wq + (nt * (C / 32) + kp) * 32 + lane);
+        mma16816(acc[nt], a0, b.x, b.y);
+        mma16816(acc[nt], a1, b.z, b.w);
+      }
+    }
+    // ---- softmax over each head's 32 dims (rows g and g+8 of this warp's 16); scale is folded into M
+    uint32_t aq[8][4];
+#pragma unroll
+    for (int hh = 0; hh < 4; ++hh) {
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        float mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) mx = fmaxf(mx, fmaxf(acc[4 * hh + j][2 * r], acc[4 * hh + j][2 * r + 1]));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float e0 = __expf(acc[4 * hh + j][2 * r] - mx), e1 = __expf(acc[4 * hh + j][2 * r + 1] - mx);
+          acc[4 * hh + j][2 * r] = e0;
+          acc[4 * hh + j][2 * r + 1] = e1;
+          sum += e0 + e1;
+        }
+        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+        const float inv = 1.0f / sum;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          acc[4 * hh + j][2 * r] *= inv;
+          acc[4 * hh + j][2 * r + 1] *= inv;
+        }
+      }
+#pragma unroll
+      for (int k2 = 0; k2 < 2; ++k2) {
+        const int ks = 2 * hh + k2;
+        aq[ks][0] = pack_h2(acc[2 * ks][0], acc[2 * ks][1]);
+        aq[ks][1] = pack_h2(acc[2 * ks][2], acc[2 * ks][3]);
+        aq[ks][2] = pack_h2(acc[2 * ks + 1][0], acc[2 * ks + 1][1]);
+        aq[ks][3] = pack_h2(acc[2 * ks + 1][2], acc[2 * ks + 1][3]);
+      }
+    }
+    // ---- y = q M^T + bias, 64 output channels at a time, written over this warp's own (dead) xn rows
+    const uint4* mp = mp_img + lane;
+    __syncwarp();
+#pragma unroll 1
+    for (int cc = 0; cc < C / 64; ++cc) {
+      float yacc[8][4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) yacc[i][c] = 0.f;
+#pragma unroll
+      for (int kp = 0; kp < 4; ++kp) {
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          const uint4 b = __ldg(mp + ((cc * 8 + nt) * 4 + kp) * 32);
+          mma16816(yacc[nt], aq[2 * kp], b.x, b.y);
+          mma16816(yacc[nt], aq[2 * kp + 1], b.z, b.w);
+        }
+      }
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const int c = cc * 64 + nt * 8 + 2 * q;
+        const float b0 = bias ? __ldg(bias + c) : 0.f, b1 = bias ? __ldg(bias + c + 1) : 0.f;
+        *reinterpret_cast<uint32_t*>(xn + (g) * XS + c) = pack_h2(yacc[nt][0] + b0, yacc[nt][1] + b1);
+        *reinterpret_cast<uint32_t*>(xn + (g + 8) * XS + c) = pack_h2(yacc[nt][2] + b0, yacc[nt][3] + b1);
+      }
+    }
+    __syncwarp();
+    // ---- + residual (from the raw tile in shared memory), coalesced store of this warp's 16 rows
+    constexpr int CPR = C / 8;  // 16-byte chunks per row
+#pragma unroll
+    for (int it = 0; it < 16 * CPR / 32; ++it) {
+      const int idx = it * 32 + lane;
+      const int r = idx / CPR, ch = idx - r * CPR;
+      const int row = r;
+      if (row < rows_valid) {
+        uint4 v = *reinterpret_cast<const uint4*>(xn + row * XS + ch * 8);
+        const uint4 rv = *reinterpret_cast<const uint4*>(rawb + row * C + ch * 8);
+        __half2* vh = reinterpret_cast<__half2*>(&v);
+        const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 a2 = __half22float2(vh[i]), b2 = __half22float2(rh[i]);
+          vh[i] = __floats2half2_rn(a2.x + b2.x, a2.y + b2.y);
+        }
+        *(reinterpret_cast<uint4*>(yt + static_cast<size_t>(row) * C) + ch) = v;
+      }
+    }
+  }
+}
+
 // ================================================================== temporal attention block
 // Residual(PreNorm(dim, EinopsToAndFrom('b c f h w', 'b (h w) f c', Attention(dim, heads=4, dim_head=32, rotary))))
 // reference conv3d.py:165-184, 262-353 (focus_present_mask all False), 74-112 (T5 relative position bias).
@@ -1274,6 +1469,23 @@ static int launch_linattn(const __half* x, __half* y, const float* gamma, const 
              eps);
   launch_pdl(la_mid_kernel, dim3(n_img), dim3(256), static_cast<size_t>(C * kLaHid * 2), st, static_cast<const float*>(part), wout,
              mpack, C, nparts, scale);
+  static const bool use_warp = [] { const char* e = getenv("WDNO_LA2_WARP"); return !(e && e[0] == '0'); }();
+  if (use_warp) {
+    const int smem_w = 4 * (16 * (C + 8) + 2 * 16 * C) * 2;
+    static bool configured_w = false;
+    if (!configured_w) {
+      cudaError_t e = cudaFuncSetAttribute(la2_warp_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_w);
+      if (e != cudaSuccess) return set_cuda_error(e, "linattn_block: cudaFuncSetAttribute");
+      configured_w = true;
+    }
+    const int tiles16 = (n_pos + 15) / 16;
+    const long long items16 = static_cast<long long>(n_img) * tiles16;
+    if (items16 > 2147483647LL) return set_error(WDNO_E_INVALID, "linattn_block: too many tiles");
+    const long long want = (items16 + 3) / 4, capw = static_cast<long long>(num_sms()) * 4;
+    launch_pdl(la2_warp_kernel<C>, dim3(static_cast<unsigned>(want < capw ? want : capw)), dim3(128), static_cast<size_t>(smem_w), st, x,
+               y, gamma, wq, reinterpret_cast<const uint4*>(mpack), bias, n_pos, tiles16, static_cast<int>(items16), eps);
+    return check_launch("linattn_block");
+  }
   const int tiles = (n_pos + 127) / 128;
   const int n_items = n_img * tiles;
   const int cap = num_sms() * 2;
