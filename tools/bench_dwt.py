@@ -1,0 +1,65 @@
+#!/usr/bin/env python
+"""Throughput of the wavelet transforms at the BASELINE shapes (device-timed, inputs resident, L2 flushed between runs):
+  3-D  wavedec3 / waverec3, bior1.3 'zero':  [16*5, 32, 64, 64] <-> 8 x [80, 18, 34, 34]      (smoke, C3/C5 batch)
+  2-D  DWTForward / DWTInverse, bior2.4 'periodization': [256, 2, 81, 120] <-> [256,2,41,60] + [256,2,3,41,60]  (Burgers, C2 batch)
+Reports algorithmic GB/s (5.95 MB per sample per 3-D transform, 156.5 KB per sample 2-D) against the
+measured HBM peak, plus the adjoint (autograd backward) of the inverse used by guided sampling."""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+from wdno_b200 import wavelets as W  # noqa: E402
+
+peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6538.0) if os.path.exists(
+    os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6538.0
+flush = torch.empty(256 * 1024 * 1024 // 4, device="cuda")
+
+
+def timed(fn, n=10):
+    fn()
+    torch.cuda.synchronize()
+    tot = 0.0
+    for _ in range(n):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        tot += e0.elapsed_time(e1)
+    return tot / n
+
+
+def line(name, ms, nbytes):
+    gbs = nbytes / (ms * 1e-3) / 1e9
+    print(json.dumps({"transform": name, "ms": ms, "algorithmic_MB": nbytes / 1e6, "algorithmic_GBps": gbs,
+                      "frac_of_hbm_peak": gbs / peak, "peak_GBps": peak}), flush=True)
+
+
+B = 16
+x3 = torch.randn(B * 5, 32, 64, 64, device="cuda")
+wv = W.Wavelet("bior1.3")
+c3 = W.wavedec3(x3, wv, mode="zero", level=1)
+bytes3 = 4 * (x3.numel() + 8 * c3[0].numel())
+with torch.no_grad():
+    line("wavedec3 bior1.3 zero [80,32,64,64]", timed(lambda: W.wavedec3(x3, wv, mode="zero", level=1)), bytes3)
+    line("waverec3 bior1.3 zero -> [80,32,64,64]", timed(lambda: W.waverec3(c3, wv)), bytes3)
+leaves = [c3[0].clone().requires_grad_()] + [v.clone().requires_grad_() for v in c3[1].values()]
+
+
+def fwd_bwd():
+    y = W.waverec3([leaves[0], dict(zip(c3[1].keys(), leaves[1:]))], wv)
+    torch.autograd.grad(y.square().sum(), leaves)
+
+
+line("waverec3 + adjoint (guidance gradient) [80,32,64,64]", timed(fwd_bwd), 2 * bytes3)
+x2 = torch.randn(256, 2, 81, 120, device="cuda")
+f2, i2 = W.DWTForward(J=1, wave="bior2.4", mode="periodization"), W.DWTInverse(wave="bior2.4", mode="periodization")
+yl, yh = f2(x2)
+bytes2 = 4 * (x2.numel() + yl.numel() + yh[0].numel())
+with torch.no_grad():
+    line("DWTForward bior2.4 per [256,2,81,120]", timed(lambda: f2(x2)), bytes2)
+    line("DWTInverse bior2.4 per -> [256,2,82,120]", timed(lambda: i2((yl, yh))), bytes2)
