@@ -237,6 +237,19 @@ int wdno_dwt_synthesis_axis(const float* lo, const float* hi, float* y, int64_t 
                             int64_t lo_ostride, int64_t hi_ostride, int64_t y_ostride, const float* taps_lo_host,
                             const float* taps_hi_host, int L, int off, int periodic, void* stream);
 
+/* Fused single-pass 3-D transforms ('zero' mode, level 1): ptwt.wavedec3 / waverec3 (call sites
+ * smoke/inference_2d.py:41,141,184,220,250, wave_trans_2d.py:129-149) and, with the other filter pair, their adjoints (the
+ * gradient of the guidance objective, every guided step).  One launch, all three passes in shared memory.
+ * bands8: HOST array of 8 DEVICE pointers in ptwt key order aaa,aad,ada,add,daa,dad,dda,ddd (letters = D,H,W; a = low),
+ * each [B][nd][nh][nw] with batch stride band_bstride (elements) and contiguous planes; x / y: [B][Nd][Nh][Nw] contiguous.
+ *   analysis : band[i_d,i_h,i_w] = sum x(2i+k-off) t_d[k] t_h[k'] t_w[k'']      synthesis: the transposed-convolution form
+ * wdno_dwt3d_supported: 1 if the tile plan fits shared memory for (L, nw, Nw); otherwise use the per-axis entry points. */
+int wdno_dwt3d_supported(int L, int nw, int Nw);
+int wdno_dwt3d_synthesis(const float* const* bands8, int64_t band_bstride, float* y, int64_t B, int nd, int nh, int nw, int Nd,
+                         int Nh, int Nw, const float* taps_lo_host, const float* taps_hi_host, int L, int off, void* stream);
+int wdno_dwt3d_analysis(const float* x, float* const* bands8, int64_t band_bstride, int64_t B, int Nd, int Nh, int Nw, int nd,
+                        int nh, int nw, const float* taps_lo_host, const float* taps_hi_host, int L, int off, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

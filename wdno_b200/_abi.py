@@ -38,6 +38,9 @@ SIGNATURES = {
     "wdno_step_begin": [P, P, P, P, P, I, I, P],
     "wdno_dwt_analysis_axis": [P, P, P, L64, I, L64, I, L64, L64, L64, P, P, I, I, I, P],
     "wdno_dwt_synthesis_axis": [P, P, P, L64, I, L64, I, L64, L64, L64, P, P, I, I, I, P],
+    "wdno_dwt3d_supported": [I, I, I],
+    "wdno_dwt3d_synthesis": [P, L64, P, L64, I, I, I, I, I, I, P, P, I, I, P],
+    "wdno_dwt3d_analysis": [P, P, L64, L64, I, I, I, I, I, I, P, P, I, I, P],
 }
 
 

@@ -13,6 +13,7 @@ fp32 CUDA tensors only; there is no CPU path.
 """
 import ctypes as C
 import math
+import os
 
 import torch
 from torch import nn
@@ -293,6 +294,83 @@ class DWT1DInverse(nn.Module):
 
 # ---------------------------------------------------------------- ptwt-style 3-D transform
 KEYS3 = ("aad", "ada", "add", "daa", "dad", "dda", "ddd")
+_FUSED3D = os.environ.get("WDNO_DWT3D_FUSED", "1") != "0"   # csrc/dwt3d.cu: one launch per 3-D transform / adjoint
+
+
+def _band_ptrs(bands):
+    return (C.c_void_p * 8)(*[b.data_ptr() for b in bands])
+
+
+def _ana3d_raw(x, t_lo, t_hi, off, nout):
+    """x [B,Nd,Nh,Nw] contiguous fp32 -> stacked bands [8,B,nd,nh,nw] (band = 4 d + 2 h + w, 0 = low-pass)"""
+    B, Nd, Nh, Nw = x.shape
+    nd, nh, nw = nout
+    out = torch.empty((8, B, nd, nh, nw), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.lib().wdno_dwt3d_analysis(x.data_ptr(), _band_ptrs([out[i] for i in range(8)]), nd * nh * nw, B, Nd, Nh, Nw,
+                                              nd, nh, nw, _farr(t_lo), _farr(t_hi), len(t_lo), off, _lib.current_stream_ptr()),
+               "dwt3d_analysis")
+    return out
+
+
+def _syn3d_raw(bands, t_lo, t_hi, off, nout):
+    """bands: 8 fp32 tensors [B,nd,nh,nw] (contiguous planes, one common batch stride) -> y [B,Nd,Nh,Nw]"""
+    B, nd, nh, nw = bands[0].shape
+    Nd, Nh, Nw = nout
+    ok = all(b.shape == bands[0].shape and b.stride(3) == 1 and b.stride(2) == nw and b.stride(1) == nh * nw
+             and b.stride(0) == bands[0].stride(0) for b in bands)
+    if not ok:
+        bands = [b.contiguous() for b in bands]
+    y = torch.empty((B, Nd, Nh, Nw), dtype=torch.float32, device=bands[0].device)
+    _lib.check(_lib.lib().wdno_dwt3d_synthesis(_band_ptrs(bands), bands[0].stride(0) if B > 1 else nd * nh * nw, y.data_ptr(), B,
+                                               nd, nh, nw, Nd, Nh, Nw, _farr(t_lo), _farr(t_hi), len(t_lo), off,
+                                               _lib.current_stream_ptr()), "dwt3d_synthesis")
+    return y
+
+
+def _fused3d_ok(L, nw, Nw, *tensors):
+    return (_FUSED3D and all(t.dim() == 4 and t.is_cuda for t in tensors) and tensors[0].shape[0] <= 65535
+            and bool(_lib.lib().wdno_dwt3d_supported(L, nw, Nw)))
+
+
+class _Analysis3D(torch.autograd.Function):
+    """stacked bands [8,B,nd,nh,nw] = wavedec3(x) ('zero'); backward = the fused synthesis with the same filters"""
+
+    @staticmethod
+    def forward(ctx, x, wname):
+        w = Wavelet(wname)
+        L = w.dec_len
+        x = x.to(torch.float32).contiguous()
+        geo = [_geom(n, L, "zero") for n in x.shape[1:]]
+        ctx.cfg = (wname, tuple(x.shape[1:]), geo[0][1])
+        return _ana3d_raw(x, w.dec_lo[::-1], w.dec_hi[::-1], geo[0][1], tuple(g[0] for g in geo))
+
+    @staticmethod
+    def backward(ctx, g):
+        wname, N3, off = ctx.cfg
+        w = Wavelet(wname)
+        g = g.to(torch.float32).contiguous()
+        return _syn3d_raw([g[i] for i in range(8)], w.dec_lo[::-1], w.dec_hi[::-1], off, N3), None
+
+
+class _Synthesis3D(torch.autograd.Function):
+    """y = waverec3(8 bands) ('zero'); backward = the fused analysis with the reconstruction filters"""
+
+    @staticmethod
+    def forward(ctx, wname, *bands):
+        w = Wavelet(wname)
+        L = w.dec_len
+        bands = [b.to(torch.float32) for b in bands]
+        n3 = tuple(bands[0].shape[1:])
+        ctx.cfg = (wname, n3, L - 2)
+        return _syn3d_raw(bands, w.rec_lo, w.rec_hi, L - 2, tuple(2 * n - L + 2 for n in n3))
+
+    @staticmethod
+    def backward(ctx, gy):
+        wname, n3, off = ctx.cfg
+        w = Wavelet(wname)
+        g = _ana3d_raw(gy.to(torch.float32).contiguous(), w.rec_lo, w.rec_hi, off, n3)
+        return (None,) + tuple(g[i] for i in range(8))
+
 
 
 def wavedec3(data, wavelet, *, mode="zero", level=1):
@@ -303,6 +381,9 @@ def wavedec3(data, wavelet, *, mode="zero", level=1):
     if _mode_id(mode) != 0:
         raise NotImplementedError("WDNO only uses mode='zero' for the 3-D transform")
     w = _wave(wavelet)
+    if _fused3d_ok(w.dec_len, _geom(data.shape[3], w.dec_len, "zero")[0], data.shape[3], data):
+        bands = _Analysis3D.apply(data, w.name)
+        return [bands[0], {k: bands[i + 1] for i, k in enumerate(KEYS3)}]
     out = {}
     for kd, xd in zip("ad", afb1d(data, w, "zero", axis=1)):
         for kh, xh in zip("ad", afb1d(xd, w, "zero", axis=2)):
@@ -317,6 +398,10 @@ def waverec3(coeffs, wavelet):
     _check(aaa)
     b = dict(d)
     b["aaa"] = aaa
+    L = w.dec_len
+    if all(k in b for k in KEYS3) and _fused3d_ok(L, aaa.shape[-1], 2 * aaa.shape[-1] - L + 2, *[b[k] for k in ("aaa",) + KEYS3]) \
+            and all(b[k].shape == aaa.shape for k in KEYS3):
+        return _Synthesis3D.apply(w.name, *[b[k] for k in ("aaa",) + KEYS3])
     xd = {}
     for kd in "ad":
         xh = {}
