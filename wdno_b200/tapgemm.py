@@ -300,7 +300,10 @@ class TapGemm:
                     # A-stationary 1x1 plans carry no estimate: more planes per item = fewer weight re-streams
                     take = bool(pf.reuse) and pf.ZT > chosen.ZT
                 else:
-                    take = est0 is not None and self._last_est is not None and self._last_est < 0.8 * est0  # clear wins only
+                    # clear wins only, and only planes that fit one 128-position tile (8x8): measured on the Burgers U-Net,
+                    # folding 16x16 / 32x32 layers (ZT = 4, PT = 1) loses 10-30 % against ZT = 1, PT = 4
+                    take = (est0 is not None and self._last_est is not None and self._last_est < 0.8 * est0
+                            and H * (W + self.KW // 2) <= 128)
                 if take or force:
                     chosen = pf
                 break
