@@ -36,24 +36,27 @@ __device__ __forceinline__ void stage_weights(uint4* dst, const uint4* __restric
 constexpr int kLaPart = 64 + 32 * 32;  // floats per (image, part, head): max[32], sum[32], S[32][32]
 
 // ------------------------------------------------------------------ la1: context partials
-template <int C, bool WS>
-__global__ void __launch_bounds__(256, 2) la1_kernel(const __half* __restrict__ x, const float* __restrict__ gamma,
-                                                  const uint4* wkv, float* __restrict__ part, int n, int split,
-                                                  float eps) {
+// NPH = position halves per block: 2 -> 8 warps share a 64-position LayerNorm tile (two block barriers per tile);
+// 1 -> 4 warps (one per head) per 32-position tile, twice as many blocks resident per SM -- the barriers couple fewer warps
+template <int C, bool WS, int NPH>
+__global__ void __launch_bounds__(128 * NPH, (NPH == 2) ? 2 : 4) la1_kernel(const __half* __restrict__ x, const float* __restrict__ gamma,
+                                                                         const uint4* wkv, float* __restrict__ part, int n, int split,
+                                                                         float eps) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   pdl_trigger();
-  __half* xn = reinterpret_cast<__half*>(smem_raw);  // [64][C + 8]
+  constexpr int TP = 32 * NPH, NT_ = 128 * NPH;   // positions per tile, threads per block
+  __half* xn = reinterpret_cast<__half*>(smem_raw);  // [TP][C + 8]
   constexpr int XS = C + 8;
   constexpr int KS = C / 16;
   const int img = blockIdx.x / split, sp = blockIdx.x - img * split;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, q = lane & 3;
   const int h = warp & 3, ph = warp >> 2;
-  const int tiles = (n + 63) >> 6;
+  const int tiles = (n + TP - 1) / TP;
   const int t0 = (tiles * sp) / split, t1 = (tiles * (sp + 1)) / split;
   if constexpr (WS) {
-    uint4* wsm = reinterpret_cast<uint4*>(smem_raw + 64 * XS * 2);
-    stage_weights(wsm, wkv, 2 * 4 * 2 * KS * 32, threadIdx.x, 256);
+    uint4* wsm = reinterpret_cast<uint4*>(smem_raw + TP * XS * 2);
+    stage_weights(wsm, wkv, 2 * 4 * 2 * KS * 32, threadIdx.x, NT_);
     wkv = wsm;  // visible after the first barrier of the tile loop
   }
   const uint4* wk = wkv + static_cast<size_t>((0 * 4 + h) * 2) * KS * 32 + lane;
@@ -77,8 +80,8 @@ __global__ void __launch_bounds__(256, 2) la1_kernel(const __half* __restrict__ 
   pdl_wait();  // weights above are plan constants; x is the predecessor's output
   for (int t = t0; t < t1; ++t) {
     __syncthreads();
-    const int p0 = t * 64;
-    ln_tile<C, 64, 256>(ximg + static_cast<size_t>(p0) * C, min(64, n - p0), gamma, xn, eps);
+    const int p0 = t * TP;
+    ln_tile<C, TP, NT_>(ximg + static_cast<size_t>(p0) * C, min(TP, n - p0), gamma, xn, eps);
     __syncthreads();
     // ---- k^T[d][p] = Wk_h xn^T
     float acc[2][4][4];
@@ -185,7 +188,7 @@ __global__ void __launch_bounds__(256, 2) la1_kernel(const __half* __restrict__ 
     }
   }
   // ---- partial of this (image, part = 2*sp + ph, head)
-  float* dst = part + (static_cast<size_t>(img * (split * 2) + sp * 2 + ph) * kLaHeads + h) * kLaPart;
+  float* dst = part + (static_cast<size_t>(img * (split * NPH) + sp * NPH + ph) * kLaHeads + h) * kLaPart;
 #pragma unroll
   for (int ri = 0; ri < 4; ++ri) {
     float zz = z[ri];
@@ -1453,20 +1456,27 @@ static int launch_linattn(const __half* x, __half* y, const float* gamma, const 
   const int nparts = split * 2;
   float* part = static_cast<float*>(work);
   __half* mpack = reinterpret_cast<__half*>(part + static_cast<size_t>(n_img) * nparts * kLaHeads * kLaPart);
-  constexpr bool WS1 = (C <= 128);  // la1: K/V weight fragments staged in shared memory while two blocks still fit per SM
+  constexpr bool WS1 = (C <= 128);  // la1: K/V weight fragments staged in shared memory while the blocks still fit per SM
+  static const bool la1_small = [] { const char* e = getenv("WDNO_LA1_NPH"); return !(e && e[0] == '2'); }();
   constexpr bool WS2 = (C == 64);   // la2: Wq and the image's M fragments in shared memory
   const int smem1 = 64 * (C + 8) * 2 + (WS1 ? 2 * 4 * 2 * (C / 16) * 32 * 16 : 0);
+  const int smem1s = 32 * (C + 8) * 2 + (WS1 ? 2 * 4 * 2 * (C / 16) * 32 * 16 : 0);
   const int smem2 = 128 * (C + 8) * 2 + 2 * 128 * C * 2 + (WS2 ? (16 * (C / 32) + (C / 8) * 4) * 32 * 16 : 0);
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(la2_kernel<C, WS2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(la_mid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * kLaHid * 2);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(la1_kernel<C, WS1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(la1_kernel<C, WS1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(la1_kernel<C, WS1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1s);
     if (e != cudaSuccess) return set_cuda_error(e, "linattn_block: cudaFuncSetAttribute");
     configured = true;
   }
-  launch_pdl(la1_kernel<C, WS1>, dim3(n_img * split), dim3(256), static_cast<size_t>(smem1), st, x, gamma, wkv, part, n_pos, split,
-             eps);
+  if (la1_small)   // same number of partials (split * 2): twice the blocks, one 32-position column each
+    launch_pdl(la1_kernel<C, WS1, 1>, dim3(n_img * split * 2), dim3(128), static_cast<size_t>(smem1s), st, x, gamma, wkv, part, n_pos,
+               split * 2, eps);
+  else
+    launch_pdl(la1_kernel<C, WS1, 2>, dim3(n_img * split), dim3(256), static_cast<size_t>(smem1), st, x, gamma, wkv, part, n_pos, split,
+               eps);
   launch_pdl(la_mid_kernel, dim3(n_img), dim3(256), static_cast<size_t>(C * kLaHid * 2), st, static_cast<const float*>(part), wout,
              mpack, C, nparts, scale);
   static const bool use_warp = [] { const char* e = getenv("WDNO_LA2_WARP"); return !(e && e[0] == '0'); }();
