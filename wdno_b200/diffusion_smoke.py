@@ -6,6 +6,7 @@ The sampling loop keeps the state `x` [B,F,C,H,W] fp32 resident in HBM; one step
 captured once in a CUDA graph and replayed per step (per-step scalars come from device tables).
 """
 import math
+import os
 
 import torch
 import torch.nn.functional as F
@@ -119,9 +120,20 @@ class StepRunner:
         self.use_graph = use_graph
         self.launches_per_step = None
 
+    def _net(self):
+        """eps = model(x, t) with the engine told that t is batch-uniform (step_begin writes one value to every row)"""
+        eng = self.model.engine() if hasattr(self.model, "engine") else None
+        if eng is None or not hasattr(eng, "forward") or os.environ.get("WDNO_TIME_UNIFORM", "1") == "0":
+            return self.model(self.x, self.time_f)
+        eng.time_uniform = True
+        try:
+            return self.model(self.x, self.time_f)
+        finally:
+            eng.time_uniform = False
+
     def _body(self, with_noise, guidance=None):
         ops.step_begin(self.step, self.time_table, self.coef_table, self.time_f, self.coef, self.n)
-        eps = self.model(self.x, self.time_f)
+        eps = self._net()
         fn = ops.ddim_step if self.kind == "ddim" else ops.ddpm_step
         fn(self.x, eps, self.noise if with_noise else None, self.coef, self.prog, self.cond_mode, guidance=guidance)
         return eps
@@ -132,7 +144,7 @@ class StepRunner:
     def step_guided(self, with_noise, design):
         """design(x0) -> gradient tensor (user code; torch autograd) ; eps += gscale * g inside the fused kernel."""
         ops.step_begin(self.step, self.time_table, self.coef_table, self.time_f, self.coef, self.n)
-        eps = self.model(self.x, self.time_f)
+        eps = self._net()
         x0 = ops.predict_x0(self.x, eps, self.coef, clip=(self.kind == "ddim"))
         g = design(x0)
         if not torch.is_tensor(g):

@@ -217,7 +217,8 @@ class Unet2DEngine:
         count = float(D * H * W * (p.cout // G))
         st1, st2 = stats[p.stat1], stats[p.stat2]
         y1 = p.conv1(src0, src1, stats=st1, groups=G)
-        a1, c1 = ops.gn_finalize(st1, p.g1, p.b1, ss, p.ss_off, ss.shape[1], B, p.cout, G, count)
+        a1, c1 = ops.gn_finalize(st1, p.g1, p.b1, ss, p.ss_off, ss.shape[1] if self._ss_stride is None else self._ss_stride,
+                                 B, p.cout, G, count)
         y2 = p.conv2(y1, coef0=(a1, c1), stats=st2, groups=G)
         a2, c2 = ops.gn_finalize(st2, p.g2, p.b2, None, 0, 0, B, p.cout, G, count)
         self.launches += 5
@@ -247,6 +248,10 @@ class Unet2DEngine:
         x = x.contiguous().float()
         B, C, H, W = x.shape
         tf = time.to(device=x.device, dtype=torch.float32).contiguous()
+        self._ss_stride = None  # see Unet3DEngine.forward: batch-uniform time -> one embedded row, zero row stride
+        if getattr(self, "time_uniform", False):
+            tf = tf[:1]
+            self._ss_stride = 0
         emb, emb_silu = ops.time_mlp(tf, self.tw1, self.tb1, self.tw2, self.tb2, theta=self.theta)
         ss = ops.small_linear(emb_silu, self.mlp_w, self.mlp_b)
         stats = torch.zeros((self.stats_slots, B, self.groups, 2), dtype=torch.float64, device=x.device)

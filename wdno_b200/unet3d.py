@@ -321,7 +321,8 @@ class Unet3DEngine:
         st1, st2 = stats[p.stat1], stats[p.stat2]
         y1 = p.conv1(src0, src1, stats=st1, groups=self.groups)
         a1, c1 = ops.gn_finalize(st1, p.g1, p.b1, ss if p.ss_off is not None else None, p.ss_off or 0,
-                                 0 if ss is None else ss.shape[1], B, p.cout, self.groups, count)
+                                 0 if ss is None else (ss.shape[1] if self._ss_stride is None else self._ss_stride), B, p.cout,
+                                 self.groups, count)
         y2 = p.conv2(y1, coef0=(a1, c1), stats=st2, groups=self.groups)
         a2, c2 = ops.gn_finalize(st2, p.g2, p.b2, None, 0, 0, B, p.cout, self.groups, count)
         self.launches += 4
@@ -357,6 +358,12 @@ class Unet3DEngine:
         x = x.contiguous().float()
         B = x.shape[0]
         tf = time.to(device=x.device, dtype=torch.float32).contiguous()
+        # the samplers feed one batch-uniform time per step (StepRunner sets time_uniform): embed ONE row and let every
+        # sample read it through a zero row stride (the block MLPs are 1 ms of a batch-256 Burgers step otherwise)
+        self._ss_stride = None
+        if getattr(self, "time_uniform", False):
+            tf = tf[:1]
+            self._ss_stride = 0
         emb, emb_silu = ops.time_mlp(tf, self.tw1, self.tb1, self.tw2, self.tb2)
         ss = ops.small_linear(emb_silu, self.mlp_w, self.mlp_b)
         stats = torch.zeros((self.stats_slots, B, self.groups, 2), dtype=torch.float64, device=x.device)
