@@ -167,9 +167,7 @@ class GaussianDiffusion(nn.Module):
 
     def _guided_step(self, run, with_noise, nabla_J, sched, proj):
         """eps' = proj_guidance(eps, nablaJ(x0) * J_scheduler(t))  (user callables, torch), then the fused update"""
-        ops.step_begin(run.step, run.time_table, run.coef_table, run.time_f, run.coef, run.n)
-        eps = run._net()
-        x0 = ops.predict_x0(run.x, eps, run.coef, clip=(run.kind == "ddim"))
+        eps, x0 = run.guided_head()   # step_begin -> U-Net -> x0, replayed from its own CUDA graph
         t = int(run.times[int(run.step.item()) - 1])
         with torch.enable_grad():
             g = nabla_J(x0[:, 0]) * sched(t)

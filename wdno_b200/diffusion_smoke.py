@@ -141,11 +141,33 @@ class StepRunner:
     def step_eager(self, with_noise):
         self._body(with_noise)
 
+    def guided_head(self):
+        """step_begin -> U-Net -> x0 prediction of a guided step: -> (eps, x0).  Everything before the user's callback is
+        replayed from a CUDA graph of its own (static eps / x0 buffers), so a guided step costs one graph launch + the
+        callback + the fused update instead of ~125 eager launches."""
+        clip = self.kind == "ddim"
+
+        def head():
+            ops.step_begin(self.step, self.time_table, self.coef_table, self.time_f, self.coef, self.n)
+            eps = self._net()
+            return eps, ops.predict_x0(self.x, eps, self.coef, clip=clip)
+        if not self.use_graph:
+            return head()
+        if getattr(self, "_head_graph", None) is None:
+            s0 = self.step.clone()
+            head()                      # warm-up outside capture (lazy plans, table uploads); x is not modified
+            torch.cuda.synchronize()
+            self.step.copy_(s0)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._head_out = head()
+            self._head_graph = g
+        self._head_graph.replay()
+        return self._head_out
+
     def step_guided(self, with_noise, design):
         """design(x0) -> gradient tensor (user code; torch autograd) ; eps += gscale * g inside the fused kernel."""
-        ops.step_begin(self.step, self.time_table, self.coef_table, self.time_f, self.coef, self.n)
-        eps = self._net()
-        x0 = ops.predict_x0(self.x, eps, self.coef, clip=(self.kind == "ddim"))
+        eps, x0 = self.guided_head()
         g = design(x0)
         if not torch.is_tensor(g):
             g = None
