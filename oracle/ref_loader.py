@@ -121,7 +121,7 @@ def install_wavelet_shims():
     own glue code (inference_2d.py guidance_fn / InferencePipeline, eval_ddpm_burgers.py helpers) runs unchanged."""
     from . import wavelets_torch as wt
     _install_shims()
-    for name, attrs in (("pywt", dict(Wavelet=wt.Wavelet)),
+    for name, attrs in (("pywt", dict(Wavelet=wt.Wavelet, dwt_max_level=wt.dwt_max_level)),
                         ("ptwt", dict(wavedec3=wt.wavedec3, waverec3=wt.waverec3)),
                         ("pytorch_wavelets", dict(DWTForward=wt.DWTForward, DWTInverse=wt.DWTInverse,
                                                   DWT1DForward=wt.DWT1DForward, DWT1DInverse=wt.DWT1DInverse))):
@@ -213,3 +213,30 @@ def burgers():
                                model_utils=model_utils, wavelet_utils=wavelet_utils, wave_trans=wt)
     _cache["burgers"] = ns
     return ns
+
+
+def run_reference_main(rel_path, cwd):
+    """Execute a reference script's `__main__` block unchanged (runpy, run_name='__main__') with `cwd` as the working
+    directory -- used for the offline coefficient builders (smoke/wave_trans_2d.py:61-189, burgers/wave_trans.py:66-127),
+    whose inputs and outputs are relative paths.  The wavelet stand-ins must be installed first (install_wavelet_shims).
+    Returns the exception that ended the script, if any (the smoke builder loops over 20 000 hard-coded simulation ids and
+    stops at the first missing directory, after having saved the files of the simulations that exist)."""
+    import runpy
+    assert available(), "reference tree not mounted"
+    install_wavelet_shims()
+    path = os.path.join(REF_ROOT, rel_path)
+    sdir = os.path.dirname(path)
+    old, added = os.getcwd(), False
+    if sdir not in sys.path:
+        sys.path.insert(0, sdir)
+        added = True
+    os.chdir(cwd)
+    try:
+        runpy.run_path(path, run_name="__main__")
+        return None
+    except (FileNotFoundError, OSError) as e:
+        return e
+    finally:
+        os.chdir(old)
+        if added:
+            sys.path.remove(sdir)

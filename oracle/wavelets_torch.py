@@ -34,6 +34,19 @@ class Wavelet:
         return self.dec_len
 
 
+def dwt_max_level(data_len, filter_len):
+    """pywt.dwt_max_level: floor(log2(data_len / (filter_len - 1))), 0 if the filter is longer than the signal; the second
+    argument may be a wavelet name (wave_trans.py:87, wave_trans_2d.py:92)"""
+    import math
+    if isinstance(filter_len, str):
+        filter_len = len(filter_bank(filter_len)[0])
+    elif hasattr(filter_len, "dec_len"):
+        filter_len = filter_len.dec_len
+    if filter_len < 2 or data_len < filter_len - 1:
+        return 0
+    return int(math.floor(math.log2(data_len / (filter_len - 1))))
+
+
 def _name(w):
     return w if isinstance(w, str) else w.name
 

@@ -252,7 +252,81 @@ def burgers_cascade_fixture():
     print("burgers_cascade", float(g.norm()), [l["u_norm"] for l in res["levels"]], [l["shapes"] for l in res["levels"]])
 
 
+# ------------------------------------------------------------------ offline coefficient builders
+BUILDER_STRIDE = 3
+
+
+def builder_inputs_smoke(n_sims=2, T=16, H=16, seed=77):
+    """synthetic raw simulations in the reference's .npy layouts (wave_trans_2d.py:99-108): Density [H,W,1,T],
+    Velocity / Control [H,W,2,T], Smoke [T,2] (positive)"""
+    g = torch.Generator().manual_seed(seed)
+    sims = []
+    for _ in range(n_sims):
+        sims.append(dict(Density=torch.randn(H, H, 1, T, generator=g).numpy(), Velocity=torch.randn(H, H, 2, T, generator=g).numpy(),
+                         Control=torch.randn(H, H, 2, T, generator=g).numpy(),
+                         Smoke=(torch.rand(T, 2, generator=g) + 0.1).numpy()))
+    return sims
+
+
+def builder_inputs_burgers(N=3, seed=78):
+    g = torch.Generator().manual_seed(seed)
+    return dict(u=torch.randn(N, 81, 120, generator=g), f=torch.randn(N, 80, 120, generator=g))
+
+
+def write_smoke_sims(root, sims):
+    import numpy as np
+    for i, sim in enumerate(sims):
+        d = os.path.join(root, "data", "2d", "train", "sim_{:06d}".format(i))
+        os.makedirs(d, exist_ok=True)
+        for k, v in sim.items():
+            np.save(os.path.join(d, k + ".npy"), v)
+
+
+def summarise(rec):
+    """strided sub-samples + norms of every tensor of a saved record (files are MBs; the layout is what is pinned)"""
+    out = {}
+    for k, v in rec.items():
+        if isinstance(v, list) and v and torch.is_tensor(v[0]):
+            out[k] = [dict(shape=tuple(t.shape), sub=sub(t, BUILDER_STRIDE), norm=float(t.double().norm())) for t in v]
+        elif isinstance(v, list):
+            out[k] = [tuple(x) for x in v]
+            out[k + "_type"] = type(v[0]).__name__
+        else:
+            out[k] = tuple(v)
+            out[k + "_type"] = type(v).__name__
+    return out
+
+
+def builders_fixture():
+    """run the reference's own __main__ builders (unchanged, wavelet stand-ins installed) on synthetic raw data in a
+    temporary working directory and keep summaries of the files they write"""
+    import tempfile
+    res = dict(stride=BUILDER_STRIDE, smoke_seed=77, burgers_seed=78)
+    with tempfile.TemporaryDirectory() as tmp:
+        sims = builder_inputs_smoke()
+        write_smoke_sims(tmp, sims)
+        err = ref_loader.run_reference_main("smoke/wave_trans_2d.py", tmp)
+        assert isinstance(err, FileNotFoundError) and "sim_000002" in str(err), err  # 20 000 ids are hard-coded
+        wave_dir = os.path.join(tmp, "data", "2d", "train", "bior1.3_zero")
+        res["smoke"] = {kind: [summarise(torch.load(os.path.join(wave_dir, kind + "_downsample", "{:06d}".format(i)),
+                                                    weights_only=False)) for i in range(len(sims))]
+                        for kind in ("time", "space")}
+        os.makedirs(os.path.join(tmp, "data", "1d"), exist_ok=True)
+        torch.save(builder_inputs_burgers(), os.path.join(tmp, "data", "1d", "train"))
+        err = ref_loader.run_reference_main("burgers/wave_trans.py", tmp)
+        assert err is None, err
+        res["burgers"] = summarise(torch.load(os.path.join(tmp, "data", "1d", "coef_bior2.4_periodization_super"),
+                                              weights_only=False))
+    torch.save(res, os.path.join(HERE, "coef_builders.pt"))
+    print("coef_builders", [c["shape"] for c in res["smoke"]["time"][0]["coef"]],
+          [c["shape"] for c in res["smoke"]["space"][0]["coef"]], res["smoke"]["time"][0]["shape"],
+          [c["shape"] for c in res["burgers"]["coef"]], res["burgers"]["shape"], res["burgers"]["ori_shape"])
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "builders":
+        builders_fixture()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "burgers_cascade":
         burgers_cascade_fixture()
         sys.exit(0)

@@ -33,6 +33,27 @@ def timed(fn, n=10):
     return tot / n
 
 
+def graph_timed(make_fn, nsets=4, reps=5):
+    """GPU time per call with the Python / launch overhead removed: the call is captured once per input set into a CUDA
+    graph (nsets distinct input and output buffers, together larger than the 126 MB L2) and the graph is replayed."""
+    fns = [make_fn(i) for i in range(nsets)]
+    keep = [f() for f in fns]  # warm-up (plans, attributes)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        keep = [f() for f in fns]
+    g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    del keep
+    return e0.elapsed_time(e1) / (reps * nsets)
+
+
 def line(name, ms, nbytes):
     gbs = nbytes / (ms * 1e-3) / 1e9
     print(json.dumps({"transform": name, "ms": ms, "algorithmic_MB": nbytes / 1e6, "algorithmic_GBps": gbs,
@@ -63,3 +84,19 @@ bytes2 = 4 * (x2.numel() + yl.numel() + yh[0].numel())
 with torch.no_grad():
     line("DWTForward bior2.4 per [256,2,81,120]", timed(lambda: f2(x2)), bytes2)
     line("DWTInverse bior2.4 per -> [256,2,82,120]", timed(lambda: i2((yl, yh))), bytes2)
+
+# ---- the same transforms without host overhead (CUDA-graph replays over 4 rotating buffer sets, 380 MB > L2)
+xs = [torch.randn_like(x3) for _ in range(4)]
+cs = [W.wavedec3(x, wv, mode="zero", level=1) for x in xs]
+with torch.no_grad():
+    line("graph: wavedec3 bior1.3 zero [80,32,64,64]", graph_timed(lambda i: (lambda: W.wavedec3(xs[i], wv, mode="zero", level=1))), bytes3)
+    line("graph: wavedec3_packed (builder layout) [80,32,64,64]", graph_timed(lambda i: (lambda: W.wavedec3_packed(xs[i], wv))), bytes3)
+    line("graph: waverec3 bior1.3 zero -> [80,32,64,64]", graph_timed(lambda i: (lambda: W.waverec3(cs[i], wv))), bytes3)
+    x5 = [x[:40] for x in xs]
+    c5 = [W.wavedec3(x, wv, mode="zero", level=1) for x in x5]
+    line("graph: waverec3 [40,32,64,64] (C5 per-GPU batch)", graph_timed(lambda i: (lambda: W.waverec3(c5[i], wv))), bytes3 // 2)
+    line("graph: wavedec3 [40,32,64,64] (C5 adjoint shape)", graph_timed(lambda i: (lambda: W.wavedec3(x5[i], wv, mode="zero", level=1))), bytes3 // 2)
+    x2s = [torch.randn_like(x2) for _ in range(4)]
+    y2s = [f2(x) for x in x2s]
+    line("graph: DWTForward bior2.4 per [256,2,81,120]", graph_timed(lambda i: (lambda: f2(x2s[i]))), bytes2)
+    line("graph: DWTInverse bior2.4 per -> [256,2,82,120]", graph_timed(lambda i: (lambda: i2(y2s[i]))), bytes2)

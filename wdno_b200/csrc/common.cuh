@@ -21,6 +21,13 @@ int launch_short_attn_mma(const void* qkv, void* out, const float* bias, const f
 int launch_flash_attn_mma(const void* qkv, void* out, long long n_seq, int n_tok, long long inner, long long outerT,
                           long long innerT, long long tokT, float scale, cudaStream_t st);
 
+// dwt3d_stream.cu: streaming (register sliding-window) form of the fused 3-D transforms; return 1 = launched, 0 = shape or
+// alignment outside the envelope (use the tile kernels of dwt3d.cu), < 0 = error
+int launch_ana3d_stream(const float* x, float* const* bands8, long long band_bstride, long long B, int Nd, int Nh, int Nw, int nd,
+                        int nh, int nw, const float* t0, const float* t1, int L, int off, cudaStream_t st);
+int launch_syn3d_stream(const float* const* bands8, long long band_bstride, float* y, long long B, int nd, int nh, int nw, int Nd,
+                        int Nh, int Nw, const float* t0, const float* t1, int L, int off, cudaStream_t st);
+
 // ---- programmatic dependent launch (PDL): a kernel launched through launch_pdl may start (run its prologue) while
 // the previous kernel of the stream drains; it must execute pdl_wait() before touching anything a predecessor wrote.
 // Every kernel calls pdl_trigger() first so that its successor can be scheduled as early as resources allow.

@@ -281,6 +281,9 @@ extern "C" int wdno_dwt3d_synthesis(const float* const* bands8, int64_t band_bst
   }
   int rc = fill(p, taps_lo_host, taps_hi_host, L);
   if (rc) return rc;
+  rc = launch_syn3d_stream(bands8, band_bstride, y, B, nd, nh, nw, Nd, Nh, Nw, taps_lo_host, taps_hi_host, L, off,
+                           static_cast<cudaStream_t>(stream));
+  if (rc != 0) return rc < 0 ? rc : WDNO_OK;   // 0: outside the streaming kernel's envelope -> tile kernel below
   p.y = y;
   p.band_bstride = band_bstride;
   p.sig_bstride = static_cast<long long>(Nd) * Nh * Nw;
@@ -315,6 +318,9 @@ extern "C" int wdno_dwt3d_analysis(const float* x, float* const* bands8, int64_t
   }
   int rc = fill(p, taps_lo_host, taps_hi_host, L);
   if (rc) return rc;
+  rc = launch_ana3d_stream(x, bands8, band_bstride, B, Nd, Nh, Nw, nd, nh, nw, taps_lo_host, taps_hi_host, L, off,
+                           static_cast<cudaStream_t>(stream));
+  if (rc != 0) return rc < 0 ? rc : WDNO_OK;   // 0: outside the streaming kernel's envelope -> tile kernel below
   p.x = x;
   p.band_bstride = band_bstride;
   p.sig_bstride = static_cast<long long>(Nd) * Nh * Nw;

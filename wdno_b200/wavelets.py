@@ -409,3 +409,47 @@ def waverec3(coeffs, wavelet):
             xh[kh] = sfb1d(b[kd + kh + "a"], b[kd + kh + "d"], w, "zero", axis=3)
         xd[kd] = sfb1d(xh["a"], xh["d"], w, "zero", axis=2)
     return sfb1d(xd["a"], xd["d"], w, "zero", axis=1)
+
+
+# ---------------------------------------------------------------- packed forms for the offline coefficient builders
+def wavedec3_packed(data, wavelet, *, mode="zero"):
+    """data [B,D,H,W] -> [B,8,nd,nh,nw], bit-identical to smoke `coef_to_tensor(ptwt.wavedec3(data, ...))`
+    (wave_trans_2d.py:55-58,129-130): the fused kernel writes the eight sub-bands straight into their slots of the
+    packed tensor (band pointers = out[:, i], batch stride 8 nd nh nw), so the stack/cat pass never runs.  No autograd."""
+    _check(data)
+    if _mode_id(mode) != 0:
+        raise NotImplementedError("WDNO only uses mode='zero' for the 3-D transform")
+    w = _wave(wavelet)
+    L = w.dec_len
+    x = data.detach().to(torch.float32).contiguous()
+    geo = [_geom(n, L, "zero") for n in x.shape[1:]]
+    nd, nh, nw = (g[0] for g in geo)
+    if not _fused3d_ok(L, nw, x.shape[3], x):
+        yl, yh = wavedec3(x, w, mode=mode)
+        return torch.cat((yl[:, None], torch.stack([yh[k] for k in KEYS3], dim=1)), dim=1)
+    B = x.shape[0]
+    out = torch.empty((B, 8, nd, nh, nw), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.lib().wdno_dwt3d_analysis(x.data_ptr(), _band_ptrs([out[:, i] for i in range(8)]), 8 * nd * nh * nw, B,
+                                              x.shape[1], x.shape[2], x.shape[3], nd, nh, nw, _farr(w.dec_lo[::-1]),
+                                              _farr(w.dec_hi[::-1]), L, geo[0][1], _lib.current_stream_ptr()),
+               "dwt3d_analysis")
+    return out
+
+
+def dwt2_packed(x, wave, mode):
+    """x [B,C,H,W] -> [B,C,4,h,w] = (LL, LH, HL, HH) of one level: `cat((Yl[:, :, None], Yh[0]), 2)` of
+    DWTForward(J=1), i.e. Burgers `coef_to_tensor(Yl, Yh)` for J = 1 (wave_trans.py:43-52,107-108) and, for C = 1, the smoke
+    builder's `cat((Yl0, Yh0[0][:, 0]), 1)` (wave_trans_2d.py:136-137).  The column pass writes into the packed tensor."""
+    _check(x)
+    w = _wave(wave)
+    L = w.dec_len
+    x = x.detach().to(torch.float32).contiguous()
+    B, Cc, H, W = x.shape
+    nw_, offw, per = _geom(W, L, mode)
+    nh_, offh, _ = _geom(H, L, mode)
+    tl, th = w.dec_lo[::-1], w.dec_hi[::-1]
+    lo_w, hi_w = _analysis_raw(x, 3, tl, th, offw, per, nw_)
+    out = torch.empty((B, Cc, 4, nh_, nw_), dtype=torch.float32, device=x.device)
+    _analysis_raw(lo_w, 2, tl, th, offh, per, nh_, lo=out[:, :, 0], hi=out[:, :, 1])
+    _analysis_raw(hi_w, 2, tl, th, offh, per, nh_, lo=out[:, :, 2], hi=out[:, :, 3])
+    return out
