@@ -61,11 +61,13 @@ def line(name, ms, nbytes):
 
 
 B = 16
+GRAPH3D_ONLY = "--graph3d" in sys.argv  # tile sweeps: only the host-overhead-free 3-D lines
 x3 = torch.randn(B * 5, 32, 64, 64, device="cuda")
 wv = W.Wavelet("bior1.3")
 c3 = W.wavedec3(x3, wv, mode="zero", level=1)
 bytes3 = 4 * (x3.numel() + 8 * c3[0].numel())
 with torch.no_grad():
+  if not GRAPH3D_ONLY:
     line("wavedec3 bior1.3 zero [80,32,64,64]", timed(lambda: W.wavedec3(x3, wv, mode="zero", level=1)), bytes3)
     line("waverec3 bior1.3 zero -> [80,32,64,64]", timed(lambda: W.waverec3(c3, wv)), bytes3)
 leaves = [c3[0].clone().requires_grad_()] + [v.clone().requires_grad_() for v in c3[1].values()]
@@ -76,12 +78,14 @@ def fwd_bwd():
     torch.autograd.grad(y.square().sum(), leaves)
 
 
-line("waverec3 + adjoint (guidance gradient) [80,32,64,64]", timed(fwd_bwd), 2 * bytes3)
+if not GRAPH3D_ONLY:
+    line("waverec3 + adjoint (guidance gradient) [80,32,64,64]", timed(fwd_bwd), 2 * bytes3)
 x2 = torch.randn(256, 2, 81, 120, device="cuda")
 f2, i2 = W.DWTForward(J=1, wave="bior2.4", mode="periodization"), W.DWTInverse(wave="bior2.4", mode="periodization")
 yl, yh = f2(x2)
 bytes2 = 4 * (x2.numel() + yl.numel() + yh[0].numel())
 with torch.no_grad():
+  if not GRAPH3D_ONLY:
     line("DWTForward bior2.4 per [256,2,81,120]", timed(lambda: f2(x2)), bytes2)
     line("DWTInverse bior2.4 per -> [256,2,82,120]", timed(lambda: i2((yl, yh))), bytes2)
 
@@ -96,6 +100,10 @@ with torch.no_grad():
     c5 = [W.wavedec3(x, wv, mode="zero", level=1) for x in x5]
     line("graph: waverec3 [40,32,64,64] (C5 per-GPU batch)", graph_timed(lambda i: (lambda: W.waverec3(c5[i], wv))), bytes3 // 2)
     line("graph: wavedec3 [40,32,64,64] (C5 adjoint shape)", graph_timed(lambda i: (lambda: W.wavedec3(x5[i], wv, mode="zero", level=1))), bytes3 // 2)
+    # adjoint of waverec3 (guidance gradient): the analysis kernel with the reconstruction filters
+    line("graph: waverec3 adjoint [80,32,64,64]", graph_timed(lambda i: (lambda: W._ana3d_raw(xs[i], wv.rec_lo, wv.rec_hi, 4, (18, 34, 34)))), bytes3)
+    if GRAPH3D_ONLY:
+        sys.exit(0)
     x2s = [torch.randn_like(x2) for _ in range(4)]
     y2s = [f2(x) for x in x2s]
     line("graph: DWTForward bior2.4 per [256,2,81,120]", graph_timed(lambda i: (lambda: f2(x2s[i]))), bytes2)

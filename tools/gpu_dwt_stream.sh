@@ -1,9 +1,17 @@
-# streaming 3-D DWT kernels: parity tests, then throughput per tile configuration
-python -m pytest tests/test_gpu_wavelets.py tests/test_coef_builders.py tests/test_gpu_pipeline.py -x -q -m gpu 2>&1 | tail -5
-echo "== default"; python tools/bench_dwt.py 2>&1 | head -3 | cut -c1-140
-echo "== tile kernels"; WDNO_DWT3D_STREAM=0 python tools/bench_dwt.py 2>&1 | head -3 | cut -c1-140
-for cfg in "17 18 16 16" "9 9 8 8" "9 6 8 6" "6 18 4 16" "17 9 16 8" "12 18 11 16"; do
-  set -- $cfg
-  echo "== ATH=$1 ATD=$2 STH=$3 STD=$4"
-  WDNO_DWT3D_ATH=$1 WDNO_DWT3D_ATD=$2 WDNO_DWT3D_STH=$3 WDNO_DWT3D_STD=$4 python tools/bench_dwt.py 2>&1 | head -3 | cut -c1-140
-done
+# streaming 3-D DWT kernels: parity tests, then GPU time per tile configuration (CUDA-graph replays)
+python -m pytest tests/test_gpu_wavelets.py tests/test_coef_builders.py tests/test_gpu_pipeline.py tests/test_gpu_smoke.py -x -q -m gpu 2>&1 | tail -5
+run() { echo "== $*"; env "$@" python tools/bench_dwt.py --graph3d 2>&1 | python -c "
+import sys, json
+for l in sys.stdin:
+    try: d = json.loads(l)
+    except Exception: print(l.rstrip()[:200]); continue
+    print('   %-58s %7.1f us  %6.0f GB/s' % (d['transform'], d['ms'] * 1e3, d['algorithmic_GBps']))"; }
+run WDNO_X=default
+run WDNO_DWT3D_ANR=1
+run WDNO_DWT3D_ATHREADS=320
+run WDNO_DWT3D_ATHREADS=192
+run WDNO_DWT3D_ATH=12 WDNO_DWT3D_ATD=18 WDNO_DWT3D_STH=16 WDNO_DWT3D_STD=16
+run WDNO_DWT3D_ATH=12 WDNO_DWT3D_ATD=6 WDNO_DWT3D_STH=8 WDNO_DWT3D_STD=4
+run WDNO_DWT3D_ATH=18 WDNO_DWT3D_ATD=9 WDNO_DWT3D_STH=16 WDNO_DWT3D_STD=8
+run WDNO_DWT3D_ATH=6 WDNO_DWT3D_ATD=18 WDNO_DWT3D_STH=4 WDNO_DWT3D_STD=16
+run WDNO_DWT3D_ATH=8 WDNO_DWT3D_ATD=9 WDNO_DWT3D_STH=11 WDNO_DWT3D_STD=8

@@ -36,7 +36,9 @@ struct S3 {
   int nd, nh, nw, Nd, Nh, Nw;
   int off;
   int TH, TD;        // output rows / output planes per CTA (coefficient units for analysis, signal pairs for synthesis)
-  int R, RS;         // tile rows, tile row stride (floats)
+  int R, RS;         // tile rows; analysis: tile row stride, synthesis: band tile size (floats)
+  int nq_shift;      // analysis: log2(Nw / 4) or -1
+  int v16;           // synthesis: band runs are 16-byte aligned
   float t0[10], t1[10];
 };
 
@@ -54,12 +56,22 @@ __device__ __forceinline__ void cpa_commit() { asm volatile("cp.async.commit_gro
 template <int N>
 __device__ __forceinline__ void cpa_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// tap masks: bit k of M0 / M1 set = taps t0[k] / t1[k] may be non-zero.  bior1.3 has two non-zero taps of six in its
+// high-pass analysis filter (and in the low-pass reconstruction filter); skipping the products with exact zeros leaves the
+// results unchanged (acc + 0 * v) and lets the compiler drop the loads and whole row passes that only fed them.
+template <unsigned M>
+__device__ __forceinline__ float fm(int k, float a, float t, float acc) {
+  return ((M >> k) & 1u) ? fmaf(a, t, acc) : acc;
+}
+
 // ---------------------------------------------------------------- analysis
-// grid (h strips, d chunks, B); block >= TH * nw threads.  Tile of one signal plane: R = 2 TH + L - 2 rows of RS floats,
-// column c of the tile = signal column c - off (left / right pads and rows outside [0, Nh) stay zero from the initial fill).
-template <int L>
+// grid (h strips, d chunks, B); block >= (TH / NR) * nw threads; a thread owns NR consecutive output rows at one column
+// (their 6-row input windows overlap: L + 2 (NR - 1) row passes serve NR outputs).  Tile of one signal plane:
+// R = 2 TH + L - 2 rows of RS floats, tile column c = signal column c - off (pads and rows outside [0, Nh) stay zero).
+template <int L, int NR, unsigned M0, unsigned M1>
 __global__ void __launch_bounds__(640) ana3d_stream_kernel(const S3 p) {
   extern __shared__ __align__(16) float sm[];
+  constexpr int KR = L + 2 * (NR - 1);
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int b = blockIdx.z;
   const int ih0 = blockIdx.x * p.TH, id0 = blockIdx.y * p.TD;
@@ -67,20 +79,19 @@ __global__ void __launch_bounds__(640) ana3d_stream_kernel(const S3 p) {
   const int nw = p.nw, Nw = p.Nw, R = p.R, RS = p.RS;
   const int PT = R * RS;
   for (int i = tid; i < kStages * PT; i += nthr) sm[i] = 0.f;
-  // rows of the tile that exist in the signal: tile row r <-> signal row xr0 + r
-  const int xr0 = 2 * ih0 - p.off;
+  const int xr0 = 2 * ih0 - p.off;                          // tile row r <-> signal row xr0 + r
   const int r_lo = max(0, -xr0), r_hi = min(R, p.Nh - xr0);
   const int nq = Nw >> 2;                                   // 16-byte chunks per row
   const int nchunk = max(0, r_hi - r_lo) * nq;
   const float* xb = p.x + b * p.sig_bstride + static_cast<long long>(xr0 + r_lo) * Nw;
-  const int NP = 2 * (id1 - id0) + L - 2;                   // planes this CTA streams
+  const int NP = 2 * (id1 - id0) + L - 2;                   // planes this CTA streams (even)
   const int gd0 = 2 * id0 - p.off;                          // signal plane of step 0
-  // this thread's position
-  const int pos = tid < p.TH * nw ? tid : 0;
-  const int ihl = pos / nw, iw = pos - ihl * nw;
-  const int ih = ih0 + ihl;
-  const bool live = tid < p.TH * nw && ih < p.nh;
-  const int tbase = (2 * ihl) * RS + 2 * iw;
+  const int ngrp = p.TH / NR;
+  const int pos = tid < ngrp * nw ? tid : 0;
+  const int ihg = pos / nw, iw = pos - ihg * nw;
+  const int ihb = ih0 + NR * ihg;                           // first of this thread's NR output rows
+  const bool mine = tid < ngrp * nw;
+  const int tbase = (2 * NR * ihg) * RS + 2 * iw;
   __syncthreads();
 
   auto issue = [&](int s) {
@@ -88,32 +99,31 @@ __global__ void __launch_bounds__(640) ana3d_stream_kernel(const S3 p) {
     if (s < NP && gd >= 0 && gd < p.Nd) {
       float* dst = sm + (s % kStages) * PT + r_lo * RS + p.off;
       const float* src = xb + static_cast<long long>(gd) * p.Nh * Nw;
-      for (int c = tid; c < nchunk; c += nthr) {
-        const int r = c / nq, q = c - r * nq;
-        cpa16(dst + r * RS + 4 * q, src + static_cast<long long>(r) * Nw + 4 * q);
+      if (p.nq_shift >= 0) {
+        for (int c = tid; c < nchunk; c += nthr) {
+          const int r = c >> p.nq_shift, q = c & (nq - 1);
+          cpa16(dst + r * RS + 4 * q, src + r * Nw + 4 * q);
+        }
+      } else {
+        for (int c = tid; c < nchunk; c += nthr) {
+          const int r = c / nq, q = c - r * nq;
+          cpa16(dst + r * RS + 4 * q, src + r * Nw + 4 * q);
+        }
       }
     }
     cpa_commit();
   };
+  // W + H passes of one plane for this thread's NR rows: a[r][2 hb + wb]
+  auto plane = [&](int s, float (&a)[NR][4]) {
 #pragma unroll
-  for (int s = 0; s < kStages - 1; ++s) issue(s);
-
-  float win[4][L];
+    for (int r = 0; r < NR; ++r)
 #pragma unroll
-  for (int c = 0; c < 4; ++c)
-#pragma unroll
-    for (int k = 0; k < L; ++k) win[c][k] = 0.f;
-
-  for (int s = 0; s < NP; ++s) {
-    cpa_wait<kStages - 2>();
-    __syncthreads();              // plane s has landed for everyone; everyone is done with plane s - 1 (its slot is refilled next)
-    issue(s + kStages - 1);
+      for (int c = 0; c < 4; ++c) a[r][c] = 0.f;
     const int gd = gd0 + s;
-    float a[4] = {0.f, 0.f, 0.f, 0.f};
     if (gd >= 0 && gd < p.Nd) {
       const float* tp = sm + (s % kStages) * PT + tbase;
 #pragma unroll
-      for (int kh = 0; kh < L; ++kh) {
+      for (int kh = 0; kh < KR; ++kh) {
         float v[L];
 #pragma unroll
         for (int j = 0; j < L / 2; ++j) {
@@ -124,35 +134,70 @@ __global__ void __launch_bounds__(640) ana3d_stream_kernel(const S3 p) {
         float wl = 0.f, wh = 0.f;
 #pragma unroll
         for (int k = 0; k < L; ++k) {
-          wl = fmaf(v[k], p.t0[k], wl);
-          wh = fmaf(v[k], p.t1[k], wh);
+          wl = fm<M0>(k, v[k], p.t0[k], wl);
+          wh = fm<M1>(k, v[k], p.t1[k], wh);
         }
-        a[0] = fmaf(wl, p.t0[kh], a[0]);   // hw = 2 hb + wb
-        a[1] = fmaf(wh, p.t0[kh], a[1]);
-        a[2] = fmaf(wl, p.t1[kh], a[2]);
-        a[3] = fmaf(wh, p.t1[kh], a[3]);
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+          const int k = kh - 2 * r;
+          if (k >= 0 && k < L) {
+            a[r][0] = fm<M0>(k, wl, p.t0[k], a[r][0]);
+            a[r][1] = fm<M0>(k, wh, p.t0[k], a[r][1]);
+            a[r][2] = fm<M1>(k, wl, p.t1[k], a[r][2]);
+            a[r][3] = fm<M1>(k, wh, p.t1[k], a[r][3]);
+          }
+        }
       }
     }
+  };
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+  for (int s = 0; s < kStages - 1; ++s) issue(s);
+
+  float win[NR][4][L];
 #pragma unroll
-      for (int k = 0; k < L - 1; ++k) win[c][k] = win[c][k + 1];
-      win[c][L - 1] = a[c];
-    }
-    const int e = s - (L - 1);
-    if (e >= 0 && !(e & 1) && live) {   // window = planes 2 m .. 2 m + L - 1 of the chunk: coefficient plane id0 + m
-      const int gid = id0 + (e >> 1);
-      const long long o = b * p.band_bstride + (static_cast<long long>(gid) * p.nh + ih) * nw + iw;
+  for (int r = 0; r < NR; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int k = 0; k < L; ++k) win[r][c][k] = 0.f;
+
+  for (int sp = 0; 2 * sp < NP; ++sp) {   // two planes per iteration: the window moves by 2, one coefficient plane comes out
+    float a0[NR][4], a1[NR][4];
+    cpa_wait<kStages - 2>();
+    __syncthreads();              // plane s has landed for everyone; everyone is done with plane s - 1 (its slot is refilled next)
+    issue(2 * sp + kStages - 1);
+    plane(2 * sp, a0);
+    cpa_wait<kStages - 2>();
+    __syncthreads();
+    issue(2 * sp + kStages);
+    plane(2 * sp + 1, a1);
+#pragma unroll
+    for (int r = 0; r < NR; ++r)
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        float lo = 0.f, hi = 0.f;
 #pragma unroll
-        for (int k = 0; k < L; ++k) {
-          lo = fmaf(win[c][k], p.t0[k], lo);
-          hi = fmaf(win[c][k], p.t1[k], hi);
+        for (int k = 0; k + 2 < L; ++k) win[r][c][k] = win[r][c][k + 2];
+        win[r][c][L - 2] = a0[r][c];
+        win[r][c][L - 1] = a1[r][c];
+      }
+    const int m = sp + 1 - L / 2;  // window = planes 2 m .. 2 m + L - 1 of the chunk: coefficient plane id0 + m
+    if (m >= 0 && mine) {
+      const int gid = id0 + m;
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        if (ihb + r >= p.nh) continue;
+        const long long o = b * p.band_bstride + (static_cast<long long>(gid) * p.nh + ihb + r) * nw + iw;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float lo = 0.f, hi = 0.f;
+#pragma unroll
+          for (int k = 0; k < L; ++k) {
+            lo = fm<M0>(k, win[r][c][k], p.t0[k], lo);
+            hi = fm<M1>(k, win[r][c][k], p.t1[k], hi);
+          }
+          p.band_out[c][o] = lo;
+          p.band_out[4 + c][o] = hi;
         }
-        p.band_out[c][o] = lo;
-        p.band_out[4 + c][o] = hi;
       }
     }
   }
@@ -162,7 +207,7 @@ __global__ void __launch_bounds__(640) ana3d_stream_kernel(const S3 p) {
 // ---------------------------------------------------------------- synthesis
 // grid (h strips, d chunks, B); block >= TH * (Nw / 2) threads.  Tile of one coefficient plane: 8 bands x R = TH + L/2 - 1
 // rows x nw floats (a flat copy of the contiguous run of each band plane; rows at or beyond nh stay zero).
-template <int L>
+template <int L, unsigned M0, unsigned M1>
 __global__ void __launch_bounds__(640) syn3d_stream_kernel(const S3 p) {
   extern __shared__ __align__(16) float sm[];
   constexpr int H = L / 2;
@@ -172,10 +217,10 @@ __global__ void __launch_bounds__(640) syn3d_stream_kernel(const S3 p) {
   const int QD = (p.Nd + 1) >> 1, QW = p.Nw >> 1;
   const int qd1 = min(qd0 + p.TD, QD);
   const int nw = p.nw, R = p.R;
-  const int BT = R * nw, PT = 8 * BT;
+  const int BT = p.RS, PT = 8 * BT;                         // band tile (R nw rounded up to 16 bytes), plane tile
   for (int i = tid; i < kStages * PT; i += nthr) sm[i] = 0.f;
   const int r_hi = min(R, p.nh - qh0);
-  const int nchunk = max(0, r_hi) * (nw >> 1);              // 8-byte chunks per band
+  const int nfl = max(0, r_hi) * nw;                        // floats per band run (even)
   const long long run0 = b * p.band_bstride + static_cast<long long>(qh0) * nw;
   const int NP = (qd1 - qd0) + H - 1;
   const int pos = tid < p.TH * QW ? tid : 0;
@@ -183,6 +228,7 @@ __global__ void __launch_bounds__(640) syn3d_stream_kernel(const S3 p) {
   const int qh = qh0 + qhl;
   const bool live = tid < p.TH * QW && 2 * qh < p.Nh;
   const int tbase = qhl * nw + qw;
+  const int warp = tid >> 5, lane = tid & 31, nwarps = nthr >> 5;
   __syncthreads();
 
   auto issue = [&](int s) {
@@ -190,10 +236,20 @@ __global__ void __launch_bounds__(640) syn3d_stream_kernel(const S3 p) {
     if (s < NP && gid < p.nd) {
       float* dst = sm + (s % kStages) * PT;
       const long long o = run0 + static_cast<long long>(gid) * p.nh * nw;
+      if (p.v16) {                                          // a warp per band, 16-byte chunks (+ one 8-byte tail)
+        const int n16 = nfl >> 2;
+        for (int bd = warp; bd < 8; bd += nwarps) {
+          const float* src = p.band_in[bd] + o;
+          float* d = dst + bd * BT;
+          for (int c = lane; c < n16; c += 32) cpa16(d + 4 * c, src + 4 * c);
+          if ((nfl & 2) && lane == 0) cpa8(d + 4 * n16, src + 4 * n16);
+        }
+      } else {
 #pragma unroll
-      for (int bd = 0; bd < 8; ++bd) {
-        const float* src = p.band_in[bd] + o;
-        for (int c = tid; c < nchunk; c += nthr) cpa8(dst + bd * BT + 2 * c, src + 2 * c);
+        for (int bd = 0; bd < 8; ++bd) {
+          const float* src = p.band_in[bd] + o;
+          for (int c = tid; 2 * c < nfl; c += nthr) cpa8(dst + bd * BT + 2 * c, src + 2 * c);
+        }
       }
     }
     cpa_commit();
@@ -233,10 +289,10 @@ __global__ void __launch_bounds__(640) syn3d_stream_kernel(const S3 p) {
             float e = 0.f, o = 0.f;
 #pragma unroll
             for (int jw = 0; jw < H; ++jw) {
-              e = fmaf(cl[H - 1 - jw], p.t0[2 * jw], e);
-              e = fmaf(ch[H - 1 - jw], p.t1[2 * jw], e);
-              o = fmaf(cl[H - 1 - jw], p.t0[2 * jw + 1], o);
-              o = fmaf(ch[H - 1 - jw], p.t1[2 * jw + 1], o);
+              e = fm<M0>(2 * jw, cl[H - 1 - jw], p.t0[2 * jw], e);
+              e = fm<M1>(2 * jw, ch[H - 1 - jw], p.t1[2 * jw], e);
+              o = fm<M0>(2 * jw + 1, cl[H - 1 - jw], p.t0[2 * jw + 1], o);
+              o = fm<M1>(2 * jw + 1, ch[H - 1 - jw], p.t1[2 * jw + 1], o);
             }
             w[hb][0] = e;
             w[hb][1] = o;
@@ -246,8 +302,8 @@ __global__ void __launch_bounds__(640) syn3d_stream_kernel(const S3 p) {
 #pragma unroll
             for (int wp = 0; wp < 2; ++wp) {
               float acc = a[4 * db + 2 * hp + wp];
-              acc = fmaf(w[0][wp], p.t0[2 * j + hp], acc);
-              acc = fmaf(w[1][wp], p.t1[2 * j + hp], acc);
+              acc = fm<M0>(2 * j + hp, w[0][wp], p.t0[2 * j + hp], acc);
+              acc = fm<M1>(2 * j + hp, w[1][wp], p.t1[2 * j + hp], acc);
               a[4 * db + 2 * hp + wp] = acc;
             }
         }
@@ -274,10 +330,10 @@ __global__ void __launch_bounds__(640) syn3d_stream_kernel(const S3 p) {
           float acc0 = 0.f, acc1 = 0.f;
 #pragma unroll
           for (int j = 0; j < H; ++j) {
-            acc0 = fmaf(win[H - 1 - j][2 * hp + 0], p.t0[2 * j + dp], acc0);
-            acc0 = fmaf(win[H - 1 - j][4 + 2 * hp + 0], p.t1[2 * j + dp], acc0);
-            acc1 = fmaf(win[H - 1 - j][2 * hp + 1], p.t0[2 * j + dp], acc1);
-            acc1 = fmaf(win[H - 1 - j][4 + 2 * hp + 1], p.t1[2 * j + dp], acc1);
+            acc0 = fm<M0>(2 * j + dp, win[H - 1 - j][2 * hp + 0], p.t0[2 * j + dp], acc0);
+            acc0 = fm<M1>(2 * j + dp, win[H - 1 - j][4 + 2 * hp + 0], p.t1[2 * j + dp], acc0);
+            acc1 = fm<M0>(2 * j + dp, win[H - 1 - j][2 * hp + 1], p.t0[2 * j + dp], acc1);
+            acc1 = fm<M1>(2 * j + dp, win[H - 1 - j][4 + 2 * hp + 1], p.t1[2 * j + dp], acc1);
           }
           out.x = acc0;
           out.y = acc1;
@@ -324,6 +380,51 @@ int prep(K kernel, size_t smem, const char* where) {
   return e == cudaSuccess ? WDNO_OK : set_cuda_error(e, where);
 }
 
+unsigned nz_mask(const float* t, int L) {
+  unsigned m = 0;
+  for (int k = 0; k < L; ++k)
+    if (t[k] != 0.f) m |= 1u << k;
+  return m;
+}
+
+void fill_taps(S3& p, const float* t0, const float* t1, int L) {
+  for (int k = 0; k < 10; ++k) {
+    p.t0[k] = k < L ? t0[k] : 0.f;
+    p.t1[k] = k < L ? t1[k] : 0.f;
+  }
+}
+
+template <typename K>
+int launch(K kernel, size_t& cfg, dim3 grid, int block, size_t smem, cudaStream_t st, const S3& p, const char* where) {
+  if (smem > cfg) {
+    int rc = prep(kernel, smem, where);
+    if (rc) return rc;
+    cfg = smem;
+  }
+  kernel<<<grid, block, smem, st>>>(p);
+  return check_launch(where);
+}
+
+template <int L, int NR>
+int launch_ana(unsigned nz0, unsigned nz1, dim3 grid, int block, size_t smem, cudaStream_t st, const S3& p) {
+  const char* where = "dwt3d_analysis(stream)";
+  constexpr unsigned F = (1u << L) - 1u, MID = 3u << (L / 2 - 1);   // all taps / the two centre taps
+  static size_t c0 = 0, c1 = 0, c2 = 0;
+  if (L == 6 && !(nz1 & ~MID)) return launch(ana3d_stream_kernel<L, NR, F, MID>, c1, grid, block, smem, st, p, where);
+  if (L == 6 && !(nz0 & ~MID)) return launch(ana3d_stream_kernel<L, NR, MID, F>, c2, grid, block, smem, st, p, where);
+  return launch(ana3d_stream_kernel<L, NR, F, F>, c0, grid, block, smem, st, p, where);
+}
+
+template <int L>
+int launch_syn(unsigned nz0, unsigned nz1, dim3 grid, int block, size_t smem, cudaStream_t st, const S3& p) {
+  const char* where = "dwt3d_synthesis(stream)";
+  constexpr unsigned F = (1u << L) - 1u, MID = 3u << (L / 2 - 1);
+  static size_t c0 = 0, c1 = 0, c2 = 0;
+  if (L == 6 && !(nz1 & ~MID)) return launch(syn3d_stream_kernel<L, F, MID>, c1, grid, block, smem, st, p, where);
+  if (L == 6 && !(nz0 & ~MID)) return launch(syn3d_stream_kernel<L, MID, F>, c2, grid, block, smem, st, p, where);
+  return launch(syn3d_stream_kernel<L, F, F>, c0, grid, block, smem, st, p, where);
+}
+
 }  // namespace
 
 // returns 1 if the streaming kernel was launched, 0 if the shape / alignment is outside its envelope (caller falls back to the
@@ -336,39 +437,36 @@ int launch_ana3d_stream(const float* x, float* const* bands8, long long band_bst
   if (nw > 640 || B > 65535) return 0;
   S3 p = {};
   for (int i = 0; i < 8; ++i) p.band_out[i] = bands8[i];
-  for (int k = 0; k < 10; ++k) {
-    p.t0[k] = k < L ? t0[k] : 0.f;
-    p.t1[k] = k < L ? t1[k] : 0.f;
-  }
+  fill_taps(p, t0, t1, L);
   p.x = x;
   p.band_bstride = band_bstride;
   p.sig_bstride = static_cast<long long>(Nd) * Nh * Nw;
   p.nd = nd; p.nh = nh; p.nw = nw; p.Nd = Nd; p.Nh = Nh; p.Nw = Nw; p.off = off;
   static const int th_env = env_int("WDNO_DWT3D_ATH", 0), td_env = env_int("WDNO_DWT3D_ATD", 0);
-  p.TH = th_env > 0 ? (th_env < nh ? th_env : nh) : pick_rows(nh, nw, 320);
-  if (p.TH * nw > 640) p.TH = 640 / nw;
+  static const int nr_env = env_int("WDNO_DWT3D_ANR", 1), thr_env = env_int("WDNO_DWT3D_ATHREADS", 256);
+  const int NR = (nr_env == 2 && nh >= 2 && L <= 6) ? 2 : 1;  // output rows per thread (2: measured 7 % slower, fewer warps)
+  p.TH = th_env > 0 ? (th_env < nh ? th_env : nh) : pick_rows(nh, (nw + NR - 1) / NR, thr_env);
+  p.TH = ((p.TH + NR - 1) / NR) * NR;
+  while (p.TH > NR && (p.TH / NR) * nw > 640) p.TH -= NR;
+  if ((p.TH / NR) * nw > 640) return 0;
   const int strips = (nh + p.TH - 1) / p.TH;
   p.TD = td_env > 0 ? (td_env < nd ? td_env : nd) : pick_planes(nd, static_cast<long long>(strips) * B);
   p.R = 2 * p.TH + L - 2;
   p.RS = ((2 * nw + L - 2 > off + Nw ? 2 * nw + L - 2 : off + Nw) + 3) & ~3;
+  const int nq = Nw >> 2;
+  p.nq_shift = -1;
+  for (int sh = 0; sh < 16; ++sh)
+    if ((1 << sh) == nq) p.nq_shift = sh;
   const size_t smem = sizeof(float) * kStages * static_cast<size_t>(p.R) * p.RS;
   if (smem > 200 * 1024) return 0;
-  const int block = ((p.TH * nw + 31) / 32) * 32;
+  const int block = (((p.TH / NR) * nw + 31) / 32) * 32;
   dim3 grid(strips, (nd + p.TD - 1) / p.TD, static_cast<unsigned>(B));
   if (grid.y > 65535) return 0;
+  const unsigned nz0 = nz_mask(t0, L), nz1 = nz_mask(t1, L);
   int rc;
-#define WDNO_AS(LL)                                                                  \
-  {                                                                                  \
-    static size_t cfg = 0;                                                           \
-    if (smem > cfg) {                                                                \
-      if ((rc = prep(ana3d_stream_kernel<LL>, smem, "dwt3d_analysis(stream)"))) return rc; \
-      cfg = smem;                                                                    \
-    }                                                                                \
-    ana3d_stream_kernel<LL><<<grid, block, smem, st>>>(p);                           \
-  }
-  if (L == 6) WDNO_AS(6) else if (L == 10) WDNO_AS(10) else WDNO_AS(2)
-#undef WDNO_AS
-  rc = check_launch("dwt3d_analysis(stream)");
+  if (L == 6) rc = NR == 2 ? launch_ana<6, 2>(nz0, nz1, grid, block, smem, st, p) : launch_ana<6, 1>(nz0, nz1, grid, block, smem, st, p);
+  else if (L == 10) rc = NR == 2 ? launch_ana<10, 2>(nz0, nz1, grid, block, smem, st, p) : launch_ana<10, 1>(nz0, nz1, grid, block, smem, st, p);
+  else rc = NR == 2 ? launch_ana<2, 2>(nz0, nz1, grid, block, smem, st, p) : launch_ana<2, 1>(nz0, nz1, grid, block, smem, st, p);
   return rc ? rc : 1;
 }
 
@@ -377,18 +475,18 @@ int launch_syn3d_stream(const float* const* bands8, long long band_bstride, floa
   if (!stream_enabled()) return 0;
   if (L != 2 && L != 6 && L != 10) return 0;
   if (off != L - 2 || (Nw & 1) || (nw & 1) || (band_bstride & 1) || (reinterpret_cast<uintptr_t>(y) & 7)) return 0;
-  for (int i = 0; i < 8; ++i)
+  bool a16 = !(band_bstride & 3) && !((static_cast<long long>(nh) * nw) & 3);
+  for (int i = 0; i < 8; ++i) {
     if (reinterpret_cast<uintptr_t>(bands8[i]) & 7) return 0;
+    if (reinterpret_cast<uintptr_t>(bands8[i]) & 15) a16 = false;
+  }
   // every coefficient an output needs must exist: N <= 2 n - L + 2 per axis
   if (Nd > 2 * nd - L + 2 || Nh > 2 * nh - L + 2 || Nw > 2 * nw - L + 2) return 0;
   const int QW = Nw >> 1, QH = (Nh + 1) >> 1, QD = (Nd + 1) >> 1;
   if (QW > 640 || B > 65535) return 0;
   S3 p = {};
   for (int i = 0; i < 8; ++i) p.band_in[i] = bands8[i];
-  for (int k = 0; k < 10; ++k) {
-    p.t0[k] = k < L ? t0[k] : 0.f;
-    p.t1[k] = k < L ? t1[k] : 0.f;
-  }
+  fill_taps(p, t0, t1, L);
   p.y = y;
   p.band_bstride = band_bstride;
   p.sig_bstride = static_cast<long long>(Nd) * Nh * Nw;
@@ -399,25 +497,18 @@ int launch_syn3d_stream(const float* const* bands8, long long band_bstride, floa
   const int strips = (QH + p.TH - 1) / p.TH;
   p.TD = td_env > 0 ? (td_env < QD ? td_env : QD) : pick_planes(QD, static_cast<long long>(strips) * B);
   p.R = p.TH + L / 2 - 1;
-  p.RS = nw;
-  const size_t smem = sizeof(float) * kStages * 8 * static_cast<size_t>(p.R) * nw;
+  p.RS = (p.R * nw + 3) & ~3;                               // band tile, 16-byte multiple
+  p.v16 = (a16 && !((static_cast<long long>(p.TH) * nw) & 3)) ? 1 : 0;   // every strip's run starts on a 16-byte boundary
+  const size_t smem = sizeof(float) * kStages * 8 * static_cast<size_t>(p.RS);
   if (smem > 200 * 1024) return 0;
   const int block = ((p.TH * QW + 31) / 32) * 32;
   dim3 grid(strips, (QD + p.TD - 1) / p.TD, static_cast<unsigned>(B));
   if (grid.y > 65535) return 0;
+  const unsigned nz0 = nz_mask(t0, L), nz1 = nz_mask(t1, L);
   int rc;
-#define WDNO_SS(LL)                                                                  \
-  {                                                                                  \
-    static size_t cfg = 0;                                                           \
-    if (smem > cfg) {                                                                \
-      if ((rc = prep(syn3d_stream_kernel<LL>, smem, "dwt3d_synthesis(stream)"))) return rc; \
-      cfg = smem;                                                                    \
-    }                                                                                \
-    syn3d_stream_kernel<LL><<<grid, block, smem, st>>>(p);                           \
-  }
-  if (L == 6) WDNO_SS(6) else if (L == 10) WDNO_SS(10) else WDNO_SS(2)
-#undef WDNO_SS
-  rc = check_launch("dwt3d_synthesis(stream)");
+  if (L == 6) rc = launch_syn<6>(nz0, nz1, grid, block, smem, st, p);
+  else if (L == 10) rc = launch_syn<10>(nz0, nz1, grid, block, smem, st, p);
+  else rc = launch_syn<2>(nz0, nz1, grid, block, smem, st, p);
   return rc ? rc : 1;
 }
 
