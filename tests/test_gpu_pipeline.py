@@ -101,6 +101,37 @@ def test_guided_base_pipeline_vs_reference_golden():
     assert abs(float(out.norm()) - gold["out_norm"]) < 1e-2 * gold["out_norm"]
 
 
+def test_guided_sampling_whole_step_graph_matches_eager_callback():
+    """opt-in capture of design_fn with the step (graph_design_fn): same trajectory as the default path, also when a second
+    sample() call binds different init_u / init tensors (the graph is re-captured per design closure)"""
+    from wdno_b200.diffusion_smoke import GaussianDiffusion
+    from wdno_b200.smoke import inference_2d as inf
+    m = _model(42).cuda().eval()
+    shape, ori_shape = [18, 34, 34], [32, 64, 64]
+    rescaler = torch.linspace(0.5, 3.0, 42).reshape(1, 1, 42, 1, 1).cuda()
+    gd = GaussianDiffusion(m, rescaler, False, True, True, False, "bior1.3", "zero", shape, ori_shape, image_size=40,
+                           frames=24, timesteps=1000, sampling_timesteps=4, ddim_sampling_eta=1.0,
+                           standard_fixed_ratio=100.0).cuda()
+    args = _args(False, False)
+    args.w_energy, args.w_init = 0.5, 0.1
+    design_fn = inf.make_design_fn(args, shape, ori_shape, rescaler)
+    gen = torch.Generator().manual_seed(5)
+    outs = {}
+    for call in range(2):
+        init = torch.randn(2, 24, 40, 40, generator=gen).cuda()
+        init_u = torch.randn(2, 64, 64, generator=gen).cuda()
+        for mode in (False, True):
+            gd.graph_design_fn = mode
+            gd._noise_source = _tape(31 + call)
+            outs[(call, mode)] = gd.sample(batch_size=2, design_fn=design_fn, design_guidance="standard", init=init,
+                                           init_u=init_u)
+        a, b = outs[(call, False)], outs[(call, True)]
+        assert torch.isfinite(b).all() and rel_l2(b, a) < 1e-4, (call, rel_l2(b, a))
+    assert rel_l2(outs[(1, True)], outs[(0, True)]) > 1e-2   # the second call really used its own conditions
+    run = next(iter(gd._runners.values()))
+    assert not getattr(run, "_gg_failed", False) and len(run._gg[1]) == 2   # with / without noise, both captured
+
+
 def test_super_resolution_cascade_vs_reference_golden():
     """C4 shape at batch 1: base DDIM -> x2 coefficient up-sampling -> 82-channel model on [1,24,82,80,80]
     (`low` conditioning, replicate-padded control coefficients, N_upsample=1) -> fields at 64^2 and 128^2"""

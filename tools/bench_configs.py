@@ -137,8 +137,20 @@ def c5(steps):
             run.noise.normal_()
             run.step_eager(True)
         ms_plain = timed(step_plain, steps)
+
+        def step_gg():
+            run.noise.normal_()
+            run.step_guided(True, design, graph=True)
+        ms_gg = timed(step_gg, steps)
+
+        def step_graph():
+            run.noise.normal_()
+            run.step_graph(True)
+        ms_graph = timed(step_graph, steps)
     report("C5", "smoke control: base Unet3D, guided DDIM-500 (inverse DWT + adjoint per step), batch 8 per GPU", ms,
-           326.35e9 * B, {"ms_per_step_unguided_eager": ms_plain, "guidance_overhead_ms": ms - ms_plain})
+           326.35e9 * B, {"ms_per_step_unguided_eager": ms_plain, "guidance_overhead_ms": ms - ms_plain,
+            "ms_per_step_whole_step_graph(graph_design_fn=True)": ms_gg, "steps_per_s_whole_step_graph": 1e3 / ms_gg,
+            "ms_per_step_unguided_graph": ms_graph, "guidance_overhead_ms_whole_step_graph": ms_gg - ms_graph})
 
 
 if __name__ == "__main__":

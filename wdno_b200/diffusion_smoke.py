@@ -165,9 +165,14 @@ class StepRunner:
         self._head_graph.replay()
         return self._head_out
 
-    def step_guided(self, with_noise, design):
+    def _guided_body(self, with_noise, design, head_graph):
         """design(x0) -> gradient tensor (user code; torch autograd) ; eps += gscale * g inside the fused kernel."""
-        eps, x0 = self.guided_head()
+        if head_graph:
+            eps, x0 = self.guided_head()
+        else:
+            ops.step_begin(self.step, self.time_table, self.coef_table, self.time_f, self.coef, self.n)
+            eps = self._net()
+            x0 = ops.predict_x0(self.x, eps, self.coef, clip=self.kind == "ddim")
         g = design(x0)
         if not torch.is_tensor(g):
             g = None
@@ -175,6 +180,40 @@ class StepRunner:
             g = g.detach().to(torch.float32).contiguous()
         fn = ops.ddim_step if self.kind == "ddim" else ops.ddpm_step
         fn(self.x, eps, self.noise if with_noise else None, self.coef, self.prog, self.cond_mode, guidance=g)
+
+    def step_guided(self, with_noise, design, graph=False):
+        """One guided step.  Default: graph of the head + eager callback + fused update.  graph=True (opt-in,
+        `GaussianDiffusion.graph_design_fn` / WDNO_GRAPH_GUIDANCE=1): the WHOLE step, callback included, is captured
+        once per `design` closure and replayed -- valid when the callback is pure device work on its argument (the stock
+        objectives of inference_2d.py / eval_ddpm_burgers.py are: transforms, reductions, autograd.grad; no host reads).
+        A callback that cannot be captured (host synchronisation) falls back to the default path for good."""
+        if graph and self.use_graph and not getattr(self, "_gg_failed", False):
+            cache = getattr(self, "_gg", None)
+            if cache is None or cache[0] is not design:   # the closure binds this call's init / low / init_u tensors
+                cache = self._gg = (design, {})
+            graphs = cache[1]
+            if with_noise not in graphs:
+                s0, xs = self.step.clone(), self.x.clone()
+                try:
+                    self._guided_body(with_noise, design, False)   # warm-up outside capture, then rewind
+                    torch.cuda.synchronize()
+                    self.step.copy_(s0)
+                    self.x.copy_(xs)
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        self._guided_body(with_noise, design, False)
+                    graphs[with_noise] = g
+                except Exception as e:  # noqa: BLE001 - user code under capture
+                    import warnings
+                    warnings.warn(f"guided step not capturable ({type(e).__name__}: {e}); running the callback eagerly")
+                    self._gg_failed = True
+                    torch.cuda.synchronize()
+                    self.step.copy_(s0)
+                    self.x.copy_(xs)
+            if with_noise in graphs:
+                graphs[with_noise].replay()
+                return
+        self._guided_body(with_noise, design, True)
 
     def step_graph(self, with_noise):
         if not self.use_graph:
@@ -243,6 +282,7 @@ class GaussianDiffusion(nn.Module):
             clipped.clamp_(max=min_snr_gamma)
         self.register_buffer("loss_weight", (clipped / snr).to(torch.float32))
         self.use_cuda_graph = True
+        self.graph_design_fn = os.environ.get("WDNO_GRAPH_GUIDANCE", "0") == "1"   # capture design_fn with the step (opt-in)
         self._noise_source = None  # tests: callable(shape, device) replacing torch.randn (injected noise)
         self.last_launches_per_step = None
 
@@ -361,7 +401,7 @@ class GaussianDiffusion(nn.Module):
             if not last:
                 run.noise.copy_(self._randn(shape, dev)) if self._noise_source is not None else run.noise.normal_()
             if design is not None:
-                run.step_guided(not last, design)
+                run.step_guided(not last, design, graph=self.graph_design_fn)
             else:
                 run.step_graph(not last)
         self.last_launches_per_step = self.model.engine().launches + 2
@@ -382,7 +422,7 @@ class GaussianDiffusion(nn.Module):
             if with_noise:
                 run.noise.copy_(self._randn(shape, dev)) if self._noise_source is not None else run.noise.normal_()
             if design is not None:
-                run.step_guided(with_noise, design)
+                run.step_guided(with_noise, design, graph=self.graph_design_fn)
             else:
                 run.step_graph(with_noise)
         self.last_launches_per_step = self.model.engine().launches + 2
