@@ -250,6 +250,23 @@ int wdno_dwt3d_synthesis(const float* const* bands8, int64_t band_bstride, float
 int wdno_dwt3d_analysis(const float* x, float* const* bands8, int64_t band_bstride, int64_t B, int Nd, int Nh, int Nw, int nd,
                         int nh, int nw, const float* taps_lo_host, const float* taps_hi_host, int L, int off, void* stream);
 
+/* Fused one-level 2-D transforms of n_img images (modes 'zero' and 'periodization'): pytorch_wavelets DWTForward / DWTInverse,
+ * one level per call (call sites burgers/eval_ddpm_burgers.py:134-136,188-194,
+ * burgers/ddpm_burgers/test_util.py:200-203, data_burgers_1d.py:66-68, burgers/wave_trans.py:103-108,
+ * smoke/inference_2d.py:178-180,244-246, smoke/wave_trans_2d.py:135-137).  One launch instead of three per-axis passes.
+ * x / y: [n_img][H][W] contiguous.  bands4: HOST array of 4 DEVICE pointers (LL, LH, HL, HH) = (lo_w lo_h, lo_w hi_h,
+ * hi_w lo_h, hi_w hi_h), each [n_img][nh][nw] with contiguous planes and its own image stride band_istride4[i] (elements), so
+ * the detail bands may be the three slices of a [.., 3, nh, nw] tensor or slots of a packed [.., 4, nh, nw] tensor.
+ * Per-axis formulas as wdno_dwt_analysis_axis / wdno_dwt_synthesis_axis with (offh, offw) and the same periodic flag.
+ * wdno_dwt2d_supported: 1 if the geometry fits (else use the per-axis entry points). */
+int wdno_dwt2d_supported(int L, int H, int W, int nh, int nw, int periodic);
+int wdno_dwt2d_analysis(const float* x, float* const* bands4, const int64_t* band_istride4, int64_t n_img, int H, int W, int nh,
+                        int nw, const float* taps_lo_host, const float* taps_hi_host, int L, int offh, int offw, int periodic,
+                        void* stream);
+int wdno_dwt2d_synthesis(const float* const* bands4, const int64_t* band_istride4, float* y, int64_t n_img, int nh, int nw, int H,
+                         int W, const float* taps_lo_host, const float* taps_hi_host, int L, int offh, int offw, int periodic,
+                         void* stream);
+
 #ifdef __cplusplus
 }
 #endif

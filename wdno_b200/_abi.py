@@ -41,6 +41,9 @@ SIGNATURES = {
     "wdno_dwt3d_supported": [I, I, I],
     "wdno_dwt3d_synthesis": [P, L64, P, L64, I, I, I, I, I, I, P, P, I, I, P],
     "wdno_dwt3d_analysis": [P, P, L64, L64, I, I, I, I, I, I, P, P, I, I, P],
+    "wdno_dwt2d_supported": [I, I, I, I, I, I],
+    "wdno_dwt2d_analysis": [P, P, P, L64, I, I, I, I, P, P, I, I, I, I, P],
+    "wdno_dwt2d_synthesis": [P, P, P, L64, I, I, I, I, P, P, I, I, I, I, P],
 }
 
 

@@ -56,6 +56,14 @@ __device__ __forceinline__ void cpa_commit() { asm volatile("cp.async.commit_gro
 template <int N>
 __device__ __forceinline__ void cpa_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// keep a kernel parameter in a vector register: without the opaque move the compiler re-loads it from the constant bank
+// (LDCU + uniform-register operand) at every use, 8 % of the instructions of these kernels
+__device__ __forceinline__ float pin_reg(float v) {
+  float r;
+  asm volatile("mov.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
+}
+
 // tap masks: bit k of M0 / M1 set = taps t0[k] / t1[k] may be non-zero.  bior1.3 has two non-zero taps of six in its
 // high-pass analysis filter (and in the low-pass reconstruction filter); skipping the products with exact zeros leaves the
 // results unchanged (acc + 0 * v) and lets the compiler drop the loads and whole row passes that only fed them.
@@ -68,7 +76,8 @@ __device__ __forceinline__ float fm(int k, float a, float t, float acc) {
 // grid (h strips, d chunks, B); block >= (TH / NR) * nw threads; a thread owns NR consecutive output rows at one column
 // (their 6-row input windows overlap: L + 2 (NR - 1) row passes serve NR outputs).  Tile of one signal plane:
 // R = 2 TH + L - 2 rows of RS floats, tile column c = signal column c - off (pads and rows outside [0, Nh) stay zero).
-template <int L, int NR, unsigned M0, unsigned M1>
+// CRS: compile-time tile row stride (0 = run-time p.RS): the 18 float2 loads of a plane become one base register + immediates
+template <int L, int NR, unsigned M0, unsigned M1, int CRS>
 __global__ void __launch_bounds__(640) ana3d_stream_kernel(const S3 p) {
   extern __shared__ __align__(16) float sm[];
   constexpr int KR = L + 2 * (NR - 1);
@@ -76,7 +85,13 @@ __global__ void __launch_bounds__(640) ana3d_stream_kernel(const S3 p) {
   const int b = blockIdx.z;
   const int ih0 = blockIdx.x * p.TH, id0 = blockIdx.y * p.TD;
   const int id1 = min(id0 + p.TD, p.nd);
-  const int nw = p.nw, Nw = p.Nw, R = p.R, RS = p.RS;
+  const int nw = p.nw, Nw = p.Nw, R = p.R, RS = CRS ? CRS : p.RS;
+  float t0[L], t1[L];                                       // taps in registers (the masked-out ones are dead)
+#pragma unroll
+  for (int k = 0; k < L; ++k) {
+    t0[k] = pin_reg(p.t0[k]);
+    t1[k] = pin_reg(p.t1[k]);
+  }
   const int PT = R * RS;
   for (int i = tid; i < kStages * PT; i += nthr) sm[i] = 0.f;
   const int xr0 = 2 * ih0 - p.off;                          // tile row r <-> signal row xr0 + r
@@ -134,17 +149,17 @@ __global__ void __launch_bounds__(640) ana3d_stream_kernel(const S3 p) {
         float wl = 0.f, wh = 0.f;
 #pragma unroll
         for (int k = 0; k < L; ++k) {
-          wl = fm<M0>(k, v[k], p.t0[k], wl);
-          wh = fm<M1>(k, v[k], p.t1[k], wh);
+          wl = fm<M0>(k, v[k], t0[k], wl);
+          wh = fm<M1>(k, v[k], t1[k], wh);
         }
 #pragma unroll
         for (int r = 0; r < NR; ++r) {
           const int k = kh - 2 * r;
           if (k >= 0 && k < L) {
-            a[r][0] = fm<M0>(k, wl, p.t0[k], a[r][0]);
-            a[r][1] = fm<M0>(k, wh, p.t0[k], a[r][1]);
-            a[r][2] = fm<M1>(k, wl, p.t1[k], a[r][2]);
-            a[r][3] = fm<M1>(k, wh, p.t1[k], a[r][3]);
+            a[r][0] = fm<M0>(k, wl, t0[k], a[r][0]);
+            a[r][1] = fm<M0>(k, wh, t0[k], a[r][1]);
+            a[r][2] = fm<M1>(k, wl, t1[k], a[r][2]);
+            a[r][3] = fm<M1>(k, wh, t1[k], a[r][3]);
           }
         }
       }
@@ -192,8 +207,8 @@ __global__ void __launch_bounds__(640) ana3d_stream_kernel(const S3 p) {
           float lo = 0.f, hi = 0.f;
 #pragma unroll
           for (int k = 0; k < L; ++k) {
-            lo = fm<M0>(k, win[r][c][k], p.t0[k], lo);
-            hi = fm<M1>(k, win[r][c][k], p.t1[k], hi);
+            lo = fm<M0>(k, win[r][c][k], t0[k], lo);
+            hi = fm<M1>(k, win[r][c][k], t1[k], hi);
           }
           p.band_out[c][o] = lo;
           p.band_out[4 + c][o] = hi;
@@ -207,7 +222,8 @@ __global__ void __launch_bounds__(640) ana3d_stream_kernel(const S3 p) {
 // ---------------------------------------------------------------- synthesis
 // grid (h strips, d chunks, B); block >= TH * (Nw / 2) threads.  Tile of one coefficient plane: 8 bands x R = TH + L/2 - 1
 // rows x nw floats (a flat copy of the contiguous run of each band plane; rows at or beyond nh stay zero).
-template <int L, unsigned M0, unsigned M1>
+// CNW / CBT: compile-time coefficient row length and band tile size (0 = run-time): every LDS offset becomes an immediate
+template <int L, unsigned M0, unsigned M1, int CNW, int CBT>
 __global__ void __launch_bounds__(640) syn3d_stream_kernel(const S3 p) {
   extern __shared__ __align__(16) float sm[];
   constexpr int H = L / 2;
@@ -216,8 +232,14 @@ __global__ void __launch_bounds__(640) syn3d_stream_kernel(const S3 p) {
   const int qh0 = blockIdx.x * p.TH, qd0 = blockIdx.y * p.TD;
   const int QD = (p.Nd + 1) >> 1, QW = p.Nw >> 1;
   const int qd1 = min(qd0 + p.TD, QD);
-  const int nw = p.nw, R = p.R;
-  const int BT = p.RS, PT = 8 * BT;                         // band tile (R nw rounded up to 16 bytes), plane tile
+  const int nw = CNW ? CNW : p.nw, R = p.R;
+  const int BT = CBT ? CBT : p.RS, PT = 8 * BT;             // band tile (R nw rounded up to 16 bytes), plane tile
+  float t0[L], t1[L];
+#pragma unroll
+  for (int k = 0; k < L; ++k) {
+    t0[k] = pin_reg(p.t0[k]);
+    t1[k] = pin_reg(p.t1[k]);
+  }
   for (int i = tid; i < kStages * PT; i += nthr) sm[i] = 0.f;
   const int r_hi = min(R, p.nh - qh0);
   const int nfl = max(0, r_hi) * nw;                        // floats per band run (even)
@@ -289,10 +311,10 @@ __global__ void __launch_bounds__(640) syn3d_stream_kernel(const S3 p) {
             float e = 0.f, o = 0.f;
 #pragma unroll
             for (int jw = 0; jw < H; ++jw) {
-              e = fm<M0>(2 * jw, cl[H - 1 - jw], p.t0[2 * jw], e);
-              e = fm<M1>(2 * jw, ch[H - 1 - jw], p.t1[2 * jw], e);
-              o = fm<M0>(2 * jw + 1, cl[H - 1 - jw], p.t0[2 * jw + 1], o);
-              o = fm<M1>(2 * jw + 1, ch[H - 1 - jw], p.t1[2 * jw + 1], o);
+              e = fm<M0>(2 * jw, cl[H - 1 - jw], t0[2 * jw], e);
+              e = fm<M1>(2 * jw, ch[H - 1 - jw], t1[2 * jw], e);
+              o = fm<M0>(2 * jw + 1, cl[H - 1 - jw], t0[2 * jw + 1], o);
+              o = fm<M1>(2 * jw + 1, ch[H - 1 - jw], t1[2 * jw + 1], o);
             }
             w[hb][0] = e;
             w[hb][1] = o;
@@ -302,8 +324,8 @@ __global__ void __launch_bounds__(640) syn3d_stream_kernel(const S3 p) {
 #pragma unroll
             for (int wp = 0; wp < 2; ++wp) {
               float acc = a[4 * db + 2 * hp + wp];
-              acc = fm<M0>(2 * j + hp, w[0][wp], p.t0[2 * j + hp], acc);
-              acc = fm<M1>(2 * j + hp, w[1][wp], p.t1[2 * j + hp], acc);
+              acc = fm<M0>(2 * j + hp, w[0][wp], t0[2 * j + hp], acc);
+              acc = fm<M1>(2 * j + hp, w[1][wp], t1[2 * j + hp], acc);
               a[4 * db + 2 * hp + wp] = acc;
             }
         }
@@ -330,10 +352,10 @@ __global__ void __launch_bounds__(640) syn3d_stream_kernel(const S3 p) {
           float acc0 = 0.f, acc1 = 0.f;
 #pragma unroll
           for (int j = 0; j < H; ++j) {
-            acc0 = fm<M0>(2 * j + dp, win[H - 1 - j][2 * hp + 0], p.t0[2 * j + dp], acc0);
-            acc0 = fm<M1>(2 * j + dp, win[H - 1 - j][4 + 2 * hp + 0], p.t1[2 * j + dp], acc0);
-            acc1 = fm<M0>(2 * j + dp, win[H - 1 - j][2 * hp + 1], p.t0[2 * j + dp], acc1);
-            acc1 = fm<M1>(2 * j + dp, win[H - 1 - j][4 + 2 * hp + 1], p.t1[2 * j + dp], acc1);
+            acc0 = fm<M0>(2 * j + dp, win[H - 1 - j][2 * hp + 0], t0[2 * j + dp], acc0);
+            acc0 = fm<M1>(2 * j + dp, win[H - 1 - j][4 + 2 * hp + 0], t1[2 * j + dp], acc0);
+            acc1 = fm<M0>(2 * j + dp, win[H - 1 - j][2 * hp + 1], t0[2 * j + dp], acc1);
+            acc1 = fm<M1>(2 * j + dp, win[H - 1 - j][4 + 2 * hp + 1], t1[2 * j + dp], acc1);
           }
           out.x = acc0;
           out.y = acc1;
@@ -410,9 +432,19 @@ int launch_ana(unsigned nz0, unsigned nz1, dim3 grid, int block, size_t smem, cu
   const char* where = "dwt3d_analysis(stream)";
   constexpr unsigned F = (1u << L) - 1u, MID = 3u << (L / 2 - 1);   // all taps / the two centre taps
   static size_t c0 = 0, c1 = 0, c2 = 0;
-  if (L == 6 && !(nz1 & ~MID)) return launch(ana3d_stream_kernel<L, NR, F, MID>, c1, grid, block, smem, st, p, where);
-  if (L == 6 && !(nz0 & ~MID)) return launch(ana3d_stream_kernel<L, NR, MID, F>, c2, grid, block, smem, st, p, where);
-  return launch(ana3d_stream_kernel<L, NR, F, F>, c0, grid, block, smem, st, p, where);
+  if constexpr (L == 6 && NR == 1) {
+    static size_t d1 = 0, d2 = 0, e1 = 0, e2 = 0;
+    // the two smoke geometries (64- and 128-wide planes) with compile-time row strides
+    if (p.RS == 72 && !(nz1 & ~MID)) return launch(ana3d_stream_kernel<L, NR, F, MID, 72>, d1, grid, block, smem, st, p, where);
+    if (p.RS == 72 && !(nz0 & ~MID)) return launch(ana3d_stream_kernel<L, NR, MID, F, 72>, d2, grid, block, smem, st, p, where);
+    if (p.RS == 136 && !(nz1 & ~MID)) return launch(ana3d_stream_kernel<L, NR, F, MID, 136>, e1, grid, block, smem, st, p, where);
+    if (p.RS == 136 && !(nz0 & ~MID)) return launch(ana3d_stream_kernel<L, NR, MID, F, 136>, e2, grid, block, smem, st, p, where);
+  }
+  if constexpr (L == 6) {
+    if (!(nz1 & ~MID)) return launch(ana3d_stream_kernel<L, NR, F, MID, 0>, c1, grid, block, smem, st, p, where);
+    if (!(nz0 & ~MID)) return launch(ana3d_stream_kernel<L, NR, MID, F, 0>, c2, grid, block, smem, st, p, where);
+  }
+  return launch(ana3d_stream_kernel<L, NR, F, F, 0>, c0, grid, block, smem, st, p, where);
 }
 
 template <int L>
@@ -420,9 +452,17 @@ int launch_syn(unsigned nz0, unsigned nz1, dim3 grid, int block, size_t smem, cu
   const char* where = "dwt3d_synthesis(stream)";
   constexpr unsigned F = (1u << L) - 1u, MID = 3u << (L / 2 - 1);
   static size_t c0 = 0, c1 = 0, c2 = 0;
-  if (L == 6 && !(nz1 & ~MID)) return launch(syn3d_stream_kernel<L, F, MID>, c1, grid, block, smem, st, p, where);
-  if (L == 6 && !(nz0 & ~MID)) return launch(syn3d_stream_kernel<L, MID, F>, c2, grid, block, smem, st, p, where);
-  return launch(syn3d_stream_kernel<L, F, F>, c0, grid, block, smem, st, p, where);
+  if constexpr (L == 6) {
+    static size_t d1 = 0, d2 = 0, e1 = 0, e2 = 0;
+    // the two smoke geometries (34- and 66-wide coefficient rows at the default strip heights)
+    if (p.nw == 34 && p.RS == 340 && !(nz1 & ~MID)) return launch(syn3d_stream_kernel<L, F, MID, 34, 340>, d1, grid, block, smem, st, p, where);
+    if (p.nw == 34 && p.RS == 340 && !(nz0 & ~MID)) return launch(syn3d_stream_kernel<L, MID, F, 34, 340>, d2, grid, block, smem, st, p, where);
+    if (p.nw == 66 && p.RS == 396 && !(nz1 & ~MID)) return launch(syn3d_stream_kernel<L, F, MID, 66, 396>, e1, grid, block, smem, st, p, where);
+    if (p.nw == 66 && p.RS == 396 && !(nz0 & ~MID)) return launch(syn3d_stream_kernel<L, MID, F, 66, 396>, e2, grid, block, smem, st, p, where);
+    if (!(nz1 & ~MID)) return launch(syn3d_stream_kernel<L, F, MID, 0, 0>, c1, grid, block, smem, st, p, where);
+    if (!(nz0 & ~MID)) return launch(syn3d_stream_kernel<L, MID, F, 0, 0>, c2, grid, block, smem, st, p, where);
+  }
+  return launch(syn3d_stream_kernel<L, F, F, 0, 0>, c0, grid, block, smem, st, p, where);
 }
 
 }  // namespace

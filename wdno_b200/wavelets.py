@@ -165,24 +165,29 @@ class _Analysis(torch.autograd.Function):
     @staticmethod
     def backward(ctx, glo, ghi):
         axis, wname, mode, N = ctx.cfg
-        w = Wavelet(wname)
-        L = w.dec_len
-        _, off, per = _geom(N, L, mode)
-        glo, ghi = _prep(glo, axis), _prep(ghi, axis)
-        if per:
-            Np = N + (N & 1)
-            g = _synthesis_raw(glo, ghi, axis, w.dec_lo[::-1], w.dec_hi[::-1], off, 1, Np)
-            if Np != N:  # the repeated edge sample folds back onto the last real sample
-                idx = [slice(None)] * g.dim()
-                idx[axis] = slice(0, N)
-                gx = g[tuple(idx)].clone()
-                last, ext = list(idx), list(idx)
-                last[axis], ext[axis] = slice(N - 1, N), slice(N, N + 1)
-                gx[tuple(last)] += g[tuple(ext)]
-                g = gx
-        else:
-            g = _synthesis_raw(glo, ghi, axis, w.dec_lo[::-1], w.dec_hi[::-1], off, 0, N)
-        return g, None, None, None
+        return _analysis_adjoint(glo, ghi, axis, wname, mode, N), None, None, None
+
+
+def _analysis_adjoint(glo, ghi, axis, wname, mode, N):
+    """gradient of (lo, hi) = afb1d(x) w.r.t. x: the synthesis kernel with the analysis taps (+ the odd-N fold of 'per')"""
+    w = Wavelet(wname)
+    L = w.dec_len
+    _, off, per = _geom(N, L, mode)
+    glo, ghi = _prep(glo, axis), _prep(ghi, axis)
+    if per:
+        Np = N + (N & 1)
+        g = _synthesis_raw(glo, ghi, axis, w.dec_lo[::-1], w.dec_hi[::-1], off, 1, Np)
+        if Np != N:  # the repeated edge sample folds back onto the last real sample
+            idx = [slice(None)] * g.dim()
+            idx[axis] = slice(0, N)
+            gx = g[tuple(idx)].clone()
+            last, ext = list(idx), list(idx)
+            last[axis], ext[axis] = slice(N - 1, N), slice(N, N + 1)
+            gx[tuple(last)] += g[tuple(ext)]
+            g = gx
+    else:
+        g = _synthesis_raw(glo, ghi, axis, w.dec_lo[::-1], w.dec_hi[::-1], off, 0, N)
+    return g
 
 
 class _Synthesis(torch.autograd.Function):
@@ -219,6 +224,149 @@ def sfb1d(lo, hi, wave, mode, axis=-1):
     return _Synthesis.apply(lo, hi, axis % lo.dim(), _wave(wave).name, mode)
 
 
+# ---------------------------------------------------------------- fused one-level 2-D transforms (csrc/dwt2d.cu)
+_FUSED2D = os.environ.get("WDNO_DWT2D_FUSED", "1") != "0"   # 0: three per-axis launches per level (csrc/dwt.cu)
+
+
+def _img_stride(t):
+    """element stride between consecutive images of t [..., h, w] when the leading dims collapse to one uniformly strided
+    image index and the planes are contiguous; None otherwise"""
+    h, w = t.shape[-2], t.shape[-1]
+    if (w != 1 and t.stride(-1) != 1) or (h != 1 and t.stride(-2) != w):
+        return None
+    st = run = None
+    for d in range(t.dim() - 3, -1, -1):
+        if t.shape[d] == 1:
+            continue
+        if st is None:
+            st, run = t.stride(d), t.stride(d) * t.shape[d]
+        elif t.stride(d) != run:
+            return None
+        else:
+            run = t.stride(d) * t.shape[d]
+    return h * w if st is None else st
+
+
+def _planes(t):
+    """-> (tensor usable by the 2-D kernels, image stride)"""
+    st = _img_stride(t) if t.dtype == torch.float32 else None
+    if st is None:
+        t = t.to(torch.float32).contiguous()
+        st = t.shape[-2] * t.shape[-1]
+    return t, st
+
+
+def _fused2d_ok(L, H, W, nh, nw, per, t):
+    n_img = t.numel() // max(1, t.shape[-2] * t.shape[-1])
+    return (_FUSED2D and t.is_cuda and t.dim() >= 2 and 1 <= n_img <= 65535
+            and bool(_lib.lib().wdno_dwt2d_supported(L, H, W, nh, nw, per)))
+
+
+def _ana2d_raw(x, bands, t_lo, t_hi, geo_h, geo_w):
+    """x [..., H, W] contiguous fp32 -> the four given band views [..., nh, nw] (ll, lh, hl, hh), one launch"""
+    H, W = x.shape[-2], x.shape[-1]
+    n_img = x.numel() // (H * W)
+    strides = []
+    for b in bands:
+        st = _img_stride(b)
+        assert st is not None, "sub-band views must have contiguous planes"
+        strides.append(st)
+    _lib.check(_lib.lib().wdno_dwt2d_analysis(
+        x.data_ptr(), (C.c_void_p * 4)(*[b.data_ptr() for b in bands]), (C.c_int64 * 4)(*strides), n_img, H, W, geo_h[0], geo_w[0],
+        _farr(t_lo), _farr(t_hi), len(t_lo), geo_h[1], geo_w[1], geo_h[2], _lib.current_stream_ptr()), "dwt2d_analysis")
+
+
+def _syn2d_raw(bands, t_lo, t_hi, off, per, HW):
+    """(ll, lh, hl, hh) [..., nh, nw] -> y [..., H, W], one launch"""
+    prepared = [_planes(b) for b in bands]
+    nh, nw = bands[0].shape[-2], bands[0].shape[-1]
+    lead = tuple(bands[0].shape[:-2])
+    y = torch.empty(lead + tuple(HW), dtype=torch.float32, device=bands[0].device)
+    n_img = y.numel() // (HW[0] * HW[1])
+    _lib.check(_lib.lib().wdno_dwt2d_synthesis(
+        (C.c_void_p * 4)(*[b.data_ptr() for b, _ in prepared]), (C.c_int64 * 4)(*[st for _, st in prepared]), y.data_ptr(), n_img,
+        nh, nw, HW[0], HW[1], _farr(t_lo), _farr(t_hi), len(t_lo), off, off, per, _lib.current_stream_ptr()), "dwt2d_synthesis")
+    return y
+
+
+class _Analysis2D(torch.autograd.Function):
+    """(ll [..., nh, nw], yh [..., 3, nh, nw]) = one DWTForward level of x [..., H, W]; backward = the per-axis adjoints"""
+
+    @staticmethod
+    def forward(ctx, x, wname, mode):
+        w = Wavelet(wname)
+        L = w.dec_len
+        x = x.to(torch.float32).contiguous()
+        H, W = x.shape[-2], x.shape[-1]
+        gh, gw = _geom(H, L, mode), _geom(W, L, mode)
+        lead = tuple(x.shape[:-2])
+        ll = torch.empty(lead + (gh[0], gw[0]), dtype=torch.float32, device=x.device)
+        yh = torch.empty(lead + (3, gh[0], gw[0]), dtype=torch.float32, device=x.device)
+        _ana2d_raw(x, [ll, yh.select(-3, 0), yh.select(-3, 1), yh.select(-3, 2)], w.dec_lo[::-1], w.dec_hi[::-1], gh, gw)
+        ctx.cfg = (wname, mode, H, W)
+        return ll, yh
+
+    @staticmethod
+    def backward(ctx, gll, gyh):
+        wname, mode, H, W = ctx.cfg
+        ax_h, ax_w = gll.dim() - 2, gll.dim() - 1
+        g_lo_w = _analysis_adjoint(gll, gyh.select(-3, 0), ax_h, wname, mode, H)
+        g_hi_w = _analysis_adjoint(gyh.select(-3, 1), gyh.select(-3, 2), ax_h, wname, mode, H)
+        return _analysis_adjoint(g_lo_w, g_hi_w, ax_w, wname, mode, W), None, None
+
+
+class _Synthesis2D(torch.autograd.Function):
+    """y = one DWTInverse level of (ll, lh, hl, hh); backward = the per-axis analysis passes with the reconstruction taps"""
+
+    @staticmethod
+    def forward(ctx, ll, lh, hl, hh, wname, mode):
+        w = Wavelet(wname)
+        L = w.dec_len
+        per = _mode_id(mode)
+        nh, nw = ll.shape[-2], ll.shape[-1]
+        off = L // 2 - 1 if per else L - 2
+        HW = (2 * nh, 2 * nw) if per else (2 * nh - L + 2, 2 * nw - L + 2)
+        ctx.cfg = (wname, nh, nw, off, per)
+        return _syn2d_raw([ll, lh, hl, hh], w.rec_lo, w.rec_hi, off, per, HW)
+
+    @staticmethod
+    def backward(ctx, gy):
+        wname, nh, nw, off, per = ctx.cfg
+        w = Wavelet(wname)
+        gy = gy.to(torch.float32).contiguous()
+        ax_h, ax_w = gy.dim() - 2, gy.dim() - 1
+        g_lo, g_hi = _analysis_raw(gy, ax_w, w.rec_lo, w.rec_hi, off, per, nw)
+        g_ll, g_lh = _analysis_raw(g_lo, ax_h, w.rec_lo, w.rec_hi, off, per, nh)
+        g_hl, g_hh = _analysis_raw(g_hi, ax_h, w.rec_lo, w.rec_hi, off, per, nh)
+        return g_ll, g_lh, g_hl, g_hh, None, None
+
+
+def _dwt2_level(x, w, mode):
+    """one analysis level of x [..., H, W] -> (ll, yh [..., 3, nh, nw])"""
+    L = w.dec_len
+    H, W = x.shape[-2], x.shape[-1]
+    gh, gw = _geom(H, L, mode), _geom(W, L, mode)
+    if _fused2d_ok(L, H, W, gh[0], gw[0], gh[2], x):
+        return _Analysis2D.apply(x, w.name, mode)
+    lo_w, hi_w = afb1d(x, w, mode, axis=-1)
+    ll, lh = afb1d(lo_w, w, mode, axis=-2)
+    hl, hh = afb1d(hi_w, w, mode, axis=-2)
+    return ll, torch.stack((lh, hl, hh), dim=-3)
+
+
+def _idwt2_level(ll, h, w, mode):
+    """one synthesis level: ll [..., nh, nw], h [..., 3, nh, nw] -> [..., H, W]"""
+    L = w.dec_len
+    per = _mode_id(mode)
+    nh, nw = ll.shape[-2], ll.shape[-1]
+    HW = (2 * nh, 2 * nw) if per else (2 * nh - L + 2, 2 * nw - L + 2)
+    if HW[0] >= 1 and HW[1] >= 1 and _fused2d_ok(L, HW[0], HW[1], nh, nw, per, ll):
+        return _Synthesis2D.apply(ll, h.select(-3, 0), h.select(-3, 1), h.select(-3, 2), w.name, mode)
+    lo = sfb1d(ll, h.select(-3, 0), w, mode, axis=-2)
+    hi = sfb1d(h.select(-3, 1), h.select(-3, 2), w, mode, axis=-2)
+    return sfb1d(lo, hi, w, mode, axis=-1)
+
+
 # ---------------------------------------------------------------- pytorch_wavelets-style modules
 class DWTForward(nn.Module):
     def __init__(self, J=1, wave="db1", mode="zero"):
@@ -230,10 +378,8 @@ class DWTForward(nn.Module):
         _check(x)
         ll, yh = x, []
         for _ in range(self.J):
-            lo_w, hi_w = afb1d(ll, self.wave, self.mode, axis=-1)
-            ll, lh = afb1d(lo_w, self.wave, self.mode, axis=-2)
-            hl, hh = afb1d(hi_w, self.wave, self.mode, axis=-2)
-            yh.append(torch.stack((lh, hl, hh), dim=2))
+            ll, h = _dwt2_level(ll, self.wave, self.mode)
+            yh.append(h)
         return ll, yh
 
 
@@ -253,10 +399,7 @@ class DWTInverse(nn.Module):
                 ll = ll[..., :-1, :]
             if ll.shape[-1] > h.shape[-1]:
                 ll = ll[..., :-1]
-            lh, hl, hh = h[:, :, 0], h[:, :, 1], h[:, :, 2]
-            lo = sfb1d(ll, lh, self.wave, self.mode, axis=-2)
-            hi = sfb1d(hl, hh, self.wave, self.mode, axis=-2)
-            ll = sfb1d(lo, hi, self.wave, self.mode, axis=-1)
+            ll = _idwt2_level(ll, h, self.wave, self.mode)
         return ll
 
 
@@ -448,8 +591,11 @@ def dwt2_packed(x, wave, mode):
     nw_, offw, per = _geom(W, L, mode)
     nh_, offh, _ = _geom(H, L, mode)
     tl, th = w.dec_lo[::-1], w.dec_hi[::-1]
-    lo_w, hi_w = _analysis_raw(x, 3, tl, th, offw, per, nw_)
     out = torch.empty((B, Cc, 4, nh_, nw_), dtype=torch.float32, device=x.device)
+    if _fused2d_ok(L, H, W, nh_, nw_, per, x):
+        _ana2d_raw(x, [out[:, :, i] for i in range(4)], tl, th, _geom(H, L, mode), _geom(W, L, mode))
+        return out
+    lo_w, hi_w = _analysis_raw(x, 3, tl, th, offw, per, nw_)
     _analysis_raw(lo_w, 2, tl, th, offh, per, nh_, lo=out[:, :, 0], hi=out[:, :, 1])
     _analysis_raw(hi_w, 2, tl, th, offh, per, nh_, lo=out[:, :, 2], hi=out[:, :, 3])
     return out
