@@ -323,7 +323,38 @@ def builders_fixture():
           [c["shape"] for c in res["burgers"]["coef"]], res["burgers"]["shape"], res["burgers"]["ori_shape"])
 
 
+def train_step_fixture():
+    """loss + gradients of ONE training step of the real reference (smoke base model, dim 64, batch 1): `loss = gd.p_losses(...)`,
+    `loss.backward()`, `clip_grad_norm_(1.0)` (diffusion_2d.py:1278-1287).  The parity gate of SURVEY section 8 row f-3."""
+    s = ref_loader.smoke()
+    torch.manual_seed(0)
+    m = s.Unet3D_with_Conv3D(dim=64, dim_mults=(1, 2, 4), channels=42).train()
+    w = torch.linspace(0.5, 2.0, 42).reshape(1, 1, 42, 1, 1)
+    gd = s.GaussianDiffusion(m, w, True, True, True, False, "bior1.3", "zero", [18, 34, 34], [32, 64, 64],
+                             image_size=40, frames=24, timesteps=1000, sampling_timesteps=250, ddim_sampling_eta=1.0)
+    seed, t = 21, 433
+    g = torch.Generator().manual_seed(seed)
+    x0 = torch.randn(1, 24, 42, 40, 40, generator=g).clamp(-1, 1)
+    noise = torch.randn(1, 24, 42, 40, 40, generator=g)
+    wsum = checksum(m.state_dict())
+    loss = gd.p_losses(x0.clone(), torch.tensor([t]), noise.clone())
+    loss.backward()
+    grads = {n: p.grad.detach().clone() for n, p in m.named_parameters() if p.grad is not None}
+    total = torch.nn.utils.clip_grad_norm_(m.parameters(), 1.0)
+    keys = ["init_conv.weight", "init_temporal_attn.fn.fn.to_qkv.weight", "time_mlp.1.weight", "downs.0.0.block1.proj.weight",
+            "downs.0.0.mlp.1.weight", "downs.1.2.fn.fn.to_qkv.weight", "mid_block1.block2.norm.weight", "mid_spatial_attn.fn.fn.to_out.weight",
+            "ups.1.0.res_conv.weight", "ups.1.4.weight", "final_conv.1.weight", "time_rel_pos_bias.relative_attention_bias.weight"]
+    keys = [k for k in keys if k in grads]
+    out = dict(weights_checksum=wsum, input_seed=seed, t=t, loss=float(loss), total_norm=float(total), stride=STRIDE,
+               grad_norms={k: float(v.norm()) for k, v in grads.items()}, grad_subs={k: sub(grads[k]) for k in keys})
+    torch.save(out, os.path.join(HERE, "smoke_train_step.pt"))
+    print("smoke_train_step", out["loss"], out["total_norm"], len(grads), keys)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "train":
+        train_step_fixture()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "builders":
         builders_fixture()
         sys.exit(0)
