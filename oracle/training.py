@@ -19,6 +19,7 @@ the parity gate for the training kernels (not built in round 1; `p_losses` on th
 import torch
 
 from . import diffusion as D
+from .unet2d import Unet2DOracle
 from .unet3d import Unet3DOracle
 
 
@@ -38,6 +39,21 @@ def smoke_loss_and_grads(state_dict, sch, x_start, t, noise, coef_shape, loss_la
         orc.sd[k] = orc.sd[k].clone().requires_grad_()
     loss = D.smoke_p_losses(orc, sch, x_start, t, noise, coef_shape, loss_layer_weight, control=control, pad=pad,
                             super_model=super_model) / accumulate_every
+    grads = torch.autograd.grad(loss, [orc.sd[k] for k in names], allow_unused=True)
+    return loss.detach(), {k: (torch.zeros_like(orc.sd[k]) if g is None else g) for k, g in zip(names, grads)}
+
+
+def burgers_loss_and_grads(state_dict, sch, x_start, t, noise, coef_shape, loss_layer_weight, cond_u0=True, cond_uT=False,
+                           cond_f=True, pad=True, super_model=False, accumulate_every=1):
+    """-> (loss, {name: dloss/dparam}) of Burgers `GaussianDiffusion.forward` given the drawn (t, noise)
+    (burgers/ddpm_burgers/diffusion_1d.py:520-654 ; train_diffusion.py:200-212).  Every entry of the Unet2D state dict is
+    trainable (no rotary table)."""
+    orc = Unet2DOracle(state_dict)
+    names = list(orc.sd)
+    for k in names:
+        orc.sd[k] = orc.sd[k].clone().requires_grad_()
+    loss = D.burgers_p_losses(orc, sch, x_start, t, noise, coef_shape, loss_layer_weight, cond_u0=cond_u0, cond_uT=cond_uT,
+                              cond_f=cond_f, pad=pad, super_model=super_model) / accumulate_every
     grads = torch.autograd.grad(loss, [orc.sd[k] for k in names], allow_unused=True)
     return loss.detach(), {k: (torch.zeros_like(orc.sd[k]) if g is None else g) for k, g in zip(names, grads)}
 

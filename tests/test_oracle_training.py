@@ -58,6 +58,32 @@ def test_loss_gradients_clip_and_adam_match_reference_two_steps():
         params.update({k: after[k].detach().clone() for k in new})   # continue from the reference state
 
 
+@needs_ref
+def test_burgers_loss_and_gradients_match_reference():
+    from oracle import diffusion as D
+    from tests.test_oracle_vs_reference import _burgers_pair
+    b, m, gd, _ = _burgers_pair(None, 0.0, T=1000)
+    m.train()
+    g = torch.Generator().manual_seed(6)
+    x0 = torch.randn(2, 9, 64, 64, generator=g).clamp(-1, 1)
+    t = torch.tensor([5, 911])
+    noise = torch.randn(2, 9, 64, 64, generator=g)
+    loss_ref = gd.p_losses(x0.clone(), t, noise.clone())
+    loss_ref.backward()
+    ref_grads = {n: p.grad.detach().clone() for n, p in m.named_parameters() if p.grad is not None}
+    params = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    loss, grads = TR.burgers_loss_and_grads(params, D.schedule("cosine", 1000), x0, t, noise, [41, 60], gd.loss_layer_weight)
+    assert abs(float(loss) - float(loss_ref)) < 1e-5 * max(1.0, abs(float(loss_ref)))
+    assert set(ref_grads) <= set(grads)
+    worst = max(rel_l2(grads[k], ref_grads[k]) for k in ref_grads if float(ref_grads[k].norm()) > 1e-6)
+    assert worst < 2e-4, worst
+    for k in set(grads) - set(ref_grads):   # state-dict entries the reference does not optimise receive no gradient here either
+        assert float(grads[k].abs().max()) == 0.0, k
+    total_ref = torch.nn.utils.clip_grad_norm_(m.parameters(), 1.0)
+    total, _ = TR.clip_grad_norm(grads, 1.0)
+    assert abs(float(total) - float(total_ref)) < 1e-4 * float(total_ref)
+
+
 def test_ema_schedule_and_lr_milestones():
     assert TR.ema_decay(50) == 0.0 and TR.ema_decay(101) == 0.0
     assert abs(TR.ema_decay(110) - (1 - 10 ** (-2 / 3))) < 1e-12
