@@ -22,6 +22,16 @@ def inf(monkeypatch):
     from wdno_b200.smoke import inference_2d as m
     for n in ("waverec3", "wavedec3", "DWT1DInverse", "DWTForward", "Wavelet"):
         monkeypatch.setattr(m, n, getattr(T, n))
+
+    def waverec3_adjoint(gy, wavelet, coef_shape):
+        """adjoint of the (linear) oracle waverec3 by one autograd pass at zero"""
+        leaves = [torch.zeros(gy.shape[0], *coef_shape, requires_grad=True) for _ in range(8)]
+        with torch.enable_grad():
+            y = T.waverec3([leaves[0], dict(zip(T.KEYS3, leaves[1:]))], wavelet)
+            gs = torch.autograd.grad(y, leaves, gy)
+        return [gs[0], dict(zip(T.KEYS3, gs[1:]))]
+    monkeypatch.setattr(m, "waverec3_adjoint", waverec3_adjoint)
+    monkeypatch.setattr(m, "_SMOKE_OUT_GRAD", {})
     return m
 
 
@@ -57,6 +67,33 @@ def test_guidance_gradient_and_base_pipeline_match_reference(inf):
         out = pipe.run_model(state)
     assert tuple(out.shape) == gold["out_shape"]
     assert rel_l2(out.reshape(-1)[::gold["stride"]], gold["out_sub"]) < 1e-5
+
+
+def test_closed_form_guidance_gradient_equals_autograd_and_reference(inf):
+    """guidance_fn_closed_form (no autograd: waverec3 -> closed-form field gradient -> adjoint transform) against our autograd
+    guidance_fn and against the gradient the REAL reference guidance_fn produced (golden), control and design modes"""
+    gold = torch.load(os.path.join(GOLD, "smoke_guided_pipeline.pt"))
+    shape, ori_shape = [18, 34, 34], [32, 64, 64]
+    rescaler = torch.linspace(0.5, 3.0, 42).reshape(1, 1, 42, 1, 1)
+    gen = torch.Generator().manual_seed(gold["input_seed"])
+    state = 0.5 * torch.randn(1, 256, 6, 64, 64, generator=gen)
+    xg = torch.randn(1, 24, 42, 40, 40, generator=gen).clamp(-1, 1)
+    args = _args(False, False)
+    g = inf.guidance_fn_closed_form(xg, args, shape, ori_shape, rescaler, w_energy=0.5, w_init=0.1, init_u=state[:, 0, 0])
+    assert not g.requires_grad and rel_l2(g.reshape(-1)[::gold["stride"]], gold["grad_sub"]) < 1e-6
+    assert abs(float(g.norm()) - gold["grad_norm"]) < 1e-5 * gold["grad_norm"]
+    x2 = torch.randn(2, 24, 42, 40, 40, generator=gen).clamp(-1, 1)
+    u2 = torch.randn(2, 64, 64, generator=gen)
+    for control, we, wi in ((False, 0.5, 0.1), (False, 0.0, 0.3), (True, 0.7, 0.2)):
+        a = _args(control, False)
+        want = inf.guidance_fn(x2.clone().requires_grad_(), a, shape, ori_shape, rescaler, w_energy=we, w_init=wi, init_u=u2)
+        got = inf.guidance_fn_closed_form(x2, a, shape, ori_shape, rescaler, w_energy=we, w_init=wi, init_u=u2)
+        assert got.shape == want.shape and rel_l2(got, want) < 1e-6, (control, we, wi, rel_l2(got, want))
+    a = _args(False, False)
+    a.w_energy, a.w_init = 0.5, 0.1
+    d_cf = inf.make_design_fn(a, shape, ori_shape, rescaler, closed_form=True)(x2, init_u=u2)
+    d_ag = inf.make_design_fn(a, shape, ori_shape, rescaler)(x2.clone().requires_grad_(), init_u=u2)
+    assert rel_l2(d_cf, d_ag) < 1e-6
 
 
 def test_cascade_pipeline_matches_reference(inf):

@@ -147,10 +147,25 @@ def c5(steps):
             run.noise.normal_()
             run.step_graph(True)
         ms_graph = timed(step_graph, steps)
+        extra_cf = {}
+        try:  # closed-form guidance gradient (no autograd; opt-in, see smoke/inference_2d.py::guidance_fn_closed_form)
+            design_cf, _ = gd._guidance(inf.make_design_fn(args, shape_c, ori, R, closed_form=True), "standard", None, init, init_u)
+
+            def step_cf():
+                run.noise.normal_()
+                run.step_guided(True, design_cf)
+
+            def step_cf_gg():
+                run.noise.normal_()
+                run.step_guided(True, design_cf, graph=True)
+            extra_cf = {"ms_per_step_closed_form_guidance": timed(step_cf, steps),
+                        "ms_per_step_closed_form_guidance_whole_step_graph": timed(step_cf_gg, steps)}
+        except Exception as e:  # noqa: BLE001 - report, do not lose the other numbers
+            extra_cf = {"closed_form_guidance_error": f"{type(e).__name__}: {e}"}
     report("C5", "smoke control: base Unet3D, guided DDIM-500 (inverse DWT + adjoint per step), batch 8 per GPU", ms,
            326.35e9 * B, {"ms_per_step_unguided_eager": ms_plain, "guidance_overhead_ms": ms - ms_plain,
             "ms_per_step_whole_step_graph(graph_design_fn=True)": ms_gg, "steps_per_s_whole_step_graph": 1e3 / ms_gg,
-            "ms_per_step_unguided_graph": ms_graph, "guidance_overhead_ms_whole_step_graph": ms_gg - ms_graph})
+            "ms_per_step_unguided_graph": ms_graph, "guidance_overhead_ms_whole_step_graph": ms_gg - ms_graph, **extra_cf})
 
 
 if __name__ == "__main__":

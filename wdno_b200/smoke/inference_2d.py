@@ -19,7 +19,7 @@ import torch.nn.functional as F
 from wdno_b200.packing import smoke_coef_to_tensor as coef_to_tensor
 from wdno_b200.packing import smoke_tensor_to_coef as tensor_to_coef
 from wdno_b200.packing import smoke_upsample_coef as upsample_coef
-from wdno_b200.wavelets import DWT1DInverse, DWTForward, Wavelet, wavedec3, waverec3
+from wdno_b200.wavelets import DWT1DInverse, DWTForward, Wavelet, wavedec3, waverec3, waverec3_adjoint
 
 PAD_T, PAD_X = 24, 40          # padded frames / base padded width of the coefficient state
 
@@ -63,16 +63,73 @@ def guidance_fn(x, args, shape, ori_shape, RESCALER, w_energy=0, w_init=0, low=N
     return torch.autograd.grad(j, xs, grad_outputs=torch.ones_like(j))[0]
 
 
-def make_design_fn(args, shape, ori_shape, RESCALER):
-    """the `design_fn(x, low=, init=, init_u=)` closure of inference_2d.py:82-91"""
+_SMOKE_OUT_GRAD = {}
+
+
+def _smoke_out_grad(n_coef, n_out, pad_mode, wave_type, device):
+    """d smoke_out[n_out - 1] / d(lo, hi): the 1-D inverse transform is linear, so this is a constant pair of [n_coef] vectors
+    (one autograd pass through DWT1DInverse, cached)"""
+    key = (n_coef, n_out, pad_mode, wave_type, str(device))
+    if key not in _SMOKE_OUT_GRAD:
+        with torch.enable_grad():
+            lo = torch.zeros(1, 1, n_coef, device=device, requires_grad=True)
+            hi = torch.zeros(1, 1, n_coef, device=device, requires_grad=True)
+            y = DWT1DInverse(mode=pad_mode, wave=wave_type)((lo, [hi]))[:, 0]
+            g_lo, g_hi = torch.autograd.grad(y[:, n_out - 1].sum(), (lo, hi))
+        _SMOKE_OUT_GRAD[key] = (g_lo.reshape(-1).detach(), g_hi.reshape(-1).detach())
+    return _SMOKE_OUT_GRAD[key]
+
+
+def guidance_fn_closed_form(x, args, shape, ori_shape, RESCALER, w_energy=0, w_init=0, low=None, init=None, init_u=None):
+    """The same gradient as `guidance_fn` WITHOUT autograd (the objective is quadratic / linear in
+    the reconstructed fields, so dJ/dfields is known in closed form and dJ/d(x * RESCALER) is its image under the adjoint
+    inverse transform): one `waverec3`, a handful of elementwise writes, one `waverec3_adjoint`.
+        J = -smoke_out[T - 1] + w_energy mean(c^2) + w_init mean((rho(t = 0) - rho0*)^2)      (summed over the batch)
+        dJ/dfields[:, 3:5] = 2 w_energy c / (2 T H W) ;  dJ/dfields[:, 0, 0] = 2 w_init (rho0 - rho0*) / (H W)
+        dJ/d(last channel): the constant pair d smoke_out[T - 1] / d(lo, hi) spread over the rows each mean was taken over
+    Wavelet states only; anything else falls back to `guidance_fn`."""
+    if not args.is_wavelet:
+        return guidance_fn(x, args, shape, ori_shape, RESCALER, w_energy, w_init, low, init, init_u)
+    with torch.no_grad():
+        xs = x.detach() * RESCALER
+        B = xs.shape[0]
+        T, H, Wd = int(shape[-3]), int(shape[-2]), int(shape[-1])
+        o0, o1, o2 = int(ori_shape[0]), int(ori_shape[1]), int(ori_shape[2])
+        coef = tensor_to_coef(xs[:, :, :40].permute(0, 2, 1, 3, 4), shape)
+        rec = waverec3(coef, Wavelet(args.wave_type))
+        fields = rec[:, :o0, :o1, :o2].reshape(B, 5, o0, o1, o2)
+        g_rec = torch.zeros_like(rec).reshape(B, 5, *rec.shape[1:])
+        g_rec[:, 0, 0, :o1, :o2] = (2.0 * w_init / (o1 * o2)) * (fields[:, 0, 0] - init_u.to(fields.device))
+        if not args.is_condition_control and w_energy != 0:
+            g_rec[:, 3:5, :o0, :o1, :o2] = (2.0 * w_energy / (2 * o0 * o1 * o2)) * fields[:, 3:5]
+        g_bands = waverec3_adjoint(g_rec.reshape(-1, *rec.shape[1:]), Wavelet(args.wave_type), (T, H, Wd))
+        g40 = coef_to_tensor(g_bands).reshape(B, 40, T, H, Wd).permute(0, 2, 1, 3, 4)   # [B, T, 40, H, W]
+        g = torch.zeros_like(xs)
+        g[:, :T, :40, :H, :H] = g40[..., :H]   # the reference crops rows and columns with the same bound (tensor_to_coef)
+        if not args.is_condition_control:
+            g_lo, g_hi = _smoke_out_grad(T, o0, args.pad_mode, args.wave_type, xs.device)
+            Hx, Wx = xs.shape[-2], xs.shape[-1]
+            g[:, :T, -1, :20, :] = (-g_lo / (20 * Wx)).reshape(1, T, 1, 1)
+            g[:, :T, -1, 20:, :] = (-g_hi / ((Hx - 20) * Wx)).reshape(1, T, 1, 1)
+    return g
+
+
+def make_design_fn(args, shape, ori_shape, RESCALER, closed_form=None):
+    """the `design_fn(x, low=, init=, init_u=)` closure of inference_2d.py:82-91.  closed_form=True (or WDNO_CLOSED_FORM_GUIDANCE=1)
+    evaluates the gradient with `guidance_fn_closed_form` instead of autograd (opt-in; same values)."""
+    if closed_form is None:
+        import os
+        closed_form = os.environ.get("WDNO_CLOSED_FORM_GUIDANCE", "0") == "1"
+    guidance = guidance_fn_closed_form if closed_form else guidance_fn
+
     def design_fn(x, low=None, init=None, init_u=None):
         kw = dict(w_energy=args.w_energy, w_init=args.w_init, low=low, init=init, init_u=init_u)
         if args.is_super_model:
             if low is not None:
                 lvl = int(math.log2(low.shape[-1] / 40))
-                return guidance_fn(x, args, shape[lvl], ori_shape[lvl], RESCALER, **kw)
-            return guidance_fn(x, args, shape[0], ori_shape[0], RESCALER[:, :, 40:], **kw)
-        return guidance_fn(x, args, shape, ori_shape, RESCALER, **kw)
+                return guidance(x, args, shape[lvl], ori_shape[lvl], RESCALER, **kw)
+            return guidance(x, args, shape[0], ori_shape[0], RESCALER[:, :, 40:], **kw)
+        return guidance(x, args, shape, ori_shape, RESCALER, **kw)
     return design_fn
 
 

@@ -554,6 +554,26 @@ def waverec3(coeffs, wavelet):
     return sfb1d(xd["a"], xd["d"], w, "zero", axis=1)
 
 
+def waverec3_adjoint(gy, wavelet, coef_shape):
+    """adjoint of `waverec3` without autograd: gy [B,D,H,W] (gradient w.r.t. the reconstructed fields) ->
+    [g_aaa, {g_aad, ..., g_ddd}] each [B, *coef_shape] = the analysis kernel with the reconstruction filters (what
+    `_Synthesis3D.backward` runs).  For objectives whose field gradient is known in closed form."""
+    _check(gy)
+    w = _wave(wavelet)
+    L = w.dec_len
+    gy = gy.detach().to(torch.float32).contiguous()
+    n3 = tuple(int(v) for v in coef_shape[-3:])
+    if _fused3d_ok(L, n3[2], gy.shape[3], gy):
+        bands = _ana3d_raw(gy, w.rec_lo, w.rec_hi, L - 2, n3)
+        return [bands[0], {k: bands[i + 1] for i, k in enumerate(KEYS3)}]
+    out = {}
+    for kd, xd in zip("ad", _analysis_raw(gy, 1, w.rec_lo, w.rec_hi, L - 2, 0, n3[0])):
+        for kh, xh in zip("ad", _analysis_raw(xd, 2, w.rec_lo, w.rec_hi, L - 2, 0, n3[1])):
+            for kw, xw in zip("ad", _analysis_raw(xh, 3, w.rec_lo, w.rec_hi, L - 2, 0, n3[2])):
+                out[kd + kh + kw] = xw
+    return [out["aaa"], {k: out[k] for k in KEYS3}]
+
+
 # ---------------------------------------------------------------- packed forms for the offline coefficient builders
 def wavedec3_packed(data, wavelet, *, mode="zero"):
     """data [B,D,H,W] -> [B,8,nd,nh,nw], bit-identical to smoke `coef_to_tensor(ptwt.wavedec3(data, ...))`
