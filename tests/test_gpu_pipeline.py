@@ -132,11 +132,9 @@ def test_guided_sampling_whole_step_graph_matches_eager_callback():
     assert not getattr(run, "_gg_failed", False) and len(run._gg[1]) == 2   # with / without noise, both captured
 
 
-@pytest.mark.skipif(os.environ.get("WDNO_TEST_EXPERIMENTAL") != "1",
-                    reason="closed-form guidance on the kernels: its math is pinned on CPU (tests/test_pipeline_cpu.py), the kernel "
-                           "path (wavelets.waverec3_adjoint) was written after round 1's GPU budget was spent; run with "
-                           "WDNO_TEST_EXPERIMENTAL=1, then make closed_form the default of make_design_fn")
 def test_closed_form_guidance_matches_autograd_on_the_kernels():
+    """guidance_fn_closed_form (waverec3 -> closed-form field gradient -> waverec3_adjoint, no autograd) against the autograd
+    guidance_fn on the same kernels; its math is pinned to the reference's gradient in tests/test_pipeline_cpu.py"""
     from wdno_b200.smoke import inference_2d as inf
     shape, ori_shape = [18, 34, 34], [32, 64, 64]
     rescaler = torch.linspace(0.5, 3.0, 42).reshape(1, 1, 42, 1, 1).cuda()
