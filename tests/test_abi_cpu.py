@@ -55,3 +55,17 @@ def test_product_path_has_no_cpu_fallback():
         m(torch.zeros(1, 24, 42, 40, 40), torch.zeros(1))
     with pytest.raises(RuntimeError):
         wavelets.wavedec3(torch.zeros(1, 8, 8, 8), "bior1.3")
+
+
+def test_fused_wavelet_envelopes_are_host_decisions(lib):
+    """wdno_dwt3d_supported / wdno_dwt2d_supported are pure host code: the shapes of the reference's configurations are inside
+    the fused kernels' envelopes, degenerate ones fall back to the per-axis entry points"""
+    # 3-D: (taps, coefficient width, signal width): smoke base 34 / 64, super-resolution 66 / 128 (bior1.3, 6 taps)
+    assert lib.wdno_dwt3d_supported(6, 34, 64) == 1 and lib.wdno_dwt3d_supported(6, 66, 128) == 1
+    assert lib.wdno_dwt3d_supported(5, 34, 64) == 0 and lib.wdno_dwt3d_supported(6, 0, 64) == 0
+    # 2-D: (taps, H, W, nh, nw, periodic): Burgers 81 x 120 -> 41 x 60 and its inverse 82 x 120, cascade levels, smoke rho0
+    assert lib.wdno_dwt2d_supported(10, 81, 120, 41, 60, 1) == 1 and lib.wdno_dwt2d_supported(10, 82, 120, 41, 60, 1) == 1
+    assert lib.wdno_dwt2d_supported(10, 162, 240, 81, 120, 1) == 1 and lib.wdno_dwt2d_supported(6, 64, 64, 34, 34, 0) == 1
+    assert lib.wdno_dwt2d_supported(10, 11, 15, 6, 8, 1) == 0      # fewer coefficients than taps under 'periodization'
+    assert lib.wdno_dwt2d_supported(4, 64, 64, 32, 32, 1) == 0     # tap counts other than 2 / 6 / 10
+    assert lib.wdno_dwt2d_supported(6, 2000, 20000, 1002, 10002, 0) == 0   # a single output row does not fit shared memory
