@@ -153,3 +153,54 @@ def test_smoke_builder_full_size_roundtrip_and_batch_independence():
         for name in ("coef", "init_coef", "smokeout"):
             for a, b in zip(res[kind][name], one[kind][name]):
                 assert torch.equal(a[4:5], b), (kind, name)
+
+
+@pytest.mark.skipif(not __import__("oracle.ref_loader", fromlist=["available"]).available(), reason="/root/reference not mounted")
+def test_reference_dataset_classes_read_our_files_like_their_own(tmp_path, monkeypatch):
+    """the consumers of the on-disk format -- smoke `Smoke_wave.__getitem__` (smoke/ddpm/data_2d.py:156-221) and the Burgers
+    `get_wavelet_super_preprocess` (burgers/ddpm_burgers/data_burgers_1d.py:20-85), imported from the reference unchanged --
+    produce the same training samples from the files our builders write as from the files the reference's scripts write
+    (full-size fields, base and super-resolution variants)"""
+    import importlib
+    from oracle import ref_loader
+    from wdno_b200 import coef_builders as CB
+    monkeypatch.setattr(CB, "W", oracle_namespace())
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
+    ref_dir, our_dir = tmp_path / "ref", tmp_path / "ours"
+    sims = builder_inputs_smoke(n_sims=1, T=32, H=64, seed=91)
+    for d in (ref_dir, our_dir):
+        write_smoke_sims(str(d), sims)
+    err = ref_loader.run_reference_main("smoke/wave_trans_2d.py", str(ref_dir))
+    assert isinstance(err, FileNotFoundError)   # the script's hard-coded 20 000 ids end at the first missing simulation
+    CB.build_smoke_coef_files(os.path.join(str(our_dir), "data", "2d") + "/", "train/", range(1), batch_sims=1, device="cpu")
+    ref_loader.smoke()
+    data_2d = importlib.import_module("ddpm.data_2d")
+    real_load = torch.load
+    monkeypatch.setattr(torch, "load", lambda *a, **k: real_load(*a, **{**k, "weights_only": False}))  # files hold torch.Size
+    for sup, kind, n in ((False, "time", 0), (False, "space", 0), (True, "time", 0), (True, "space", 0), (True, "space", 1)):
+        items = []
+        for d in (ref_dir, our_dir):
+            ds = data_2d.Smoke_wave(os.path.join(str(d), "data", "2d"), "bior1.3", "zero", is_super_model=sup,
+                                    downsample_type=kind, N_downsample=n)
+            items.append(ds[0])
+        (sa, sha, oa, ida), (sb, shb, ob, idb) = items
+        assert sa.shape == sb.shape and sha == shb and oa == ob and ida == idb, (sup, kind, n)
+        assert float((sa - sb).abs().max()) <= 1e-5 * float(sa.abs().max()), (sup, kind, n)
+    # Burgers
+    for d in (ref_dir, our_dir):
+        os.makedirs(os.path.join(str(d), "data", "1d"), exist_ok=True)
+        torch.save(builder_inputs_burgers(N=3, seed=92), os.path.join(str(d), "data", "1d", "train"))
+    assert ref_loader.run_reference_main("burgers/wave_trans.py", str(ref_dir)) is None
+    CB.build_burgers_coef_file(os.path.join(str(our_dir), "data", "1d", "train"), device="cpu")
+    ref_loader.burgers()
+    ref_loader.install_wavelet_shims()
+    data_1d = importlib.import_module("ddpm_burgers.data_burgers_1d")
+    dbs = [real_load(os.path.join(str(d), "data", "1d", "coef_bior2.4_periodization_super"), weights_only=False)
+           for d in (ref_dir, our_dir)]
+    for sup, n in ((False, 0), (True, 0), (True, 1)):
+        outs = [data_1d.get_wavelet_super_preprocess(rescaler=70, is_super_model=sup, N_downsample=n, mode="periodization",
+                                                     wave_type="bior2.4", is_condition_u0=True, is_condition_uT=True)(
+                    {k: ([t.clone() for t in v] if k == "coef" else v) for k, v in db.items()}) for db in dbs]
+        (da, sha, oa), (db_, shb, ob) = outs
+        assert da.shape == db_.shape and sha == shb and oa == ob, (sup, n)
+        assert float((da - db_).abs().max()) <= 1e-5 * float(da.abs().max()), (sup, n)
