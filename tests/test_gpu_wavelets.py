@@ -155,3 +155,32 @@ def test_fused_2d_kernels_bit_equal_to_separable_passes_and_strips(monkeypatch):
         (rec.square().sum() + yl.sum()).backward()
         grads[fused] = x.grad.clone()
     assert float((grads[True] - grads[False]).abs().max()) <= 1e-5 * float(grads[False].abs().max())
+
+
+@pytest.mark.skipif(__import__("os").environ.get("WDNO_TEST_EXPERIMENTAL") != "1",
+                    reason="WDNO_DWT2D_V2=1 kernels (extension-staged row pass of the 2-D synthesis, tap-mask variants): written after "
+                           "round 1's GPU budget was spent, index scheme emulated on CPU only; run with WDNO_TEST_EXPERIMENTAL=1")
+def test_experimental_dwt2d_v2_bit_equal_to_separable_passes():
+    """the opt-in second form of the fused 2-D kernels against the per-axis passes, in a child process (the switch is read once)"""
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import numpy as np, torch
+from wdno_b200 import wavelets as W
+rng = np.random.default_rng(11)
+for shape, wave, mode in (((3, 2, 81, 120), "bior2.4", "periodization"), ((2, 1, 64, 64), "bior1.3", "zero"), ((1, 1, 300, 200), "bior2.4", "periodization"),
+                          ((2, 3, 17, 23), "bior1.3", "zero"), ((2, 1, 21, 30), "bior2.4", "periodization"), ((1, 1, 10, 12), "bior2.4", "zero")):
+    x = torch.tensor(rng.standard_normal(shape), dtype=torch.float32, device="cuda")
+    res = {}
+    for fused in (True, False):
+        W._FUSED2D = fused
+        yl, yh = W.DWTForward(J=1, wave=wave, mode=mode)(x)
+        res[fused] = (yl, yh[0], W.DWTInverse(wave=wave, mode=mode)((yl, yh)))
+    for a, b in zip(res[True], res[False]):
+        assert a.shape == b.shape and float((a - b).abs().max()) <= 1e-6 * float(b.abs().max()), (shape, wave, mode)
+print("v2 ok")
+'''
+    env = dict(os.environ, WDNO_DWT2D_V2="1")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0 and "v2 ok" in r.stdout, r.stdout + r.stderr

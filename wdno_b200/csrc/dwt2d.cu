@@ -12,6 +12,7 @@
 // Band order (LL | LH, HL, HH) = (lo_w lo_h | lo_w hi_h, hi_w lo_h, hi_w hi_h) (Appendix A.1).
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -81,7 +82,14 @@ __device__ __forceinline__ void cpa_wait_all() { asm volatile("cp.async.wait_all
 // smem: X [R][CS] (R = 2 T + L - 2 extended rows, column c <-> signal column c - offw, extension applied),
 //       LO / HI [R][nw] (row pass).  Staging is fire-and-forget (cp.async: 16-byte chunks for the interior of a row when the
 //       rows are 16-byte aligned, 4-byte copies for the extension columns), so a CTA has its whole tile in flight at once.
-template <int L>
+// tap masks: bit k of M0 / M1 set = taps t0[k] / t1[k] may be non-zero (all bits set = the plain kernel); products with exact
+// zeros are compiled out together with the loads that only fed them (bior2.4's analysis high-pass has 3 non-zero taps of 10)
+template <unsigned M>
+__device__ __forceinline__ float fm(int k, float a, float t, float acc) {
+  return ((M >> k) & 1u) ? fmaf(a, t, acc) : acc;
+}
+
+template <int L, unsigned M0, unsigned M1>
 __global__ void __launch_bounds__(256) dwt2d_analysis_kernel(const D2 p) {
   extern __shared__ __align__(16) float sm[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
@@ -121,10 +129,10 @@ __global__ void __launch_bounds__(256) dwt2d_analysis_kernel(const D2 p) {
 #pragma unroll
       for (int k = 0; k < L; k += 2) {
         const float2 v = *reinterpret_cast<const float2*>(row + 2 * i + k);
-        a0 = fmaf(v.x, p.t0[k], a0);
-        a1 = fmaf(v.x, p.t1[k], a1);
-        a0 = fmaf(v.y, p.t0[k + 1], a0);
-        a1 = fmaf(v.y, p.t1[k + 1], a1);
+        a0 = fm<M0>(k, v.x, p.t0[k], a0);
+        a1 = fm<M1>(k, v.x, p.t1[k], a1);
+        a0 = fm<M0>(k + 1, v.y, p.t0[k + 1], a0);
+        a1 = fm<M1>(k + 1, v.y, p.t1[k + 1], a1);
       }
       LO[r * nw + i] = a0;
       HI[r * nw + i] = a1;
@@ -141,10 +149,10 @@ __global__ void __launch_bounds__(256) dwt2d_analysis_kernel(const D2 p) {
 #pragma unroll
       for (int k = 0; k < L; ++k) {
         const float a = lo[k * nw], b = hi[k * nw];
-        ll = fmaf(a, p.t0[k], ll);
-        lh = fmaf(a, p.t1[k], lh);
-        hl = fmaf(b, p.t0[k], hl);
-        hh = fmaf(b, p.t1[k], hh);
+        ll = fm<M0>(k, a, p.t0[k], ll);
+        lh = fm<M1>(k, a, p.t1[k], lh);
+        hl = fm<M0>(k, b, p.t0[k], hl);
+        hh = fm<M1>(k, b, p.t1[k], hh);
       }
       p.out[0][img * p.out_istride[0] + o + iw] = ll;
       p.out[1][img * p.out_istride[1] + o + iw] = lh;
@@ -235,6 +243,92 @@ __global__ void __launch_bounds__(256) dwt2d_synthesis_kernel(const D2 p) {
   }
 }
 
+// ---------------------------------------------------------------- synthesis, second form (opt-in: WDNO_DWT2D_V2=1)
+// The row pass of the kernel above spends most of its 212 instructions per output on per-tap index maps (periodic wrap and
+// validity of every coefficient) -- profiles/r1e_dwt.md.  Here the column pass writes its result WITH the extension along W
+// already applied: LOX / HIX [T][WE], entry e <-> coefficient column e - P, P = (L/2 - 1) - offw/2, WE = W/2 + L/2 - 1 (the map is
+// evaluated once per staged column instead of once per tap), so the row pass of output pair q reads entries q + L/2 - 1 - kk
+// at compile-time offsets, without maps or branches.  Tap masks as in the analysis kernel.  Same sums in the same order.
+template <int L, unsigned M0, unsigned M1>
+__global__ void __launch_bounds__(256) dwt2d_synthesis_x_kernel(const D2 p) {
+  extern __shared__ __align__(16) float sm[];
+  constexpr int Hh = L / 2;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+  const long long img = blockIdx.y;
+  const int m0 = blockIdx.x * p.T;
+  const int R = p.R, nw = p.nw, CS = p.CS, W = p.W;
+  const int QW = W >> 1, P = (Hh - 1) - (p.offw >> 1);
+  const int WE = QW + Hh - 1, WS = (WE + 1) & ~1;          // staged columns, row stride of LOX / HIX
+  float* Cc = sm;
+  float* LOX = Cc + 4 * R * CS;
+  float* HIX = LOX + p.T * WS;
+  const int jlo = m0 + p.offh - (L - 1);
+  const int i0 = jlo >= 0 ? jlo / 2 : -((1 - jlo) / 2);
+  for (int rr = warp; rr < 4 * R; rr += nwarps) {
+    const int bd = rr / R, r = rr - bd * R;
+    const int gi = map_synthesis(i0 + r, p.nh, p.periodic);
+    float* dst = Cc + rr * CS;
+    if (gi < 0) {
+      for (int c = lane; c < nw; c += 32) dst[c] = 0.f;
+      continue;
+    }
+    const float* row = p.in[bd] + img * p.in_istride[bd] + static_cast<long long>(gi) * nw;
+    if (p.v16) {
+      for (int q = lane; 4 * q < nw; q += 32) cpa16(dst + 4 * q, row + 4 * q);
+    } else {
+      for (int c = lane; c < nw; c += 32) cpa4(dst + c, row + c);
+    }
+  }
+  cpa_wait_all();
+  __syncthreads();
+  const int rows = min(p.T, p.H - m0);
+  for (int ml = warp; ml < rows; ml += nwarps) {
+    const int j = m0 + ml + p.offh;
+    const bool odd = j & 1;
+    for (int e = lane; e < WE; e += 32) {
+      const int gi = map_synthesis1(e - P, nw, p.periodic);
+      float a = 0.f, b = 0.f;
+      if (gi >= 0) {
+#pragma unroll
+        for (int kk = 0; kk < Hh; ++kk) {
+          const int r = ((j - 2 * kk) >> 1) - i0;
+          const float* c = Cc + r * CS + gi;
+          if (((M0 >> (2 * kk)) & 3u) != 0u) {        // either tap of the pair may be non-zero
+            const float k0 = odd ? p.t0[2 * kk + 1] : p.t0[2 * kk];
+            a = fmaf(c[0], k0, a);
+            b = fmaf(c[2 * R * CS], k0, b);
+          }
+          if (((M1 >> (2 * kk)) & 3u) != 0u) {
+            const float k1 = odd ? p.t1[2 * kk + 1] : p.t1[2 * kk];
+            a = fmaf(c[R * CS], k1, a);
+            b = fmaf(c[3 * R * CS], k1, b);
+          }
+        }
+      }
+      LOX[ml * WS + e] = a;
+      HIX[ml * WS + e] = b;
+    }
+  }
+  __syncthreads();
+  float* y = p.out[0] + img * p.out_istride[0] + static_cast<long long>(m0) * W;
+  for (int ml = warp; ml < rows; ml += nwarps) {
+    const float* lo = LOX + ml * WS + (Hh - 1);
+    const float* hi = HIX + ml * WS + (Hh - 1);
+    for (int q = lane; q < QW; q += 32) {
+      float e = 0.f, o = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < Hh; ++kk) {
+        const float cl = lo[q - kk], ch = hi[q - kk];
+        e = fm<M0>(2 * kk, cl, p.t0[2 * kk], e);
+        e = fm<M1>(2 * kk, ch, p.t1[2 * kk], e);
+        o = fm<M0>(2 * kk + 1, cl, p.t0[2 * kk + 1], o);
+        o = fm<M1>(2 * kk + 1, ch, p.t1[2 * kk + 1], o);
+      }
+      *reinterpret_cast<float2*>(y + ml * W + 2 * q) = make_float2(e, o);
+    }
+  }
+}
+
 int fill(D2& p, const float* t0, const float* t1, int L) {
   if (!t0 || !t1 || L < 2 || L > WDNO_MAX_TAPS || (L & 1)) return set_error(WDNO_E_INVALID, "dwt2d: taps missing / odd length");
   for (int k = 0; k < WDNO_MAX_TAPS; ++k) {
@@ -255,6 +349,18 @@ int launch2d(K kernel, size_t& cfg, dim3 grid, size_t smem, cudaStream_t st, con
   }
   kernel<<<grid, 256, smem, st>>>(p);
   return check_launch(where);
+}
+
+unsigned nz_mask2(const float* t, int L) {
+  unsigned m = 0;
+  for (int k = 0; k < L; ++k)
+    if (t[k] != 0.f) m |= 1u << k;
+  return m;
+}
+
+bool v2_enabled() {
+  static const bool on = [] { const char* e = getenv("WDNO_DWT2D_V2"); return e && e[0] == '1'; }();
+  return on;
 }
 
 }  // namespace
@@ -304,10 +410,15 @@ extern "C" int wdno_dwt2d_analysis(const float* x, float* const* bands4, const i
   const size_t smem = sizeof(float) * static_cast<size_t>(p.R) * (p.CS + 2 * nw);
   dim3 grid(strips, static_cast<unsigned>(n_img));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  static size_t c2 = 0, c6 = 0, c10 = 0;
-  if (L == 6) return launch2d(dwt2d_analysis_kernel<6>, c6, grid, smem, st, p, "dwt2d_analysis");
-  if (L == 10) return launch2d(dwt2d_analysis_kernel<10>, c10, grid, smem, st, p, "dwt2d_analysis");
-  return launch2d(dwt2d_analysis_kernel<2>, c2, grid, smem, st, p, "dwt2d_analysis");
+  static size_t c2 = 0, c6 = 0, c10 = 0, m6 = 0, m10 = 0;
+  if (v2_enabled()) {   // opt-in: tap-mask variants for the filter pairs the reference uses (reversed bior1.3 / bior2.4 analysis taps)
+    const unsigned nz1 = nz_mask2(taps_hi_host, L);
+    if (L == 6 && !(nz1 & ~0x0Cu)) return launch2d(dwt2d_analysis_kernel<6, 0x3Fu, 0x0Cu>, m6, grid, smem, st, p, "dwt2d_analysis");
+    if (L == 10 && !(nz1 & ~0x70u)) return launch2d(dwt2d_analysis_kernel<10, 0x3FFu, 0x70u>, m10, grid, smem, st, p, "dwt2d_analysis");
+  }
+  if (L == 6) return launch2d(dwt2d_analysis_kernel<6, 0x3Fu, 0x3Fu>, c6, grid, smem, st, p, "dwt2d_analysis");
+  if (L == 10) return launch2d(dwt2d_analysis_kernel<10, 0x3FFu, 0x3FFu>, c10, grid, smem, st, p, "dwt2d_analysis");
+  return launch2d(dwt2d_analysis_kernel<2, 0x3u, 0x3u>, c2, grid, smem, st, p, "dwt2d_analysis");
 }
 
 extern "C" int wdno_dwt2d_synthesis(const float* const* bands4, const int64_t* band_istride4, float* y, int64_t n_img, int nh, int nw,
@@ -333,7 +444,9 @@ extern "C" int wdno_dwt2d_synthesis(const float* const* bands4, const int64_t* b
   p.v16 = !(nw & 3) ? 1 : 0;
   for (int i = 0; i < 4; ++i)
     if ((reinterpret_cast<uintptr_t>(bands4[i]) & 15) || (band_istride4[i] & 3)) p.v16 = 0;
-  auto need = [&](int t) { return sizeof(float) * (4ull * (t / 2 + L / 2 + 1) * p.CS + 2ull * t * nw); };
+  const bool v2 = v2_enabled();
+  const size_t ws = v2 ? static_cast<size_t>(((W >> 1) + L / 2 - 1 + 1) & ~1) : static_cast<size_t>(nw);   // column-pass row stride
+  auto need = [&](int t) { return sizeof(float) * (4ull * (t / 2 + L / 2 + 1) * p.CS + 2ull * t * ws); };
   while (T > 2 && need(T) > kSmemBudget) T = (T + 1) / 2;
   const int strips = (H + T - 1) / T;
   T = (H + strips - 1) / strips;
@@ -342,7 +455,15 @@ extern "C" int wdno_dwt2d_synthesis(const float* const* bands4, const int64_t* b
   const size_t smem = need(T);
   dim3 grid(strips, static_cast<unsigned>(n_img));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  static size_t c2 = 0, c6 = 0, c10 = 0;
+  static size_t c2 = 0, c6 = 0, c10 = 0, x2 = 0, x6 = 0, x10 = 0, m6 = 0, m10 = 0;
+  if (v2) {   // opt-in second form (extension-staged column pass, tap masks for the reference's reconstruction filters)
+    const unsigned nz0 = nz_mask2(taps_lo_host, L);
+    if (L == 6 && !(nz0 & ~0x0Cu)) return launch2d(dwt2d_synthesis_x_kernel<6, 0x0Cu, 0x3Fu>, m6, grid, smem, st, p, "dwt2d_synthesis");
+    if (L == 10 && !(nz0 & ~0x38u)) return launch2d(dwt2d_synthesis_x_kernel<10, 0x38u, 0x3FFu>, m10, grid, smem, st, p, "dwt2d_synthesis");
+    if (L == 6) return launch2d(dwt2d_synthesis_x_kernel<6, 0x3Fu, 0x3Fu>, x6, grid, smem, st, p, "dwt2d_synthesis");
+    if (L == 10) return launch2d(dwt2d_synthesis_x_kernel<10, 0x3FFu, 0x3FFu>, x10, grid, smem, st, p, "dwt2d_synthesis");
+    return launch2d(dwt2d_synthesis_x_kernel<2, 0x3u, 0x3u>, x2, grid, smem, st, p, "dwt2d_synthesis");
+  }
   if (L == 6) return launch2d(dwt2d_synthesis_kernel<6>, c6, grid, smem, st, p, "dwt2d_synthesis");
   if (L == 10) return launch2d(dwt2d_synthesis_kernel<10>, c10, grid, smem, st, p, "dwt2d_synthesis");
   return launch2d(dwt2d_synthesis_kernel<2>, c2, grid, smem, st, p, "dwt2d_synthesis");
