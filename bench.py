@@ -22,6 +22,7 @@ sys.path.insert(0, ROOT)
 B_PER_GPU = 16
 SHAPE = (24, 42, 40, 40)            # frames, channels, H, W of the wavelet-coefficient state
 FLOPS_PER_SAMPLE = 326.35e9         # contractions of one Unet3D forward (2 x MAC)
+METRIC = "DDIM steps/sec, 2D smoke Unet3D wavelet (batch 16 per GPU per step)"   # same string on both arms
 WORKLOAD = "smoke base-res sim: Unet3D_with_Conv3D(dim=64,(1,2,4),ch=42), state [16,24,42,40,40]/GPU, DDIM-250 eta=1"
 
 
@@ -139,7 +140,7 @@ def main():
             return
         steps = min(K, 3)
         rate, per = cpu_port_rate(args.cpu_batch, steps, 1, threads)
-        line = {"impl": "reference", "metric": "DDIM steps/sec, 2D smoke Unet3D wavelet (batch 16 per step)", "value": rate,
+        line = {"impl": "reference", "metric": METRIC, "value": rate,
                 "unit": "steps/s", "n_gpus": args.gpus, "steps": steps, "warmup": 1, "ms_per_step": 1e3 / rate,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": WORKLOAD},
@@ -272,7 +273,7 @@ def main():
         if world > 1:
             dist.destroy_process_group()
         return
-    line = {"metric": "DDIM steps/sec, 2D smoke Unet3D wavelet (batch 16 per GPU per step)", "value": value, "unit": "steps/s",
+    line = {"metric": METRIC, "value": value, "unit": "steps/s",
             "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f16 operands / f32 accumulate, f32 state", "data": "synthetic",
             "config": {"workload": WORKLOAD, "per_gpu_batch": B, "parallelism": f"batch-sharded x{world}, no data-path collective",
