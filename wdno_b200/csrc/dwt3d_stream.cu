@@ -56,8 +56,9 @@ __device__ __forceinline__ void cpa_commit() { asm volatile("cp.async.commit_gro
 template <int N>
 __device__ __forceinline__ void cpa_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// keep a kernel parameter in a vector register: without the opaque move the compiler re-loads it from the constant bank
-// (LDCU + uniform-register operand) at every use, 8 % of the instructions of these kernels
+// keep a kernel parameter in a vector register (opaque move, so the compiler cannot re-materialise it from the constant bank).
+// Used for the taps; it did NOT remove the LDCU traffic of these kernels (8 % of the instructions, profiles/r1e_dwt.md): those
+// loads are the other parameters (extents, band pointers) read inside the plane loop -- next candidates for the same treatment.
 __device__ __forceinline__ float pin_reg(float v) {
   float r;
   asm volatile("mov.f32 %0, %1;" : "=f"(r) : "f"(v));
