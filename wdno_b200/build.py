@@ -45,6 +45,11 @@ def build(force=False, verbose=False):
     hdrs.append(os.path.join(HERE, "..", "include", "wdno_b200.h"))
     jobs = []
     objs = []
+    # a change of compile flags (e.g. WDNO_PROF) invalidates every object: the flag set is part of the staleness check
+    stamp = os.path.join(OBJ, "flags.txt")
+    flags_now = " ".join(NVCC_FLAGS)
+    if not os.path.exists(stamp) or open(stamp).read() != flags_now:
+        force = True
     for s in srcs:
         src = os.path.join(CSRC, s)
         obj = os.path.join(OBJ, s[:-3] + ".o")
@@ -64,6 +69,8 @@ def build(force=False, verbose=False):
         list(ex.map(run, jobs))
     if jobs or force or _stale(LIB, objs):
         run([nv, "-shared", "-o", LIB] + objs)
+    with open(stamp, "w") as fh:
+        fh.write(flags_now)
     return LIB
 
 

@@ -382,6 +382,11 @@ class GaussianDiffusion(nn.Module):
         for k, v in (("init", init), ("control", control), ("low", low)):
             if r.static[k] is not None:
                 r.static[k].copy_(v, non_blocking=True)
+        if gs is not None:
+            # the guidance scale depends on design_guidance / standard_fixed_ratio / coeff_ratio of THIS call (the reference
+            # recomputes it every step, diffusion_2d.py:733-747): refresh column 6 of the device table the cached graphs read
+            col = torch.tensor([float(gs(t)) for t in r.times], dtype=torch.float32)
+            r.coef_table[:, 6].copy_(col.to(dev), non_blocking=True)
         r.step.zero_()
         return r
 

@@ -9,6 +9,7 @@ import torch
 from torch import nn
 
 from . import ops
+from ._engine_cache import EngineOwner
 from .tapgemm import TapGemm
 
 
@@ -64,7 +65,7 @@ def _attention(dim, heads=4, dim_head=32):
     return m
 
 
-class Unet2D(nn.Module):
+class Unet2D(EngineOwner, nn.Module):
     def __init__(self, dim, init_dim=None, out_dim=None, dim_mults=(1, 2, 4, 8), channels=2, self_condition=False,
                  resnet_block_groups=8, learned_variance=False, learned_sinusoidal_cond=False,
                  random_fourier_features=False, learned_sinusoidal_dim=16, sinusoidal_pos_emb_theta=10000,
@@ -108,21 +109,8 @@ class Unet2D(nn.Module):
         self.final_conv = nn.Conv2d(dim, self.out_dim, 1)
         self._engine = None
 
-    def invalidate(self):
-        self._engine = None
-
-    def _apply(self, fn, *a, **k):
-        self._engine = None
-        return super()._apply(fn, *a, **k)
-
-    def load_state_dict(self, *a, **k):
-        self._engine = None
-        return super().load_state_dict(*a, **k)
-
-    def engine(self):
-        if self._engine is None:
-            self._engine = Unet2DEngine(self)
-        return self._engine
+    def _make_engine(self):
+        return Unet2DEngine(self)
 
     def forward(self, x, time, x_self_cond=None):
         """x [B, C, H, W] fp32 CUDA, time [B] -> eps [B, out_dim, H, W] fp32"""

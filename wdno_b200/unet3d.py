@@ -18,6 +18,7 @@ from torch import nn
 
 from . import ops
 from .attn_fused import LinAttnBlock, TemporalBlock
+from ._engine_cache import EngineOwner
 from .tapgemm import TapGemm
 
 
@@ -90,7 +91,7 @@ def _spatial_linear_attention(dim, heads, dim_head=32):
     return m
 
 
-class Unet3D_with_Conv3D(nn.Module):
+class Unet3D_with_Conv3D(EngineOwner, nn.Module):
     def __init__(self, dim, cond_dim=None, out_dim=None, dim_mults=(1, 2, 4, 8), channels=6, attn_heads=4,
                  attn_dim_head=32, use_bert_text_cond=False, init_dim=None, init_kernel_size=7,
                  use_sparse_linear_attn=True, block_type="resnet", resnet_groups=8):
@@ -157,22 +158,8 @@ class Unet3D_with_Conv3D(nn.Module):
         self.final_conv = nn.Sequential(_resnet(dim * 2, dim, None, resnet_groups), nn.Conv3d(dim, out_dim, 1))
         self._engine = None
 
-    # ---- engine lifetime: plans are rebuilt whenever parameters may have changed
-    def invalidate(self):
-        self._engine = None
-
-    def _apply(self, fn, *a, **k):
-        self._engine = None
-        return super()._apply(fn, *a, **k)
-
-    def load_state_dict(self, *a, **k):
-        self._engine = None
-        return super().load_state_dict(*a, **k)
-
-    def engine(self):
-        if self._engine is None:
-            self._engine = Unet3DEngine(self)
-        return self._engine
+    def _make_engine(self):
+        return Unet3DEngine(self)
 
     def forward_with_cond_scale(self, *args, cond_scale=2.0, **kwargs):
         # has_cond is always False in WDNO -> identical to forward (conv3d.py:474-485)
