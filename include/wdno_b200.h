@@ -218,6 +218,14 @@ int wdno_mse_weighted(const float* pred, const float* target, const float* w, in
 int wdno_step_begin(int* step_dev, const float* time_table, const float* coef_table, float* time_out, float* coef_out,
                     int B, int n_steps, void* stream);
 
+/* Rows [elem_offset, elem_offset + n_local) of the tensor torch.randn(numel_full, device='cuda') would produce from
+ * Philox state (seed, philox_offset), bit for bit, without drawing the rest: the noise rule of a batch-sharded run
+ * (reference draws: diffusion_2d.py:866,907; diffusion_1d.py:389,431).  grid_full = the grid ATen launches for numel_full
+ * values: min(SMs * (max threads per SM / 256), ceil(numel_full / 256)).  The caller advances the generator by
+ * ((numel_full - 1) / (256 * grid_full * 4) + 1) * 4 afterwards, as ATen does. */
+int wdno_randn_slice(float* out, int64_t n_local, int64_t elem_offset, int64_t numel_full, int grid_full, uint64_t seed,
+                     uint64_t philox_offset, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * separable DWT / IDWT along one axis of an fp32 tensor viewed as [outer][N][inner] (element strides).
  * Replaces the arithmetic of the third-party libraries the reference calls (not vendored in its tree):

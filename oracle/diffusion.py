@@ -76,7 +76,7 @@ def smoke_ddim_sample(model, sch, shape, S, eta, noise_fn, coef_shape, init, con
     x = noise_fn(shape)
     smoke_impose(x, coef_shape, init, control, low, pad)
     for t, tn in ddim_pairs(T, S):
-        tt = torch.full((shape[0],), t, dtype=torch.long)
+        tt = torch.full((shape[0],), t, dtype=torch.long, device=x.device)
         eps = model(x, tt)
         x0 = (sch["sqrt_recip"][t] * x - sch["sqrt_recipm1"][t] * eps).clamp(-1.0, 1.0)
         if guidance is not None:
@@ -107,7 +107,7 @@ def smoke_ddpm_sample(model, sch, shape, noise_fn, coef_shape, init, control=Non
     if steps is not None:
         ts = ts[:steps]
     for t in ts:
-        tt = torch.full((shape[0],), t, dtype=torch.long)
+        tt = torch.full((shape[0],), t, dtype=torch.long, device=x.device)
         eps = model(x, tt)
         x0 = (sch["sqrt_recip"][t] * x - sch["sqrt_recipm1"][t] * eps).clamp(-1.0, 1.0)
         mean = sch["pmc1"][t] * x0 + sch["pmc2"][t] * x
@@ -163,7 +163,7 @@ def burgers_ddim_sample(model, sch, shape, S, eta, noise_fn, coef_shape, u0=None
     x = noise_fn(shape)
     for t, tn in ddim_pairs(T, S):
         burgers_impose(x, coef_shape, u0, uT, f, low, pad)
-        tt = torch.full((shape[0],), t, dtype=torch.long)
+        tt = torch.full((shape[0],), t, dtype=torch.long, device=x.device)
         eps = model(x, tt)
         x0 = (sch["sqrt_recip"][t] * x - sch["sqrt_recipm1"][t] * eps).clamp(-1.0, 1.0)
         if guidance is not None:
@@ -189,7 +189,7 @@ def burgers_ddpm_sample(model, sch, shape, noise_fn, coef_shape, u0=None, uT=Non
         ts = ts[:steps]
     for t in ts:
         burgers_impose(x, coef_shape, u0, uT, f, low, pad)
-        tt = torch.full((shape[0],), t, dtype=torch.long)
+        tt = torch.full((shape[0],), t, dtype=torch.long, device=x.device)
         eps = model(x, tt)
         x0 = (sch["sqrt_recip"][t] * x - sch["sqrt_recipm1"][t] * eps).clamp(-1.0, 1.0)
         mean = sch["pmc1"][t] * x0 + sch["pmc2"][t] * x

@@ -89,7 +89,7 @@ class Unet2DOracle:
         rec("init_conv", x)
         r = x
         half = self.dim // 2
-        f = torch.exp(torch.arange(half, dtype=self.dtype) * -(math.log(self.theta) / (half - 1)))
+        f = torch.exp(torch.arange(half, dtype=self.dtype, device=x.device) * -(math.log(self.theta) / (half - 1)))
         e = time.to(self.dtype)[:, None] * f[None, :]
         t = torch.cat((e.sin(), e.cos()), dim=-1)
         t = F.linear(F.gelu(F.linear(t, sd["time_mlp.1.weight"], sd["time_mlp.1.bias"])), sd["time_mlp.3.weight"],

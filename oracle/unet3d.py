@@ -30,16 +30,16 @@ def _rel_pos_bucket(rel, num_buckets=32, max_distance=32):
 
 def rel_pos_bias(emb_weight, n, max_distance=32):
     """-> [heads, n, n]; emb_weight = time_rel_pos_bias.relative_attention_bias.weight [32, heads]."""
-    pos = torch.arange(n)
+    pos = torch.arange(n)   # buckets on the host: float log at bucket boundaries must not depend on the device
     rel = pos[None, :] - pos[:, None]
-    bucket = _rel_pos_bucket(rel, emb_weight.shape[0], max_distance)
+    bucket = _rel_pos_bucket(rel, emb_weight.shape[0], max_distance).to(emb_weight.device)
     return emb_weight[bucket].permute(2, 0, 1)
 
 
 def rotary(t, freqs):
     """t [..., n, d]; interleaved-pair rotation by position*freq."""
     n = t.shape[-2]
-    ang = torch.arange(n, dtype=t.dtype)[:, None] * freqs.to(t.dtype)[None, :]
+    ang = torch.arange(n, dtype=t.dtype, device=t.device)[:, None] * freqs.to(t.dtype)[None, :]
     ang = ang.repeat_interleave(2, dim=-1)
     pair = t.reshape(*t.shape[:-1], -1, 2)
     rot = torch.stack((-pair[..., 1], pair[..., 0]), dim=-1).reshape(t.shape)
@@ -48,7 +48,7 @@ def rotary(t, freqs):
 
 def sinusoid(time, dim):
     half = dim // 2
-    f = torch.exp(torch.arange(half, dtype=time.dtype) * -(math.log(10000) / (half - 1)))
+    f = torch.exp(torch.arange(half, dtype=time.dtype, device=time.device) * -(math.log(10000) / (half - 1)))
     e = time[:, None] * f[None, :]
     return torch.cat((e.sin(), e.cos()), dim=-1)
 

@@ -27,6 +27,24 @@ class _FakeDiffusion:
         return init[:, None] * 2.0 + control.sum(dim=2)
 
 
+class _FakeNoisyDiffusion:
+    """sample() consumes noise the way the engine classes do: through `_noise_source` when set, else torch.randn"""
+
+    def __init__(self):
+        self._noise_source = None
+
+    def _randn(self, shape, device):
+        if self._noise_source is not None:
+            return self._noise_source(tuple(shape), device)
+        return torch.randn(shape, device=device)
+
+    def sample(self, batch_size, init=None, **kw):
+        x = self._randn((batch_size, 3, 4), init.device)
+        for _ in range(3):
+            x = 0.5 * x + init + self._randn((batch_size, 3, 4), init.device)
+        return x
+
+
 def _worker(rank, world, port, batch, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -39,7 +57,14 @@ def _worker(rank, world, port, batch, q):
     noise = P.full_batch_noise((batch, 2), world, rank, generator=torch.Generator().manual_seed(5))
     ref = torch.randn((batch, 2), generator=torch.Generator().manual_seed(5))
     lo, hi = P.shard_bounds(batch, world, rank)
-    q.put((rank, bool(out.shape == full.shape and torch.allclose(out, full, atol=1e-6)), bool(torch.equal(noise, ref[lo:hi]))))
+    # RNG rule: same seed on every rank + full-batch draws sliced per rank == the single-process trajectory
+    torch.manual_seed(7)
+    noisy = P.sample_sharded(_FakeNoisyDiffusion(), batch, init=init)
+    torch.manual_seed(7)
+    single = _FakeNoisyDiffusion().sample(batch, init=init)
+    ok_rng = bool(torch.equal(noisy, single))
+    q.put((rank, bool(out.shape == full.shape and torch.allclose(out, full, atol=1e-6)),
+           bool(torch.equal(noise, ref[lo:hi])) and ok_rng))
     dist.destroy_process_group()
 
 

@@ -36,6 +36,7 @@ SIGNATURES = {
     "wdno_q_sample": [P, P, P, P, P, P, I, L64, P],
     "wdno_mse_weighted": [P, P, P, I, I, I, I, I, I, P, P],
     "wdno_step_begin": [P, P, P, P, P, I, I, P],
+    "wdno_randn_slice": [P, L64, L64, L64, I, C.c_uint64, C.c_uint64, P],
     "wdno_dwt_analysis_axis": [P, P, P, L64, I, L64, I, L64, L64, L64, P, P, I, I, I, P],
     "wdno_dwt_synthesis_axis": [P, P, P, L64, I, L64, I, L64, L64, L64, P, P, I, I, I, P],
     "wdno_dwt3d_supported": [I, I, I],

@@ -8,7 +8,7 @@ import ctypes as C
 
 import torch
 
-from . import _lib
+from . import _lib, _timing
 
 
 def pack_b_frags(w):
@@ -64,10 +64,18 @@ class LinAttnBlock:
             assert nbytes > 0
             self._work[key] = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
         y = torch.empty_like(x)
+        # algorithmic work of the block (conv3d.py:232-258): one read + one write of the fp16 residual stream; qkv and output
+        # projections + the two 32x32-per-head context products
+        ntok = n_img * n_pos
+        with _timing.span("linattn_block", flops=2.0 * ntok * (self.C * 384 + 128 * self.C + 2 * 128 * 32),
+                          bytes=4.0 * ntok * self.C, meta=(self.C, n_img, n_pos)):
+            self._launch(L, x, y, key, n_img, n_pos, eps)
+        return y
+
+    def _launch(self, L, x, y, key, n_img, n_pos, eps):
         _lib.check(L.wdno_linattn_block(_p(x), _p(y), _p(self.gamma), _p(self.wq), _p(self.wkv), _p(self.wout), _p(self.bias),
                                         _p(self._work[key]), n_img, n_pos, self.C, self.scale, float(eps),
                                         _lib.current_stream_ptr()), "linattn_block")
-        return y
 
 
 class TemporalBlock:
@@ -98,7 +106,11 @@ class TemporalBlock:
             assert bias.dtype == torch.float32 and bias.is_contiguous() and tuple(bias.shape) == (4, D, D)
         if rc is not None:
             assert rc.dtype == torch.float32 and rc.is_contiguous() and tuple(rc.shape) == (D, 16) and tuple(rs.shape) == (D, 16)
-        _lib.check(_lib.lib().wdno_tattn_block(_p(x), _p(y), _p(self.gamma), _p(self.wqk), _p(self.wv), _p(self.wo), _p(bias),
-                                               _p(rc), _p(rs), B, D, H * W, self.C, self.scale, float(eps),
-                                               _lib.current_stream_ptr()), "tattn_block")
+        ntok = B * D * H * W
+        # algorithmic work (conv3d.py:262-353): one read + one write of the fp16 residual stream; projections + QK^T + PV
+        with _timing.span("tattn_block", flops=2.0 * ntok * (self.C * 384 + 128 * self.C + 2 * 128 * D),
+                          bytes=4.0 * ntok * self.C, meta=(self.C, B, D, H * W)):
+            _lib.check(_lib.lib().wdno_tattn_block(_p(x), _p(y), _p(self.gamma), _p(self.wqk), _p(self.wv), _p(self.wo), _p(bias),
+                                                   _p(rc), _p(rs), B, D, H * W, self.C, self.scale, float(eps),
+                                                   _lib.current_stream_ptr()), "tattn_block")
         return y

@@ -119,6 +119,13 @@ def diffuse_fields(ddpm, args, RESCALER=1, **kwargs):
     return x[:, :8], u_f[:, 0], u_f[:, 1, :ori_shape[-2] - 1]
 
 
+def coef_state_to_trajectory(x, shape, ori_shape, wave_type, pad_mode, RESCALER=1):
+    """rescaled base-model state [B,9,64,64] (what `sample()` returns) -> physical fields [B,2,Nt,Nx] (u, f) through the
+    inverse 2-D transform (eval_ddpm_burgers.py:188-194): the `post` of `wdno_b200.parallel.sample_sharded` for Burgers"""
+    Yl, Yh = tensor_to_coef(x * RESCALER, shape)
+    return DWTInverse(mode=pad_mode, wave=wave_type)((Yl, Yh))[:, :, :ori_shape[-2], :ori_shape[-1]]
+
+
 def next_level_low(sampled_coef, padded_shape_k, k, is_wavelet=True):
     """nearest x2 of the previous level's coefficients, zero-padded to the level-k padded plane"""
     low = upsample_coef(sampled_coef, padded_shape_k)

@@ -5,6 +5,7 @@
 //     reference conv3d.py:232-258; unet.py:183-223
 // heads x dim_head is fixed to 4 x 32 (both reference models use the defaults attn_heads=4, attn_dim_head=32).
 #include <cuda_fp16.h>
+#include "cvt_sat.cuh"
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -140,7 +141,7 @@ __global__ void __launch_bounds__(512) softmax_attn_kernel(const __half* __restr
         uint4 ov;
         __half2* oh = reinterpret_cast<__half2*>(&ov);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) oh[j] = __floats2half2_rn(acc[c * 8 + 2 * j] * inv, acc[c * 8 + 2 * j + 1] * inv);
+        for (int j = 0; j < 4; ++j) oh[j] = wdno::h2_sat(acc[c * 8 + 2 * j] * inv, acc[c * 8 + 2 * j + 1] * inv);
         reinterpret_cast<uint4*>(op)[c] = ov;
       }
     }
@@ -256,7 +257,7 @@ __global__ void __launch_bounds__(256) linear_attn_kernel(const __half* __restri
       uint4 ov;
       __half2* oh = reinterpret_cast<__half2*>(&ov);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) oh[j] = __floats2half2_rn(o[c * 8 + 2 * j], o[c * 8 + 2 * j + 1]);
+      for (int j = 0; j < 4; ++j) oh[j] = wdno::h2_sat(o[c * 8 + 2 * j], o[c * 8 + 2 * j + 1]);
       reinterpret_cast<uint4*>(op)[c] = ov;
     }
   }

@@ -7,6 +7,7 @@
 // 2 x 16 MMAs per (sequence, head) -- not worth a tcgen05/TMEM pipeline; HBM traffic (read 768 B, write 256 B per token)
 // is what bounds it.
 #include <cuda_fp16.h>
+#include "cvt_sat.cuh"
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -42,7 +43,7 @@ __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], 
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 __device__ __forceinline__ uint32_t pack_h2(float x, float y) {
-  const __half2 h = __floats2half2_rn(x, y);
+  const __half2 h = wdno::h2_sat(x, y);
   return *reinterpret_cast<const uint32_t*>(&h);
 }
 
@@ -108,7 +109,7 @@ __global__ void __launch_bounds__(128) short_attn_mma_kernel(const __half* __res
             x.x = x0 * cs - x1 * sn;
             x.y = x1 * cs + x0 * sn;
           }
-          hp[e] = __float22half2_rn(x);
+          hp[e] = wdno::h2_sat(x);
         }
       }
       __half* dst = (sect == 0) ? &sq[hh][f][d0] : (sect == 1) ? &sk[hh][f][d0] : &sv[hh][f][d0];
@@ -242,7 +243,7 @@ __global__ void __launch_bounds__(128) flash_attn_mma_kernel(const __half* __res
           float2 x = __half22float2(hp[e]);
           x.x *= scale;
           x.y *= scale;
-          hp[e] = __float22half2_rn(x);
+          hp[e] = wdno::h2_sat(x);
         }
       }
     }

@@ -12,6 +12,7 @@
 //   HBM traffic: x is read twice and y written once (3 x 2C bytes per voxel) instead of the ~21 x 2C bytes of the
 //   unfused LN / qkv GEMM / attention core / out GEMM chain.
 #include <cuda_fp16.h>
+#include "cvt_sat.cuh"
 #include <stdlib.h>
 #include <cuda_runtime.h>
 #include <math.h>
@@ -300,7 +301,7 @@ __global__ void __launch_bounds__(256) la_mid_kernel(const float* __restrict__ p
         s3 = fmaf(w4.w, cr[4 * e4 + 3], s3);
       }
       const int nt = c >> 3, gg = c & 7;
-      msm[((nt * 4 + (ks >> 1)) * 32 + (gg * 4 + qq)) * 8 + ((ks & 1) * 2 + reg) * 2 + half] = __float2half_rn((s0 + s1) + (s2 + s3));
+      msm[((nt * 4 + (ks >> 1)) * 32 + (gg * 4 + qq)) * 8 + ((ks & 1) * 2 + reg) * 2 + half] = wdno::h_sat((s0 + s1) + (s2 + s3));
     }
   }
   __syncthreads();
@@ -514,7 +515,7 @@ __global__ void __launch_bounds__(256, 2) la2_kernel(const __half* __restrict__ 
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const float2 a2 = __half22float2(vh[i]), b2 = __half22float2(rh[i]);
-          vh[i] = __floats2half2_rn(a2.x + b2.x, a2.y + b2.y);
+          vh[i] = wdno::h2_sat(a2.x + b2.x, a2.y + b2.y);
         }
         *(reinterpret_cast<uint4*>(yt + static_cast<size_t>(row) * C) + ch) = v;
       }
@@ -709,7 +710,7 @@ __global__ void __launch_bounds__(128, 4) la2_warp_kernel(const __half* __restri
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const float2 a2 = __half22float2(vh[i]), b2 = __half22float2(rh[i]);
-          vh[i] = __floats2half2_rn(a2.x + b2.x, a2.y + b2.y);
+          vh[i] = wdno::h2_sat(a2.x + b2.x, a2.y + b2.y);
         }
         *(reinterpret_cast<uint4*>(yt + static_cast<size_t>(row) * C) + ch) = v;
       }
@@ -1080,7 +1081,7 @@ __global__ void __launch_bounds__(256, 2) tattn_kernel(const __half* __restrict_
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const float2 a2 = __half22float2(vh[i]), b2 = __half22float2(rh[i]);
-          vh[i] = __floats2half2_rn(a2.x + b2.x, a2.y + b2.y);
+          vh[i] = wdno::h2_sat(a2.x + b2.x, a2.y + b2.y);
         }
         *(reinterpret_cast<uint4*>(yb + off) + l) = v;
       }
@@ -1399,7 +1400,7 @@ __global__ void __launch_bounds__(128, 3) tattn_warp_kernel(const __half* __rest
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const float2 a2 = __half22float2(vh[i]), b2 = __half22float2(rh[i]);
-        vh[i] = __floats2half2_rn(a2.x + b2.x, a2.y + b2.y);
+        vh[i] = wdno::h2_sat(a2.x + b2.x, a2.y + b2.y);
       }
       *(reinterpret_cast<uint4*>(yb + off) + l) = v;
     }

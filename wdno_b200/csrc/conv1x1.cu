@@ -11,6 +11,7 @@
 // planar) transaction.  The tcgen05 tap-GEMM handles these layers too (and still does when a GroupNorm prologue or
 // statistics are fused), but its persistent one-CTA-per-SM pipeline is built for long K loops; here K is 2..48 slices.
 #include <cuda_fp16.h>
+#include "cvt_sat.cuh"
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -157,7 +158,7 @@ __global__ void __launch_bounds__(kThreads, (BN == 128) ? 2 : 3) conv1x1_kernel(
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const float2 a2 = __half22float2(vh[i]), b2 = __half22float2(rh[i]);
-            vh[i] = __floats2half2_rn(a2.x + b2.x, a2.y + b2.y);
+            vh[i] = wdno::h2_sat(a2.x + b2.x, a2.y + b2.y);
           }
         }
         *reinterpret_cast<uint4*>(o16 + off) = v;

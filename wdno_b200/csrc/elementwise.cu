@@ -3,6 +3,7 @@
 // Reference arithmetic: smoke/video_diffusion_pytorch/video_diffusion_pytorch_conv3d.py:139-151 (SinusoidalPosEmb),
 // 165-174 (LayerNorm), 189-230 (Block / ResnetBlock), 405-410 (time_mlp); burgers/ddpm_burgers/unet.py:55-65,82-108,129-181.
 #include <cuda_fp16.h>
+#include "cvt_sat.cuh"
 #include <cuda_runtime.h>
 #include <math.h>
 #include <algorithm>
@@ -37,7 +38,7 @@ __global__ void pack_bfchw_kernel(const float* __restrict__ x, __half* __restric
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int c = ck * 8 + 2 * j;
-      h[j] = __floats2half2_rn(c < C ? tile[c * TP + r] : 0.f, c + 1 < C ? tile[(c + 1) * TP + r] : 0.f);
+      h[j] = wdno::h2_sat(c < C ? tile[c * TP + r] : 0.f, c + 1 < C ? tile[(c + 1) * TP + r] : 0.f);
     }
     dst[i] = v;
   }
@@ -126,7 +127,7 @@ __global__ void __launch_bounds__(256) gn_silu_add_fast_kernel(const __half* __r
           f0 += rr.x;
           f1 += rr.y;
         }
-        oh[k] = __floats2half2_rn(f0, f1);
+        oh[k] = wdno::h2_sat(f0, f1);
       }
       o4[u == 0 ? i0 : i1] = ov;
     }
@@ -176,7 +177,7 @@ __global__ void gn_silu_add_kernel(const __half* __restrict__ y, const float* __
     uint4 ov;
     __half2* oh = reinterpret_cast<__half2*>(&ov);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) oh[k] = __floats2half2_rn(f[2 * k], f[2 * k + 1]);
+    for (int k = 0; k < 4; ++k) oh[k] = wdno::h2_sat(f[2 * k], f[2 * k + 1]);
     reinterpret_cast<uint4*>(out)[i] = ov;
   }
 }
@@ -230,7 +231,7 @@ __global__ void chan_layernorm_kernel(const __half* __restrict__ x, const float*
     for (int j = 0; j < 4; ++j) {
       const float g0 = __ldg(gamma + ch + 2 * j), g1 = __ldg(gamma + ch + 2 * j + 1);
       const float2 rr = __half22float2(rh[j]);
-      oh[j] = __floats2half2_rn((f[k * 8 + 2 * j] - mean) * rstd * g0 + rr.x, (f[k * 8 + 2 * j + 1] - mean) * rstd * g1 + rr.y);
+      oh[j] = wdno::h2_sat((f[k * 8 + 2 * j] - mean) * rstd * g0 + rr.x, (f[k * 8 + 2 * j + 1] - mean) * rstd * g1 + rr.y);
     }
     reinterpret_cast<uint4*>(out + vox * C)[k * LPV + l] = ov;
   }

@@ -6,6 +6,7 @@
 // lane yields the fragments of two consecutive k-steps (B) or of one k-step (A).
 #pragma once
 #include <cuda_fp16.h>
+#include "cvt_sat.cuh"
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -34,7 +35,7 @@ __device__ __forceinline__ void mma16816(float (&d)[4], uint32_t a0, uint32_t a1
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 __device__ __forceinline__ uint32_t pack_h2(float x, float y) {
-  const __half2 h = __floats2half2_rn(x, y);
+  const __half2 h = wdno::h2_sat(x, y);
   return *reinterpret_cast<const uint32_t*>(&h);
 }
 

@@ -14,6 +14,7 @@
 //   * D: up to 4 fp32 accumulators of 128 x N in TMEM (double buffered when they fit in 512 columns);
 //   * epilogue warps: tcgen05.ld -> +bias (+residual) -> GroupNorm partial sums -> fp16 / fp32 stores.
 #include <cuda_fp16.h>
+#include "cvt_sat.cuh"
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -601,8 +602,8 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const wdno_tapgemm
         f1.x = silu_half(fmaf(a0.z, f1.x, c0.z)); f1.y = silu_half(fmaf(a0.w, f1.y, c0.w));
         f2.x = silu_half(fmaf(a1.x, f2.x, c1.x)); f2.y = silu_half(fmaf(a1.y, f2.y, c1.y));
         f3.x = silu_half(fmaf(a1.z, f3.x, c1.z)); f3.y = silu_half(fmaf(a1.w, f3.y, c1.w));
-        h[0] = __float22half2_rn(f0); h[1] = __float22half2_rn(f1);
-        h[2] = __float22half2_rn(f2); h[3] = __float22half2_rn(f3);
+        h[0] = wdno::h2_sat(f0); h[1] = wdno::h2_sat(f1);
+        h[2] = wdno::h2_sat(f2); h[3] = wdno::h2_sat(f3);
       };
 #pragma unroll
       for (int i0 = 0; i0 < kIt; i0 += 4) {  // 4 independent load -> math -> store chains in flight
@@ -844,7 +845,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const wdno_tapgemm
                   uint4 ov;
                   __half2* oh = reinterpret_cast<__half2*>(&ov);
 #pragma unroll
-                  for (int i = 0; i < 4; ++i) oh[i] = __floats2half2_rn(f[q * 8 + 2 * i], f[q * 8 + 2 * i + 1]);
+                  for (int i = 0; i < 4; ++i) oh[i] = wdno::h2_sat(f[q * 8 + 2 * i], f[q * 8 + 2 * i + 1]);
                   *reinterpret_cast<uint4*>(stage_row + (c2 * 4 + q) * 16) = ov;
                 }
               }
@@ -880,7 +881,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const wdno_tapgemm
 #pragma unroll
                       for (int i = 0; i < 4; ++i) {
                         const float2 a2 = __half22float2(vh[i]), b2 = __half22float2(rh[i]);
-                        vh[i] = __floats2half2_rn(a2.x + b2.x, a2.y + b2.y);
+                        vh[i] = wdno::h2_sat(a2.x + b2.x, a2.y + b2.y);
                       }
                     }
                   }

@@ -66,6 +66,8 @@ class GaussianDiffusion(nn.Module):
         self.ori_shape = ori_shape if ori_shape is not None else _default_ori_shape()
         self.use_cuda_graph = True
         self._noise_source = None
+        self._step_hook = None     # tests: callable(step index, state) after every sampling step
+        self.last_launches_per_step = None
 
     # ------------------------------------------------------------ helpers
     def _randn(self, shape, device):
@@ -148,16 +150,22 @@ class GaussianDiffusion(nn.Module):
         dev = self.betas.device
         srcs = self._gather_sources(kwargs, dev)
         key = (kind, tuple(shape), kwargs.get("N_upsample"), tuple((k, tuple(v.shape)) for k, v in srcs.items()),
-               self.sampling_timesteps, float(self.ddim_sampling_eta), self.use_cuda_graph)
+               self.use_cuda_graph)
+        sched_key = (kind, self.sampling_timesteps, float(self.ddim_sampling_eta))
         cache = self.__dict__.setdefault("_runners", {})
         r = cache.get(key)
+        if r is not None and r.model_engine is self.model.engine() and r.sched_key != sched_key:
+            times, table = (ddim_tables(self, self.ddim_sampling_eta) if kind == "ddim" else ddpm_tables(self))
+            r.set_schedule(times, table)
+            r.sched_key = sched_key
         if r is None or r.model_engine is not self.model.engine():
             static = {k: torch.empty(v.shape, dtype=torch.float32, device=dev) for k, v in srcs.items()}
             keep, prog = self._program(shape, self._coef_shape(kwargs), static)
             times, table = (ddim_tables(self, self.ddim_sampling_eta) if kind == "ddim" else ddpm_tables(self))
             x = torch.empty((shape[0], 1) + tuple(shape[1:]), dtype=torch.float32, device=dev)
-            r = StepRunner(_As5D(self.model), x, times, table, prog, kind, 2, use_graph=self.use_cuda_graph)
-            r.static, r.keep, r.model_engine = static, keep, self.model.engine()
+            r = StepRunner(_As5D(self.model), x, times, table, prog, kind, 2, use_graph=self.use_cuda_graph,
+                           capacity=self.num_timesteps)
+            r.static, r.keep, r.model_engine, r.sched_key = static, keep, self.model.engine(), sched_key
             cache.clear()
             cache[key] = r
         for k, v in srcs.items():
@@ -195,6 +203,9 @@ class GaussianDiffusion(nn.Module):
                 self._guided_step(run, with_noise, nabla_J, sched, proj)
             else:
                 run.step_graph(with_noise)
+            if self._step_hook is not None:
+                self._step_hook(i, run.x.reshape(shape))
+        self.last_launches_per_step = self.model.engine().launches + 2
         return run.x.reshape(shape).clone()
 
     @torch.no_grad()

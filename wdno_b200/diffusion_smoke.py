@@ -104,14 +104,16 @@ def ddpm_tables(mod, gscale_fn=None):
 class StepRunner:
     """Runs `n` sampling steps: eps = model(x, t); fused update.  Un-guided steps are replayed from one CUDA graph."""
 
-    def __init__(self, model, x, times, table, prog, kind, cond_mode, use_graph=True):
+    def __init__(self, model, x, times, table, prog, kind, cond_mode, use_graph=True, capacity=None):
         self.model, self.x, self.kind, self.cond_mode, self.prog = model, x, kind, cond_mode, prog
         dev = x.device
         self.B = x.shape[0]
-        self.n = len(times)
-        self.time_table = torch.tensor(times, dtype=torch.float32, device=dev)
-        self.coef_table = table.to(dev).contiguous()
-        self.times = times
+        # device tables with room for `capacity` steps: the captured graphs bake the table ADDRESSES and the capacity, so a
+        # new schedule (another sampling_timesteps / eta) is an upload, not a re-capture
+        self.cap = max(int(capacity or 0), len(times))
+        self.time_table = torch.zeros(self.cap, dtype=torch.float32, device=dev)
+        self.coef_table = torch.zeros(self.cap, 8, dtype=torch.float32, device=dev)
+        self.set_schedule(times, table)
         self.step = torch.zeros(1, dtype=torch.int32, device=dev)
         self.time_f = torch.zeros(self.B, dtype=torch.float32, device=dev)
         self.coef = torch.zeros(8, dtype=torch.float32, device=dev)
@@ -119,6 +121,13 @@ class StepRunner:
         self.graph = None
         self.use_graph = use_graph
         self.launches_per_step = None
+
+    def set_schedule(self, times, table):
+        n = len(times)
+        assert n <= self.cap, "schedule longer than the runner's table capacity"
+        self.times, self.n = list(times), n
+        self.time_table[:n].copy_(torch.tensor(times, dtype=torch.float32), non_blocking=True)
+        self.coef_table[:n].copy_(table.to(torch.float32), non_blocking=True)
 
     def _net(self):
         """eps = model(x, t) with the engine told that t is batch-uniform (step_begin writes one value to every row)"""
@@ -132,7 +141,7 @@ class StepRunner:
             eng.time_uniform = False
 
     def _body(self, with_noise, guidance=None):
-        ops.step_begin(self.step, self.time_table, self.coef_table, self.time_f, self.coef, self.n)
+        ops.step_begin(self.step, self.time_table, self.coef_table, self.time_f, self.coef, self.cap)
         eps = self._net()
         fn = ops.ddim_step if self.kind == "ddim" else ops.ddpm_step
         fn(self.x, eps, self.noise if with_noise else None, self.coef, self.prog, self.cond_mode, guidance=guidance)
@@ -148,7 +157,7 @@ class StepRunner:
         clip = self.kind == "ddim"
 
         def head():
-            ops.step_begin(self.step, self.time_table, self.coef_table, self.time_f, self.coef, self.n)
+            ops.step_begin(self.step, self.time_table, self.coef_table, self.time_f, self.coef, self.cap)
             eps = self._net()
             return eps, ops.predict_x0(self.x, eps, self.coef, clip=clip)
         if not self.use_graph:
@@ -170,7 +179,7 @@ class StepRunner:
         if head_graph:
             eps, x0 = self.guided_head()
         else:
-            ops.step_begin(self.step, self.time_table, self.coef_table, self.time_f, self.coef, self.n)
+            ops.step_begin(self.step, self.time_table, self.coef_table, self.time_f, self.coef, self.cap)
             eps = self._net()
             x0 = ops.predict_x0(self.x, eps, self.coef, clip=self.kind == "ddim")
         g = design(x0)
@@ -284,6 +293,7 @@ class GaussianDiffusion(nn.Module):
         self.use_cuda_graph = True
         self.graph_design_fn = os.environ.get("WDNO_GRAPH_GUIDANCE", "0") == "1"   # capture design_fn with the step (opt-in)
         self._noise_source = None  # tests: callable(shape, device) replacing torch.randn (injected noise)
+        self._step_hook = None     # tests: callable(step index, state) after every sampling step (trajectory traces)
         self.last_launches_per_step = None
 
     # ------------------------------------------------------------ helpers
@@ -360,9 +370,15 @@ class GaussianDiffusion(nn.Module):
         CUDA graph is reused; a new call only copies its conditions into the static buffers."""
         dev = self.betas.device
         key = (kind, tuple(shape), N_upsample, control is not None and self.is_condition_control, low is not None,
-               self.sampling_timesteps, float(self.ddim_sampling_eta), gs is not None, self.use_cuda_graph)
+               self.use_cuda_graph)
+        sched_key = (kind, self.sampling_timesteps, float(self.ddim_sampling_eta))
         cache = self.__dict__.setdefault("_runners", {})
         r = cache.get(key)
+        if r is not None and r.model_engine is self.model.engine() and r.sched_key != sched_key:
+            # same workload, another schedule: upload the new per-step tables; the captured graphs stay valid
+            times, table = ddim_tables(self, self.ddim_sampling_eta, gs) if kind == "ddim" else ddpm_tables(self, gs)
+            r.set_schedule(times, table)
+            r.sched_key = sched_key
         if r is None or r.model_engine is not self.model.engine():
             coef_shape = self._coef_shape(N_upsample)
             static = dict(init=torch.empty_like(init, dtype=torch.float32, device=dev).contiguous(),
@@ -375,8 +391,8 @@ class GaussianDiffusion(nn.Module):
                 times, table = ddpm_tables(self, gs)
             x = torch.empty(tuple(shape), dtype=torch.float32, device=dev)
             r = StepRunner(self.model, x, times, table, prog, kind, 1 if kind == "ddim" else 2,
-                           use_graph=self.use_cuda_graph)
-            r.static, r.keep, r.model_engine = static, keep, self.model.engine()
+                           use_graph=self.use_cuda_graph, capacity=self.num_timesteps)
+            r.static, r.keep, r.model_engine, r.sched_key = static, keep, self.model.engine(), sched_key
             cache.clear()  # one live runner: its static buffers are sized for the workload
             cache[key] = r
         for k, v in (("init", init), ("control", control), ("low", low)):
@@ -386,7 +402,7 @@ class GaussianDiffusion(nn.Module):
             # the guidance scale depends on design_guidance / standard_fixed_ratio / coeff_ratio of THIS call (the reference
             # recomputes it every step, diffusion_2d.py:733-747): refresh column 6 of the device table the cached graphs read
             col = torch.tensor([float(gs(t)) for t in r.times], dtype=torch.float32)
-            r.coef_table[:, 6].copy_(col.to(dev), non_blocking=True)
+            r.coef_table[:r.n, 6].copy_(col.to(dev), non_blocking=True)
         r.step.zero_()
         return r
 
@@ -409,6 +425,8 @@ class GaussianDiffusion(nn.Module):
                 run.step_guided(not last, design, graph=self.graph_design_fn)
             else:
                 run.step_graph(not last)
+            if self._step_hook is not None:
+                self._step_hook(i, run.x)
         self.last_launches_per_step = self.model.engine().launches + 2
         return run.x.clone()
 
@@ -430,6 +448,8 @@ class GaussianDiffusion(nn.Module):
                 run.step_guided(with_noise, design, graph=self.graph_design_fn)
             else:
                 run.step_graph(with_noise)
+            if self._step_hook is not None:
+                self._step_hook(i, run.x)
         self.last_launches_per_step = self.model.engine().launches + 2
         return run.x.clone()
 

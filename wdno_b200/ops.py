@@ -201,3 +201,62 @@ def mse_weighted(pred, target, w):
 def step_begin(step_dev, time_table, coef_table, time_out, coef_out, n_steps):
     _lib.check(_lib.lib().wdno_step_begin(_p(step_dev), _p(time_table), _p(coef_table), _p(time_out), _p(coef_out),
                                          time_out.shape[0], n_steps, _st()), "step_begin")
+
+
+# ---------------------------------------------------------------- sharded noise (row slice of a full-batch torch.randn)
+_RANDN_ROWS_OK = {}
+
+
+def _randn_rows_kernel(shape_local, full_batch, lo, device):
+    gen = torch.cuda.default_generators[device.index if device.index is not None else torch.cuda.current_device()]
+    per = 1
+    for d in shape_local[1:]:
+        per *= int(d)
+    numel_full = full_batch * per
+    props = torch.cuda.get_device_properties(device)
+    grid = min(props.multi_processor_count * (props.max_threads_per_multi_processor // 256), (numel_full + 255) // 256)
+    out = torch.empty(tuple(shape_local), dtype=torch.float32, device=device)
+    seed, off = gen.initial_seed(), gen.get_offset()
+    _lib.check(_lib.lib().wdno_randn_slice(_p(out), out.numel(), lo * per, numel_full, grid, seed, off, _st()), "randn_slice")
+    gen.set_offset(off + ((numel_full - 1) // (256 * grid * 4) + 1) * 4)
+    return out
+
+
+def _randn_rows_selfcheck(device):
+    """one-time check per device that the slice kernel reproduces this torch build's normal_ (values AND generator advance),
+    in both grid regimes (small tensor: grid = ceil(numel/256); large: grid = SMs * 8)"""
+    gen = torch.cuda.default_generators[device.index if device.index is not None else torch.cuda.current_device()]
+    state = gen.get_state()
+    ok = True
+    try:
+        for full, per, lo, hi in ((5, 1000, 1, 4), (7, 300001, 2, 5)):
+            gen.manual_seed(1234567)
+            torch.randn(3, device=device)   # non-zero starting offset
+            st0 = gen.get_state()
+            want = torch.randn((full, per), device=device)
+            off_want = gen.get_offset()
+            tail_want = torch.randn(8, device=device)
+            gen.set_state(st0)
+            got = _randn_rows_kernel((hi - lo, per), full, lo, device)
+            off_got = gen.get_offset()
+            tail_got = torch.randn(8, device=device)
+            ok = ok and bool(torch.equal(got, want[lo:hi])) and off_got == off_want and bool(torch.equal(tail_got, tail_want))
+    finally:
+        gen.set_state(state)
+    return ok
+
+
+def randn_rows(shape_local, full_batch, lo, device):
+    """== torch.randn((full_batch,) + shape_local[1:], device=device)[lo:lo + shape_local[0]] including the generator
+    advance, drawing only the requested rows (csrc/rng.cu).  Falls back to draw-and-slice if the mapping self-check fails."""
+    device = torch.device(device)
+    if device.type == "cuda":
+        key = device.index if device.index is not None else torch.cuda.current_device()
+        if key not in _RANDN_ROWS_OK:
+            try:
+                _RANDN_ROWS_OK[key] = _randn_rows_selfcheck(device)
+            except Exception:  # noqa: BLE001 - a torch build without Generator.get_offset etc.
+                _RANDN_ROWS_OK[key] = False
+        if _RANDN_ROWS_OK[key]:
+            return _randn_rows_kernel(tuple(shape_local), full_batch, lo, device)
+    return torch.randn((full_batch,) + tuple(shape_local[1:]), device=device)[lo:lo + shape_local[0]]

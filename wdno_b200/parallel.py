@@ -36,6 +36,11 @@ def all_gather_fields(local, batch, group=None):
     world = dist.get_world_size(group)
     sizes = [shard_bounds(batch, world, r) for r in range(world)]
     mx = max(hi - lo for lo, hi in sizes)
+    if all(hi - lo == mx for lo, hi in sizes):
+        # equal shards: one collective straight into the [batch, ...] result, no staging copies
+        out = local.new_empty((batch,) + tuple(local.shape[1:]))
+        dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+        return out
     pad = local
     if local.shape[0] < mx:
         pad = torch.cat((local, local.new_zeros((mx - local.shape[0],) + tuple(local.shape[1:]))), 0)
@@ -44,15 +49,46 @@ def all_gather_fields(local, batch, group=None):
     return torch.cat([o[: hi - lo] for o, (lo, hi) in zip(out, sizes)], 0)
 
 
-def sample_sharded(diffusion, batch_size, post=None, group=None, **conds):
-    """Run diffusion.sample() on this rank's slice of every batched condition, apply `post` (e.g. the inverse DWT)
-    locally, all-gather the result.  conds: init / control / low / init_u tensors with a leading batch dim."""
+class _FullBatchNoise:
+    """`_noise_source` of a sharded run: every draw is the rank's ROWS of the full-batch tensor its default generator
+    would produce (all ranks seeded alike hold the same Philox state) -- the values, and the generator state afterwards,
+    are exactly those of the single-process run (SURVEY.md section 7 'RNG parity', section 8e).  On CUDA only the rows
+    are evaluated (counter-based Philox: `ops.randn_rows`, csrc/rng.cu); elsewhere the full batch is drawn and sliced."""
+
+    def __init__(self, batch, lo, hi):
+        self.batch, self.lo, self.hi = batch, lo, hi
+
+    def __call__(self, shape, device):
+        assert shape[0] == self.hi - self.lo, (shape, self.lo, self.hi)
+        from . import ops
+        return ops.randn_rows(tuple(shape), self.batch, self.lo, device)
+
+
+def sample_sharded(diffusion, batch_size, post=None, group=None, rng_parity=True, gather=True, **conds):
+    """Run diffusion.sample() on this rank's contiguous slice of every batched condition, apply `post` (the inverse
+    transform to fields) locally, then ONE all-gather of the result (the only collective of the path).
+
+    conds: the keyword arguments of `sample()`; tensors whose leading dim is the batch are sliced.
+    rng_parity=True: noise is drawn at the full-batch shape on every rank and sliced, so that with the same
+    `torch.manual_seed` on every rank the sharded run reproduces the single-GPU trajectory sample by sample (on CUDA
+    only the rank's rows of that draw are evaluated: no extra traffic).  False: each rank draws only its own shape from its own generator state.
+    gather=False returns the local shard (for callers that reduce on their own)."""
     world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
     rank = dist.get_rank(group) if world > 1 else 0
     lo, hi = shard_bounds(batch_size, world, rank)
     local = {k: (shard(v, world, rank) if torch.is_tensor(v) and v.dim() > 0 and v.shape[0] == batch_size else v)
              for k, v in conds.items()}
-    x = diffusion.sample(batch_size=hi - lo, **local)
+    prev = getattr(diffusion, "_noise_source", None)
+    swap = rng_parity and world > 1 and prev is None and hasattr(diffusion, "_noise_source")
+    if swap:
+        diffusion._noise_source = _FullBatchNoise(batch_size, lo, hi)
+    try:
+        x = diffusion.sample(batch_size=hi - lo, **local)
+    finally:
+        if swap:
+            diffusion._noise_source = prev
     if post is not None:
         x = post(x)
+    if not gather:
+        return x
     return all_gather_fields(x, batch_size, group)

@@ -40,6 +40,18 @@ def _smoke_out_from_state(last_channel, n_coef, half, pad_mode, wave_type):
     return DWT1DInverse(mode=pad_mode, wave=wave_type)((lo, [hi]))[:, 0]
 
 
+def state_to_fields(wave_output, RESCALER, shape, ori_shape, wave_type, pad_mode, upsample_type=None):
+    """rescaled coefficient state [B,F,C,H,W] (what `sample()` returns) -> physical output [B,T,6,H,W]: 5 fields through
+    the inverse 3-D transform + the smoke-out series through the inverse 1-D transform, broadcast over the plane
+    (inference_2d.py:136-152).  This is the `post` of `wdno_b200.parallel.sample_sharded`: the fields are what is gathered."""
+    scaled40 = wave_output[:, :, :40] * RESCALER[:, :, :40]
+    fields = _fields_from_state(scaled40, shape, ori_shape, wave_type, upsample_type).permute(0, 2, 1, 3, 4)
+    last = wave_output[:, :, -1] * RESCALER[:, :, -1]
+    so = _smoke_out_from_state(last, shape[0], int(last.shape[-2] / 2), pad_mode, wave_type)
+    so = so.reshape(so.shape[0], so.shape[1], 1, 1, 1).expand(-1, -1, -1, ori_shape[1], ori_shape[2])
+    return torch.cat((fields, so), dim=2)
+
+
 def guidance_fn(x, args, shape, ori_shape, RESCALER, w_energy=0, w_init=0, low=None, init=None, init_u=None):
     """gradient of the design objective J; `low`, `init` are rescaled, `init_u` is not (reference docstring).
     The reference rebinds `x = x * RESCALER` before differentiating (inference_2d.py:35,65), so what it returns is
@@ -178,12 +190,7 @@ class InferencePipeline(object):
 
     def _to_fields(self, wave_output, shape, ori_shape, gd, upsample_type=None):
         """rescaled state [B,F,C,H,W] -> physical output [B,T,6,H,W] (5 fields + smoke-out broadcast over the plane)"""
-        scaled40 = wave_output[:, :, :40] * self.RESCALER[:, :, :40]
-        fields = _fields_from_state(scaled40, shape, ori_shape, gd.wave_type, upsample_type).permute(0, 2, 1, 3, 4)
-        last = wave_output[:, :, -1] * self.RESCALER[:, :, -1]
-        so = _smoke_out_from_state(last, shape[0], int(last.shape[-2] / 2), gd.pad_mode, gd.wave_type)
-        so = so.reshape(so.shape[0], so.shape[1], 1, 1, 1).expand(-1, -1, -1, ori_shape[1], ori_shape[2])
-        return torch.cat((fields, so), dim=2)
+        return state_to_fields(wave_output, self.RESCALER, shape, ori_shape, gd.wave_type, gd.pad_mode, upsample_type)
 
     # ------------------------------------------------------------ samplers
     def _sample(self, gd, state, wave_init, wave_control, **kw):

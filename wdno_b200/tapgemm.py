@@ -16,7 +16,7 @@ import os
 
 import torch
 
-from . import _lib
+from . import _lib, _timing
 from ._lib import KSet, NChunk, Tap, TapGemmParams
 
 _SMEM_LIMIT = 227 * 1024
@@ -533,17 +533,21 @@ class TapGemm:
             p.stats = stats.data_ptr()
             p.G, p.cpg = groups, self.cout // groups
         tm = TapGemm.timing
-        if tm is not None:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-        _lib.check(L.wdno_tapgemm(C.byref(p), _lib.current_stream_ptr()), "tapgemm")
-        if tm is not None:
-            e1.record()
+        flops = 0.0
+        if tm is not None or _timing.sink is not None:
             # algorithmic FLOPs of the reference layer (identity K-sets that carry a fused residual are not counted)
             flops = 2.0 * B * D * H * W * self.cout * getattr(self, "algo_cin", self.cin) * self.w.shape[2] * self.w.shape[3] * self.w.shape[4]
             if self.kind == "unshuffle":
                 flops *= 4
-            tm.append((e0, e1, flops, (self.kind, self.cin, self.cout, self.KD, self.KH, self.KW, B, D, H, W)))
+        meta = (self.kind, self.cin, self.cout, self.KD, self.KH, self.KW, B, D, H, W)
+        if tm is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        with _timing.span("tapgemm", flops=flops, meta=meta):
+            _lib.check(L.wdno_tapgemm(C.byref(p), _lib.current_stream_ptr()), "tapgemm")
+        if tm is not None:
+            e1.record()
+            tm.append((e0, e1, flops, meta))
         return out
 
     def _call_1x1(self, L, src0, src1, out, resid, out_fp32_bfchw):
@@ -570,15 +574,21 @@ class TapGemm:
         if tm is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        _lib.check(L.wdno_conv1x1(src0.data_ptr(), C0, src1.data_ptr() if src1 is not None else None,
-                                  src1.shape[4] if src1 is not None else 0, c1["w"].data_ptr(), c1["npad"],
-                                  c1["bias"].data_ptr() if c1["bias"] is not None else None,
-                                  resid.data_ptr() if resid is not None else None, out.data_ptr(), B * D * H * W, self.cout,
-                                  2 if out_fp32_bfchw else 0, H * W, _lib.current_stream_ptr()), "conv1x1")
+        npos = B * D * H * W
+        flops = 2.0 * npos * self.cout * getattr(self, "algo_cin", self.cin)
+        # algorithmic bytes: fp16 sources in, output (fp16, or fp32 eps) out, fp16 residual in
+        nbytes = npos * (2.0 * sum(self.src_channels) + (4.0 if out_fp32_bfchw else 2.0) * self.cout
+                         + (2.0 * self.cout if resid is not None else 0.0))
+        meta = ("conv1x1", self.cin, self.cout, 1, 1, 1, B, D, H, W)
+        with _timing.span("conv1x1", flops=flops, bytes=nbytes, meta=meta):
+            _lib.check(L.wdno_conv1x1(src0.data_ptr(), C0, src1.data_ptr() if src1 is not None else None,
+                                      src1.shape[4] if src1 is not None else 0, c1["w"].data_ptr(), c1["npad"],
+                                      c1["bias"].data_ptr() if c1["bias"] is not None else None,
+                                      resid.data_ptr() if resid is not None else None, out.data_ptr(), npos, self.cout,
+                                      2 if out_fp32_bfchw else 0, H * W, _lib.current_stream_ptr()), "conv1x1")
         if tm is not None:
             e1.record()
-            flops = 2.0 * B * D * H * W * self.cout * getattr(self, "algo_cin", self.cin)
-            tm.append((e0, e1, flops, ("conv1x1", self.cin, self.cout, 1, 1, 1, B, D, H, W)))
+            tm.append((e0, e1, flops, meta))
         return out
 
     # bench.py sets this to a list to collect (start event, end event, algorithmic FLOPs, shape) per launch
