@@ -56,7 +56,7 @@ def peaks():
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md)."""
 
-    def __init__(self, index, period=0.05):
+    def __init__(self, index, period=0.02):
         self.rows, self.stop = [], threading.Event()
         self.index, self.period = index, period
         self.th = threading.Thread(target=self._run, daemon=True)
@@ -291,10 +291,10 @@ def main():
 
     with torch.no_grad():
         # ---------------- value: W warm-up steps, clock settle, then EXACTLY K timed steps; conditions resident in HBM
-        run_chain(Wm, conds_d)              # captures the CUDA graphs, builds plans
+        run_chain(Wm, conds_d)              # W warm-up steps: captures the CUDA graphs, builds plans
         t0 = time.time()
-        while time.time() - t0 < 1.0:       # let the SM clock settle under load
-            run_chain(Wm, conds_d)
+        while time.time() - t0 < 1.0:       # let the SM clock settle under load (same chain length as the timed call)
+            run_chain(K, conds_d)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with ClockSampler(local_rank) as clk:

@@ -197,8 +197,10 @@ def test_c3_full_ddim250_trajectory_engine_vs_fp32_oracle():
     rep["final_coef"] = rel_l2(got, want)
     _record("c3_ddim250_b2", rep)
     assert torch.isfinite(got).all()
-    # stated trajectory tolerance: measured values are in gpurun_out/parity_trajectories.json
-    assert rep[1]["coef"] < 2e-2 and rep[250]["coef"] < 1.5e-1 and rep[250]["fields"] < 1.5e-1, rep
+    # stated trajectory tolerance (measured on a B200: 6.0e-4 / 2.1e-4 / 1.4e-4 / 5.7e-4 for the
+    # coefficients at steps 1 / 10 / 50 / 250, 4.1e-4 for the final fields): 5e-3 along the whole chain
+    for k in marks:
+        assert rep[k]["coef"] < 5e-3 and rep[k]["fields"] < 5e-3, rep
 
 
 def test_c2_full_ddpm1000_trajectory_engine_vs_fp32_oracle():
@@ -239,21 +241,23 @@ def test_c2_full_ddpm1000_trajectory_engine_vs_fp32_oracle():
     rep[1000] = dict(coef=rel_l2(got, want), fields=rel_l2(fields(got), fields(want)))
     _record("c2_ddpm1000_b2", rep)
     assert torch.isfinite(got).all()
-    assert rep[1]["coef"] < 2e-2 and rep[1000]["coef"] < 1.5e-1 and rep[1000]["fields"] < 1.5e-1, rep
+    # measured on a B200: 2.5e-5 / 1.5e-5 / 2.8e-5 / 2.8e-4 (coefficients at steps 1 / 10 / 100 / 1000); stated bound 3e-3
+    for k in marks:
+        assert rep[k]["coef"] < 3e-3 and rep[k]["fields"] < 3e-3, rep
 
 
 # ------------------------------------------------------------------------------------------ fp16 range
 def test_fp16_range_guard_saturates_instead_of_inf():
     """Scale the stem until its fp32 activation passes 65504 (the largest finite fp16): the engine's stored activations
     saturate at +-65504 (cvt.rn.satfinite, csrc/cvt_sat.cuh) and everything downstream stays finite.  With a moderate scale
-    (activations ~1e3, well inside the range) parity with the fp32 oracle holds at the usual bound."""
+    (activations of a few hundred, well inside the range) parity with the fp32 oracle holds at the usual bound."""
     m = _unet3d(42)
     g = torch.Generator().manual_seed(6)
     x = torch.randn(1, 24, 42, 40, 40, generator=g).cuda()
     t = torch.tensor([500]).cuda()
     with torch.no_grad():
-        m.init_conv.weight.mul_(30.0)
-        m.init_conv.bias.mul_(30.0)
+        m.init_conv.weight.mul_(100.0)
+        m.init_conv.bias.mul_(100.0)
         taps = {}
         y = m.engine().forward(x, t, taps=taps)
         yo = _oracle3d(m)(x, t)

@@ -60,9 +60,31 @@ def register_schedule(module, betas):
     return alphas, ac
 
 
+_TABLE_CACHE = {}
+
+
 def ddim_tables(mod, eta, gscale_fn=None):
     """per-step scalars of ddim_sample (diffusion_2d.py:862-911), computed with the same fp32 torch scalar ops.
-    -> (times list, coef table [S, 8] fp32 cpu)"""
+    -> (times list, coef table [S, 8] fp32 cpu).  Cached per (schedule buffers, S, eta): ~10 scalar torch ops per step on
+    the host would otherwise sit at the head of every sample() call."""
+    T, S = mod.num_timesteps, mod.sampling_timesteps
+    key = ("ddim", mod.alphas_cumprod.data_ptr(), mod.alphas_cumprod._version, T, S, float(eta))
+    if key in _TABLE_CACHE:
+        times, tab = _TABLE_CACHE[key]
+        tab = tab.clone()
+        if gscale_fn is not None:
+            for i, t in enumerate(times):
+                tab[i, 6] = gscale_fn(t)
+        return list(times), tab
+    times, tab = _ddim_tables(mod, eta, None)
+    _TABLE_CACHE[key] = (list(times), tab.clone())
+    if gscale_fn is not None:
+        for i, t in enumerate(times):
+            tab[i, 6] = gscale_fn(t)
+    return times, tab
+
+
+def _ddim_tables(mod, eta, gscale_fn=None):
     T, S = mod.num_timesteps, mod.sampling_timesteps
     times = torch.linspace(-1, T - 1, steps=S + 1)
     times = list(reversed(times.int().tolist()))
