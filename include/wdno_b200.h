@@ -218,6 +218,73 @@ int wdno_mse_weighted(const float* pred, const float* target, const float* w, in
 int wdno_step_begin(int* step_dev, const float* time_table, const float* coef_table, float* time_out, float* coef_out,
                     int B, int n_steps, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Training step (reference: Trainer.train, smoke/ddpm/diffusion_2d.py:1257-1307 and
+ * burgers/ddpm_burgers/train_diffusion.py:187-237 -- there the backward is torch autograd over cuDNN/cuBLAS).
+ * Gradients of activations are fp16 channels-last tensors in a SCALED domain (the host multiplies the loss gradient by a
+ * power of two so that fp16 neither underflows nor saturates); every parameter-gradient kernel takes `scale` = 1 / that
+ * factor and accumulates (+=) into fp32 buffers.
+ * dgrad of a convolution is the forward tap-GEMM with transposed / flipped weight tiles (wdno_tapgemm). */
+#define WDNO_WGRAD_MAX_GROUP_TAPS 3
+typedef struct {
+  int32_t dz;          /* source plane = z + dz */
+  int32_t dy;          /* row shift of every tap of the group (in the X view's grid) */
+  int32_t dx_min;      /* smallest column shift of the group */
+  int32_t span;        /* largest - smallest column shift (<= 8) */
+  int32_t n;           /* taps in the group (<= WDNO_WGRAD_MAX_GROUP_TAPS) */
+  int32_t dxo[WDNO_WGRAD_MAX_GROUP_TAPS];  /* column shift of tap i minus dx_min */
+  int64_t out[WDNO_WGRAD_MAX_GROUP_TAPS];  /* tap index of tap i inside dW's innermost axis */
+} wdno_wgrad_group;
+
+typedef struct {
+  const void* x;       /* fp16 channels-last [B][D][Hs][Ws][Cx]: the layer input (or, for the transposed conv, dY) */
+  const void* dy;      /* fp16 channels-last [B][D][H][W][Cy]: gradient of the layer output (transposed conv: the input) */
+  float* dw;           /* fp32, += : dw[(m * n_total + n_off + n) * t_total + tap]  (m: dy channel, n: x channel) */
+  float* dbias;        /* fp32 [Cy], += column sums of dy; NULL = none */
+  int32_t B, D, H, W;  /* grid of dy (the tap grid) */
+  int32_t Hs, Ws, Cx;  /* grid and channels of x */
+  int32_t sy, sx, ph_y, ph_x; /* X view: Xv[y][x] = x[sy*y + ph_y][sx*x + ph_x] (stride-2 layers: one launch per phase) */
+  int32_t Cy;          /* channels of dy (multiple of 8) */
+  int32_t m_valid;     /* rows of dW (dy channels beyond it are zero padding and are not written) */
+  int32_t cx_off, cx_n;/* channel window of x this launch covers (concatenated sources: one launch per source) */
+  int32_t n_total, n_off, t_total; /* dW geometry: total input channels, offset of this window, taps per (m, n) pair */
+  int32_t padw;        /* zero columns appended to a row when positions are linearised: max |column shift| */
+  int32_t n_groups;
+  const wdno_wgrad_group* groups; /* device array */
+  int32_t split;       /* CTAs sharing the position axis (split-K; partial sums meet in fp32 atomics) */
+  float scale;
+} wdno_wgrad_params;
+int wdno_wgrad(const wdno_wgrad_params* p, void* stream);
+
+/* GroupNorm + (scale+1, shift) + SiLU backward (conv3d.py:189-205; unet.py:129-147), z = a[b,c]*y + c[b,c], h = silu(z):
+ *   reduce : sums[b][c] = (sum dz, sum dz*y) over the voxels, dz = dh * silu'(z)                 (double, +=)
+ *   apply  : dy = a[b,c]*dz + k1[b,g]*y + k0[b,g]  -- k1, k0 from wdno_gn_bwd_finalize; fp16 out
+ * finalize (one block per sample): from sums and the forward statistics (stats[b][g] = (sum y, sum y^2), count voxels*cpg):
+ *   d_gamma[c] += A*(1+s), d_beta[c] += Bc*(1+s), d_scale[b,c] = A*gamma + Bc*beta, d_shift[b,c] = Bc   (times `scale`),
+ *   with A = rstd*(Sy - mean*S1), Bc = S1; k1 = -rstd^2 * M2, k0 = -rstd*M1 + rstd^2*M2*mean, M1/M2 group means of
+ *   gamma'(dz) and gamma'(dz*yhat).  ss = (scale|shift) row of the block's time-MLP output or NULL; d_ss likewise. */
+int wdno_gn_bwd_reduce(const void* dh, const void* y, const float* a, const float* c, double* sums, int B, int C, int64_t vox,
+                       void* stream);
+int wdno_gn_bwd_finalize(const double* sums, const double* stats, const float* gamma, const float* beta, const float* ss,
+                         int ss_stride, float* d_gamma, float* d_beta, float* d_ss, int dss_stride, float* k1, float* k0,
+                         int B, int C, int G, double count, float eps, float scale, void* stream);
+int wdno_gn_bwd_apply(const void* dh, const void* y, const float* a, const float* c, const float* k1, const float* k0,
+                      const void* add, void* dy, int B, int C, int G, int64_t vox, void* stream);
+/* d_eps (fp32 [B,F,C,H,W]) * mul -> fp16 channels-last [B,F,H,W,cp] (cp >= C, zero padded): head of the backward pass */
+int wdno_pack_grad_f16(const float* g, void* out, int B, int F, int C, int H, int W, int cp, float mul, void* stream);
+/* out[i] = a[i] + b[i] (fp16, saturating): gradient accumulation at skip connections */
+int wdno_add_f16(const void* a, const void* b, void* out, int64_t n, void* stream);
+/* channel LayerNorm backward (conv3d.py:165-174; unet.py:55-65): y = (x - mean) * rstd * gamma over C per voxel.
+ * dx = rstd*(g*dy - mean_c(g*dy) - xhat*mean_c(g*dy*xhat)) (+ add), d_gamma[c] += scale * sum dy*xhat */
+int wdno_chan_layernorm_bwd(const void* x, const void* dy, const float* gamma, const void* add, void* dx, float* d_gamma,
+                            int64_t n_vox, int C, float eps, float scale, void* stream);
+/* fused gradient clipping + Adam + EMA over flat fp32 buffers (diffusion_2d.py:1286-1297: clip_grad_norm_(1.0), Adam,
+ * ema.update()).  sumsq: device double (squared gradient norm, from wdno_sumsq); the clip factor is computed on the device. */
+int wdno_sumsq(const float* g, int64_t n, double* out, void* stream);
+int wdno_adam_clip_ema(float* p, const float* g, float* m, float* v, float* ema, int64_t n, const double* sumsq,
+                       float max_norm, float lr, float beta1, float beta2, float eps, float bc1, float bc2,
+                       float ema_decay, int ema_mode, void* stream);
+
 /* Rows [elem_offset, elem_offset + n_local) of the tensor torch.randn(numel_full, device='cuda') would produce from
  * Philox state (seed, philox_offset), bit for bit, without drawing the rest: the noise rule of a batch-sharded run
  * (reference draws: diffusion_2d.py:866,907; diffusion_1d.py:389,431).  grid_full = the grid ATen launches for numel_full

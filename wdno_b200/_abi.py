@@ -36,6 +36,14 @@ SIGNATURES = {
     "wdno_q_sample": [P, P, P, P, P, P, I, L64, P],
     "wdno_mse_weighted": [P, P, P, I, I, I, I, I, I, P, P],
     "wdno_step_begin": [P, P, P, P, P, I, I, P],
+    "wdno_gn_bwd_reduce": [P, P, P, P, P, I, I, L64, P],
+    "wdno_gn_bwd_finalize": [P, P, P, P, P, I, P, P, P, I, P, P, I, I, I, D, F, F, P],
+    "wdno_gn_bwd_apply": [P, P, P, P, P, P, P, P, I, I, I, L64, P],
+    "wdno_pack_grad_f16": [P, P, I, I, I, I, I, I, F, P],
+    "wdno_add_f16": [P, P, P, L64, P],
+    "wdno_chan_layernorm_bwd": [P, P, P, P, P, P, L64, I, F, F, P],
+    "wdno_sumsq": [P, L64, P, P],
+    "wdno_adam_clip_ema": [P, P, P, P, P, L64, P, F, F, F, F, F, F, F, F, I, P],
     "wdno_randn_slice": [P, L64, L64, L64, I, C.c_uint64, C.c_uint64, P],
     "wdno_dwt_analysis_axis": [P, P, P, L64, I, L64, I, L64, L64, L64, P, P, I, I, I, P],
     "wdno_dwt_synthesis_axis": [P, P, P, L64, I, L64, I, L64, L64, L64, P, P, I, I, I, P],

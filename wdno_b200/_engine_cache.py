@@ -36,6 +36,11 @@ class EngineOwner:
 
     def engine(self):
         fp = self._fingerprint()
+        if self._engine is not None and self._engine_fp != fp and self._engine_fp[1] == fp[1] and hasattr(self._engine, "refresh"):
+            # same storage, new values (optimiser step, EMA copy_, nested load_state_dict): re-pack the tiles in place --
+            # plans and captured graphs stay valid
+            self._engine.refresh()
+            self._engine_fp = fp
         if self._engine is None or self._engine_fp != fp:
             self._engine = self._make_engine()
             self._engine_fp = fp

@@ -39,19 +39,29 @@ class LinAttnBlock:
     def __init__(self, gamma, w_qkv, w_out, b_out, heads=4, dim_head=32, device="cuda"):
         assert heads == 4 and dim_head == 32
         dev = torch.device(device)
-        wq = w_qkv.detach().float().cpu().reshape(w_qkv.shape[0], -1)    # [384, C]
-        self.C = wq.shape[1]
-        assert wq.shape[0] == 384 and self.C in (64, 128, 256)
-        self.gamma = gamma.detach().float().reshape(-1).contiguous().to(dev)
-        self.wq = pack_b_frags(wq[:128]).to(dev)
-        # k / v: per (section, head) a [32, C] A operand
-        kv = wq[128:].reshape(2, 4, 32, self.C)
-        self.wkv = torch.stack([torch.stack([pack_a_frags(kv[s, h]) for h in range(4)]) for s in range(2)]).contiguous().to(dev)
-        self.wout = w_out.detach().float().cpu().reshape(w_out.shape[0], -1).contiguous().to(dev)   # [C, 128]
+        self._src = (gamma, w_qkv, w_out, b_out)
+        self.C = w_qkv.shape[1]
+        assert w_qkv.shape[0] == 384 and self.C in (64, 128, 256)
+        self.gamma, self.wq, self.wkv, self.wout, self.bias = (t if t is None else t.to(dev) for t in self._packed())
         assert self.wout.shape == (self.C, 128)
-        self.bias = None if b_out is None else b_out.detach().float().contiguous().to(dev)
         self.scale = dim_head ** -0.5
         self._work = {}
+
+    def _packed(self):
+        gamma, w_qkv, w_out, b_out = self._src
+        wq = w_qkv.detach().float().reshape(w_qkv.shape[0], -1)    # [384, C]
+        # k / v: per (section, head) a [32, C] A operand
+        kv = wq[128:].reshape(2, 4, 32, self.C)
+        wkv = torch.stack([torch.stack([pack_a_frags(kv[s, h]) for h in range(4)]) for s in range(2)]).contiguous()
+        return (gamma.detach().float().reshape(-1).contiguous(), pack_b_frags(wq[:128]), wkv,
+                w_out.detach().float().reshape(w_out.shape[0], -1).contiguous(),   # [C, 128]
+                None if b_out is None else b_out.detach().float().contiguous())
+
+    def refresh(self):
+        """re-pack from the live parameters into the existing device buffers (addresses stay valid for captured graphs)"""
+        for dst, src in zip((self.gamma, self.wq, self.wkv, self.wout, self.bias), self._packed()):
+            if dst is not None and dst.data_ptr() != src.data_ptr():
+                dst.copy_(src)
 
     def __call__(self, x, eps=1e-5):
         assert x.dtype == torch.float16 and x.is_contiguous() and x.dim() == 5 and x.shape[-1] == self.C
@@ -85,16 +95,23 @@ class TemporalBlock:
     def __init__(self, gamma, w_qkv, w_out, heads=4, dim_head=32, device="cuda"):
         assert heads == 4 and dim_head == 32
         dev = torch.device(device)
-        wq = w_qkv.detach().float().cpu().reshape(w_qkv.shape[0], -1)    # [384, C]
-        self.C = wq.shape[1]
-        assert wq.shape[0] == 384 and self.C in (64, 128, 256)
-        self.gamma = gamma.detach().float().reshape(-1).contiguous().to(dev)
-        self.wqk = pack_b_frags(wq[:256]).to(dev)                                             # q | k as B operands
-        self.wv = torch.stack([pack_a_frags(wq[256 + 32 * h: 288 + 32 * h]) for h in range(4)]).contiguous().to(dev)
-        wo = w_out.detach().float().cpu().reshape(w_out.shape[0], -1)    # [C, 128]
-        assert wo.shape == (self.C, 128)
-        self.wo = pack_b_frags(wo).to(dev)
+        self._src = (gamma, w_qkv, w_out)
+        self.C = w_qkv.shape[1]
+        assert w_qkv.shape[0] == 384 and self.C in (64, 128, 256) and tuple(w_out.shape[:2]) == (self.C, 128)
+        self.gamma, self.wqk, self.wv, self.wo = (t.to(dev) for t in self._packed())
         self.scale = dim_head ** -0.5
+
+    def _packed(self):
+        gamma, w_qkv, w_out = self._src
+        wq = w_qkv.detach().float().reshape(w_qkv.shape[0], -1)    # [384, C]
+        wo = w_out.detach().float().reshape(w_out.shape[0], -1)    # [C, 128]
+        return (gamma.detach().float().reshape(-1).contiguous(), pack_b_frags(wq[:256]),          # q | k as B operands
+                torch.stack([pack_a_frags(wq[256 + 32 * h: 288 + 32 * h]) for h in range(4)]).contiguous(), pack_b_frags(wo))
+
+    def refresh(self):
+        for dst, src in zip((self.gamma, self.wqk, self.wv, self.wo), self._packed()):
+            if dst.data_ptr() != src.data_ptr():
+                dst.copy_(src)
 
     def __call__(self, x, bias=None, rot=None, eps=1e-5):
         """bias fp32 [4, D, D] or None; rot = (cos, sin) fp32 [D, 16] or None."""

@@ -495,8 +495,8 @@ class GaussianDiffusion(nn.Module):
                             self.sqrt_one_minus_alphas_cumprod, t.contiguous())
 
     def p_losses(self, state_start, t, noise=None):
-        """Loss VALUE of diffusion_2d.py:988-1050 through the engine (no autograd graph: the backward kernels are the
-        'next' row f-3 of SURVEY.md section 8)."""
+        """diffusion_2d.py:988-1050.  With autograd enabled and trainable parameters the returned loss carries a grad_fn whose
+        backward runs on the engine (train3d.py); under torch.no_grad() it is the forward value only."""
         b, f, c, h, w = state_start.shape
         if self.is_super_model:
             if self.is_condition_control:
@@ -539,6 +539,19 @@ class GaussianDiffusion(nn.Module):
         # CondProgram.copy offsets the source by the box origin; for "same tensor" copies shift the pointer back
         ops.apply_conditions(state, _same_tensor_program(ps_, state_start, f, c, h, w))
         ops.apply_conditions(noise_state, pn_.build(f, c, h, w))
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.model.parameters()):
+            # training: differentiable forward, backward in libwdno_b200.so (wdno_b200/train3d.py); `loss.backward()` fills
+            # p.grad exactly like the reference's autograd step (diffusion_2d.py:1277-1284)
+            if self.loss_type != "l2":
+                raise NotImplementedError("l1 loss is never used by WDNO")
+            from .train3d import unet3d_apply
+            model_out = unet3d_apply(self.model, state, t)
+            loss = F.mse_loss(model_out, noise_state, reduction="mean")
+            lw = self.loss_layer_weight
+            if torch.is_tensor(lw):
+                lw = lw.to(loss.device)
+            loss = loss * lw
+            return loss.mean() if torch.is_tensor(loss) else loss
         with torch.no_grad():
             model_out = self.model(state, t)
         if self.loss_type == "l2":

@@ -37,7 +37,9 @@ class TapGemm:
     def __init__(self, weight, bias=None, *, kind="conv", src_channels=None, up2=False,
                  n_tile=None, device=None, kc=None):
         """weight: fp32 tensor in the reference layout of the layer kind (see module docstring)."""
-        w = weight.detach().to(torch.float32).cpu()
+        # packing runs on the device the weight lives on (training refreshes the tiles from live CUDA parameters every step;
+        # a CPU weight is packed on the host and uploaded)
+        w = weight.detach().to(torch.float32)
         self.kind = kind
         self.up2 = bool(up2)
         self.device = torch.device(device if device is not None else "cuda")
@@ -76,9 +78,9 @@ class TapGemm:
         self.cout_pad = _round_up(self.cout, self.N)
         self.kc_override = kc
         if bias is not None:
-            b = torch.zeros(self.cout_pad if kind != "up144" else self.cout_pad, dtype=torch.float32)
-            b[: self.cout] = bias.detach().float().cpu()
-            self.bias = b.to(self.device)
+            b = torch.zeros(self.cout_pad, dtype=torch.float32, device=self.device)
+            b[: self.cout] = bias.detach().float().to(self.device)
+            self.bias = b
         self._packed = {}   # KC -> dict(wpacked, chunks, sets, taps, n_chunks, tables kept alive)
         self._launch = {}   # geometry key -> (params, keepalive)
         # plain 1x1 layers (no fused GroupNorm prologue / statistics) run on the HBM-bound mma.sync kernel csrc/conv1x1.cu
@@ -86,16 +88,37 @@ class TapGemm:
         if (kind == "conv" and (self.KD, self.KH, self.KW) == (1, 1, 1) and len(self.src_channels) <= 2
                 and all(c % 32 == 0 for c in self.src_channels) and os.environ.get("WDNO_CONV1X1", "1") != "0"
                 and self.device.type == "cuda"):
-            ctot = sum(self.src_channels)
             npad = _round_up(self.cout, 64)
-            w1 = torch.zeros(npad, ctot, dtype=torch.float32)
-            w1[: self.cout, : self.cin] = w[:, :, 0, 0, 0]
             b1 = None
             if bias is not None:
-                b1 = torch.zeros(npad, dtype=torch.float32)
-                b1[: self.cout] = bias.detach().float().cpu()
-                b1 = b1.to(self.device)
-            self._c1 = dict(w=w1.to(torch.float16).to(self.device), bias=b1, npad=npad)
+                b1 = torch.zeros(npad, dtype=torch.float32, device=self.device)
+                b1[: self.cout] = bias.detach().float().to(self.device)
+            self._c1 = dict(w=self._c1_weight(npad), bias=b1, npad=npad)
+
+    def _c1_weight(self, npad):
+        w1 = torch.zeros(npad, sum(self.src_channels), dtype=torch.float32, device=self.w.device)
+        w1[: self.cout, : self.cin] = self.w[:, :, 0, 0, 0]
+        return w1.to(torch.float16).to(self.device)
+
+    def refresh(self, weight, bias=None):
+        """Re-pack the tiles of every plan built so far from a new weight tensor of the same shape, IN PLACE (device
+        addresses baked into captured graphs and launch structs stay valid).  Used by the training step after each
+        optimiser update and by engines whose parameters changed in place."""
+        w = weight.detach().to(torch.float32)
+        if w.dim() == 2:
+            w = w[:, :, None, None, None]
+        elif w.dim() == 4:
+            w = w[:, :, None]
+        assert w.shape == self.w.shape
+        self.w = w
+        for (KC, zstack), pk in self._packed.items():
+            pk["wpacked"].copy_(self._pack_weights(KC, zstack)[0].to(torch.float16))
+        if self.bias is not None and bias is not None:
+            self.bias[: self.cout].copy_(bias.detach().float())
+        if self._c1 is not None:
+            self._c1["w"].copy_(self._c1_weight(self._c1["npad"]))
+            if self._c1["bias"] is not None and bias is not None:
+                self._c1["bias"][: self.cout].copy_(bias.detach().float())
 
     # ------------------------------------------------------------------ packing
     def _virtual_cin(self):
@@ -105,6 +128,23 @@ class TapGemm:
     def _pack(self, KC, zstack=False):
         if (KC, zstack) in self._packed:
             return self._packed[(KC, zstack)]
+        wpacked, taps, sets, chunks = self._pack_weights(KC, zstack)
+        sets_c = (KSet * len(sets))(*[KSet(s["src"], s["ch_off"], s["ph_y"], s["ph_x"], s["tap_begin"], s["tap_count"])
+                                       for s in sets])
+        chunks_c = (NChunk * len(chunks))(*[NChunk(c["out_ch_off"], c["n_valid"], c["ph_y"], c["ph_x"], c["set_begin"],
+                                                   c["set_count"], c["n_tiles"], 0, c["w_tile_off"]) for c in chunks])
+        pk = dict(
+            wpacked=wpacked.to(torch.float16).to(self.device),
+            sets=_device_bytes(sets_c, self.device),
+            chunks=_device_bytes(chunks_c, self.device),
+            taps_kyx=taps, n_chunks=len(chunks), n_sets=len(sets),
+            taps_dev={},  # Wp -> device tap table
+        )
+        self._packed[(KC, zstack)] = pk
+        return pk
+
+    def _pack_weights(self, KC, zstack=False):
+        """-> (fp32 weight tiles in kernel order, tap list, K-set list, N-chunk list): a pure function of self.w"""
         N, kind = self.N, self.kind
         w = self.w
         ctot = self._virtual_cin()
@@ -130,7 +170,7 @@ class TapGemm:
 
         def padded_w(wfull):
             """[cout, cin, ...] -> zero-padded to [cout_pad, ctot, ...]"""
-            out = torch.zeros((self.cout_pad, ctot) + tuple(wfull.shape[2:]), dtype=torch.float32)
+            out = torch.zeros((self.cout_pad, ctot) + tuple(wfull.shape[2:]), dtype=torch.float32, device=wfull.device)
             out[: wfull.shape[0], : wfull.shape[1]] = wfull
             return out
 
@@ -198,7 +238,7 @@ class TapGemm:
             wpacked = torch.stack(tile_list).reshape(-1)
         elif kind == "up144":
             # w: [cin, cout, 1, 4, 4]; out phase A: taps (tky -> ky): A=0: {1:1, 0:3} ; A=1: {2:0, 1:2}
-            wt = torch.zeros((self.cout_pad, ctot, 4, 4), dtype=torch.float32)
+            wt = torch.zeros((self.cout_pad, ctot, 4, 4), dtype=torch.float32, device=w.device)
             wt[: self.cout, : self.cin] = w[:, :, 0].permute(1, 0, 2, 3)
             ph = {0: [(0, 3), (1, 1)], 1: [(1, 2), (2, 0)]}
             tile_list = []
@@ -223,7 +263,7 @@ class TapGemm:
         elif kind == "unshuffle":
             # w: [cout, 4*cin, 1,1,1] with input channel index c*4 + p1*2 + p2
             w4 = w[:, :, 0, 0, 0].reshape(self.cout, self.cin, 2, 2)
-            wp = torch.zeros((self.cout_pad, ctot, 2, 2), dtype=torch.float32)
+            wp = torch.zeros((self.cout_pad, ctot, 2, 2), dtype=torch.float32, device=w.device)
             wp[: self.cout, : self.cin] = w4
             taps.append((0, 0, 0))
             tile_list = []
@@ -243,19 +283,7 @@ class TapGemm:
         else:
             raise ValueError(kind)
 
-        sets_c = (KSet * len(sets))(*[KSet(s["src"], s["ch_off"], s["ph_y"], s["ph_x"], s["tap_begin"], s["tap_count"])
-                                       for s in sets])
-        chunks_c = (NChunk * len(chunks))(*[NChunk(c["out_ch_off"], c["n_valid"], c["ph_y"], c["ph_x"], c["set_begin"],
-                                                   c["set_count"], c["n_tiles"], 0, c["w_tile_off"]) for c in chunks])
-        pk = dict(
-            wpacked=wpacked.to(torch.float16).to(self.device),
-            sets=_device_bytes(sets_c, self.device),
-            chunks=_device_bytes(chunks_c, self.device),
-            taps_kyx=taps, n_chunks=len(chunks), n_sets=len(sets),
-            taps_dev={},  # Wp -> device tap table
-        )
-        self._packed[(KC, zstack)] = pk
-        return pk
+        return wpacked, taps, sets, chunks
 
     # ------------------------------------------------------------------ geometry / smem plan
     def _plan(self, B, D, H, W):

@@ -1,0 +1,258 @@
+"""Training step on the engine: a differentiable `model(x, t)` whose backward runs in
+libwdno_b200.so.  Reference: `Trainer.train` -> `loss = self.model(state)`; `accelerator.backward(loss)`; clip 1.0; Adam; EMA
+(smoke/ddpm/diffusion_2d.py:1257-1307, burgers/ddpm_burgers/train_diffusion.py:187-237), where every gradient comes from
+torch autograd over cuDNN / cuBLAS.
+
+What runs where (this file is host logic only):
+  * forward: the inference kernels (tap-GEMM with GroupNorm statistics in the epilogue and GroupNorm-apply + SiLU fused into
+    the next operand load, fused attention blocks), keeping the pre-norm convolution outputs y, the per-(sample, channel)
+    affine (a, c) and the block inputs;
+  * backward, convolutions (>= 93 % of the FLOPs): dgrad = the SAME tap-GEMM kernel on transposed / flipped weight tiles
+    (stride-2 conv <-> transposed conv swap kinds), wgrad = `wdno_wgrad` (csrc/wgrad.cu), GroupNorm + (scale, shift) + SiLU
+    backward = `wdno_gn_bwd_reduce / _finalize / _apply` (csrc/train.cu);
+  * backward, attention blocks and the time-embedding MLP (6 % / < 0.01 % of the FLOPs): recomputed in fp32 torch ops under
+    autograd, block by block (interim: their CUDA backward kernels are the next step; stated in DESIGN.md);
+  * activation gradients are fp16 channels-last in a scaled domain (loss gradient x 2^k, undone in the fp32 parameter-gradient
+    epilogues), parameter gradients accumulate in fp32 into ONE flat buffer (p.grad are views), so clipping, Adam, EMA and the
+    data-parallel all-reduce are single launches / collectives over flat memory.
+"""
+import ctypes as C
+import math
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import _lib, ops
+from .tapgemm import TapGemm
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class WgradGroup(C.Structure):
+    _fields_ = [("dz", C.c_int32), ("dy", C.c_int32), ("dx_min", C.c_int32), ("span", C.c_int32), ("n", C.c_int32),
+                ("dxo", C.c_int32 * 3), ("out", C.c_int64 * 3)]
+
+
+class WgradParams(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("dy", C.c_void_p), ("dw", C.c_void_p), ("dbias", C.c_void_p),
+                ("B", C.c_int32), ("D", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+                ("Hs", C.c_int32), ("Ws", C.c_int32), ("Cx", C.c_int32),
+                ("sy", C.c_int32), ("sx", C.c_int32), ("ph_y", C.c_int32), ("ph_x", C.c_int32),
+                ("Cy", C.c_int32), ("m_valid", C.c_int32), ("cx_off", C.c_int32), ("cx_n", C.c_int32),
+                ("n_total", C.c_int32), ("n_off", C.c_int32), ("t_total", C.c_int32), ("padw", C.c_int32),
+                ("n_groups", C.c_int32), ("groups", C.c_void_p), ("split", C.c_int32), ("scale", C.c_float)]
+
+
+_bound = False
+
+
+def _bind():
+    global _bound
+    if not _bound:
+        L = _lib.lib()
+        L.wdno_wgrad.restype = C.c_int
+        L.wdno_wgrad.argtypes = [C.POINTER(WgradParams), C.c_void_p]
+        _bound = True
+    return _lib.lib()
+
+
+def _groups_dev(groups, device):
+    arr = (WgradGroup * len(groups))()
+    for i, g in enumerate(groups):
+        a = arr[i]
+        a.dz, a.dy, a.dx_min, a.span, a.n = g["dz"], g["dy"], g["dx_min"], g["span"], len(g["dxo"])
+        for j, (d, o) in enumerate(zip(g["dxo"], g["out"])):
+            a.dxo[j], a.out[j] = d, o
+    return torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).clone().to(device), len(groups)
+
+
+def _chunk3(items):
+    return [items[i:i + 3] for i in range(0, len(items), 3)]
+
+
+def wgrad_groups_conv(KD, KH, KW):
+    """tap groups of a 'same' convolution: taps sharing (kz, ky), kx in runs of <= 3"""
+    gs = []
+    for kz in range(KD):
+        for ky in range(KH):
+            for run in _chunk3(list(range(KW))):
+                gs.append(dict(dz=kz - KD // 2, dy=ky - KH // 2, dx_min=run[0] - KW // 2, span=run[-1] - run[0],
+                               dxo=[k - run[0] for k in run], out=[(kz * KH + ky) * KW + k for k in run]))
+    return gs
+
+
+# (1,4,4) stride (1,2,2) pad (0,1,1): source pixel 2o + k - 1.  Phase a = its parity: a = 0 -> k in {1, 3} at view rows o + {0, 1};
+# a = 1 -> k in {0, 2} at view rows o + {-1, 0}
+_PH144 = {0: [(1, 0), (3, 1)], 1: [(0, -1), (2, 0)]}
+
+
+def wgrad_groups_144(a, b):
+    gs = []
+    for ky, dyv in _PH144[a]:
+        ent = _PH144[b]
+        dxs = [d for _, d in ent]
+        gs.append(dict(dz=0, dy=dyv, dx_min=min(dxs), span=max(dxs) - min(dxs), dxo=[d - min(dxs) for d in dxs],
+                       out=[ky * 4 + kx for kx, _ in ent]))
+    return gs
+
+
+class Wgrad:
+    """dW (+ db) of one layer.  kind: 'conv' (same padding, incl. 1x1 / Linear), 'down144', 'up144'."""
+
+    def __init__(self, kind, wshape, device):
+        self.kind, self.device = kind, torch.device(device)
+        if kind == "conv":
+            ws = tuple(wshape) + (1,) * (5 - len(wshape)) if len(wshape) == 2 else tuple(wshape)
+            if len(ws) == 4:
+                ws = ws[:2] + (1,) + ws[2:]
+            self.cout, self.cin, self.KD, self.KH, self.KW = ws
+            self.t_total = self.KD * self.KH * self.KW
+            self.tables = [(1, 1, 0, 0, self.KW // 2) + _groups_dev(wgrad_groups_conv(self.KD, self.KH, self.KW), self.device)]
+        elif kind in ("down144", "up144"):
+            # down: weight [cout, cin, 1, 4, 4], dY low-res, X high-res.  up (ConvTranspose): weight [cin, cout, 1, 4, 4]; the
+            # low-res INPUT plays dY's role and the high-res output gradient plays X's: dW[ci][co][k] = sum x[ci](i) dOut[co](2i+k-1)
+            self.cout, self.cin = wshape[0], wshape[1]
+            self.t_total = 16
+            self.tables = [(2, 2, a, b, 1) + _groups_dev(wgrad_groups_144(a, b), self.device) for a in (0, 1) for b in (0, 1)]
+        else:
+            raise ValueError(kind)
+
+    def __call__(self, x, dy, dw, dbias, scale, cx_off=0, cx_n=None, n_off=0, n_total=None, m_valid=None):
+        """x: fp16 [B,D,Hs,Ws,Cx] (X role), dy: fp16 [B,D,H,W,Cy] (dY role); dw fp32 [Cy, n_total, taps...] += ; dbias fp32 [Cy] +="""
+        L = _bind()
+        assert x.dtype == torch.float16 and dy.dtype == torch.float16 and x.is_contiguous() and dy.is_contiguous()
+        assert dw.dtype == torch.float32 and dw.is_contiguous()
+        B, D, H, W, Cy = dy.shape
+        _, _, Hs, Ws, Cx = x.shape
+        cx_n = Cx - cx_off if cx_n is None else cx_n
+        n_total = cx_n if n_total is None else n_total
+        m_valid = Cy if m_valid is None else m_valid
+        assert dw.numel() == m_valid * n_total * self.t_total, (tuple(dw.shape), m_valid, n_total, self.t_total)
+        sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+        for (sy, sx, ph_y, ph_x, padw, gdev, ng) in self.tables:
+            p = WgradParams()
+            p.x, p.dy, p.dw = x.data_ptr(), dy.data_ptr(), dw.data_ptr()
+            p.dbias = dbias.data_ptr() if (dbias is not None and ph_y == 0 and ph_x == 0) else None
+            p.B, p.D, p.H, p.W, p.Hs, p.Ws, p.Cx = B, D, H, W, Hs, Ws, Cx
+            p.sy, p.sx, p.ph_y, p.ph_x = sy, sx, ph_y, ph_x
+            p.Cy, p.m_valid, p.cx_off, p.cx_n = Cy, m_valid, cx_off, cx_n
+            p.n_total, p.n_off, p.t_total, p.padw = n_total, n_off, self.t_total, padw
+            p.n_groups, p.groups = ng, gdev.data_ptr()
+            tiles = ((Cy + 63) // 64) * ((cx_n + 63) // 64)
+            chunks = B * D * ((H * (W + padw) + 63) // 64)
+            p.split = max(1, min(chunks, (6 * sms + ng * tiles - 1) // (ng * tiles)))
+            p.scale = scale
+            _lib.check(L.wdno_wgrad(C.byref(p), _lib.current_stream_ptr()), "wgrad")
+
+
+# ---------------------------------------------------------------------------------------------- small wrappers
+def gn_bwd(dh, y, a, c, stats, gamma, beta, dgamma, dbeta, groups, count, scale, ss=None, ss_stride=0, d_ss=None,
+           dss_stride=0, add=None, eps=1e-5):
+    """-> dy (fp16) of z = a*y + c, h = silu(z) with GroupNorm statistics `stats` [B,G,2]; accumulates d_gamma / d_beta and
+    writes the (scale | shift) gradient rows"""
+    L = _lib.lib()
+    B, Cc = y.shape[0], y.shape[-1]
+    vox = y.numel() // (B * Cc)
+    sums = torch.zeros((B, Cc, 2), dtype=torch.float64, device=y.device)
+    _lib.check(L.wdno_gn_bwd_reduce(_p(dh), _p(y), _p(a), _p(c), _p(sums), B, Cc, vox, _lib.current_stream_ptr()), "gn_bwd_reduce")
+    k1 = torch.empty((B, groups), dtype=torch.float32, device=y.device)
+    k0 = torch.empty_like(k1)
+    _lib.check(L.wdno_gn_bwd_finalize(_p(sums), _p(stats), _p(gamma), _p(beta), _p(ss), ss_stride, _p(dgamma), _p(dbeta),
+                                      _p(d_ss), dss_stride, _p(k1), _p(k0), B, Cc, groups, float(count), float(eps),
+                                      float(scale), _lib.current_stream_ptr()), "gn_bwd_finalize")
+    dy = torch.empty_like(y)
+    _lib.check(L.wdno_gn_bwd_apply(_p(dh), _p(y), _p(a), _p(c), _p(k1), _p(k0), _p(add), _p(dy), B, Cc, groups, vox,
+                                   _lib.current_stream_ptr()), "gn_bwd_apply")
+    return dy
+
+
+def add_f16(a, b):
+    out = torch.empty_like(a)
+    _lib.check(_lib.lib().wdno_add_f16(_p(a), _p(b), _p(out), a.numel(), _lib.current_stream_ptr()), "add_f16")
+    return out
+
+
+def pack_grad_f16(g, cp, mul):
+    B, Fr, Cc, H, W = g.shape
+    out = torch.empty((B, Fr, H, W, cp), dtype=torch.float16, device=g.device)
+    _lib.check(_lib.lib().wdno_pack_grad_f16(_p(g), _p(out), B, Fr, Cc, H, W, cp, float(mul), _lib.current_stream_ptr()),
+               "pack_grad_f16")
+    return out
+
+
+def chan_layernorm_bwd(x, dy, gamma, dgamma, scale, add=None, eps=1e-5):
+    Cc = x.shape[-1]
+    dx = torch.empty_like(x)
+    _lib.check(_lib.lib().wdno_chan_layernorm_bwd(_p(x), _p(dy), _p(gamma), _p(add), _p(dx), _p(dgamma), x.numel() // Cc, Cc,
+                                                  float(eps), float(scale), _lib.current_stream_ptr()), "chan_layernorm_bwd")
+    return dx
+
+
+# ---------------------------------------------------------------------------------------------- conv layer with gradients
+class ConvLayer:
+    """forward plan (shared with the inference engine) + dgrad plans (one per concatenated source) + wgrad of one
+    Conv3d / Conv2d / ConvTranspose3d / Linear parameter pair."""
+
+    def __init__(self, fwd, weight, bias, kind, src_channels, need_dgrad=True):
+        self.fwd, self.weight, self.bias, self.kind = fwd, weight, bias, kind
+        self.src_channels = tuple(src_channels)
+        dev = fwd.device
+        self.wgrad = Wgrad(kind, tuple(weight.shape), dev)
+        self.dgrad = []
+        if need_dgrad:
+            for w in self._dgrad_weights():
+                if kind == "conv":
+                    self.dgrad.append(TapGemm(w, None, src_channels=(self._dy_channels(),), device=dev))
+                else:
+                    self.dgrad.append(TapGemm(w, None, kind="up144" if kind == "down144" else "down144", device=dev))
+
+    def _dy_channels(self):
+        return (self.weight.shape[0] + 7) // 8 * 8
+
+    def _dgrad_weights(self):
+        w = self.weight.detach()
+        if self.kind != "conv":
+            return [w]   # the (1,4,4) pair: strided conv <-> transposed conv with the SAME weight tensor
+        if w.dim() == 2:
+            w = w[:, :, None, None, None]
+        elif w.dim() == 4:
+            w = w[:, :, None]
+        out, off = [], 0
+        for cs in self.src_channels:
+            real = min(cs, w.shape[1] - off)
+            wt = w[:, off:off + real].transpose(0, 1).flip(2, 3, 4)     # [cin_s, cout, taps] : conv of dY with flipped taps
+            if real < cs:   # padded source channels (the stem's 42 -> 48): their gradient is never used
+                wt = torch.cat((wt, wt.new_zeros((cs - real,) + tuple(wt.shape[1:]))), 0)
+            out.append(wt.contiguous())
+            off += cs
+        return out
+
+    def refresh(self):
+        self.fwd.refresh(self.weight, self.bias)
+        for plan, w in zip(self.dgrad, self._dgrad_weights()):
+            plan.refresh(w)
+
+    def backward_input(self, dy, s, resid=None):
+        """gradient w.r.t. source `s` (fp16 channels-last), optionally + resid (fused into the epilogue)"""
+        return self.dgrad[s](dy, resid=resid)
+
+    def backward_weight(self, srcs, dy, scale):
+        """srcs: the forward sources (for 'up144': dy is the INPUT and srcs[0] the output gradient -- see Wgrad)"""
+        gw = self.weight.grad
+        gb = None if self.bias is None else self.bias.grad
+        if self.kind == "up144":
+            # weight [cin, cout, 1, 4, 4]: M = cin (the layer input), N = cout (the output gradient); bias grad = column sums of dOut
+            self.wgrad(srcs[0], dy, gw, None, scale)
+            if gb is not None:
+                gb.add_(srcs[0].float().sum(dim=(0, 1, 2, 3)) * scale)
+            return
+        off = 0
+        n_total = self.weight.shape[1]
+        for i, (src, cs) in enumerate(zip(srcs, self.src_channels)):
+            real = min(cs, n_total - off)
+            self.wgrad(src, dy, gw, gb if i == 0 else None, scale, cx_off=0, cx_n=real, n_off=off, n_total=n_total,
+                       m_valid=self.weight.shape[0])
+            off += cs

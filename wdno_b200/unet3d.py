@@ -193,7 +193,8 @@ class Unet3DEngine:
         f32 = lambda t: t.detach().to(dev, torch.float32).contiguous()
         self.cin = m.channels
         self.cin_pad = (m.channels + 15) // 16 * 16
-        self.init_conv = TapGemm(m.init_conv.weight, m.init_conv.bias, src_channels=(self.cin_pad,), device=dev)
+        self._refreshers, self._mlp_w_src, self._mlp_b_src = [], [], []
+        self.init_conv = self._conv(m.init_conv.weight, m.init_conv.bias, src_channels=(self.cin_pad,))
         self.tw1, self.tb1 = f32(m.time_mlp[1].weight), f32(m.time_mlp[1].bias)
         self.tw2, self.tb2 = f32(m.time_mlp[3].weight), f32(m.time_mlp[3].bias)
         self.dim = m.dim
@@ -207,7 +208,7 @@ class Unet3DEngine:
             self.downs.append(dict(
                 b1=self._resnet_plan(b1, None), b2=self._resnet_plan(b2, None),
                 sattn=self._lin_attn_plan(sattn), tattn=self._attn_plan(tattn, temporal=True),
-                down=None if isinstance(down, nn.Identity) else TapGemm(down.weight, down.bias, kind="down144", device=dev)))
+                down=None if isinstance(down, nn.Identity) else self._conv(down.weight, down.bias, kind="down144")))
         self.mid1 = self._resnet_plan(m.mid_block1, None)
         self.mid_sattn = self._attn_plan(m.mid_spatial_attn, temporal=False)
         self.mid_tattn = self._attn_plan(m.mid_temporal_attn, temporal=True)
@@ -218,11 +219,11 @@ class Unet3DEngine:
             self.ups.append(dict(
                 b1=self._resnet_plan(b1, (cin // 2, cin // 2)), b2=self._resnet_plan(b2, None),
                 sattn=self._lin_attn_plan(sattn), tattn=self._attn_plan(tattn, temporal=True),
-                up=None if isinstance(up, nn.Identity) else TapGemm(up.weight, up.bias, kind="up144", device=dev)))
+                up=None if isinstance(up, nn.Identity) else self._conv(up.weight, up.bias, kind="up144")))
         fc = m.final_conv[0]
         cin = fc.block1.proj.weight.shape[1]
         self.final_block = self._resnet_plan(fc, (cin // 2, cin // 2))
-        self.final_conv = TapGemm(m.final_conv[1].weight, m.final_conv[1].bias, device=dev)
+        self.final_conv = self._conv(m.final_conv[1].weight, m.final_conv[1].bias)
         self.mlp_w = torch.cat(self._mlp_w, 0).contiguous() if self._mlp_w else None
         self.mlp_b = torch.cat(self._mlp_b, 0).contiguous() if self._mlp_b else None
         self.freqs = m.init_temporal_attn.fn.fn.fn.rotary_emb.freqs.detach().float().cpu()
@@ -239,49 +240,88 @@ class Unet3DEngine:
         p = _ResnetPlan()
         w1 = blk.block1.proj.weight
         p.cout = w1.shape[0]
-        p.conv1 = TapGemm(w1, blk.block1.proj.bias, src_channels=src_channels, device=self.dev)
-        p.conv2 = TapGemm(blk.block2.proj.weight, blk.block2.proj.bias, device=self.dev)
+        p.conv1 = self._conv(w1, blk.block1.proj.bias, src_channels=src_channels)
+        p.conv2 = self._conv(blk.block2.proj.weight, blk.block2.proj.bias)
+        p.mod = blk
         p.g1, p.b1 = self._f32(blk.block1.norm.weight), self._f32(blk.block1.norm.bias)
         p.g2, p.b2 = self._f32(blk.block2.norm.weight), self._f32(blk.block2.norm.bias)
         p.res = None
         if not isinstance(blk.res_conv, nn.Identity):
-            p.res = TapGemm(blk.res_conv.weight, blk.res_conv.bias, src_channels=src_channels, device=self.dev)
+            p.res = self._conv(blk.res_conv.weight, blk.res_conv.bias, src_channels=src_channels)
         p.ss_off = None
         if blk.mlp is not None:
             p.ss_off = self._mlp_off
             self._mlp_w.append(self._f32(blk.mlp[1].weight))
             self._mlp_b.append(self._f32(blk.mlp[1].bias))
+            self._mlp_w_src.append(blk.mlp[1].weight)
+            self._mlp_b_src.append(blk.mlp[1].bias)
             self._mlp_off += 2 * p.cout
         p.stat1, p.stat2 = self.stats_slots, self.stats_slots + 1
         self.stats_slots += 2
         return p
 
+    @staticmethod
+    def _w_plus_identity(weight):
+        w = weight.detach().float().reshape(weight.shape[0], -1)
+        return torch.cat((w, torch.eye(w.shape[0], device=w.device)), dim=1)
+
     def _out_plus_residual(self, weight, bias):
         """to_out(o) + x as ONE GEMM: the residual stream x is appended as an extra K-set with identity weights
         ([W | I] over the concatenated sources (o, x)); x*1.0 accumulates exactly in fp32, and the residual is read by
         the deep asynchronous operand pipeline instead of the epilogue."""
-        w = weight.detach().float().cpu().reshape(weight.shape[0], -1)
-        c = w.shape[0]
-        plan = TapGemm(torch.cat((w, torch.eye(c)), dim=1), bias, src_channels=(w.shape[1], c), device=self.dev)
-        plan.algo_cin = w.shape[1]
+        c, k = weight.shape[0], weight.reshape(weight.shape[0], -1).shape[1]
+        plan = TapGemm(self._w_plus_identity(weight), bias, src_channels=(k, c), device=self.dev)
+        plan.algo_cin = k
+        self._refreshers.append(lambda: plan.refresh(self._w_plus_identity(weight), bias))
         return plan
+
+    def _conv(self, mod_or_weight, bias=None, **kw):
+        """TapGemm of a parameter pair, registered for in-place refresh"""
+        weight = mod_or_weight
+        plan = TapGemm(weight, bias, device=self.dev, **kw)
+        self._refreshers.append(lambda: plan.refresh(weight, bias))
+        return plan
+
+    def refresh(self):
+        """Re-pack every weight-derived buffer from the live parameters IN PLACE (an optimiser step, an EMA update or a
+        checkpoint load changed values, not shapes): plans, launch structs and captured CUDA graphs stay valid."""
+        for fn in self._refreshers:
+            fn()
+        if self._mlp_w:
+            self.mlp_w.copy_(torch.cat([w.detach().float() for w in self._mlp_w_src], 0))
+            self.mlp_b.copy_(torch.cat([b.detach().float() for b in self._mlp_b_src], 0))
+        self.rel_emb = self.m.time_rel_pos_bias.relative_attention_bias.weight.detach().float().cpu()
+        for n, (bias, rot) in list(self._tables.items()):
+            bias.copy_(self._rel_bias(n))
 
     def _attn_plan(self, res, temporal):
         attn = res.fn.fn.fn
         if temporal:
-            return TemporalBlock(res.fn.norm.gamma, attn.to_qkv.weight, attn.to_out.weight, device=self.dev)
-        return dict(gamma=self._f32(res.fn.norm.gamma.reshape(-1)),
-                    qkv=TapGemm(attn.to_qkv.weight, None, device=self.dev),
-                    out=self._out_plus_residual(attn.to_out.weight, None), temporal=temporal)
+            blk = TemporalBlock(res.fn.norm.gamma, attn.to_qkv.weight, attn.to_out.weight, device=self.dev)
+            blk.mod = res
+            self._refreshers.append(blk.refresh)
+            return blk
+        return dict(gamma=self._f32(res.fn.norm.gamma.reshape(-1)), qkv=self._conv(attn.to_qkv.weight, None),
+                    out=self._out_plus_residual(attn.to_out.weight, None), temporal=temporal, mod=res)
 
     def _lin_attn_plan(self, res):
         attn = res.fn.fn
-        return LinAttnBlock(res.fn.norm.gamma, attn.to_qkv.weight, attn.to_out.weight, attn.to_out.bias, device=self.dev)
+        blk = LinAttnBlock(res.fn.norm.gamma, attn.to_qkv.weight, attn.to_out.weight, attn.to_out.bias, device=self.dev)
+        blk.mod = res
+        self._refreshers.append(blk.refresh)
+        return blk
 
     def _rel_tables(self, n):
         """T5 relative-position bias [heads][n][n] (conv3d.py:74-112) and rotary cos/sin [n][16]."""
         if n in self._tables:
             return self._tables[n]
+        bias = self._rel_bias(n)
+        ang = torch.arange(n, dtype=torch.float32)[:, None] * self.freqs[None, :]
+        tabs = (bias, (ang.cos().contiguous().to(self.dev), ang.sin().contiguous().to(self.dev)))
+        self._tables[n] = tabs
+        return tabs
+
+    def _rel_bias(self, n):
         pos = torch.arange(n)
         rel = pos[None, :] - pos[:, None]
         nb = self.rel_emb.shape[0]
@@ -295,11 +335,7 @@ class Unet3DEngine:
                              * (half - max_exact)).long()
         large = torch.min(large, torch.full_like(large, half - 1))
         bucket = ret + torch.where(small, k, large)
-        bias = self.rel_emb[bucket].permute(2, 0, 1).contiguous().to(self.dev)
-        ang = torch.arange(n, dtype=torch.float32)[:, None] * self.freqs[None, :]
-        tabs = (bias, (ang.cos().contiguous().to(self.dev), ang.sin().contiguous().to(self.dev)))
-        self._tables[n] = tabs
-        return tabs
+        return self.rel_emb[bucket].permute(2, 0, 1).contiguous().to(self.dev)
 
     # ------------------------------------------------------------ blocks
     def _resnet(self, p, src0, src1, ss, stats):
