@@ -28,5 +28,26 @@ def test_sample_sharded_nccl_world2_matches_single_gpu():
     for B, d in res.items():
         assert d["finite"] and d["same_everywhere"], (B, d)
         assert all(d["shard_equal"]), f"batch {B}: a shard differs from the single-process run of that shard: {d}"
-        # 3 DDIM steps from t = 999: identical noise, identical kernels; only the batch-dependent plan may regroup fp32 sums
-        assert d["rel_l2_vs_single_gpu"] < 1e-3, (B, d)
+        # vs the single-GPU run of the WHOLE batch: identical noise and kernels, but the planner picks K-set width / plane
+        # groups of the Cout >= 128 layers by batch size, which regroups fp32 sums; a few fp16 roundings flip (measured 9e-4 per
+        # forward, tools/diag_batch_invariance.py) and 3 steps from t = 999 amplify that: round-off only
+        assert d["rel_l2_vs_single_gpu"] < 3e-2, (B, d)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_ddp_gradients_world2_nccl_equal_the_mean_of_single_rank_gradients():
+    """data-parallel training step, bucketed all-reduce launched from inside the backward"""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port),
+                        os.path.join(HERE, "helpers", "ddp_probe.py")], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-5000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("DDP_JSON ")][-1]
+    d = json.loads(line[len("DDP_JSON "):])
+    assert d["finite"] and d["same_params"] and d["buckets"] >= 2, d
+    # the same kernels on the same per-rank inputs: sums of fp32 atomics differ in order only
+    assert d["rel_grad"] < 1e-4, d

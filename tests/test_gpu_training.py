@@ -155,10 +155,11 @@ def test_p_losses_backward_reproduces_reference_golden():
     out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
     os.makedirs(out, exist_ok=True)
     json.dump(report, open(os.path.join(out, "train_parity.json"), "w"), indent=1)
-    # stated bounds: total gradient norm 1 %, every per-parameter norm 3 %, strided gradient samples 5 % rel-L2
-    assert abs(total - gold["total_norm"]) < 1e-2 * gold["total_norm"], report
-    assert worst_norm[1] < 3e-2, report
-    assert worst_sub[1] < 5e-2, report
+    # stated bounds (measured on a B200: total norm 2.2e-4, worst per-parameter norm 4.9e-4, worst strided sample 3.0e-3):
+    # total gradient norm 0.2 %, every per-parameter norm 0.5 %, strided gradient samples 1.5 % rel-L2
+    assert abs(total - gold["total_norm"]) < 2e-3 * gold["total_norm"], report
+    assert worst_norm[1] < 5e-3, report
+    assert worst_sub[1] < 1.5e-2, report
 
 
 def test_two_optimizer_steps_track_the_fp32_oracle():
@@ -194,3 +195,42 @@ def test_two_optimizer_steps_track_the_fp32_oracle():
         num += float(((du - dw).double() ** 2).sum())
         den += float((dw.double() ** 2).sum())
     assert (num / den) ** 0.5 < 0.15, (num / den) ** 0.5   # Adam normalises by sqrt(v): sign-level agreement of fp16-noise gradients
+
+
+def test_fused_trainer_step_matches_torch_clip_adam_on_the_same_gradients():
+    """FusedTrainer (flat buffers, one clip + Adam + EMA launch) vs torch.nn.utils.clip_grad_norm_ + torch.optim.Adam driven by
+    the same engine gradients, two steps; EMA follows ema_pytorch's schedule (copy during warm-up)."""
+    from wdno_b200.trainer import FusedTrainer
+    g = torch.Generator().manual_seed(5)
+    x0 = torch.randn(1, 24, 42, 40, 40, generator=g).clamp(-1, 1).cuda()
+    ma, gda = _model_and_diffusion()
+    mb, gdb = _model_and_diffusion()
+    tr = FusedTrainer(gda, lr=1e-4, betas=(0.9, 0.99), max_norm=1.0, ema_update_every=2, ema_update_after_step=100)
+    opt = torch.optim.Adam(mb.parameters(), lr=1e-4, betas=(0.9, 0.99))
+    for step in range(2):
+        torch.manual_seed(100 + step)      # same (t, noise) draw for both
+        la = tr.step(x0)
+        torch.manual_seed(100 + step)
+        lb = gdb(x0)
+        lb.backward()
+        total = torch.nn.utils.clip_grad_norm_(mb.parameters(), 1.0)
+        opt.step()
+        opt.zero_grad()
+        assert abs(float(la) - float(lb)) < 1e-5 * abs(float(lb)) + 1e-7, (step, float(la), float(lb))
+        assert abs(tr.grad_norm() - float(total)) < 1e-4 * float(total), (tr.grad_norm(), float(total))
+    pa, pb = dict(ma.named_parameters()), dict(mb.named_parameters())
+    for k in pa:
+        if pa[k].requires_grad:
+            assert torch.allclose(pa[k], pb[k], atol=3e-7, rtol=1e-5), (k, float((pa[k] - pb[k]).abs().max()))
+    ema = tr.ema_state_dict()
+    for k in pa:
+        if pa[k].requires_grad:
+            assert torch.equal(ema[k], pa[k].detach()), k     # call 2 of update_every=2 inside the warm-up: a copy
+    # the engine must see the updated weights: a fresh model loaded with the trained weights gives the same forward
+    from wdno_b200.unet3d import Unet3D_with_Conv3D
+    mc = Unet3D_with_Conv3D(dim=64, dim_mults=(1, 2, 4), channels=42).cuda().eval()
+    mc.load_state_dict(ma.state_dict())
+    t = torch.tensor([7]).cuda()
+    with torch.no_grad():
+        ya, yc = ma.eval()(x0, t), mc(x0, t)
+    assert torch.equal(ya, yc), rel_l2(ya, yc)

@@ -168,10 +168,39 @@ def c5(steps):
             "ms_per_step_unguided_graph": ms_graph, "guidance_overhead_ms_whole_step_graph": ms_gg - ms_graph, **extra_cf})
 
 
+def t3(steps):
+    """training step of the smoke base model at the reference's batch size (train_2d.py:37: batch 6): forward + backward on the
+    engine + fused clip/Adam/EMA.  FLOPs: 3 x the forward contractions (dgrad + wgrad), SURVEY.md section 8 row a8."""
+    from wdno_b200.diffusion_smoke import GaussianDiffusion
+    from wdno_b200.trainer import FusedTrainer
+    from wdno_b200.unet3d import Unet3D_with_Conv3D
+    torch.manual_seed(0)
+    B = 6
+    m = Unet3D_with_Conv3D(dim=64, dim_mults=(1, 2, 4), channels=42).cuda().train()
+    gd = GaussianDiffusion(m, torch.linspace(0.5, 3.0, 42).reshape(1, 1, 42, 1, 1), True, True, True, False, "bior1.3", "zero",
+                           [18, 34, 34], [32, 64, 64], image_size=40, frames=24, timesteps=1000, sampling_timesteps=250).cuda()
+    tr = FusedTrainer(gd, lr=1e-4)
+    x0 = torch.randn(B, 24, 42, 40, 40, device="cuda").clamp(-1, 1)
+    ms = timed(lambda: tr.step(x0), steps, warmup=3, settle=1.0)
+    # split: forward only (no grad), forward + backward, optimiser
+    with torch.no_grad():
+        t = torch.randint(0, 1000, (B,), device="cuda")
+        ms_fwd = timed(lambda: m(x0, t), steps, warmup=2, settle=0.3)
+
+    def fb():
+        tr.g.zero_()
+        tr.backward(gd(x0))
+    ms_fb = timed(fb, steps, warmup=2, settle=0.3)
+    ms_opt = timed(tr.optimizer_step, steps, warmup=2, settle=0.2)
+    report("T3", "smoke base training step (p_losses fwd + engine backward + fused clip/Adam/EMA), batch 6, 1 GPU", ms,
+           3 * 326.35e9 * B, {"samples_per_s": B * 1e3 / ms, "ms_forward_only": ms_fwd, "ms_forward_backward": ms_fb,
+                              "ms_optimizer": ms_opt, "mem_GB": torch.cuda.max_memory_allocated() / 2 ** 30})
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("configs", nargs="*", default=["C2", "C4", "C5"])
     ap.add_argument("--steps", type=int, default=20)
     a = ap.parse_args()
     for c in a.configs:
-        {"C2": c2, "C4": c4, "C5": c5}[c](a.steps)
+        {"C2": c2, "C4": c4, "C5": c5, "T3": t3}[c](a.steps)

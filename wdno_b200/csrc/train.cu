@@ -214,14 +214,23 @@ __global__ void __launch_bounds__(256) chan_ln_bwd_kernel(const __half* __restri
 #pragma unroll
     for (int k = 0; k < 8; ++k) dg[j][k] = 0.f;
   }
-  for (size_t v = static_cast<size_t>(blockIdx.x) * VPB + r; v < nvox; v += static_cast<size_t>(gridDim.x) * VPB) {
+  // the trip count is uniform over the block (warp shuffles below use the full mask): voxels past the end are computed on
+  // zeros and not stored
+  for (size_t v0 = static_cast<size_t>(blockIdx.x) * VPB; v0 < nvox; v0 += static_cast<size_t>(gridDim.x) * VPB) {
+    const size_t v = v0 + r;
+    const bool valid = v < nvox;
     float fx[CPL][8], fd[CPL][8];
     float sum = 0.f;
 #pragma unroll
     for (int j = 0; j < CPL; ++j) {
       const size_t i = v * (C / 8) + j * LPV + l;
-      unpack8(__ldg(reinterpret_cast<const uint4*>(x) + i), fx[j]);
-      unpack8(__ldg(reinterpret_cast<const uint4*>(dy) + i), fd[j]);
+      uint4 rx = make_uint4(0u, 0u, 0u, 0u), rd = make_uint4(0u, 0u, 0u, 0u);
+      if (valid) {
+        rx = __ldg(reinterpret_cast<const uint4*>(x) + i);
+        rd = __ldg(reinterpret_cast<const uint4*>(dy) + i);
+      }
+      unpack8(rx, fx[j]);
+      unpack8(rd, fd[j]);
 #pragma unroll
       for (int k = 0; k < 8; ++k) sum += fx[j][k];
     }
@@ -263,13 +272,15 @@ __global__ void __launch_bounds__(256) chan_ln_bwd_kernel(const __half* __restri
       float o[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) o[k] = rstd * (fd[j][k] - m1 - fx[j][k] * m2);
-      if (add != nullptr) {
-        float fa[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(add) + i), fa);
+      if (valid) {
+        if (add != nullptr) {
+          float fa[8];
+          unpack8(__ldg(reinterpret_cast<const uint4*>(add) + i), fa);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) o[k] += fa[k];
+          for (int k = 0; k < 8; ++k) o[k] += fa[k];
+        }
+        reinterpret_cast<uint4*>(dx)[i] = pack8(o);
       }
-      reinterpret_cast<uint4*>(dx)[i] = pack8(o);
     }
   }
   // d_gamma: reduce over the block's voxel rows, then one atomic per channel

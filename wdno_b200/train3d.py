@@ -343,8 +343,28 @@ class Unet3DTrainEngine:
                                              dy, inv))
             else:
                 raise AssertionError(kind)
+            if self.on_record_done is not None:
+                self.on_record_done(rec)
         self.tape = None
         return self.d_ss
+
+    on_record_done = None   # optional callable(record): the trainer launches bucket all-reduces from here
+
+    def record_params(self, rec):
+        """parameters whose gradient is FINAL once `rec` has been processed by backward() (the relative-position embedding
+        is shared by every temporal block and the time-embedding MLPs get their gradients from autograd afterwards: both late)"""
+        kind = rec[0]
+        if kind in ("final", "conv"):
+            layer = self.layers[id(rec[1])]
+            return [p for p in (layer.weight, layer.bias) if p is not None]
+        if kind == "resnet":
+            blk = rec[1].mod
+            mods = [blk.block1.proj, blk.block1.norm, blk.block2.proj, blk.block2.norm]
+            if not isinstance(blk.res_conv, nn.Identity):
+                mods.append(blk.res_conv)
+            return [p for m_ in mods for p in m_.parameters()]
+        mod = rec[1]["mod"] if kind == "mattn" else rec[1].mod
+        return [p for n, p in mod.named_parameters() if p.requires_grad]
 
     # slices of the (scale | shift) rows of one ResnetBlock inside ss / d_ss
     def _ss_slice(self, rp):
