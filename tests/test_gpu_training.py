@@ -198,30 +198,30 @@ def test_two_optimizer_steps_track_the_fp32_oracle():
 
 
 def test_fused_trainer_step_matches_torch_clip_adam_on_the_same_gradients():
-    """FusedTrainer (flat buffers, one clip + Adam + EMA launch) vs torch.nn.utils.clip_grad_norm_ + torch.optim.Adam driven by
-    the same engine gradients, two steps; EMA follows ema_pytorch's schedule (copy during warm-up)."""
+    """FusedTrainer (flat buffers, one clip + Adam + EMA launch) vs torch.nn.utils.clip_grad_norm_ + torch.optim.Adam fed with
+    the SAME gradient values, two steps (Adam normalises by sqrt(v), so independently recomputed gradients whose near-zero
+    entries differ in fp32-atomic order would not be a test of the optimiser); EMA follows ema_pytorch's schedule."""
     from wdno_b200.trainer import FusedTrainer
     g = torch.Generator().manual_seed(5)
     x0 = torch.randn(1, 24, 42, 40, 40, generator=g).clamp(-1, 1).cuda()
     ma, gda = _model_and_diffusion()
-    mb, gdb = _model_and_diffusion()
+    mb, _ = _model_and_diffusion()
     tr = FusedTrainer(gda, lr=1e-4, betas=(0.9, 0.99), max_norm=1.0, ema_update_every=2, ema_update_after_step=100)
     opt = torch.optim.Adam(mb.parameters(), lr=1e-4, betas=(0.9, 0.99))
-    for step in range(2):
-        torch.manual_seed(100 + step)      # same (t, noise) draw for both
-        la = tr.step(x0)
-        torch.manual_seed(100 + step)
-        lb = gdb(x0)
-        lb.backward()
-        total = torch.nn.utils.clip_grad_norm_(mb.parameters(), 1.0)
-        opt.step()
-        opt.zero_grad()
-        assert abs(float(la) - float(lb)) < 1e-5 * abs(float(lb)) + 1e-7, (step, float(la), float(lb))
-        assert abs(tr.grad_norm() - float(total)) < 1e-4 * float(total), (tr.grad_norm(), float(total))
     pa, pb = dict(ma.named_parameters()), dict(mb.named_parameters())
-    for k in pa:
-        if pa[k].requires_grad:
-            assert torch.allclose(pa[k], pb[k], atol=3e-7, rtol=1e-5), (k, float((pa[k] - pb[k]).abs().max()))
+    for step in range(2):
+        tr.g.zero_()
+        tr.backward(gda(x0))
+        for k in pa:
+            if pa[k].requires_grad:
+                pb[k].grad = pa[k].grad.detach().clone()
+        total = torch.nn.utils.clip_grad_norm_([p for p in mb.parameters() if p.grad is not None], 1.0)
+        opt.step()
+        tr.optimizer_step()
+        assert abs(tr.grad_norm() - float(total)) < 1e-5 * float(total), (tr.grad_norm(), float(total))
+        for k in pa:
+            if pa[k].requires_grad:
+                assert torch.allclose(pa[k], pb[k], atol=2e-7, rtol=1e-5), (step, k, float((pa[k] - pb[k]).abs().max()))
     ema = tr.ema_state_dict()
     for k in pa:
         if pa[k].requires_grad:

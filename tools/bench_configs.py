@@ -192,6 +192,20 @@ def t3(steps):
         tr.backward(gd(x0))
     ms_fb = timed(fb, steps, warmup=2, settle=0.3)
     ms_opt = timed(tr.optimizer_step, steps, warmup=2, settle=0.2)
+    # where the backward goes: CUDA events around every tape record of one step
+    te = m._train_engine
+    te.profile = []
+    fb()
+    torch.cuda.synchronize()
+    agg = {}
+    for kind, ch, grid, a, b in te.profile:
+        k = f"{kind}:{ch}:{'x'.join(map(str, grid))}"
+        agg[k] = agg.get(k, 0.0) + a.elapsed_time(b)
+    te.profile = None
+    by_kind = {}
+    for k, v in agg.items():
+        by_kind[k.split(":")[0]] = by_kind.get(k.split(":")[0], 0.0) + v
+    print(json.dumps({"T3_backward_ms_by_kind": by_kind, "T3_backward_ms_by_record": dict(sorted(agg.items(), key=lambda kv: -kv[1])[:12])}), flush=True)
     report("T3", "smoke base training step (p_losses fwd + engine backward + fused clip/Adam/EMA), batch 6, 1 GPU", ms,
            3 * 326.35e9 * B, {"samples_per_s": B * 1e3 / ms, "ms_forward_only": ms_fwd, "ms_forward_backward": ms_fb,
                               "ms_optimizer": ms_opt, "mem_GB": torch.cuda.max_memory_allocated() / 2 ** 30})

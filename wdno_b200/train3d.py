@@ -276,8 +276,12 @@ class Unet3DTrainEngine:
 
         rotary = self.m.init_temporal_attn.fn.fn.fn.rotary_emb.freqs
         rel_emb = self.m.time_rel_pos_bias.relative_attention_bias.weight
+        prof = self.profile
         for rec in reversed(tape):
             kind = rec[0]
+            if prof is not None:
+                ev0 = torch.cuda.Event(enable_timing=True)
+                ev0.record()
             if kind == "final":
                 _, plan, (h,), out = rec
                 layer = self.layers[id(plan)]
@@ -343,11 +347,17 @@ class Unet3DTrainEngine:
                                              dy, inv))
             else:
                 raise AssertionError(kind)
+            if prof is not None:
+                ev1 = torch.cuda.Event(enable_timing=True)
+                ev1.record()
+                ch = rec[2].shape[-1] if kind in ("tattn", "lattn", "mattn") else (rec[1].cout if kind == "resnet" else 0)
+                prof.append((kind, ch, tuple(rec[2].shape[1:4]) if kind != "conv" and kind != "final" else (), ev0, ev1))
             if self.on_record_done is not None:
                 self.on_record_done(rec)
         self.tape = None
         return self.d_ss
 
+    profile = None          # set to a list to collect (kind, channels, grid, start event, end event) per tape record
     on_record_done = None   # optional callable(record): the trainer launches bucket all-reduces from here
 
     def record_params(self, rec):
