@@ -278,6 +278,17 @@ int wdno_add_f16(const void* a, const void* b, void* out, int64_t n, void* strea
  * dx = rstd*(g*dy - mean_c(g*dy) - xhat*mean_c(g*dy*xhat)) (+ add), d_gamma[c] += scale * sum dy*xhat */
 int wdno_chan_layernorm_bwd(const void* x, const void* dy, const float* gamma, const void* add, void* dx, float* d_gamma,
                             int64_t n_vox, int C, float eps, float scale, void* stream);
+/* attention cores, backward (conv3d.py:241-257,294-353; unet.py:203-222,236-259).  qkv / dqkv: fp16 token rows [.., 384]
+ * (q | k | v, 4 heads x 32), d_out: fp16 [.., 128] = gradient of the core's output (before to_out); token addressing as in
+ * wdno_softmax_attn.  n_tok <= 32: rotary tables and the additive bias [4][n][n] are supported and dbias (fp32 [4][n][n]) += the
+ * bias gradient; 32 < n_tok <= 512: plain softmax attention only. */
+int wdno_softmax_attn_bwd(const void* qkv, const void* d_out, const float* bias, const float* rot_cos, const float* rot_sin,
+                          void* dqkv, float* dbias, int64_t n_seq, int n_tok, int64_t inner, int64_t outerT, int64_t innerT,
+                          int64_t tokT, float scale, void* stream);
+/* linear attention over n_img images of n_pos positions; work: wdno_linear_attn_bwd_work_bytes(n_img) bytes of scratch */
+int64_t wdno_linear_attn_bwd_work_bytes(int64_t n_img);
+int wdno_linear_attn_bwd(const void* qkv, const void* d_out, void* dqkv, void* work, int64_t n_img, int n_pos, float scale,
+                         void* stream);
 /* fused gradient clipping + Adam + EMA over flat fp32 buffers (diffusion_2d.py:1286-1297: clip_grad_norm_(1.0), Adam,
  * ema.update()).  sumsq: device double (squared gradient norm, from wdno_sumsq); the clip factor is computed on the device. */
 int wdno_sumsq(const float* g, int64_t n, double* out, void* stream);

@@ -234,3 +234,44 @@ def test_fused_trainer_step_matches_torch_clip_adam_on_the_same_gradients():
     with torch.no_grad():
         ya, yc = ma.eval()(x0, t), mc(x0, t)
     assert torch.equal(ya, yc), rel_l2(ya, yc)
+
+
+def test_attention_block_backward_kernels_vs_torch_autograd():
+    """Residual(PreNorm(attention)) backward through the kernels (LayerNorm / core / projection gradients) vs fp32 torch autograd
+    of the same block (wdno_b200/train3d.py keeps the torch form as the cross-check path)."""
+    from wdno_b200 import train3d as T3
+    from wdno_b200.training import AttnGrad
+    m, _ = _model_and_diffusion()
+    T3.flat_grads(m)
+    e = m.engine()
+    rel = m.time_rel_pos_bias.relative_attention_bias.weight
+    rotary = m.init_temporal_attn.fn.fn.fn.rotary_emb.freqs.detach()
+    g = torch.Generator().manual_seed(8)
+    cases = [("temporal", m.downs[0][3], (1, 24, 10, 12, 64)), ("temporal", m.mid_temporal_attn, (1, 24, 5, 6, 256)),
+             ("linear", m.downs[1][2], (1, 6, 20, 20, 128)), ("linear", m.ups[2][2], (2, 3, 40, 40, 64)),
+             ("spatial", m.mid_spatial_attn, (1, 5, 10, 10, 256))]
+    for kind, mod, shape in cases:
+        a = mod.fn.fn if kind == "linear" else mod.fn.fn.fn
+        x = torch.randn(*shape, generator=g).cuda().half()
+        dy = torch.randn(*shape, generator=g).cuda().half()
+        params = [mod.fn.norm.gamma, a.to_qkv.weight, a.to_out.weight]
+        if kind == "linear":
+            params.append(a.to_out.bias)
+            fn = T3.linattn_block_torch
+        elif kind == "temporal":
+            params.append(rel)
+            fn = lambda xx, gm, wq, wo, re: T3.temporal_block_torch(xx, gm, wq, wo, re, rotary)
+        else:
+            fn = T3.mid_spatial_block_torch
+        for p in params:
+            p.grad.zero_()
+        dx_ref = T3._torch_block_backward(fn, x, params, dy, 1.0)
+        ref = [p.grad.clone() for p in params]
+        for p in params:
+            p.grad.zero_()
+        ag = AttnGrad(kind, mod.fn.norm.gamma, a.to_qkv, a.to_out, "cuda", rel_emb=rel)
+        tables = e._rel_tables(shape[1]) if kind == "temporal" else None
+        dx = ag.backward(x, dy, 1.0, tables=tables)
+        assert rel_l2(dx.float(), dx_ref.float()) < 4e-3, (kind, shape, "dx", rel_l2(dx.float(), dx_ref.float()))
+        for p, r, name in zip(params, ref, ("gamma", "to_qkv", "to_out", "bias/rel_emb")):
+            assert rel_l2(p.grad, r) < 6e-3, (kind, shape, name, rel_l2(p.grad, r))

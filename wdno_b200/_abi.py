@@ -42,6 +42,8 @@ SIGNATURES = {
     "wdno_pack_grad_f16": [P, P, I, I, I, I, I, I, F, P],
     "wdno_add_f16": [P, P, P, L64, P],
     "wdno_chan_layernorm_bwd": [P, P, P, P, P, P, L64, I, F, F, P],
+    "wdno_softmax_attn_bwd": [P, P, P, P, P, P, P, L64, I, L64, L64, L64, L64, F, P],
+    "wdno_linear_attn_bwd": [P, P, P, P, L64, I, F, P],
     "wdno_sumsq": [P, L64, P, P],
     "wdno_adam_clip_ema": [P, P, P, P, P, L64, P, F, F, F, F, F, F, F, F, I, P],
     "wdno_randn_slice": [P, L64, L64, L64, I, C.c_uint64, C.c_uint64, P],
@@ -63,3 +65,5 @@ def bind(lib):
         fn.argtypes = argtypes
     lib.wdno_linattn_work_bytes.restype = C.c_int64
     lib.wdno_linattn_work_bytes.argtypes = [L64, I, I]
+    lib.wdno_linear_attn_bwd_work_bytes.restype = C.c_int64
+    lib.wdno_linear_attn_bwd_work_bytes.argtypes = [L64]

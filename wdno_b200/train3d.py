@@ -10,7 +10,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from . import ops
-from .training import ConvLayer, add_f16, chan_layernorm_bwd, gn_bwd, pack_grad_f16
+from .training import AttnGrad, ConvLayer, add_f16, chan_layernorm_bwd, gn_bwd, pack_grad_f16
 
 HEADS, DH = 4, 32
 
@@ -153,6 +153,22 @@ class Unet3DTrainEngine:
             if lv["up"] is not None:
                 reg(lv["up"], mods[4].weight, mods[4].bias, kind="up144")
         reg(e.final_conv, m.final_conv[1].weight, m.final_conv[1].bias)
+        # attention blocks: backward plans keyed by the forward plan object
+        rel = m.time_rel_pos_bias.relative_attention_bias.weight
+        self.attn = {}
+        dev = e.dev
+
+        def reg_attn(plan, mod, kind):
+            a = mod.fn.fn if kind == "linear" else mod.fn.fn.fn
+            self.attn[id(plan)] = AttnGrad(kind, mod.fn.norm.gamma, a.to_qkv, a.to_out, dev, rel_emb=rel)
+
+        reg_attn(e.init_tattn, m.init_temporal_attn, "temporal")
+        for lv, mods in list(zip(e.downs, m.downs)) + list(zip(e.ups, m.ups)):
+            reg_attn(lv["sattn"], mods[2], "linear")
+            reg_attn(lv["tattn"], mods[3], "temporal")
+        reg_attn(e.mid_sattn, m.mid_spatial_attn, "spatial")
+        reg_attn(e.mid_tattn, m.mid_temporal_attn, "temporal")
+        self.use_torch_attention = False   # True: differentiate the attention blocks with fp32 torch ops (cross-check path)
         self._versions = None
 
     def _resnet_plans(self):
@@ -171,8 +187,9 @@ class Unet3DTrainEngine:
         v = sum(p._version for p in self.m.parameters())
         if v != self._versions:
             for layer in self.layers.values():
-                for plan, w in zip(layer.dgrad, layer._dgrad_weights()):
-                    plan.refresh(w)
+                layer.refresh(fwd=False)
+            for ag in self.attn.values():
+                ag.refresh()
             self._versions = v
 
     # ------------------------------------------------------------------ forward (records the tape)
@@ -323,6 +340,11 @@ class Unet3DTrainEngine:
                     lr.backward_weight(srcs, dout, inv)
                     for i, s in enumerate(srcs):
                         acc(s, l1.backward_input(dy1, i, resid=lr.backward_input(dout, i)))
+            elif kind in ("tattn", "lattn", "mattn") and not self.use_torch_attention:
+                _, plan, h, out = rec
+                dy = grads.pop(id(out))
+                tables = self.eng._rel_tables(h.shape[1]) if kind == "tattn" else None
+                acc(h, self.attn[id(plan)].backward(h, dy, inv, tables=tables))
             elif kind == "tattn":
                 _, blk, h, out = rec
                 mod = blk.mod

@@ -230,8 +230,9 @@ class ConvLayer:
             off += cs
         return out
 
-    def refresh(self):
-        self.fwd.refresh(self.weight, self.bias)
+    def refresh(self, fwd=True):
+        if fwd:
+            self.fwd.refresh(self.weight, self.bias)
         for plan, w in zip(self.dgrad, self._dgrad_weights()):
             plan.refresh(w)
 
@@ -256,3 +257,96 @@ class ConvLayer:
             self.wgrad(src, dy, gw, gb if i == 0 else None, scale, cx_off=0, cx_n=real, n_off=off, n_total=n_total,
                        m_valid=self.weight.shape[0])
             off += cs
+
+
+# ---------------------------------------------------------------------------------------------- attention cores, backward
+def softmax_attn_bwd(qkv, d_o, n_seq, n_tok, inner, outerT, innerT, tokT, scale, bias=None, rot=None, dbias=None):
+    """qkv fp16 [.., 384], d_o fp16 [.., 128] (gradient of the core output) -> dqkv fp16 [.., 384]; dbias fp32 [4,n,n] +="""
+    assert qkv.dtype == torch.float16 and d_o.dtype == torch.float16 and qkv.is_contiguous() and d_o.is_contiguous()
+    dqkv = torch.empty_like(qkv)
+    rc, rs = (None, None) if rot is None else rot
+    _lib.check(_lib.lib().wdno_softmax_attn_bwd(_p(qkv), _p(d_o), _p(bias), _p(rc), _p(rs), _p(dqkv), _p(dbias), n_seq, n_tok,
+                                                inner, outerT, innerT, tokT, float(scale), _lib.current_stream_ptr()),
+               "softmax_attn_bwd")
+    return dqkv
+
+
+_LA_WORK = {}
+
+
+def linear_attn_bwd(qkv, d_o, n_img, n_pos, scale):
+    assert qkv.dtype == torch.float16 and d_o.dtype == torch.float16 and qkv.is_contiguous() and d_o.is_contiguous()
+    L = _lib.lib()
+    key = (qkv.device, n_img)
+    if key not in _LA_WORK:
+        _LA_WORK[key] = torch.empty(L.wdno_linear_attn_bwd_work_bytes(n_img), dtype=torch.uint8, device=qkv.device)
+    dqkv = torch.empty_like(qkv)
+    _lib.check(L.wdno_linear_attn_bwd(_p(qkv), _p(d_o), _p(dqkv), _p(_LA_WORK[key]), n_img, n_pos, float(scale),
+                                      _lib.current_stream_ptr()), "linear_attn_bwd")
+    return dqkv
+
+
+class AttnGrad:
+    """Backward of Residual(PreNorm(dim, attention)) around one of the three attention cores (conv3d.py:165-184, 232-353):
+    recompute LayerNorm -> to_qkv -> core (unfused kernels), then to_out wgrad / dgrad -> core backward -> to_qkv wgrad / dgrad ->
+    LayerNorm backward + the residual.  kind: 'temporal' | 'spatial' | 'linear'."""
+
+    def __init__(self, kind, gamma, to_qkv, to_out, device, rel_emb=None):
+        self.kind, self.gamma, self.rel_emb = kind, gamma, rel_emb
+        C_ = to_qkv.weight.shape[1]
+        bo = getattr(to_out, "bias", None)
+        self.qkv = ConvLayer(TapGemm(to_qkv.weight, None, device=device), to_qkv.weight, None, "conv", (C_,))
+        self.out = ConvLayer(TapGemm(to_out.weight, bo, device=device), to_out.weight, bo, "conv", (128,))
+        self.own = (self.qkv, self.out)
+
+    def refresh(self):
+        for l in self.own:
+            l.refresh()
+
+    def backward(self, x, dy, inv, tables=None, scale=32 ** -0.5):
+        B, D, H, W, Cc = x.shape
+        g = self.gamma.detach().reshape(-1)
+        xn = ops.chan_layernorm(x, g)
+        qkv = self.qkv.fwd(xn)
+        if self.kind == "linear":
+            o = ops.linear_attn(qkv, B * D, H * W, scale)
+        elif self.kind == "temporal":
+            bias, rot = tables
+            amap = (B * H * W, D, H * W, D * H * W, 1, H * W)
+            o = ops.softmax_attn(qkv, *amap, scale, bias=bias, rot=rot)
+        else:
+            amap = (B * D, H * W, 1, H * W, 0, 1)
+            o = ops.softmax_attn(qkv, *amap, scale)
+        self.out.backward_weight((o,), dy, inv)
+        d_o = self.out.backward_input(dy, 0)
+        del o
+        if self.kind == "linear":
+            dqkv = linear_attn_bwd(qkv, d_o, B * D, H * W, scale)
+        elif self.kind == "temporal":
+            dbias = torch.zeros_like(bias)
+            dqkv = softmax_attn_bwd(qkv, d_o, *amap, scale, bias=bias, rot=rot, dbias=dbias)
+            # bias[h, i, j] = emb[bucket(i, j), h]  (RelativePositionBias, conv3d.py:74-112)
+            self.rel_emb.grad.index_add_(0, self.bucket(D, x.device), dbias.permute(1, 2, 0).reshape(-1, dbias.shape[0]), alpha=inv)
+        else:
+            dqkv = softmax_attn_bwd(qkv, d_o, *amap, scale)
+        del qkv, d_o
+        self.qkv.backward_weight((xn,), dqkv, inv)
+        dxn = self.qkv.backward_input(dqkv, 0)
+        return chan_layernorm_bwd(x, dxn, g, self.gamma.grad, inv, add=dy)
+
+    _buckets = {}
+
+    @classmethod
+    def bucket(cls, n, device, num_buckets=32, max_distance=32):
+        key = (n, str(device))
+        if key not in cls._buckets:
+            pos = torch.arange(n)
+            k = -(pos[None, :] - pos[:, None])
+            half = num_buckets // 2
+            ret = (k < 0).long() * half
+            k = k.abs()
+            max_exact = half // 2
+            large = max_exact + (torch.log(k.float() / max_exact) / math.log(max_distance / max_exact) * (half - max_exact)).long()
+            large = torch.min(large, torch.full_like(large, half - 1))
+            cls._buckets[key] = (ret + torch.where(k < max_exact, k, large)).reshape(-1).to(device)
+        return cls._buckets[key]
