@@ -45,3 +45,35 @@ class EngineOwner:
             self._engine = self._make_engine()
             self._engine_fp = fp
         return self._engine
+
+
+class GraphedRefresh:
+    """Runs `fn` (a fixed sequence of device ops on static addresses) eagerly the first time and replays it from a CUDA graph
+    afterwards.  `signature()` describes the set of buffers `fn` touches (e.g. how many packed-weight entries exist): when it
+    changes (a plan for a new geometry was built) the graph is dropped and re-captured.  Falls back to eager execution for
+    good if capture fails (e.g. an op that synchronises)."""
+
+    def __init__(self, fn, signature=None):
+        self.fn, self.signature = fn, signature
+        self.graph, self.failed, self.sig, self.eager_runs = None, False, None, 0
+
+    def __call__(self):
+        import torch
+        sig = self.signature() if self.signature is not None else None
+        if sig != self.sig:
+            self.graph, self.sig, self.eager_runs = None, sig, 0
+        if self.failed or self.eager_runs == 0 or not torch.cuda.is_available() or torch.cuda.is_current_stream_capturing():
+            self.eager_runs += 1
+            return self.fn()
+        if self.graph is None:
+            try:
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self.fn()
+                self.graph = g
+            except Exception:  # noqa: BLE001
+                self.failed = True
+                torch.cuda.synchronize()
+                return self.fn()
+        self.graph.replay()

@@ -168,6 +168,7 @@ class Unet3DTrainEngine:
             reg_attn(lv["tattn"], mods[3], "temporal")
         reg_attn(e.mid_sattn, m.mid_spatial_attn, "spatial")
         reg_attn(e.mid_tattn, m.mid_temporal_attn, "temporal")
+        self._graphed = None
         self.use_torch_attention = False   # True: differentiate the attention blocks with fp32 torch ops (cross-check path)
         self._versions = None
 
@@ -186,11 +187,23 @@ class Unet3DTrainEngine:
         """dgrad tiles follow the live parameters (the forward tiles are refreshed by model.engine())"""
         v = sum(p._version for p in self.m.parameters())
         if v != self._versions:
-            for layer in self.layers.values():
-                layer.refresh(fwd=False)
-            for ag in self.attn.values():
-                ag.refresh()
+            if self._graphed is None:
+                from ._engine_cache import GraphedRefresh
+                self._graphed = GraphedRefresh(self._refresh_eager, self._refresh_signature)
+            self._graphed()
             self._versions = v
+
+    def _refresh_signature(self):
+        n = sum(len(p._packed) for layer in self.layers.values() for p in layer.dgrad)
+        for ag in self.attn.values():
+            n += sum(len(p._packed) + len(l.fwd._packed) for l in ag.own for p in l.dgrad)
+        return n
+
+    def _refresh_eager(self):
+        for layer in self.layers.values():
+            layer.refresh(fwd=False)
+        for ag in self.attn.values():
+            ag.refresh()
 
     # ------------------------------------------------------------------ forward (records the tape)
     def forward(self, x, time, ss):

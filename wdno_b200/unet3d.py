@@ -193,7 +193,7 @@ class Unet3DEngine:
         f32 = lambda t: t.detach().to(dev, torch.float32).contiguous()
         self.cin = m.channels
         self.cin_pad = (m.channels + 15) // 16 * 16
-        self._refreshers, self._mlp_w_src, self._mlp_b_src = [], [], []
+        self._refreshers, self._mlp_w_src, self._mlp_b_src, self._plans = [], [], [], []
         self.init_conv = self._conv(m.init_conv.weight, m.init_conv.bias, src_channels=(self.cin_pad,))
         self.tw1, self.tb1 = f32(m.time_mlp[1].weight), f32(m.time_mlp[1].bias)
         self.tw2, self.tb2 = f32(m.time_mlp[3].weight), f32(m.time_mlp[3].bias)
@@ -227,9 +227,8 @@ class Unet3DEngine:
         self.mlp_w = torch.cat(self._mlp_w, 0).contiguous() if self._mlp_w else None
         self.mlp_b = torch.cat(self._mlp_b, 0).contiguous() if self._mlp_b else None
         self.freqs = m.init_temporal_attn.fn.fn.fn.rotary_emb.freqs.detach().float().cpu()
-        self.rel_emb = m.time_rel_pos_bias.relative_attention_bias.weight.detach().float().cpu()
         self.max_distance = m.rel_pos_max_distance
-        self._tables = {}
+        self._tables, self._buckets = {}, {}
         self.launches = 0
 
     # ------------------------------------------------------------ plan builders
@@ -272,6 +271,7 @@ class Unet3DEngine:
         c, k = weight.shape[0], weight.reshape(weight.shape[0], -1).shape[1]
         plan = TapGemm(self._w_plus_identity(weight), bias, src_channels=(k, c), device=self.dev)
         plan.algo_cin = k
+        self._plans.append(plan)
         self._refreshers.append(lambda: plan.refresh(self._w_plus_identity(weight), bias))
         return plan
 
@@ -279,18 +279,28 @@ class Unet3DEngine:
         """TapGemm of a parameter pair, registered for in-place refresh"""
         weight = mod_or_weight
         plan = TapGemm(weight, bias, device=self.dev, **kw)
+        self._plans.append(plan)
         self._refreshers.append(lambda: plan.refresh(weight, bias))
         return plan
 
     def refresh(self):
         """Re-pack every weight-derived buffer from the live parameters IN PLACE (an optimiser step, an EMA update or a
-        checkpoint load changed values, not shapes): plans, launch structs and captured CUDA graphs stay valid."""
+        checkpoint load changed values, not shapes): plans, launch structs and captured CUDA graphs stay valid.  The re-pack is
+        ~1 500 small device ops; from its second use on it is replayed from ONE CUDA graph (all addresses are static)."""
+        from ._engine_cache import GraphedRefresh
+        if getattr(self, "_graphed_refresh", None) is None:
+            self._graphed_refresh = GraphedRefresh(self._refresh_eager, self._refresh_signature)
+        self._graphed_refresh()
+
+    def _refresh_signature(self):
+        return (sum(len(p._packed) for p in self._plans), len(self._tables))
+
+    def _refresh_eager(self):
         for fn in self._refreshers:
             fn()
         if self._mlp_w:
             self.mlp_w.copy_(torch.cat([w.detach().float() for w in self._mlp_w_src], 0))
             self.mlp_b.copy_(torch.cat([b.detach().float() for b in self._mlp_b_src], 0))
-        self.rel_emb = self.m.time_rel_pos_bias.relative_attention_bias.weight.detach().float().cpu()
         for n, (bias, rot) in list(self._tables.items()):
             bias.copy_(self._rel_bias(n))
 
@@ -322,20 +332,23 @@ class Unet3DEngine:
         return tabs
 
     def _rel_bias(self, n):
-        pos = torch.arange(n)
-        rel = pos[None, :] - pos[:, None]
-        nb = self.rel_emb.shape[0]
-        k = -rel
-        half = nb // 2
-        ret = (k < 0).long() * half
-        k = k.abs()
-        max_exact = half // 2
-        small = k < max_exact
-        large = max_exact + (torch.log(k.float() / max_exact) / math.log(self.max_distance / max_exact)
-                             * (half - max_exact)).long()
-        large = torch.min(large, torch.full_like(large, half - 1))
-        bucket = ret + torch.where(small, k, large)
-        return self.rel_emb[bucket].permute(2, 0, 1).contiguous().to(self.dev)
+        """T5 relative-position bias [heads][n][n] from the LIVE embedding (device op: no host round trip)"""
+        if n not in self._buckets:
+            pos = torch.arange(n)
+            rel = pos[None, :] - pos[:, None]
+            nb = self.m.time_rel_pos_bias.relative_attention_bias.weight.shape[0]
+            k = -rel
+            half = nb // 2
+            ret = (k < 0).long() * half
+            k = k.abs()
+            max_exact = half // 2
+            small = k < max_exact
+            large = max_exact + (torch.log(k.float() / max_exact) / math.log(self.max_distance / max_exact)
+                                 * (half - max_exact)).long()
+            large = torch.min(large, torch.full_like(large, half - 1))
+            self._buckets[n] = (ret + torch.where(small, k, large)).to(self.dev)
+        emb = self.m.time_rel_pos_bias.relative_attention_bias.weight.detach().float()
+        return emb[self._buckets[n]].permute(2, 0, 1).contiguous()
 
     # ------------------------------------------------------------ blocks
     def _resnet(self, p, src0, src1, ss, stats):
