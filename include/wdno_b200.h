@@ -274,6 +274,10 @@ int wdno_gn_bwd_apply(const void* dh, const void* y, const float* a, const float
 int wdno_pack_grad_f16(const float* g, void* out, int B, int F, int C, int H, int W, int cp, float mul, void* stream);
 /* out[i] = a[i] + b[i] (fp16, saturating): gradient accumulation at skip connections */
 int wdno_add_f16(const void* a, const void* b, void* out, int64_t n, void* stream);
+/* nearest x2 up-sampling of H, W (nn.Upsample(scale_factor=2, 'nearest'), unet.py:35-39; x: fp16 [N][H][W][C] -> y [N][2H][2W][C]) --
+ * the weight gradient of the convolution behind it needs the materialised input -- and its adjoint, the 2x2 sum (y -> x) */
+int wdno_upsample2x_f16(const void* x, void* y, int64_t N, int H, int W, int C, void* stream);
+int wdno_sumpool2x2_f16(const void* y, void* x, int64_t N, int H, int W, int C, void* stream);
 /* channel LayerNorm backward (conv3d.py:165-174; unet.py:55-65): y = (x - mean) * rstd * gamma over C per voxel.
  * dx = rstd*(g*dy - mean_c(g*dy) - xhat*mean_c(g*dy*xhat)) (+ add), d_gamma[c] += scale * sum dy*xhat */
 int wdno_chan_layernorm_bwd(const void* x, const void* dy, const float* gamma, const void* add, void* dx, float* d_gamma,

@@ -275,3 +275,41 @@ def test_attention_block_backward_kernels_vs_torch_autograd():
         assert rel_l2(dx.float(), dx_ref.float()) < 4e-3, (kind, shape, "dx", rel_l2(dx.float(), dx_ref.float()))
         for p, r, name in zip(params, ref, ("gamma", "to_qkv", "to_out", "bias/rel_emb")):
             assert rel_l2(p.grad, r) < 6e-3, (kind, shape, name, rel_l2(p.grad, r))
+
+
+def test_burgers_p_losses_backward_vs_fp32_oracle_autograd():
+    """Burgers Unet2D(dim=128) training step (train_diffusion.py:200-212): loss and every parameter gradient of the engine vs
+    autograd through the fp32 oracle network (oracle/training.py, pinned to the reference's backward on CPU)."""
+    from oracle import diffusion as D
+    from oracle import training as TR
+    from wdno_b200.diffusion_burgers import GaussianDiffusion
+    from wdno_b200.unet2d import Unet2D
+    torch.manual_seed(0)
+    m = Unet2D(dim=128, dim_mults=[1, 2, 4, 8], channels=9, out_dim=9, resnet_block_groups=1).cuda().train()
+    lw = torch.linspace(0.5, 2.0, 9).reshape(1, 9, 1, 1)
+    gd = GaussianDiffusion(m, seq_length=(64, 64), is_wavelet=True, pad_mode="periodization", wave_type="bior2.4",
+                           padded_shape=[41, 60], ori_shape=[81, 120], timesteps=1000, sampling_timesteps=1000,
+                           is_condition_u0=True, is_condition_f=True, loss_layer_weight=lw).cuda()
+    g = torch.Generator().manual_seed(6)
+    x0 = torch.randn(2, 9, 64, 64, generator=g).clamp(-1, 1).cuda()
+    t = torch.tensor([5, 911]).cuda()
+    noise = torch.randn(2, 9, 64, 64, generator=g).cuda()
+    loss = gd.p_losses(x0, t, noise.clone())
+    assert loss.grad_fn is not None
+    loss.backward()
+    params = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    sch = {k: v.cuda() for k, v in D.schedule("cosine", 1000).items()}
+    lo, grads = TR.burgers_loss_and_grads(params, sch, x0, t, noise.clone(), [41, 60], lw.cuda())
+    assert abs(float(loss) - float(lo)) < 5e-3 * abs(float(lo)), (float(loss), float(lo))
+    named = dict(m.named_parameters())
+    tot_e = float(torch.sqrt(sum((named[k].grad.double() ** 2).sum() for k in grads if k in named)))
+    tot_o = float(torch.sqrt(sum((grads[k].double() ** 2).sum() for k in grads if k in named)))
+    assert abs(tot_e - tot_o) < 5e-3 * tot_o, (tot_e, tot_o)
+    worst = ("", 0.0)
+    for k, go in grads.items():
+        if k in named and float(go.norm()) > 1e-6 * tot_o:
+            e = rel_l2(named[k].grad, go)
+            if e > worst[1]:
+                worst = (k, e)
+    print("BURGERS_TRAIN_PARITY", dict(loss=float(loss), loss_ref=float(lo), total=tot_e, total_ref=tot_o, worst=worst))
+    assert worst[1] < 3e-2, worst

@@ -7,7 +7,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
-from bench import B_PER_GPU, SHAPE, build_engine  # noqa: E402
+from bench_r1_loop import B_PER_GPU, SHAPE, build_engine  # noqa: E402  (round-1 private-runner loop: same model and shapes)
 from wdno_b200 import _lib, ops  # noqa: E402
 
 L = _lib.lib()

@@ -44,6 +44,8 @@ SIGNATURES = {
     "wdno_chan_layernorm_bwd": [P, P, P, P, P, P, L64, I, F, F, P],
     "wdno_softmax_attn_bwd": [P, P, P, P, P, P, P, L64, I, L64, L64, L64, L64, F, P],
     "wdno_linear_attn_bwd": [P, P, P, P, L64, I, F, P],
+    "wdno_upsample2x_f16": [P, P, L64, I, I, I, P],
+    "wdno_sumpool2x2_f16": [P, P, L64, I, I, I, P],
     "wdno_sumsq": [P, L64, P, P],
     "wdno_adam_clip_ema": [P, P, P, P, P, L64, P, F, F, F, F, F, F, F, F, I, P],
     "wdno_randn_slice": [P, L64, L64, L64, I, C.c_uint64, C.c_uint64, P],

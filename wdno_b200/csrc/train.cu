@@ -195,6 +195,48 @@ __global__ void add_f16_kernel(const uint4* __restrict__ a, const uint4* __restr
   }
 }
 
+// nearest x2 up-sampling of the two inner spatial axes (nn.Upsample(scale_factor=2), unet.py:35-39) and its adjoint (2x2 sum):
+// fp16 [N][H][W][C] <-> [N][2H][2W][C]; one thread per 16-byte chunk of the LOW-resolution tensor
+__global__ void up2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int H, int W, int cpv, size_t total) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % cpv);
+    size_t t = i / cpv;
+    const int xw = static_cast<int>(t % W);
+    t /= W;
+    const int yh = static_cast<int>(t % H);
+    const size_t n = t / H;
+    const uint4 v = __ldg(x + i);
+    const size_t o = ((n * 2 * H + 2 * yh) * 2 * W + 2 * xw) * cpv + c;
+    y[o] = v;
+    y[o + cpv] = v;
+    y[o + static_cast<size_t>(2 * W) * cpv] = v;
+    y[o + static_cast<size_t>(2 * W) * cpv + cpv] = v;
+  }
+}
+__global__ void sumpool2x2_kernel(const uint4* __restrict__ y, uint4* __restrict__ x, int H, int W, int cpv, size_t total) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % cpv);
+    size_t t = i / cpv;
+    const int xw = static_cast<int>(t % W);
+    t /= W;
+    const int yh = static_cast<int>(t % H);
+    const size_t n = t / H;
+    const size_t o = ((n * 2 * H + 2 * yh) * 2 * W + 2 * xw) * cpv + c;
+    float a[8], b[8];
+    unpack8(__ldg(y + o), a);
+    unpack8(__ldg(y + o + cpv), b);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] += b[k];
+    unpack8(__ldg(y + o + static_cast<size_t>(2 * W) * cpv), b);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] += b[k];
+    unpack8(__ldg(y + o + static_cast<size_t>(2 * W) * cpv + cpv), b);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] += b[k];
+    x[i] = pack8(a);
+  }
+}
+
 // ------------------------------------------------------------------ channel LayerNorm backward
 // LPV lanes per voxel, each lane CPL chunks of 8 channels (chunk j of lane l = channels (j*LPV + l)*8 ..).  A thread keeps
 // its channels for the whole grid-stride loop, so d_gamma accumulates in registers.
@@ -448,4 +490,20 @@ extern "C" int wdno_adam_clip_ema(float* p, const float* g, float* m, float* v, 
   adam_clip_ema_kernel<<<ew_grid_(static_cast<size_t>(n)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       p, g, m, v, ema, static_cast<size_t>(n), sumsq, max_norm, lr, beta1, beta2, eps, bc1, bc2, ema_decay, ema_mode);
   return check_launch("adam_clip_ema");
+}
+
+extern "C" int wdno_upsample2x_f16(const void* x, void* y, int64_t N, int H, int W, int C, void* stream) {
+  if (!x || !y || N < 1 || H < 1 || W < 1 || C < 8 || (C & 7)) return set_error(WDNO_E_INVALID, "upsample2x_f16: bad arguments");
+  const size_t total = static_cast<size_t>(N) * H * W * (C >> 3);
+  up2x_kernel<<<ew_grid_(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint4*>(x), static_cast<uint4*>(y), H, W,
+                                                                          C >> 3, total);
+  return check_launch("upsample2x_f16");
+}
+
+extern "C" int wdno_sumpool2x2_f16(const void* y, void* x, int64_t N, int H, int W, int C, void* stream) {
+  if (!x || !y || N < 1 || H < 1 || W < 1 || C < 8 || (C & 7)) return set_error(WDNO_E_INVALID, "sumpool2x2_f16: bad arguments");
+  const size_t total = static_cast<size_t>(N) * H * W * (C >> 3);
+  sumpool2x2_kernel<<<ew_grid_(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint4*>(y), static_cast<uint4*>(x),
+                                                                                H, W, C >> 3, total);
+  return check_launch("sumpool2x2_f16");
 }

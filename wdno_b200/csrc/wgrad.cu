@@ -73,37 +73,48 @@ __global__ void __launch_bounds__(kThreads) wgrad_kernel(const wdno_wgrad_params
   const int q_shift = grp.dy * Wp + grp.dx_min;    // slab row r holds X_lin[q0 + q_shift + r]
 
   // ---- loader: one stage = dY tile [64 positions][64 channels of the M tile] + X slab [64 + span][64 channels of the N tile]
+  // A thread copies chunk column c8 of rows r0, r0 + 16, ...: ONE division per tile locates row r0, the others follow by
+  // adding 16 positions with a carry into the next padded row (the loader was 60 % of the instruction stream with a
+  // division per copy: ncu, profiles/r2_wgrad.md).
+  const int r0 = tid >> 3, c8 = tid & 7;
+  const bool m_ok = (m0 + c8 * 8) < p.Cy, n_ok = (n0 + c8 * 8) < p.cx_n;
+  const int step_y = 16 / Wp, step_x = 16 - step_y * Wp;   // 16 positions = step_y rows + step_x columns
   auto load = [&](long long chunk, int st) {
     const long long plane = chunk / cpp;
     const int q0 = static_cast<int>(chunk - plane * cpp) * kKC;
     const int z = static_cast<int>(plane % p.D);
     const long long b = plane / p.D;
-    const uint32_t s_dy = sbase + st * kStageBytes, s_x = s_dy + kDyBytes;
-    const __half* dyp = pdy_ + (plane * p.H * p.W) * p.Cy + m0;
+    const uint32_t s_dy = sbase + st * kStageBytes + static_cast<uint32_t>((r0 * kPitch + c8 * 8) * 2);
+    const uint32_t s_x = sbase + st * kStageBytes + kDyBytes + static_cast<uint32_t>((r0 * kPitch + c8 * 8) * 2);
+    const __half* dyp = pdy_ + (plane * p.H * p.W) * p.Cy + m0 + c8 * 8;
+    {
+      const int q = q0 + r0;
+      int y = q / Wp, x = q - y * Wp;
 #pragma unroll
-    for (int i = 0; i < (kKC * 8) / kThreads; ++i) {
-      const int e = tid + i * kThreads;
-      const int r = e >> 3, c8 = e & 7;
-      const int q = q0 + r;
-      const int y = q / Wp, x = q - y * Wp;
-      const bool ok = (y < p.H) && (x < p.W) && (m0 + c8 * 8 < p.Cy);
-      cp16z(s_dy + static_cast<uint32_t>((r * kPitch + c8 * 8) * 2), ok ? dyp + (static_cast<long long>(y) * p.W + x) * p.Cy + c8 * 8 : pdy_, ok);
+      for (int i = 0; i < kKC / 16; ++i) {
+        const bool ok = m_ok && (y < p.H) && (x < p.W);
+        cp16z(s_dy + static_cast<uint32_t>(i * 16 * kPitch * 2), ok ? dyp + (static_cast<long long>(y) * p.W + x) * p.Cy : pdy_, ok);
+        x += step_x;
+        y += step_y;
+        if (x >= Wp) { x -= Wp; ++y; }
+      }
     }
     const int zs = z + grp.dz;
-    const bool zok = zs >= 0 && zs < p.D;
-    const __half* xp = px_ + ((b * p.D + (zok ? zs : 0)) * p.Hs * p.Ws) * static_cast<long long>(p.Cx) + p.cx_off + n0;
-    for (int e = tid; e < slab_rows * 8; e += kThreads) {
-      const int r = e >> 3, c8 = e & 7;
-      const int q = q0 + q_shift + r;
-      int y = 0, x = 0;
-      bool ok = zok && q >= 0;
-      if (ok) {
-        y = q / Wp;
-        x = q - y * Wp;
-        ok = (y < Hv) && (x < Wv) && (n0 + c8 * 8 < p.cx_n);
+    const bool zok = n_ok && zs >= 0 && zs < p.D;
+    const __half* xp = px_ + ((b * p.D + (zok ? zs : 0)) * p.Hs * p.Ws) * static_cast<long long>(p.Cx) + p.cx_off + n0 + c8 * 8;
+    {
+      // slab row r holds X_lin[q0 + q_shift + r]; negative positions (above the plane) are zero
+      const int q = q0 + q_shift + r0;
+      int y = (q >= 0) ? q / Wp : -((-q + Wp - 1) / Wp);
+      int x = q - y * Wp;
+      for (int r = r0; r < slab_rows; r += 16) {
+        const bool ok = zok && (y >= 0) && (y < Hv) && (x < Wv);
+        const long long off = (static_cast<long long>(p.sy * y + p.ph_y) * p.Ws + (p.sx * x + p.ph_x)) * p.Cx;
+        cp16z(s_x + static_cast<uint32_t>((r - r0) * kPitch * 2), ok ? xp + off : px_, ok);
+        x += step_x;
+        y += step_y;
+        if (x >= Wp) { x -= Wp; ++y; }
       }
-      const long long off = (static_cast<long long>(p.sy * y + p.ph_y) * p.Ws + (p.sx * x + p.ph_x)) * p.Cx + c8 * 8;
-      cp16z(s_x + static_cast<uint32_t>((r * kPitch + c8 * 8) * 2), ok ? xp + off : px_, ok);
     }
   };
 

@@ -9,6 +9,7 @@ which is what the fused DDIM/DDPM step kernel does (cond_mode = 2).
 import math
 
 import torch
+import torch.nn.functional as F
 from torch import nn
 
 from . import ops
@@ -273,6 +274,15 @@ class GaussianDiffusion(nn.Module):
         zsrc = {k: torch.zeros_like(v) for k, v in src.items()}
         _, prog_n = self._program((b, c, nt, nx), coef_shape, zsrc)
         ops.apply_conditions(noise.reshape(b, 1, c, nt, nx), prog_n)
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.model.parameters()):
+            # training: differentiable forward, backward in libwdno_b200.so (wdno_b200/train2d.py); diffusion_1d.py:639-645
+            from .train2d import unet2d_apply
+            out = unet2d_apply(self.model, x, t)
+            loss = F.mse_loss(out, noise, reduction="none")
+            lw = self.loss_layer_weight
+            loss = loss * (lw.to(loss.device) if torch.is_tensor(lw) else lw)
+            loss = loss.reshape(b, -1).mean(dim=1)
+            return (loss * self.loss_weight[t]).mean()
         with torch.no_grad():
             out = self.model(x, t)
         lw = self.loss_layer_weight

@@ -160,7 +160,8 @@ class Unet3DTrainEngine:
 
         def reg_attn(plan, mod, kind):
             a = mod.fn.fn if kind == "linear" else mod.fn.fn.fn
-            self.attn[id(plan)] = AttnGrad(kind, mod.fn.norm.gamma, a.to_qkv, a.to_out, dev, rel_emb=rel)
+            key = plan["qkv"] if isinstance(plan, dict) else plan
+            self.attn[id(key)] = AttnGrad(kind, mod.fn.norm.gamma, a.to_qkv, a.to_out, dev, rel_emb=rel)
 
         reg_attn(e.init_tattn, m.init_temporal_attn, "temporal")
         for lv, mods in list(zip(e.downs, m.downs)) + list(zip(e.ups, m.ups)):
@@ -304,8 +305,8 @@ class Unet3DTrainEngine:
             k = id(t)
             grads[k] = g if k not in grads else add_f16(grads[k], g)
 
-        rotary = self.m.init_temporal_attn.fn.fn.fn.rotary_emb.freqs
-        rel_emb = self.m.time_rel_pos_bias.relative_attention_bias.weight
+        rotary = self.m.init_temporal_attn.fn.fn.fn.rotary_emb.freqs if hasattr(self.m, "init_temporal_attn") else None
+        rel_emb = self.m.time_rel_pos_bias.relative_attention_bias.weight if hasattr(self.m, "time_rel_pos_bias") else None
         prof = self.profile
         for rec in reversed(tape):
             kind = rec[0]
@@ -357,7 +358,7 @@ class Unet3DTrainEngine:
                 _, plan, h, out = rec
                 dy = grads.pop(id(out))
                 tables = self.eng._rel_tables(h.shape[1]) if kind == "tattn" else None
-                acc(h, self.attn[id(plan)].backward(h, dy, inv, tables=tables))
+                acc(h, self.attn[id(plan if not isinstance(plan, dict) else plan["qkv"])].backward(h, dy, inv, tables=tables))
             elif kind == "tattn":
                 _, blk, h, out = rec
                 mod = blk.mod

@@ -117,6 +117,13 @@ class Wgrad:
             self.cout, self.cin = wshape[0], wshape[1]
             self.t_total = 16
             self.tables = [(2, 2, a, b, 1) + _groups_dev(wgrad_groups_144(a, b), self.device) for a in (0, 1) for b in (0, 1)]
+        elif kind == "unshuffle":
+            # Rearrange('b c (h p1) (w p2) -> b (c p1 p2) h w') + Conv2d(4c, c', 1) (unet.py:41-45): per phase (p1, p2) a 1x1 layer on
+            # the stride-2 view; weight column c*4 + p1*2 + p2 = (input channel c, "tap" p1*2 + p2)
+            self.cout, self.cin = wshape[0], wshape[1] // 4
+            self.t_total = 4
+            self.tables = [(2, 2, a, b, 0) + _groups_dev([dict(dz=0, dy=0, dx_min=0, span=0, dxo=[0], out=[a * 2 + b])], self.device)
+                           for a in (0, 1) for b in (0, 1)]
         else:
             raise ValueError(kind)
 
@@ -199,6 +206,7 @@ class ConvLayer:
     def __init__(self, fwd, weight, bias, kind, src_channels, need_dgrad=True):
         self.fwd, self.weight, self.bias, self.kind = fwd, weight, bias, kind
         self.src_channels = tuple(src_channels)
+        self.up2 = bool(getattr(fwd, "up2", False))   # nearest x2 up-sampling fused into the forward operand load
         dev = fwd.device
         self.wgrad = Wgrad(kind, tuple(weight.shape), dev)
         self.dgrad = []
@@ -207,13 +215,21 @@ class ConvLayer:
                 if kind == "conv":
                     self.dgrad.append(TapGemm(w, None, src_channels=(self._dy_channels(),), device=dev))
                 else:
-                    self.dgrad.append(TapGemm(w, None, kind="up144" if kind == "down144" else "down144", device=dev))
+                    self.dgrad.append(TapGemm(w, None, kind={"down144": "up144", "up144": "down144", "unshuffle": "up144"}[kind],
+                                              device=dev))
 
     def _dy_channels(self):
         return (self.weight.shape[0] + 7) // 8 * 8
 
     def _dgrad_weights(self):
         w = self.weight.detach()
+        if self.kind == "unshuffle":
+            # dx[2y+p1][2x+p2][c] = sum_co W[co][c*4 + p1*2 + p2] dy[y][x][co]: a transposed (1,4,4) stride-2 convolution whose only
+            # non-zero taps are k = p + 1 (each output pixel sees exactly its own source pixel)
+            co, c4 = w.shape[0], w.shape[1]
+            wt = w.new_zeros((co, c4 // 4, 1, 4, 4))
+            wt[:, :, 0, 1:3, 1:3] = w.reshape(co, c4 // 4, 2, 2)
+            return [wt]
         if self.kind != "conv":
             return [w]   # the (1,4,4) pair: strided conv <-> transposed conv with the SAME weight tensor
         if w.dim() == 2:
@@ -238,6 +254,13 @@ class ConvLayer:
 
     def backward_input(self, dy, s, resid=None):
         """gradient w.r.t. source `s` (fp16 channels-last), optionally + resid (fused into the epilogue)"""
+        if self.up2:
+            g = self.dgrad[s](dy)            # gradient of the up-sampled operand; its adjoint is the 2x2 sum
+            B, D, H2, W2, Cc = g.shape
+            out = torch.empty((B, D, H2 // 2, W2 // 2, Cc), dtype=torch.float16, device=g.device)
+            _lib.check(_lib.lib().wdno_sumpool2x2_f16(_p(g), _p(out), B * D, H2 // 2, W2 // 2, Cc, _lib.current_stream_ptr()),
+                       "sumpool2x2_f16")
+            return out if resid is None else add_f16(out, resid)
         return self.dgrad[s](dy, resid=resid)
 
     def backward_weight(self, srcs, dy, scale):
@@ -250,8 +273,16 @@ class ConvLayer:
             if gb is not None:
                 gb.add_(srcs[0].float().sum(dim=(0, 1, 2, 3)) * scale)
             return
+        if self.up2:
+            ups = []
+            for src in srcs:
+                B, D, H, W, Cc = src.shape
+                u = torch.empty((B, D, 2 * H, 2 * W, Cc), dtype=torch.float16, device=src.device)
+                _lib.check(_lib.lib().wdno_upsample2x_f16(_p(src), _p(u), B * D, H, W, Cc, _lib.current_stream_ptr()), "upsample2x_f16")
+                ups.append(u)
+            srcs = ups
         off = 0
-        n_total = self.weight.shape[1]
+        n_total = self.weight.shape[1] // (4 if self.kind == "unshuffle" else 1)
         for i, (src, cs) in enumerate(zip(srcs, self.src_channels)):
             real = min(cs, n_total - off)
             self.wgrad(src, dy, gw, gb if i == 0 else None, scale, cx_off=0, cx_n=real, n_off=off, n_total=n_total,
@@ -291,8 +322,9 @@ class AttnGrad:
     recompute LayerNorm -> to_qkv -> core (unfused kernels), then to_out wgrad / dgrad -> core backward -> to_qkv wgrad / dgrad ->
     LayerNorm backward + the residual.  kind: 'temporal' | 'spatial' | 'linear'."""
 
-    def __init__(self, kind, gamma, to_qkv, to_out, device, rel_emb=None):
-        self.kind, self.gamma, self.rel_emb = kind, gamma, rel_emb
+    def __init__(self, kind, gamma, to_qkv, to_out, device, rel_emb=None, out_norm=None):
+        """out_norm: gain of the channel LayerNorm that follows to_out in the Burgers LinearAttention (unet.py:190-199) or None"""
+        self.kind, self.gamma, self.rel_emb, self.out_norm = kind, gamma, rel_emb, out_norm
         C_ = to_qkv.weight.shape[1]
         bo = getattr(to_out, "bias", None)
         self.qkv = ConvLayer(TapGemm(to_qkv.weight, None, device=device), to_qkv.weight, None, "conv", (C_,))
@@ -317,8 +349,14 @@ class AttnGrad:
         else:
             amap = (B * D, H * W, 1, H * W, 0, 1)
             o = ops.softmax_attn(qkv, *amap, scale)
-        self.out.backward_weight((o,), dy, inv)
-        d_o = self.out.backward_input(dy, 0)
+        dt = dy
+        if self.out_norm is not None:
+            # y = LayerNorm(to_out(o)) + x: differentiate the output norm first (its input is recomputed)
+            t = self.out.fwd(o)
+            dt = chan_layernorm_bwd(t, dy, self.out_norm.detach().reshape(-1), self.out_norm.grad, inv)
+            del t
+        self.out.backward_weight((o,), dt, inv)
+        d_o = self.out.backward_input(dt, 0)
         del o
         if self.kind == "linear":
             dqkv = linear_attn_bwd(qkv, d_o, B * D, H * W, scale)

@@ -139,36 +139,38 @@ class Unet2DEngine:
         f32 = self._f32
         self.cin = m.channels
         self.cin_pad = (m.channels + 15) // 16 * 16
-        self.init_conv = TapGemm(m.init_conv.weight, m.init_conv.bias, src_channels=(self.cin_pad,), device=dev)
+        self._refreshers, self._plans = [], []
+        self.init_conv = self._conv(m.init_conv.weight, m.init_conv.bias, src_channels=(self.cin_pad,))
         self.tw1, self.tb1 = f32(m.time_mlp[1].weight), f32(m.time_mlp[1].bias)
         self.tw2, self.tb2 = f32(m.time_mlp[3].weight), f32(m.time_mlp[3].bias)
         self._mlp_w, self._mlp_b, self._mlp_off, self.stats_slots = [], [], 0, 0
+        self._mlp_w_src, self._mlp_b_src = [], []
         self.downs = []
         for b1, b2, attn, down in m.downs:
             if isinstance(down, nn.Sequential):
-                dn = TapGemm(down[1].weight, down[1].bias, kind="unshuffle", device=dev)
+                dn = self._conv(down[1].weight, down[1].bias, kind="unshuffle")
             else:
-                dn = TapGemm(down.weight, down.bias, device=dev)
+                dn = self._conv(down.weight, down.bias)
             self.downs.append(dict(b1=self._resnet_plan(b1, None), b2=self._resnet_plan(b2, None),
                                    attn=self._lin_attn_plan(attn), down=dn))
         self.mid1 = self._resnet_plan(m.mid_block1, None)
         a = m.mid_attn.fn.fn
-        self.mid_attn = dict(g=f32(m.mid_attn.fn.norm.g.reshape(-1)), qkv=TapGemm(a.to_qkv.weight, None, device=dev),
-                             out=TapGemm(a.to_out.weight, a.to_out.bias, device=dev))
+        self.mid_attn = dict(g=f32(m.mid_attn.fn.norm.g.reshape(-1)), qkv=self._conv(a.to_qkv.weight, None),
+                             out=self._conv(a.to_out.weight, a.to_out.bias))
         self.mid2 = self._resnet_plan(m.mid_block2, None)
         self.ups = []
         for b1, b2, attn, up in m.ups:
             do = b1.block1.proj.weight.shape[0]
             di = b1.block1.proj.weight.shape[1] - do
             if isinstance(up, nn.Sequential):
-                u = TapGemm(up[1].weight, up[1].bias, up2=True, device=dev)
+                u = self._conv(up[1].weight, up[1].bias, up2=True)
             else:
-                u = TapGemm(up.weight, up.bias, device=dev)
+                u = self._conv(up.weight, up.bias)
             self.ups.append(dict(b1=self._resnet_plan(b1, (do, di)), b2=self._resnet_plan(b2, (do, di)),
                                  attn=self._lin_attn_plan(attn), up=u))
         d = m.dim
         self.final_block = self._resnet_plan(m.final_res_block, (d, d))
-        self.final_conv = TapGemm(m.final_conv.weight, m.final_conv.bias, device=dev)
+        self.final_conv = self._conv(m.final_conv.weight, m.final_conv.bias)
         self.mlp_w = torch.cat(self._mlp_w, 0).contiguous()
         self.mlp_b = torch.cat(self._mlp_b, 0).contiguous()
         self.launches = 0
@@ -176,19 +178,41 @@ class Unet2DEngine:
     def _f32(self, t):
         return t.detach().to(self.dev, torch.float32).contiguous()
 
+    def _conv(self, weight, bias=None, **kw):
+        """TapGemm of a parameter pair, registered for in-place refresh"""
+        plan = TapGemm(weight, bias, device=self.dev, **kw)
+        self._plans.append(plan)
+        self._refreshers.append(lambda: plan.refresh(weight, bias))
+        return plan
+
+    def refresh(self):
+        """re-pack every weight-derived buffer from the live parameters in place (see Unet3DEngine.refresh)"""
+        from ._engine_cache import GraphedRefresh
+        if getattr(self, "_graphed_refresh", None) is None:
+            self._graphed_refresh = GraphedRefresh(self._refresh_eager, lambda: sum(len(p._packed) for p in self._plans))
+        self._graphed_refresh()
+
+    def _refresh_eager(self):
+        for fn in self._refreshers:
+            fn()
+        self.mlp_w.copy_(torch.cat([w.detach().float() for w in self._mlp_w_src], 0))
+        self.mlp_b.copy_(torch.cat([b.detach().float() for b in self._mlp_b_src], 0))
+
     def _resnet_plan(self, blk, src_channels):
         p = _RP()
         p.cout = blk.block1.proj.weight.shape[0]
-        p.conv1 = TapGemm(blk.block1.proj.weight, blk.block1.proj.bias, src_channels=src_channels, device=self.dev)
-        p.conv2 = TapGemm(blk.block2.proj.weight, blk.block2.proj.bias, device=self.dev)
+        p.conv1 = self._conv(blk.block1.proj.weight, blk.block1.proj.bias, src_channels=src_channels)
+        p.conv2 = self._conv(blk.block2.proj.weight, blk.block2.proj.bias)
         p.g1, p.b1 = self._f32(blk.block1.norm.weight), self._f32(blk.block1.norm.bias)
         p.g2, p.b2 = self._f32(blk.block2.norm.weight), self._f32(blk.block2.norm.bias)
         p.res = None
         if not isinstance(blk.res_conv, nn.Identity):
-            p.res = TapGemm(blk.res_conv.weight, blk.res_conv.bias, src_channels=src_channels, device=self.dev)
+            p.res = self._conv(blk.res_conv.weight, blk.res_conv.bias, src_channels=src_channels)
         p.ss_off = self._mlp_off
         self._mlp_w.append(self._f32(blk.mlp[1].weight))
         self._mlp_b.append(self._f32(blk.mlp[1].bias))
+        self._mlp_w_src.append(blk.mlp[1].weight)
+        self._mlp_b_src.append(blk.mlp[1].bias)
         self._mlp_off += 2 * p.cout
         p.stat1, p.stat2 = self.stats_slots, self.stats_slots + 1
         self.stats_slots += 2
@@ -196,8 +220,8 @@ class Unet2DEngine:
 
     def _lin_attn_plan(self, res):
         a = res.fn.fn
-        return dict(g=self._f32(res.fn.norm.g.reshape(-1)), qkv=TapGemm(a.to_qkv.weight, None, device=self.dev),
-                    out=TapGemm(a.to_out[0].weight, a.to_out[0].bias, device=self.dev), g_out=self._f32(a.to_out[1].g.reshape(-1)))
+        return dict(g=self._f32(res.fn.norm.g.reshape(-1)), qkv=self._conv(a.to_qkv.weight, None),
+                    out=self._conv(a.to_out[0].weight, a.to_out[0].bias), g_out=self._f32(a.to_out[1].g.reshape(-1)))
 
     def _resnet(self, p, src0, src1, ss, stats):
         B, D, H, W, _ = src0.shape
