@@ -157,11 +157,8 @@ def test_fused_2d_kernels_bit_equal_to_separable_passes_and_strips(monkeypatch):
     assert float((grads[True] - grads[False]).abs().max()) <= 1e-5 * float(grads[False].abs().max())
 
 
-@pytest.mark.skipif(__import__("os").environ.get("WDNO_TEST_EXPERIMENTAL") != "1",
-                    reason="WDNO_DWT2D_V2=1 kernels (extension-staged row pass of the 2-D synthesis, tap-mask variants): written after "
-                           "round 1's GPU budget was spent, index scheme emulated on CPU only; run with WDNO_TEST_EXPERIMENTAL=1")
-def test_experimental_dwt2d_v2_bit_equal_to_separable_passes():
-    """the opt-in second form of the fused 2-D kernels against the per-axis passes, in a child process (the switch is read once)"""
+def test_fused_dwt2d_more_shapes_equal_to_separable_passes():
+    """the fused 2-D kernels (extension-staged synthesis, tap-mask variants) against the per-axis passes on odd / tiny shapes"""
     import os
     import subprocess
     import sys
@@ -181,6 +178,6 @@ for shape, wave, mode in (((3, 2, 81, 120), "bior2.4", "periodization"), ((2, 1,
         assert a.shape == b.shape and float((a - b).abs().max()) <= 1e-6 * float(b.abs().max()), (shape, wave, mode)
 print("v2 ok")
 '''
-    env = dict(os.environ, WDNO_DWT2D_V2="1")
+    env = dict(os.environ)
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert r.returncode == 0 and "v2 ok" in r.stdout, r.stdout + r.stderr

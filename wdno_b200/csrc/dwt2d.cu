@@ -163,89 +163,9 @@ __global__ void __launch_bounds__(256) dwt2d_analysis_kernel(const D2 p) {
 }
 
 // ---------------------------------------------------------------- synthesis
-// column (H) pass first, as DWTInverse does: lo = sfb(ll, lh), hi = sfb(hl, hh) along H, then y = sfb(lo, hi) along W.
-// smem: C [4][R][CS] (R coefficient rows starting at i0, extension applied: row r <-> coefficient row i0 + r),
-//       LOH / HIH [T][nw] (column pass for the T output rows of the strip)
-template <int L>
-__global__ void __launch_bounds__(256) dwt2d_synthesis_kernel(const D2 p) {
-  extern __shared__ __align__(16) float sm[];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
-  const long long img = blockIdx.y;
-  const int m0 = blockIdx.x * p.T;
-  const int R = p.R, nw = p.nw, CS = p.CS, W = p.W;
-  float* Cc = sm;
-  float* LOH = Cc + 4 * R * CS;
-  float* HIH = LOH + p.T * nw;
-  // first coefficient row any output row of the strip reads: floor((m0 + offh - (L - 1)) / 2)
-  const int jlo = m0 + p.offh - (L - 1);
-  const int i0 = jlo >= 0 ? jlo / 2 : -((1 - jlo) / 2);
-  for (int rr = warp; rr < 4 * R; rr += nwarps) {
-    const int bd = rr / R, r = rr - bd * R;
-    const int gi = map_synthesis(i0 + r, p.nh, p.periodic);
-    float* dst = Cc + rr * CS;
-    if (gi < 0) {
-      for (int c = lane; c < nw; c += 32) dst[c] = 0.f;
-      continue;
-    }
-    const float* row = p.in[bd] + img * p.in_istride[bd] + static_cast<long long>(gi) * nw;
-    if (p.v16) {
-      for (int q = lane; 4 * q < nw; q += 32) cpa16(dst + 4 * q, row + 4 * q);
-    } else {
-      for (int c = lane; c < nw; c += 32) cpa4(dst + c, row + c);
-    }
-  }
-  cpa_wait_all();
-  __syncthreads();
-  const int rows = min(p.T, p.H - m0);
-  for (int ml = warp; ml < rows; ml += nwarps) {
-    const int j = m0 + ml + p.offh;
-    const bool odd = j & 1;                    // warp-uniform: taps of one parity class, selected from static indices
-    for (int iw = lane; iw < nw; iw += 32) {
-      float a = 0.f, b = 0.f;
-#pragma unroll
-      for (int kk = 0; kk < L / 2; ++kk) {
-        const float k0 = odd ? p.t0[2 * kk + 1] : p.t0[2 * kk];
-        const float k1 = odd ? p.t1[2 * kk + 1] : p.t1[2 * kk];
-        const int r = ((j - 2 * kk) >> 1) - i0;   // (j - k) / 2 for k = 2 kk + parity; rows outside the band were staged as zeros / wrapped rows
-        const float* c = Cc + r * CS + iw;
-        a = fmaf(c[0], k0, a);
-        a = fmaf(c[R * CS], k1, a);
-        b = fmaf(c[2 * R * CS], k0, b);
-        b = fmaf(c[3 * R * CS], k1, b);
-      }
-      LOH[ml * nw + iw] = a;
-      HIH[ml * nw + iw] = b;
-    }
-  }
-  __syncthreads();
-  float* y = p.out[0] + img * p.out_istride[0] + static_cast<long long>(m0) * W;
-  // row (W) pass: a thread owns the output pair (2 q, 2 q + 1) -- offw and W are even for the supported tap counts, the two
-  // outputs read the same L / 2 coefficients (q + offw / 2 - kk) with the even / odd taps
-  const int QW = W >> 1, oh = p.offw >> 1;
-  for (int ml = warp; ml < rows; ml += nwarps) {
-    const float* lo = LOH + ml * nw;
-    const float* hi = HIH + ml * nw;
-    for (int q = lane; q < QW; q += 32) {
-      float e = 0.f, o = 0.f;
-#pragma unroll
-      for (int kk = 0; kk < L / 2; ++kk) {
-        const int i = map_synthesis1(q + oh - kk, nw, p.periodic);
-        if (i >= 0) {
-          const float cl = lo[i], ch = hi[i];
-          e = fmaf(cl, p.t0[2 * kk], e);
-          e = fmaf(ch, p.t1[2 * kk], e);
-          o = fmaf(cl, p.t0[2 * kk + 1], o);
-          o = fmaf(ch, p.t1[2 * kk + 1], o);
-        }
-      }
-      *reinterpret_cast<float2*>(y + ml * W + 2 * q) = make_float2(e, o);
-    }
-  }
-}
-
-// ---------------------------------------------------------------- synthesis, second form (opt-in: WDNO_DWT2D_V2=1)
-// The row pass of the kernel above spends most of its 212 instructions per output on per-tap index maps (periodic wrap and
-// validity of every coefficient) -- profiles/r1e_dwt.md.  Here the column pass writes its result WITH the extension along W
+// (The first form of this kernel evaluated the periodic wrap / validity map of every coefficient once per TAP in its row pass:
+// 212 instructions per output, profiles/r1e_dwt.md; measured 41.3 us vs 34.6 us for this form on the Burgers shapes,
+// profiles/r2_dwt.md, and was removed.)  The column pass writes its result WITH the extension along W
 // already applied: LOX / HIX [T][WE], entry e <-> coefficient column e - P, P = (L/2 - 1) - offw/2, WE = W/2 + L/2 - 1 (the map is
 // evaluated once per staged column instead of once per tap), so the row pass of output pair q reads entries q + L/2 - 1 - kk
 // at compile-time offsets, without maps or branches.  Tap masks as in the analysis kernel.  Same sums in the same order.
@@ -358,11 +278,6 @@ unsigned nz_mask2(const float* t, int L) {
   return m;
 }
 
-bool v2_enabled() {
-  static const bool on = [] { const char* e = getenv("WDNO_DWT2D_V2"); return e && e[0] == '1'; }();
-  return on;
-}
-
 }  // namespace
 
 }  // namespace wdno
@@ -411,7 +326,7 @@ extern "C" int wdno_dwt2d_analysis(const float* x, float* const* bands4, const i
   dim3 grid(strips, static_cast<unsigned>(n_img));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   static size_t c2 = 0, c6 = 0, c10 = 0, m6 = 0, m10 = 0;
-  if (v2_enabled()) {   // opt-in: tap-mask variants for the filter pairs the reference uses (reversed bior1.3 / bior2.4 analysis taps)
+  {   // tap-mask variants for the filter pairs the reference uses (reversed bior1.3 / bior2.4 analysis taps: 2 / 3 non-zero high-pass taps)
     const unsigned nz1 = nz_mask2(taps_hi_host, L);
     if (L == 6 && !(nz1 & ~0x0Cu)) return launch2d(dwt2d_analysis_kernel<6, 0x3Fu, 0x0Cu>, m6, grid, smem, st, p, "dwt2d_analysis");
     if (L == 10 && !(nz1 & ~0x70u)) return launch2d(dwt2d_analysis_kernel<10, 0x3FFu, 0x70u>, m10, grid, smem, st, p, "dwt2d_analysis");
@@ -444,8 +359,7 @@ extern "C" int wdno_dwt2d_synthesis(const float* const* bands4, const int64_t* b
   p.v16 = !(nw & 3) ? 1 : 0;
   for (int i = 0; i < 4; ++i)
     if ((reinterpret_cast<uintptr_t>(bands4[i]) & 15) || (band_istride4[i] & 3)) p.v16 = 0;
-  const bool v2 = v2_enabled();
-  const size_t ws = v2 ? static_cast<size_t>(((W >> 1) + L / 2 - 1 + 1) & ~1) : static_cast<size_t>(nw);   // column-pass row stride
+  const size_t ws = static_cast<size_t>(((W >> 1) + L / 2 - 1 + 1) & ~1);   // column-pass row stride (extension staged)
   auto need = [&](int t) { return sizeof(float) * (4ull * (t / 2 + L / 2 + 1) * p.CS + 2ull * t * ws); };
   while (T > 2 && need(T) > kSmemBudget) T = (T + 1) / 2;
   const int strips = (H + T - 1) / T;
@@ -455,8 +369,8 @@ extern "C" int wdno_dwt2d_synthesis(const float* const* bands4, const int64_t* b
   const size_t smem = need(T);
   dim3 grid(strips, static_cast<unsigned>(n_img));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  static size_t c2 = 0, c6 = 0, c10 = 0, x2 = 0, x6 = 0, x10 = 0, m6 = 0, m10 = 0;
-  if (v2) {   // opt-in second form (extension-staged column pass, tap masks for the reference's reconstruction filters)
+  static size_t x2 = 0, x6 = 0, x10 = 0, m6 = 0, m10 = 0;
+  {   // tap masks for the reference's reconstruction filters
     const unsigned nz0 = nz_mask2(taps_lo_host, L);
     if (L == 6 && !(nz0 & ~0x0Cu)) return launch2d(dwt2d_synthesis_x_kernel<6, 0x0Cu, 0x3Fu>, m6, grid, smem, st, p, "dwt2d_synthesis");
     if (L == 10 && !(nz0 & ~0x38u)) return launch2d(dwt2d_synthesis_x_kernel<10, 0x38u, 0x3FFu>, m10, grid, smem, st, p, "dwt2d_synthesis");
@@ -464,7 +378,4 @@ extern "C" int wdno_dwt2d_synthesis(const float* const* bands4, const int64_t* b
     if (L == 10) return launch2d(dwt2d_synthesis_x_kernel<10, 0x3FFu, 0x3FFu>, x10, grid, smem, st, p, "dwt2d_synthesis");
     return launch2d(dwt2d_synthesis_x_kernel<2, 0x3u, 0x3u>, x2, grid, smem, st, p, "dwt2d_synthesis");
   }
-  if (L == 6) return launch2d(dwt2d_synthesis_kernel<6>, c6, grid, smem, st, p, "dwt2d_synthesis");
-  if (L == 10) return launch2d(dwt2d_synthesis_kernel<10>, c10, grid, smem, st, p, "dwt2d_synthesis");
-  return launch2d(dwt2d_synthesis_kernel<2>, c2, grid, smem, st, p, "dwt2d_synthesis");
 }

@@ -127,11 +127,13 @@ def guidance_fn_closed_form(x, args, shape, ori_shape, RESCALER, w_energy=0, w_i
 
 
 def make_design_fn(args, shape, ori_shape, RESCALER, closed_form=None):
-    """the `design_fn(x, low=, init=, init_u=)` closure of inference_2d.py:82-91.  closed_form=True (or WDNO_CLOSED_FORM_GUIDANCE=1)
-    evaluates the gradient with `guidance_fn_closed_form` instead of autograd (opt-in; same values)."""
+    """the `design_fn(x, low=, init=, init_u=)` closure of inference_2d.py:82-91.  The gradient is evaluated with
+    `guidance_fn_closed_form` (one waverec3, elementwise field gradient, one waverec3_adjoint: measured 5.60 ms per C5 step vs
+    5.92 ms through autograd, profiles/r2_bench_configs.jsonl; same values, tests/test_gpu_pipeline.py); closed_form=False or
+    WDNO_CLOSED_FORM_GUIDANCE=0 selects `guidance_fn` (torch.autograd.grad of the reference's objective through the kernels)."""
     if closed_form is None:
         import os
-        closed_form = os.environ.get("WDNO_CLOSED_FORM_GUIDANCE", "0") == "1"
+        closed_form = os.environ.get("WDNO_CLOSED_FORM_GUIDANCE", "1") != "0"
     guidance = guidance_fn_closed_form if closed_form else guidance_fn
 
     def design_fn(x, low=None, init=None, init_u=None):
