@@ -218,6 +218,13 @@ int wdno_mse_weighted(const float* pred, const float* target, const float* w, in
 int wdno_step_begin(int* step_dev, const float* time_table, const float* coef_table, float* time_out, float* coef_out,
                     int B, int n_steps, void* stream);
 
+/* Temporal attention block at C = 64 with both projections on tcgen05 (csrc/tattn_tc.cu): same operation and arguments as
+ * wdno_tattn_block, weights in the UMMA canonical K-major layout instead of mma.sync fragment order:
+ *   wqkv_canon fp16 [C/8][384][8]  (= to_qkv.weight[n][8c + j]),  wout_canon fp16 [16][C][8]  (= to_out.weight[n][8c + j]) */
+int wdno_tattn_block_tc(const void* x, void* y, const float* gamma, const void* wqkv_canon, const void* wout_canon,
+                        const float* bias, const float* rot_cos, const float* rot_sin, int64_t n_samples, int n_frames,
+                        int64_t hw, int C, float scale, float eps, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Training step (reference: Trainer.train, smoke/ddpm/diffusion_2d.py:1257-1307 and
  * burgers/ddpm_burgers/train_diffusion.py:187-237 -- there the backward is torch autograd over cuDNN/cuBLAS).

@@ -100,6 +100,19 @@ class TemporalBlock:
         assert w_qkv.shape[0] == 384 and self.C in (64, 128, 256) and tuple(w_out.shape[:2]) == (self.C, 128)
         self.gamma, self.wqk, self.wv, self.wo = (t.to(dev) for t in self._packed())
         self.scale = dim_head ** -0.5
+        # C = 64 (the full-resolution instances): projections on tcgen05 (csrc/tattn_tc.cu); WDNO_TATTN_TC=0 keeps the mma.sync kernel
+        import os
+        self.tc = self.C == 64 and os.environ.get("WDNO_TATTN_TC", "1") != "0"
+        if self.tc:
+            self.wqkv_c, self.wo_c = (t.to(dev) for t in self._packed_canon())
+
+    def _packed_canon(self):
+        """UMMA canonical K-major operands: [K/8][rows][8]"""
+        _, w_qkv, w_out = self._src
+        wq = w_qkv.detach().float().reshape(w_qkv.shape[0], -1)    # [384, C]
+        wo = w_out.detach().float().reshape(w_out.shape[0], -1)    # [C, 128]
+        canon = lambda w: w.reshape(w.shape[0], w.shape[1] // 8, 8).permute(1, 0, 2).contiguous().to(torch.float16)
+        return canon(wq), canon(wo)
 
     def _packed(self):
         gamma, w_qkv, w_out = self._src
@@ -111,6 +124,9 @@ class TemporalBlock:
     def refresh(self):
         for dst, src in zip((self.gamma, self.wqk, self.wv, self.wo), self._packed()):
             if dst.data_ptr() != src.data_ptr():
+                dst.copy_(src)
+        if self.tc:
+            for dst, src in zip((self.wqkv_c, self.wo_c), self._packed_canon()):
                 dst.copy_(src)
 
     def __call__(self, x, bias=None, rot=None, eps=1e-5):
@@ -127,6 +143,11 @@ class TemporalBlock:
         # algorithmic work (conv3d.py:262-353): one read + one write of the fp16 residual stream; projections + QK^T + PV
         with _timing.span("tattn_block", flops=2.0 * ntok * (self.C * 384 + 128 * self.C + 2 * 128 * D),
                           bytes=4.0 * ntok * self.C, meta=(self.C, B, D, H * W)):
+            if self.tc:
+                _lib.check(_lib.lib().wdno_tattn_block_tc(_p(x), _p(y), _p(self.gamma), _p(self.wqkv_c), _p(self.wo_c), _p(bias),
+                                                          _p(rc), _p(rs), B, D, H * W, self.C, self.scale, float(eps),
+                                                          _lib.current_stream_ptr()), "tattn_block_tc")
+                return y
             _lib.check(_lib.lib().wdno_tattn_block(_p(x), _p(y), _p(self.gamma), _p(self.wqk), _p(self.wv), _p(self.wo), _p(bias),
                                                    _p(rc), _p(rs), B, D, H * W, self.C, self.scale, float(eps),
                                                    _lib.current_stream_ptr()), "tattn_block")

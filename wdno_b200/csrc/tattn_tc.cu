@@ -1,0 +1,420 @@
+// Temporal attention block of the smoke U-Net at C = 64 (the four full-resolution instances: 14 % of a DDIM step) with the
+// projections on tcgen05:   y = x + to_out(softmax(rot(q) rot(k)^T + rel_pos_bias) v),  (q, k, v) = to_qkv(LayerNorm(x))
+// reference: Residual(PreNorm(dim, EinopsToAndFrom('b c f h w', 'b (h w) f c', Attention))), conv3d.py:165-184, 262-353, 383.
+//
+// Why: in the warp-per-pixel mma.sync kernel (attn_fused.cu) every warp streams all 64 KB of weight fragments through the
+// shared-memory port for ONE pixel's 32 token rows -- 0.034 B/FLOP against a 128 B/clk port caps it at half the tensor rate,
+// and 82 % of its MMAs are the two projections.  Here a CTA owns tiles of 4 pixels x 32 token rows = one M = 128 UMMA tile:
+//   raw tokens (cp.async, next tile prefetched) -> LayerNorm by the lane that owns the token -> A operand in the UMMA
+//   canonical K-major layout -> ONE thread issues  QKV[128 x 384] = A[128 x 64] Wqkv^T  (tcgen05.mma, weights resident in
+//   shared memory for the CTA's lifetime, accumulators in TMEM columns 0..383) -> each warp pulls ITS pixel's q / k / v rows
+//   out of TMEM (lane = token), applies scale + rotary, and runs the 24 x 24 attention of the four heads on mma.sync from a
+//   private fp16 staging tile (no block barrier) -> O[128 x 128] written straight into the canonical A layout ->
+//   Y[128 x 64] = O Wout^T (tcgen05.mma, TMEM columns 384..447) -> + residual from the raw tile -> 128-byte row stores.
+// HBM traffic: one read + one write of the fp16 residual stream (the algorithmic minimum); q / k / v / o never leave the SM.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/wdno_b200.h"
+#include "common.cuh"
+#include "cvt_sat.cuh"
+#include "mma_sync.cuh"
+#include "ptx.cuh"
+
+namespace wdno {
+
+namespace {
+
+constexpr int C = 64, kHid = 128, kQkv = 384;
+constexpr int kThreads = 128;
+constexpr int kRawPitch = C * 2 + 16;            // 144 B per raw token row
+constexpr int kStPitch = 40;                     // halfs per staging row (80 B)
+constexpr int BS = 40, RS = 20;                  // bias / rotary table pitches
+// shared-memory map (bytes)
+constexpr int oBar = 0;                                   // 2 mbarriers + tmem base
+constexpr int oWq = 128;                                  // [8][384][8] fp16
+constexpr int oWo = oWq + kQkv * C * 2;                   // [16][64][8] fp16
+constexpr int oAO = oWo + C * kHid * 2;                   // A [8][128][8] (16 KB) aliased by O [16][128][8] (32 KB)
+constexpr int oRaw = oAO + 128 * kHid * 2;                // 2 x [128][144 B]
+constexpr int oStage = oRaw + 2 * 128 * kRawPitch;        // 4 warps x 3 x [32][80 B]
+constexpr int oBias = oStage + 4 * 3 * 32 * kStPitch * 2; // [4][32][BS] fp32
+constexpr int oRot = oBias + 4 * 32 * BS * 4;             // [32][RS] float2
+constexpr int oGamma = oRot + 32 * RS * 8;                // [C] fp32
+constexpr int kSmem = oGamma + C * 4;
+
+__device__ __forceinline__ uint64_t desc(uint32_t saddr, uint32_t lbo16) {
+  // K-major, no swizzle: start >> 4 | (LBO >> 4) << 16 | (SBO = 128 B >> 4) << 32 | version 1 << 46
+  return static_cast<uint64_t>(((saddr >> 4) & 0x3FFFu) | (lbo16 << 16)) | (static_cast<uint64_t>(8u | (1u << 14)) << 32);
+}
+
+__global__ void __launch_bounds__(kThreads, 1) tattn_tc_kernel(const __half* __restrict__ x, __half* __restrict__ y,
+                                                               const float* __restrict__ gamma, const uint4* __restrict__ wq,
+                                                               const uint4* __restrict__ wo, const float* __restrict__ bias,
+                                                               const float* __restrict__ rot_cos, const float* __restrict__ rot_sin,
+                                                               long long n_pix, long long hw, int n, float scale, float eps) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + oBar);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + oBar + 32);
+  float* sbias = reinterpret_cast<float*>(smem + oBias);
+  float2* scs = reinterpret_cast<float2*>(smem + oRot);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, q = lane & 3;
+  const uint32_t s0 = ptx::smem_u32(smem);
+  pdl_trigger();
+
+  // ---------------------------------------------------------------- one-time setup: weights, tables, TMEM, barriers
+  for (int i = tid; i < kQkv * C / 8; i += kThreads) reinterpret_cast<uint4*>(smem + oWq)[i] = __ldg(wq + i);
+  for (int i = tid; i < C * kHid / 8; i += kThreads) reinterpret_cast<uint4*>(smem + oWo)[i] = __ldg(wo + i);
+  for (int i = tid; i < 4 * 32 * 32; i += kThreads) {
+    const int hh = i >> 10, r = (i >> 5) & 31, c = i & 31;
+    float b = 0.f;
+    if (c >= n) b = -INFINITY;
+    else if (r < n && bias != nullptr) b = __ldg(bias + (static_cast<size_t>(hh) * n + r) * n + c);
+    sbias[(hh * 32 + r) * BS + c] = b;
+  }
+  for (int i = tid; i < 32 * 16; i += kThreads) {
+    const int f = i >> 4;
+    scs[f * RS + (i & 15)] = make_float2((rot_cos != nullptr && f < n) ? __ldg(rot_cos + f * 16 + (i & 15)) : 1.0f,
+                                         (rot_sin != nullptr && f < n) ? __ldg(rot_sin + f * 16 + (i & 15)) : 0.0f);
+  }
+  for (int i = tid; i < 128 * kHid / 8; i += kThreads) reinterpret_cast<uint4*>(smem + oAO)[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = tid; i < 4 * 3 * 32 * kStPitch / 8; i += kThreads) reinterpret_cast<uint4*>(smem + oStage)[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (tid == 0) {
+    ptx::mbar_init(&bars[0], 1);
+    ptx::mbar_init(&bars[1], 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 0) {
+    ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  float* sgm = reinterpret_cast<float*>(smem + oGamma);
+  for (int j = tid; j < C; j += kThreads) sgm[j] = __ldg(gamma + j);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t lane_t = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+  pdl_wait();
+
+  const long long n_tiles = (n_pix + 3) >> 2;
+  const int row = warp * 32 + lane;                       // this thread's row of the M = 128 tile (pixel slot = warp, token = lane)
+  const bool tok = lane < n;
+  // staging tiles of this warp
+  __half* Qs = reinterpret_cast<__half*>(smem + oStage) + warp * 3 * 32 * kStPitch;
+  __half* Ks = Qs + 32 * kStPitch;
+  __half* Vs = Ks + 32 * kStPitch;
+  const uint32_t qs_s = ptx::smem_u32(Qs), ks_s = ptx::smem_u32(Ks), vs_s = ptx::smem_u32(Vs);
+  const uint32_t a_off = static_cast<uint32_t>(((lane & 15) * kStPitch + 8 * (lane >> 4)) * 2);        // A frags: rows = queries
+  const uint32_t k_off = static_cast<uint32_t>(((lane & 7) * kStPitch + 8 * (lane >> 3)) * 2);         // B frags of K: 4 dim chunks
+  const uint32_t v_off = static_cast<uint32_t>((((lane & 7) + 8 * ((lane >> 3) & 1)) * kStPitch + 8 * (lane >> 4)) * 2);  // trans
+
+  auto prefetch = [&](long long tile, int buf) {
+    const long long pix = tile * 4 + warp;
+    if (tile < n_tiles && pix < n_pix && tok) {
+      const long long bimg = pix / hw, pin = pix - bimg * hw;
+      const __half* src = x + ((bimg * n + lane) * hw + pin) * C;
+      const uint32_t dst = s0 + oRaw + buf * 128 * kRawPitch + row * kRawPitch;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) ptx::cp_async16_zfill(dst + c * 16, src + c * 8, 16u);
+    }
+    ptx::cp_async_commit();
+  };
+
+  uint32_t ph = 0;
+  int it = 0;
+  prefetch(blockIdx.x, 0);
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    const int buf = it & 1;
+    prefetch(tile + gridDim.x, buf ^ 1);
+    ptx::cp_async_wait<1>();                              // this thread's own row of the current tile has landed
+    const long long pix = tile * 4 + warp;
+    const bool live = tok && pix < n_pix;
+    const uint8_t* rawrow = smem + oRaw + buf * 128 * kRawPitch + row * kRawPitch;
+
+    // ---- LayerNorm of the token this lane owns -> A operand [C/8][128][8]
+    {
+      float f[C];
+      float sum = 0.f;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (live) v = *reinterpret_cast<const uint4*>(rawrow + c * 16);
+        const __half2* hh = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 t = __half22float2(hh[j]);
+          f[c * 8 + 2 * j] = t.x;
+          f[c * 8 + 2 * j + 1] = t.y;
+          sum += t.x + t.y;
+        }
+      }
+      const float mean = sum * (1.0f / C);
+      float sq = 0.f;
+#pragma unroll
+      for (int j = 0; j < C; ++j) {
+        f[j] -= mean;
+        sq = fmaf(f[j], f[j], sq);
+      }
+      const float rstd = live ? rsqrtf(sq * (1.0f / C) + eps) : 0.f;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint4 ov;
+        uint32_t* o = reinterpret_cast<uint32_t*>(&ov);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 gg = *reinterpret_cast<const float2*>(sgm + c * 8 + 2 * j);   // broadcast read
+          o[j] = pack_h2(f[c * 8 + 2 * j] * rstd * gg.x, f[c * 8 + 2 * j + 1] * rstd * gg.y);
+        }
+        *reinterpret_cast<uint4*>(smem + oAO + (c * 128 + row) * 16) = ov;
+      }
+    }
+    ptx::fence_proxy_async_smem();
+    ptx::tc_fence_before();
+    __syncthreads();
+    // ---- QKV = A Wqkv^T : M = 128, N = 256 + 128, K = 64 (4 k-steps)
+    if (tid == 0) {
+      ptx::tc_fence_after();
+      const uint32_t id256 = ptx::make_idesc_f16(256, 0), id128 = ptx::make_idesc_f16(128, 0);
+#pragma unroll
+      for (int ks = 0; ks < C / 16; ++ks) {
+        const uint64_t ad = desc(s0 + oAO + ks * 2 * 128 * 16, 128u);
+        const uint64_t bd = desc(s0 + oWq + ks * 2 * kQkv * 16, static_cast<uint32_t>(kQkv));
+        ptx::tc_mma_f16(tmem, ad, bd, id256, ks > 0 ? 1u : 0u);
+        ptx::tc_mma_f16(tmem + 256u, ad, bd + 256u, id128, ks > 0 ? 1u : 0u);   // rows 256..383 of Wqkv: + 256 x 16 B
+      }
+      ptx::tc_commit(&bars[0]);
+    }
+    ptx::mbar_wait(&bars[0], ph);
+    ptx::tc_fence_after();
+
+    // ---- attention of this warp's pixel, head by head (all warp-local)
+#pragma unroll 1
+    for (int h = 0; h < 4; ++h) {
+      {
+        uint32_t r[32];
+        // q: scale + rotary (position = lane)
+        ptx::tmem_ld32(lane_t + static_cast<uint32_t>(h * 32), r);
+        ptx::tmem_ld_wait();
+        __syncwarp();   // previous head's fragments have been read
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint4 ov;
+          uint32_t* o = reinterpret_cast<uint32_t*>(&ov);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 cs = scs[lane * RS + c * 4 + j];
+            const float a = __uint_as_float(r[c * 8 + 2 * j]) * scale, b = __uint_as_float(r[c * 8 + 2 * j + 1]) * scale;
+            o[j] = pack_h2(a * cs.x - b * cs.y, b * cs.x + a * cs.y);
+          }
+          *reinterpret_cast<uint4*>(Qs + lane * kStPitch + c * 8) = ov;
+        }
+        ptx::tmem_ld32(lane_t + static_cast<uint32_t>(kHid + h * 32), r);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint4 ov;
+          uint32_t* o = reinterpret_cast<uint32_t*>(&ov);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 cs = scs[lane * RS + c * 4 + j];
+            const float a = __uint_as_float(r[c * 8 + 2 * j]), b = __uint_as_float(r[c * 8 + 2 * j + 1]);
+            o[j] = pack_h2(a * cs.x - b * cs.y, b * cs.x + a * cs.y);
+          }
+          *reinterpret_cast<uint4*>(Ks + lane * kStPitch + c * 8) = ov;
+        }
+        ptx::tmem_ld32(lane_t + static_cast<uint32_t>(2 * kHid + h * 32), r);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint4 ov;
+          uint32_t* o = reinterpret_cast<uint32_t*>(&ov);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) o[j] = pack_h2(__uint_as_float(r[c * 8 + 2 * j]), __uint_as_float(r[c * 8 + 2 * j + 1]));
+          *reinterpret_cast<uint4*>(Vs + lane * kStPitch + c * 8) = ov;
+        }
+      }
+      __syncwarp();
+      // S = Q K^T (+ bias, keys >= n masked by the table), softmax over the keys
+      uint32_t qa[2][2][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks)
+          ldsm_x4(qs_s + a_off + static_cast<uint32_t>((mt * 16 * kStPitch + ks * 16) * 2), qa[mt][ks][0], qa[mt][ks][1], qa[mt][ks][2],
+                  qa[mt][ks][3]);
+      float sfr[2][4][4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4(ks_s + k_off + static_cast<uint32_t>(j * 8 * kStPitch * 2), b0, b1, b2, b3);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) sfr[mt][j][c] = 0.f;
+          mma16816(sfr[mt][j], qa[mt][0], b0, b1);
+          mma16816(sfr[mt][j], qa[mt][1], b2, b3);
+        }
+      }
+      uint32_t pa[2][2][4];
+      float inv[2][2];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const float* brow = sbias + (h * 32 + 16 * mt + g + 8 * r) * BS + 2 * q;
+          float mx = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 bv = *reinterpret_cast<const float2*>(brow + 8 * j);
+            sfr[mt][j][2 * r] += bv.x;
+            sfr[mt][j][2 * r + 1] += bv.y;
+            mx = fmaxf(mx, fmaxf(sfr[mt][j][2 * r], sfr[mt][j][2 * r + 1]));
+          }
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+          float sum = 0.f;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float p0 = __expf(sfr[mt][j][2 * r] - mx), p1 = __expf(sfr[mt][j][2 * r + 1] - mx);
+            sfr[mt][j][2 * r] = p0;
+            sfr[mt][j][2 * r + 1] = p1;
+            sum += p0 + p1;
+          }
+          sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+          sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+          inv[mt][r] = 1.0f / sum;
+        }
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+          pa[mt][kk][0] = pack_h2(sfr[mt][2 * kk][0], sfr[mt][2 * kk][1]);
+          pa[mt][kk][1] = pack_h2(sfr[mt][2 * kk][2], sfr[mt][2 * kk][3]);
+          pa[mt][kk][2] = pack_h2(sfr[mt][2 * kk + 1][0], sfr[mt][2 * kk + 1][1]);
+          pa[mt][kk][3] = pack_h2(sfr[mt][2 * kk + 1][2], sfr[mt][2 * kk + 1][3]);
+        }
+      }
+      // O = P V (V^T fragments by ldmatrix.trans), normalised, written into the canonical A layout of the output projection
+#pragma unroll
+      for (int np = 0; np < 2; ++np) {      // pairs of 8-wide dim tiles
+        float ofr[2][2][4];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) ofr[i][j][c] = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+          uint32_t b0, b1, b2, b3;
+          asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                       : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3)
+                       : "r"(vs_s + v_off + static_cast<uint32_t>((kk * 16 * kStPitch + np * 16) * 2)));
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) {
+            mma16816(ofr[mt][0], pa[mt][kk], b0, b1);
+            mma16816(ofr[mt][1], pa[mt][kk], b2, b3);
+          }
+        }
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const int chunk = h * 4 + np * 2 + j;       // 8-channel chunk of the 128 hidden channels
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+              const int rr = warp * 32 + 16 * mt + g + 8 * r;
+              *reinterpret_cast<uint32_t*>(smem + oAO + (chunk * 128 + rr) * 16 + q * 4) =
+                  pack_h2(ofr[mt][j][2 * r] * inv[mt][r], ofr[mt][j][2 * r + 1] * inv[mt][r]);
+            }
+          }
+      }
+    }
+    ptx::fence_proxy_async_smem();
+    ptx::tc_fence_before();
+    __syncthreads();
+    // ---- Y = O Wout^T : M = 128, N = 64, K = 128 (8 k-steps), TMEM columns 384..447
+    if (tid == 0) {
+      ptx::tc_fence_after();
+      const uint32_t id64 = ptx::make_idesc_f16(64, 0);
+#pragma unroll
+      for (int ks = 0; ks < kHid / 16; ++ks) {
+        const uint64_t ad = desc(s0 + oAO + ks * 2 * 128 * 16, 128u);
+        const uint64_t bd = desc(s0 + oWo + ks * 2 * C * 16, static_cast<uint32_t>(C));
+        ptx::tc_mma_f16(tmem + 384u, ad, bd, id64, ks > 0 ? 1u : 0u);
+      }
+      ptx::tc_commit(&bars[1]);
+    }
+    ptx::mbar_wait(&bars[1], ph);
+    ptx::tc_fence_after();
+    ph ^= 1u;
+    // ---- y = Y + x : this lane's token row (128 B), residual from the raw tile
+    {
+      uint32_t r0[32], r1[32];
+      ptx::tmem_ld32(lane_t + 384u, r0);
+      ptx::tmem_ld32(lane_t + 416u, r1);
+      ptx::tmem_ld_wait();
+      if (live) {
+        const long long bimg = pix / hw, pin = pix - bimg * hw;
+        __half* dst = y + ((bimg * n + lane) * hw + pin) * C;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint4 xv = *reinterpret_cast<const uint4*>(rawrow + c * 16);
+          const __half2* xh = reinterpret_cast<const __half2*>(&xv);
+          uint4 ov;
+          __half2* oh = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int col = c * 8 + 2 * j;
+            const float2 xr = __half22float2(xh[j]);
+            const float a = __uint_as_float(col < 32 ? r0[col] : r1[col - 32]) + xr.x;
+            const float b = __uint_as_float(col < 32 ? r0[col + 1] : r1[col - 31]) + xr.y;
+            oh[j] = h2_sat(a, b);
+          }
+          *reinterpret_cast<uint4*>(dst + c * 8) = ov;
+        }
+      }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();   // TMEM and the A / O region are free for the next tile
+  }
+  ptx::cp_async_wait<0>();
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem, 512);
+  }
+}
+
+}  // namespace
+
+}  // namespace wdno
+
+extern "C" int wdno_tattn_block_tc(const void* x, void* y, const float* gamma, const void* wqkv_canon, const void* wout_canon,
+                                   const float* bias, const float* rot_cos, const float* rot_sin, int64_t n_samples, int n_frames,
+                                   int64_t hw, int C, float scale, float eps, void* stream) {
+  using namespace wdno;
+  if (!x || !y || !gamma || !wqkv_canon || !wout_canon || n_samples < 1 || hw < 1)
+    return set_error(WDNO_E_INVALID, "tattn_block_tc: bad arguments");
+  if (C != 64) return set_error(WDNO_E_INVALID, "tattn_block_tc: built for C = 64 (use wdno_tattn_block otherwise)");
+  if (n_frames < 1 || n_frames > 32) return set_error(WDNO_E_INVALID, "tattn_block_tc: frames must be in [1,32]");
+  if ((rot_cos == nullptr) != (rot_sin == nullptr)) return set_error(WDNO_E_INVALID, "tattn_block_tc: rotary tables must both be given");
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(tattn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    if (e != cudaSuccess) return set_cuda_error(e, "tattn_block_tc: cudaFuncSetAttribute");
+    configured = true;
+  }
+  const long long n_pix = n_samples * hw;
+  const long long tiles = (n_pix + 3) / 4;
+  const long long cap = num_sms();
+  const unsigned grid = static_cast<unsigned>(tiles < cap ? tiles : cap);
+  cudaError_t le = launch_pdl(tattn_tc_kernel, dim3(grid), dim3(kThreads), static_cast<size_t>(kSmem), static_cast<cudaStream_t>(stream),
+                              static_cast<const __half*>(x), static_cast<__half*>(y), gamma, static_cast<const uint4*>(wqkv_canon),
+                              static_cast<const uint4*>(wout_canon), bias, rot_cos, rot_sin, n_pix, static_cast<long long>(hw), n_frames,
+                              scale, eps);
+  if (le != cudaSuccess) return set_cuda_error(le, "tattn_block_tc: launch");
+  return check_launch("tattn_block_tc");
+}
