@@ -28,21 +28,25 @@ namespace wdno {
 namespace {
 
 constexpr int C = 64, kHid = 128, kQkv = 384;
-constexpr int kThreads = 128;
+constexpr int kThreads = 512;                    // 16 warps: warp = 4 * head + pixel slot (TMEM lane quarter = warp % 4)
 constexpr int kRawPitch = C * 2 + 16;            // 144 B per raw token row
-constexpr int kStPitch = 40;                     // halfs per staging row (80 B)
-constexpr int BS = 40, RS = 20;                  // bias / rotary table pitches
+constexpr int kStRow = 64;                       // bytes per staging row: 32 halfs, 16-byte chunks XOR-swizzled by (row >> 1) & 3
+constexpr int BS = 40, RS = 20;                  // bias (fp16) / rotary table pitches
 // shared-memory map (bytes)
 constexpr int oBar = 0;                                   // 2 mbarriers + tmem base
 constexpr int oWq = 128;                                  // [8][384][8] fp16
 constexpr int oWo = oWq + kQkv * C * 2;                   // [16][64][8] fp16
 constexpr int oAO = oWo + C * kHid * 2;                   // A [8][128][8] (16 KB) aliased by O [16][128][8] (32 KB)
-constexpr int oRaw = oAO + 128 * kHid * 2;                // 2 x [128][144 B]
-constexpr int oStage = oRaw + 2 * 128 * kRawPitch;        // 4 warps x 3 x [32][80 B]
-constexpr int oBias = oStage + 4 * 3 * 32 * kStPitch * 2; // [4][32][BS] fp32
-constexpr int oRot = oBias + 4 * 32 * BS * 4;             // [32][RS] float2
+constexpr int oRaw = oAO + 128 * kHid * 2;                // [128][144 B]: next tile's raw tokens (LayerNorm input)
+constexpr int oStage = oRaw + 128 * kRawPitch;            // 16 warps x 3 x [32][64 B]
+constexpr int oBias = oStage + 16 * 3 * 32 * kStRow;      // [4][32][BS] fp16
+constexpr int oRot = oBias + 4 * 32 * BS * 2;             // [32][RS] float2
 constexpr int oGamma = oRot + 32 * RS * 8;                // [C] fp32
 constexpr int kSmem = oGamma + C * 4;
+static_assert(kSmem <= 227 * 1024, "tattn_tc shared-memory plan");
+
+// byte offset of 16-byte chunk `c` of staging row `r`
+__device__ __forceinline__ uint32_t st_off(int r, int c) { return static_cast<uint32_t>(r * kStRow + ((c ^ ((r >> 1) & 3)) << 4)); }
 
 __device__ __forceinline__ uint64_t desc(uint32_t saddr, uint32_t lbo16) {
   // K-major, no swizzle: start >> 4 | (LBO >> 4) << 16 | (SBO = 128 B >> 4) << 32 | version 1 << 46
@@ -57,7 +61,7 @@ __global__ void __launch_bounds__(kThreads, 1) tattn_tc_kernel(const __half* __r
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + oBar);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + oBar + 32);
-  float* sbias = reinterpret_cast<float*>(smem + oBias);
+  __half* sbias = reinterpret_cast<__half*>(smem + oBias);
   float2* scs = reinterpret_cast<float2*>(smem + oRot);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, q = lane & 3;
@@ -72,7 +76,7 @@ __global__ void __launch_bounds__(kThreads, 1) tattn_tc_kernel(const __half* __r
     float b = 0.f;
     if (c >= n) b = -INFINITY;
     else if (r < n && bias != nullptr) b = __ldg(bias + (static_cast<size_t>(hh) * n + r) * n + c);
-    sbias[(hh * 32 + r) * BS + c] = b;
+    sbias[(hh * 32 + r) * BS + c] = __float2half(b);
   }
   for (int i = tid; i < 32 * 16; i += kThreads) {
     const int f = i >> 4;
@@ -80,7 +84,7 @@ __global__ void __launch_bounds__(kThreads, 1) tattn_tc_kernel(const __half* __r
                                          (rot_sin != nullptr && f < n) ? __ldg(rot_sin + f * 16 + (i & 15)) : 0.0f);
   }
   for (int i = tid; i < 128 * kHid / 8; i += kThreads) reinterpret_cast<uint4*>(smem + oAO)[i] = make_uint4(0u, 0u, 0u, 0u);
-  for (int i = tid; i < 4 * 3 * 32 * kStPitch / 8; i += kThreads) reinterpret_cast<uint4*>(smem + oStage)[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = tid; i < 16 * 3 * 32 * kStRow / 16; i += kThreads) reinterpret_cast<uint4*>(smem + oStage)[i] = make_uint4(0u, 0u, 0u, 0u);
   if (tid == 0) {
     ptx::mbar_init(&bars[0], 1);
     ptx::mbar_init(&bars[1], 1);
@@ -96,46 +100,43 @@ __global__ void __launch_bounds__(kThreads, 1) tattn_tc_kernel(const __half* __r
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t lane_t = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+  const int slot = warp & 3, head = warp >> 2;            // pixel slot (= TMEM lane quarter) and head of this warp
+  const uint32_t lane_t = tmem + (static_cast<uint32_t>(slot * 32) << 16);
   pdl_wait();
 
   const long long n_tiles = (n_pix + 3) >> 2;
-  const int row = warp * 32 + lane;                       // this thread's row of the M = 128 tile (pixel slot = warp, token = lane)
+  const int row = slot * 32 + lane;                       // this thread's row of the M = 128 tile (token = lane)
   const bool tok = lane < n;
-  // staging tiles of this warp
-  __half* Qs = reinterpret_cast<__half*>(smem + oStage) + warp * 3 * 32 * kStPitch;
-  __half* Ks = Qs + 32 * kStPitch;
-  __half* Vs = Ks + 32 * kStPitch;
+  // staging tiles of this warp: q', k', v rows of ITS head
+  uint8_t* Qs = smem + oStage + warp * 3 * 32 * kStRow;
+  uint8_t* Ks = Qs + 32 * kStRow;
+  uint8_t* Vs = Ks + 32 * kStRow;
   const uint32_t qs_s = ptx::smem_u32(Qs), ks_s = ptx::smem_u32(Ks), vs_s = ptx::smem_u32(Vs);
-  const uint32_t a_off = static_cast<uint32_t>(((lane & 15) * kStPitch + 8 * (lane >> 4)) * 2);        // A frags: rows = queries
-  const uint32_t k_off = static_cast<uint32_t>(((lane & 7) * kStPitch + 8 * (lane >> 3)) * 2);         // B frags of K: 4 dim chunks
-  const uint32_t v_off = static_cast<uint32_t>((((lane & 7) + 8 * ((lane >> 3) & 1)) * kStPitch + 8 * (lane >> 4)) * 2);  // trans
 
-  auto prefetch = [&](long long tile, int buf) {
-    const long long pix = tile * 4 + warp;
-    if (tile < n_tiles && pix < n_pix && tok) {
-      const long long bimg = pix / hw, pin = pix - bimg * hw;
-      const __half* src = x + ((bimg * n + lane) * hw + pin) * C;
-      const uint32_t dst = s0 + oRaw + buf * 128 * kRawPitch + row * kRawPitch;
+  // warps 0..3 (head 0) fetch the raw rows of a tile: lane = token
+  auto prefetch = [&](long long tile) {
+    if (head == 0) {
+      const long long pix = tile * 4 + slot;
+      if (tile < n_tiles && pix < n_pix && tok) {
+        const long long bimg = pix / hw, pin = pix - bimg * hw;
+        const __half* src = x + ((bimg * n + lane) * hw + pin) * C;
+        const uint32_t dst = s0 + oRaw + row * kRawPitch;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) ptx::cp_async16_zfill(dst + c * 16, src + c * 8, 16u);
+        for (int c = 0; c < 8; ++c) ptx::cp_async16_zfill(dst + c * 16, src + c * 8, 16u);
+      }
+      ptx::cp_async_commit();
     }
-    ptx::cp_async_commit();
   };
 
   uint32_t ph = 0;
-  int it = 0;
-  prefetch(blockIdx.x, 0);
-  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-    const int buf = it & 1;
-    prefetch(tile + gridDim.x, buf ^ 1);
-    ptx::cp_async_wait<1>();                              // this thread's own row of the current tile has landed
-    const long long pix = tile * 4 + warp;
+  prefetch(blockIdx.x);
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long pix = tile * 4 + slot;
     const bool live = tok && pix < n_pix;
-    const uint8_t* rawrow = smem + oRaw + buf * 128 * kRawPitch + row * kRawPitch;
-
-    // ---- LayerNorm of the token this lane owns -> A operand [C/8][128][8]
-    {
+    // ---- LayerNorm of the token this lane owns (warps 0..3) -> A operand [C/8][128][8]
+    if (head == 0) {
+      ptx::cp_async_wait<0>();                            // this thread's own row has landed
+      const uint8_t* rawrow = smem + oRaw + row * kRawPitch;
       float f[C];
       float sum = 0.f;
 #pragma unroll
@@ -170,6 +171,7 @@ __global__ void __launch_bounds__(kThreads, 1) tattn_tc_kernel(const __half* __r
         }
         *reinterpret_cast<uint4*>(smem + oAO + (c * 128 + row) * 16) = ov;
       }
+      prefetch(tile + gridDim.x);                         // the raw tile is consumed: fetch the next one behind the MMAs / attention
     }
     ptx::fence_proxy_async_smem();
     ptx::tc_fence_before();
@@ -190,15 +192,14 @@ __global__ void __launch_bounds__(kThreads, 1) tattn_tc_kernel(const __half* __r
     ptx::mbar_wait(&bars[0], ph);
     ptx::tc_fence_after();
 
-    // ---- attention of this warp's pixel, head by head (all warp-local)
-#pragma unroll 1
-    for (int h = 0; h < 4; ++h) {
+    // ---- attention of (pixel slot, head) = this warp: all warp-local, 16 warps in flight
+    {
+      const int h = head;
       {
         uint32_t r[32];
         // q: scale + rotary (position = lane)
         ptx::tmem_ld32(lane_t + static_cast<uint32_t>(h * 32), r);
         ptx::tmem_ld_wait();
-        __syncwarp();   // previous head's fragments have been read
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           uint4 ov;
@@ -209,7 +210,7 @@ __global__ void __launch_bounds__(kThreads, 1) tattn_tc_kernel(const __half* __r
             const float a = __uint_as_float(r[c * 8 + 2 * j]) * scale, b = __uint_as_float(r[c * 8 + 2 * j + 1]) * scale;
             o[j] = pack_h2(a * cs.x - b * cs.y, b * cs.x + a * cs.y);
           }
-          *reinterpret_cast<uint4*>(Qs + lane * kStPitch + c * 8) = ov;
+          *reinterpret_cast<uint4*>(Qs + st_off(lane, c)) = ov;
         }
         ptx::tmem_ld32(lane_t + static_cast<uint32_t>(kHid + h * 32), r);
         ptx::tmem_ld_wait();
@@ -223,7 +224,7 @@ __global__ void __launch_bounds__(kThreads, 1) tattn_tc_kernel(const __half* __r
             const float a = __uint_as_float(r[c * 8 + 2 * j]), b = __uint_as_float(r[c * 8 + 2 * j + 1]);
             o[j] = pack_h2(a * cs.x - b * cs.y, b * cs.x + a * cs.y);
           }
-          *reinterpret_cast<uint4*>(Ks + lane * kStPitch + c * 8) = ov;
+          *reinterpret_cast<uint4*>(Ks + st_off(lane, c)) = ov;
         }
         ptx::tmem_ld32(lane_t + static_cast<uint32_t>(2 * kHid + h * 32), r);
         ptx::tmem_ld_wait();
@@ -233,7 +234,7 @@ __global__ void __launch_bounds__(kThreads, 1) tattn_tc_kernel(const __half* __r
           uint32_t* o = reinterpret_cast<uint32_t*>(&ov);
 #pragma unroll
           for (int j = 0; j < 4; ++j) o[j] = pack_h2(__uint_as_float(r[c * 8 + 2 * j]), __uint_as_float(r[c * 8 + 2 * j + 1]));
-          *reinterpret_cast<uint4*>(Vs + lane * kStPitch + c * 8) = ov;
+          *reinterpret_cast<uint4*>(Vs + st_off(lane, c)) = ov;
         }
       }
       __syncwarp();
@@ -242,14 +243,13 @@ __global__ void __launch_bounds__(kThreads, 1) tattn_tc_kernel(const __half* __r
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-        for (int ks = 0; ks < 2; ++ks)
-          ldsm_x4(qs_s + a_off + static_cast<uint32_t>((mt * 16 * kStPitch + ks * 16) * 2), qa[mt][ks][0], qa[mt][ks][1], qa[mt][ks][2],
-                  qa[mt][ks][3]);
+        for (int ks = 0; ks < 2; ++ks)   // A frags: rows = queries mt*16 + (lane & 15), dim chunk 2 ks + (lane >> 4)
+          ldsm_x4(qs_s + st_off(mt * 16 + (lane & 15), 2 * ks + (lane >> 4)), qa[mt][ks][0], qa[mt][ks][1], qa[mt][ks][2], qa[mt][ks][3]);
       float sfr[2][4][4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        uint32_t b0, b1, b2, b3;
-        ldsm_x4(ks_s + k_off + static_cast<uint32_t>(j * 8 * kStPitch * 2), b0, b1, b2, b3);
+        uint32_t b0, b1, b2, b3;         // B frags of K: keys j*8 + (lane & 7), dim chunk lane >> 3
+        ldsm_x4(ks_s + st_off(j * 8 + (lane & 7), lane >> 3), b0, b1, b2, b3);
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) {
 #pragma unroll
@@ -264,11 +264,11 @@ __global__ void __launch_bounds__(kThreads, 1) tattn_tc_kernel(const __half* __r
       for (int mt = 0; mt < 2; ++mt) {
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
-          const float* brow = sbias + (h * 32 + 16 * mt + g + 8 * r) * BS + 2 * q;
+          const __half* brow = sbias + (h * 32 + 16 * mt + g + 8 * r) * BS + 2 * q;
           float mx = -INFINITY;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const float2 bv = *reinterpret_cast<const float2*>(brow + 8 * j);
+            const float2 bv = __half22float2(*reinterpret_cast<const __half2*>(brow + 8 * j));
             sfr[mt][j][2 * r] += bv.x;
             sfr[mt][j][2 * r + 1] += bv.y;
             mx = fmaxf(mx, fmaxf(sfr[mt][j][2 * r], sfr[mt][j][2 * r + 1]));
@@ -307,10 +307,10 @@ __global__ void __launch_bounds__(kThreads, 1) tattn_tc_kernel(const __half* __r
             for (int c = 0; c < 4; ++c) ofr[i][j][c] = 0.f;
 #pragma unroll
         for (int kk = 0; kk < 2; ++kk) {
-          uint32_t b0, b1, b2, b3;
+          uint32_t b0, b1, b2, b3;         // keys kk*16 + (lane & 7) + 8 ((lane >> 3) & 1), dim chunk 2 np + (lane >> 4)
           asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
                        : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3)
-                       : "r"(vs_s + v_off + static_cast<uint32_t>((kk * 16 * kStPitch + np * 16) * 2)));
+                       : "r"(vs_s + st_off(kk * 16 + (lane & 7) + 8 * ((lane >> 3) & 1), 2 * np + (lane >> 4))));
 #pragma unroll
           for (int mt = 0; mt < 2; ++mt) {
             mma16816(ofr[mt][0], pa[mt][kk], b0, b1);
@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(kThreads, 1) tattn_tc_kernel(const __half* __r
             const int chunk = h * 4 + np * 2 + j;       // 8-channel chunk of the 128 hidden channels
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
-              const int rr = warp * 32 + 16 * mt + g + 8 * r;
+              const int rr = slot * 32 + 16 * mt + g + 8 * r;
               *reinterpret_cast<uint32_t*>(smem + oAO + (chunk * 128 + rr) * 16 + q * 4) =
                   pack_h2(ofr[mt][j][2 * r] * inv[mt][r], ofr[mt][j][2 * r + 1] * inv[mt][r]);
             }
@@ -349,30 +349,26 @@ __global__ void __launch_bounds__(kThreads, 1) tattn_tc_kernel(const __half* __r
     ptx::mbar_wait(&bars[1], ph);
     ptx::tc_fence_after();
     ph ^= 1u;
-    // ---- y = Y + x : this lane's token row (128 B), residual from the raw tile
+    // ---- y = Y + x : warp (slot, head) stores columns 16 head .. 16 head + 15 of its pixel's token rows (residual re-read: L2)
     {
-      uint32_t r0[32], r1[32];
-      ptx::tmem_ld32(lane_t + 384u, r0);
-      ptx::tmem_ld32(lane_t + 416u, r1);
+      uint32_t r0[16];
+      ptx::tmem_ld16(lane_t + 384u + static_cast<uint32_t>(head * 16), r0);
       ptx::tmem_ld_wait();
       if (live) {
         const long long bimg = pix / hw, pin = pix - bimg * hw;
-        __half* dst = y + ((bimg * n + lane) * hw + pin) * C;
+        const size_t off = static_cast<size_t>(((bimg * n + lane) * hw + pin) * C + head * 16);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const uint4 xv = *reinterpret_cast<const uint4*>(rawrow + c * 16);
+        for (int c = 0; c < 2; ++c) {
+          const uint4 xv = __ldg(reinterpret_cast<const uint4*>(x + off) + c);
           const __half2* xh = reinterpret_cast<const __half2*>(&xv);
           uint4 ov;
           __half2* oh = reinterpret_cast<__half2*>(&ov);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const int col = c * 8 + 2 * j;
             const float2 xr = __half22float2(xh[j]);
-            const float a = __uint_as_float(col < 32 ? r0[col] : r1[col - 32]) + xr.x;
-            const float b = __uint_as_float(col < 32 ? r0[col + 1] : r1[col - 31]) + xr.y;
-            oh[j] = h2_sat(a, b);
+            oh[j] = h2_sat(__uint_as_float(r0[c * 8 + 2 * j]) + xr.x, __uint_as_float(r0[c * 8 + 2 * j + 1]) + xr.y);
           }
-          *reinterpret_cast<uint4*>(dst + c * 8) = ov;
+          *(reinterpret_cast<uint4*>(y + off) + c) = ov;
         }
       }
     }
