@@ -31,7 +31,7 @@ constexpr int C = 64, kHid = 128, kQkv = 384;
 constexpr int kThreads = 512;                    // 16 warps: warp = 4 * head + pixel slot (TMEM lane quarter = warp % 4)
 constexpr int kRawPitch = C * 2 + 16;            // 144 B per raw token row
 constexpr int kStRow = 64;                       // bytes per staging row: 32 halfs, 16-byte chunks XOR-swizzled by (row >> 1) & 3
-constexpr int BS = 40, RS = 20;                  // bias (fp16) / rotary table pitches
+constexpr int BS = 40, RS = 17;                  // bias (fp16) / rotary (float2: 136 B rows, lane-strided reads are conflict-free) table pitches
 // shared-memory map (bytes)
 constexpr int oBar = 0;                                   // 2 mbarriers + tmem base
 constexpr int oWq = 128;                                  // [8][384][8] fp16
@@ -113,19 +113,21 @@ __global__ void __launch_bounds__(kThreads, 1) tattn_tc_kernel(const __half* __r
   uint8_t* Vs = Ks + 32 * kStRow;
   const uint32_t qs_s = ptx::smem_u32(Qs), ks_s = ptx::smem_u32(Ks), vs_s = ptx::smem_u32(Vs);
 
-  // warps 0..3 (head 0) fetch the raw rows of a tile: lane = token
+  // raw tokens / LayerNorm: warp (slot, head) owns tokens 8 head .. 8 head + 7 of its pixel slot, 4 lanes per token (16 channels
+  // each) -- the thread that fetched a piece normalises it, so no block barrier sits between the copy and the LayerNorm
+  const int ln_t = head * 8 + (lane >> 2), ln_q = lane & 3;
+  const bool ln_tok = ln_t < n;
+  const int ln_row = slot * 32 + ln_t;
   auto prefetch = [&](long long tile) {
-    if (head == 0) {
-      const long long pix = tile * 4 + slot;
-      if (tile < n_tiles && pix < n_pix && tok) {
-        const long long bimg = pix / hw, pin = pix - bimg * hw;
-        const __half* src = x + ((bimg * n + lane) * hw + pin) * C;
-        const uint32_t dst = s0 + oRaw + row * kRawPitch;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) ptx::cp_async16_zfill(dst + c * 16, src + c * 8, 16u);
-      }
-      ptx::cp_async_commit();
+    const long long pix = tile * 4 + slot;
+    if (tile < n_tiles && pix < n_pix && ln_tok) {
+      const long long bimg = pix / hw, pin = pix - bimg * hw;
+      const __half* src = x + ((bimg * n + ln_t) * hw + pin) * C + ln_q * 16;
+      const uint32_t dst = s0 + oRaw + ln_row * kRawPitch + ln_q * 32;
+      ptx::cp_async16_zfill(dst, src, 16u);
+      ptx::cp_async16_zfill(dst + 16, src + 8, 16u);
     }
+    ptx::cp_async_commit();
   };
 
   uint32_t ph = 0;
@@ -133,16 +135,17 @@ __global__ void __launch_bounds__(kThreads, 1) tattn_tc_kernel(const __half* __r
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const long long pix = tile * 4 + slot;
     const bool live = tok && pix < n_pix;
-    // ---- LayerNorm of the token this lane owns (warps 0..3) -> A operand [C/8][128][8]
-    if (head == 0) {
-      ptx::cp_async_wait<0>();                            // this thread's own row has landed
-      const uint8_t* rawrow = smem + oRaw + row * kRawPitch;
-      float f[C];
+    // ---- LayerNorm: 4 lanes per token -> A operand [C/8][128][8]
+    {
+      ptx::cp_async_wait<0>();                            // this thread's own piece has landed
+      const bool ln_live = ln_tok && pix < n_pix;
+      const uint8_t* rawp = smem + oRaw + ln_row * kRawPitch + ln_q * 32;
+      float f[16];
       float sum = 0.f;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (live) v = *reinterpret_cast<const uint4*>(rawrow + c * 16);
+        if (ln_live) v = *reinterpret_cast<const uint4*>(rawp + c * 16);
         const __half2* hh = reinterpret_cast<const __half2*>(&v);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -152,26 +155,32 @@ __global__ void __launch_bounds__(kThreads, 1) tattn_tc_kernel(const __half* __r
           sum += t.x + t.y;
         }
       }
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
       const float mean = sum * (1.0f / C);
       float sq = 0.f;
 #pragma unroll
-      for (int j = 0; j < C; ++j) {
+      for (int j = 0; j < 16; ++j) {
         f[j] -= mean;
         sq = fmaf(f[j], f[j], sq);
       }
-      const float rstd = live ? rsqrtf(sq * (1.0f / C) + eps) : 0.f;
+      sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+      sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+      const float rstd = ln_live ? rsqrtf(sq * (1.0f / C) + eps) : 0.f;
+      if (ln_t < 32) {
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        uint4 ov;
-        uint32_t* o = reinterpret_cast<uint32_t*>(&ov);
+        for (int c = 0; c < 2; ++c) {
+          uint4 ov;
+          uint32_t* o = reinterpret_cast<uint32_t*>(&ov);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 gg = *reinterpret_cast<const float2*>(sgm + c * 8 + 2 * j);   // broadcast read
-          o[j] = pack_h2(f[c * 8 + 2 * j] * rstd * gg.x, f[c * 8 + 2 * j + 1] * rstd * gg.y);
+          for (int j = 0; j < 4; ++j) {
+            const float2 gg = *reinterpret_cast<const float2*>(sgm + ln_q * 16 + c * 8 + 2 * j);
+            o[j] = pack_h2(f[c * 8 + 2 * j] * rstd * gg.x, f[c * 8 + 2 * j + 1] * rstd * gg.y);
+          }
+          *reinterpret_cast<uint4*>(smem + oAO + ((ln_q * 2 + c) * 128 + ln_row) * 16) = ov;
         }
-        *reinterpret_cast<uint4*>(smem + oAO + (c * 128 + row) * 16) = ov;
       }
-      prefetch(tile + gridDim.x);                         // the raw tile is consumed: fetch the next one behind the MMAs / attention
+      prefetch(tile + gridDim.x);                         // the raw piece is consumed: fetch the next tile's behind the MMAs / attention
     }
     ptx::fence_proxy_async_smem();
     ptx::tc_fence_before();
@@ -346,6 +355,15 @@ __global__ void __launch_bounds__(kThreads, 1) tattn_tc_kernel(const __half* __r
       }
       ptx::tc_commit(&bars[1]);
     }
+    // the residual (L2-resident: this tile was read a few microseconds ago) is fetched while the MMA runs
+    uint4 xres[2] = {make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u)};
+    size_t yoff = 0;
+    if (live) {
+      const long long bimg = pix / hw, pin = pix - bimg * hw;
+      yoff = static_cast<size_t>(((bimg * n + lane) * hw + pin) * C + head * 16);
+      xres[0] = __ldg(reinterpret_cast<const uint4*>(x + yoff));
+      xres[1] = __ldg(reinterpret_cast<const uint4*>(x + yoff) + 1);
+    }
     ptx::mbar_wait(&bars[1], ph);
     ptx::tc_fence_after();
     ph ^= 1u;
@@ -355,12 +373,9 @@ __global__ void __launch_bounds__(kThreads, 1) tattn_tc_kernel(const __half* __r
       ptx::tmem_ld16(lane_t + 384u + static_cast<uint32_t>(head * 16), r0);
       ptx::tmem_ld_wait();
       if (live) {
-        const long long bimg = pix / hw, pin = pix - bimg * hw;
-        const size_t off = static_cast<size_t>(((bimg * n + lane) * hw + pin) * C + head * 16);
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-          const uint4 xv = __ldg(reinterpret_cast<const uint4*>(x + off) + c);
-          const __half2* xh = reinterpret_cast<const __half2*>(&xv);
+          const __half2* xh = reinterpret_cast<const __half2*>(&xres[c]);
           uint4 ov;
           __half2* oh = reinterpret_cast<__half2*>(&ov);
 #pragma unroll
@@ -368,7 +383,7 @@ __global__ void __launch_bounds__(kThreads, 1) tattn_tc_kernel(const __half* __r
             const float2 xr = __half22float2(xh[j]);
             oh[j] = h2_sat(__uint_as_float(r0[c * 8 + 2 * j]) + xr.x, __uint_as_float(r0[c * 8 + 2 * j + 1]) + xr.y);
           }
-          *(reinterpret_cast<uint4*>(y + off) + c) = ov;
+          *(reinterpret_cast<uint4*>(y + yoff) + c) = ov;
         }
       }
     }
