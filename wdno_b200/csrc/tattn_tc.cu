@@ -205,44 +205,29 @@ __global__ void __launch_bounds__(kThreads, 1) tattn_tc_kernel(const __half* __r
     {
       const int h = head;
       {
-        uint32_t r[32];
-        // q: scale + rotary (position = lane)
-        ptx::tmem_ld32(lane_t + static_cast<uint32_t>(h * 32), r);
+        // one TMEM round trip for q, k, v of this head (lane = token), then scale + rotary and the fp16 staging rows
+        uint32_t rq[32], rk[32], rv[32];
+        ptx::tmem_ld32(lane_t + static_cast<uint32_t>(h * 32), rq);
+        ptx::tmem_ld32(lane_t + static_cast<uint32_t>(kHid + h * 32), rk);
+        ptx::tmem_ld32(lane_t + static_cast<uint32_t>(2 * kHid + h * 32), rv);
         ptx::tmem_ld_wait();
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          uint4 ov;
-          uint32_t* o = reinterpret_cast<uint32_t*>(&ov);
+          uint4 oq, ok, ov;
+          uint32_t* pq = reinterpret_cast<uint32_t*>(&oq);
+          uint32_t* pk = reinterpret_cast<uint32_t*>(&ok);
+          uint32_t* pv = reinterpret_cast<uint32_t*>(&ov);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const float2 cs = scs[lane * RS + c * 4 + j];
-            const float a = __uint_as_float(r[c * 8 + 2 * j]) * scale, b = __uint_as_float(r[c * 8 + 2 * j + 1]) * scale;
-            o[j] = pack_h2(a * cs.x - b * cs.y, b * cs.x + a * cs.y);
+            const float a = __uint_as_float(rq[c * 8 + 2 * j]) * scale, b = __uint_as_float(rq[c * 8 + 2 * j + 1]) * scale;
+            pq[j] = pack_h2(a * cs.x - b * cs.y, b * cs.x + a * cs.y);
+            const float d = __uint_as_float(rk[c * 8 + 2 * j]), e = __uint_as_float(rk[c * 8 + 2 * j + 1]);
+            pk[j] = pack_h2(d * cs.x - e * cs.y, e * cs.x + d * cs.y);
+            pv[j] = pack_h2(__uint_as_float(rv[c * 8 + 2 * j]), __uint_as_float(rv[c * 8 + 2 * j + 1]));
           }
-          *reinterpret_cast<uint4*>(Qs + st_off(lane, c)) = ov;
-        }
-        ptx::tmem_ld32(lane_t + static_cast<uint32_t>(kHid + h * 32), r);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint4 ov;
-          uint32_t* o = reinterpret_cast<uint32_t*>(&ov);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 cs = scs[lane * RS + c * 4 + j];
-            const float a = __uint_as_float(r[c * 8 + 2 * j]), b = __uint_as_float(r[c * 8 + 2 * j + 1]);
-            o[j] = pack_h2(a * cs.x - b * cs.y, b * cs.x + a * cs.y);
-          }
-          *reinterpret_cast<uint4*>(Ks + st_off(lane, c)) = ov;
-        }
-        ptx::tmem_ld32(lane_t + static_cast<uint32_t>(2 * kHid + h * 32), r);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint4 ov;
-          uint32_t* o = reinterpret_cast<uint32_t*>(&ov);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) o[j] = pack_h2(__uint_as_float(r[c * 8 + 2 * j]), __uint_as_float(r[c * 8 + 2 * j + 1]));
+          *reinterpret_cast<uint4*>(Qs + st_off(lane, c)) = oq;
+          *reinterpret_cast<uint4*>(Ks + st_off(lane, c)) = ok;
           *reinterpret_cast<uint4*>(Vs + st_off(lane, c)) = ov;
         }
       }
