@@ -263,6 +263,43 @@ typedef struct {
 } wdno_wgrad_params;
 int wdno_wgrad(const wdno_wgrad_params* p, void* stream);
 
+/* Weight gradient of the stride-1 'same' convolutions on tcgen05 (csrc/wgrad_tc.cu): MN-major UMMA operands straight from
+ * the channels-last tensors, accumulators of up to 8 in-plane taps in TMEM, two dY planes stacked along M for 64-channel
+ * layers (`stack`: rows 0..63 collect depth tap job.kz, rows 64..127 depth tap job.kz - 1).  Same dW indexing as wdno_wgrad. */
+typedef struct {
+  int32_t kz;          /* depth tap of the tile (rows 0..63 of a stacked tile) */
+  int32_t n_taps;      /* in-plane taps of this job (<= 8) */
+  int32_t qmin;        /* smallest linear in-plane shift (ky - py) * Wp + (kx - px) of the job: position of X slab row 0 */
+  int32_t span;        /* largest - smallest linear shift */
+  int32_t m0, n0;      /* first dY channel of the tile (unstacked) / first X channel inside the window */
+  int32_t shift[8];    /* linear shift of tap i minus qmin */
+  int64_t out_hi[8];   /* tap index inside dW (rows 0..63 of a stacked tile / the whole tile) */
+  int64_t out_lo[8];   /* tap index for rows 64..127 of a stacked tile; -1 = discard */
+} wdno_wgrad_tc_job;
+
+typedef struct {
+  const void* x;       /* fp16 channels-last [B][D][H][W][Cx] */
+  const void* dy;      /* fp16 channels-last [B][D][H][W][Cy] */
+  float* dw;           /* fp32, += : dw[(m * n_total + n_off + n) * t_total + tap] */
+  int32_t B, D, H, W;
+  int32_t Cx, Cy, m_valid;
+  int32_t cx_off, cx_n, n_total, n_off, t_total;
+  int32_t padw, pz;    /* zero columns per linearised row (max |column shift|); depth padding */
+  int32_t stack;       /* 1: Cy == 64, planes (z, z + 1) stacked along M; 0: 128 dY channels per tile */
+  int32_t nx, ncols;   /* MMA N (X channels per tile, multiple of 16, <= 64) and TMEM column stride per tap */
+  int32_t stages;      /* cp.async ring depth (2 or 3) */
+  int32_t n_jobs;
+  const wdno_wgrad_tc_job* jobs;  /* device array */
+  int32_t split;       /* CTAs per job along the position axis */
+  float scale;
+  int32_t swap_lbo_sbo;/* probe switch: exchange the two descriptor strides (tools/probe_wgrad_tc.py); product value: 0 */
+  int32_t reserved0;
+} wdno_wgrad_tc_params;
+int64_t wdno_wgrad_tc_smem_bytes(const wdno_wgrad_tc_params* p, int span);
+int wdno_wgrad_tc(const wdno_wgrad_tc_params* p, int max_span, void* stream);
+/* out[c] += scale * sum over positions of dy[pos][c]  (bias gradient; fp16 channels-last in, fp32 out) */
+int wdno_colsum_f16(const void* dy, int64_t n_pos, int C, float* out, float scale, void* stream);
+
 /* GroupNorm + (scale+1, shift) + SiLU backward (conv3d.py:189-205; unet.py:129-147), z = a[b,c]*y + c[b,c], h = silu(z):
  *   reduce : sums[b][c] = (sum dz, sum dz*y) over the voxels, dz = dh * silu'(z)                 (double, +=)
  *   apply  : dy = a[b,c]*dz + k1[b,g]*y + k0[b,g]  -- k1, k0 from wdno_gn_bwd_finalize; fp16 out

@@ -24,7 +24,7 @@ def test_exports_every_declared_symbol(lib):
     missing = [n for n in names if not hasattr(lib, n)]
     assert not missing, missing
     from wdno_b200 import _abi
-    declared = {n for n in set(names) - {"wdno_last_error", "wdno_version", "wdno_device_cc", "wdno_tapgemm", "wdno_wgrad"} if not n.endswith("_bytes")}   # struct-taking entry points are bound next to their ctypes structs
+    declared = {n for n in set(names) - {"wdno_last_error", "wdno_version", "wdno_device_cc", "wdno_tapgemm", "wdno_wgrad", "wdno_wgrad_tc"} if not n.endswith("_bytes")}   # struct-taking entry points are bound next to their ctypes structs
     assert declared == set(_abi.SIGNATURES), declared ^ set(_abi.SIGNATURES)
 
 
@@ -35,6 +35,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_abi.CondOp) == 96
     from wdno_b200 import training
     assert C.sizeof(training.WgradGroup) == 56          # 5 + 3 int32, 3 int64
+    assert C.sizeof(training.WgradTcJob) == 184 and C.sizeof(training.WgradTcParams) == 128 and training.WgradTcParams.jobs.offset == 104
     assert C.sizeof(training.WgradParams) == 128 and training.WgradParams.groups.offset == 112   # == the C struct (g++ sizeof / offsetof)
 
 

@@ -47,6 +47,7 @@ SIGNATURES = {
     "wdno_linear_attn_bwd": [P, P, P, P, L64, I, F, P],
     "wdno_upsample2x_f16": [P, P, L64, I, I, I, P],
     "wdno_sumpool2x2_f16": [P, P, L64, I, I, I, P],
+    "wdno_colsum_f16": [P, L64, I, P, F, P],
     "wdno_sumsq": [P, L64, P, P],
     "wdno_adam_clip_ema": [P, P, P, P, P, L64, P, F, F, F, F, F, F, F, F, I, P],
     "wdno_randn_slice": [P, L64, L64, L64, I, C.c_uint64, C.c_uint64, P],

@@ -388,3 +388,117 @@ class AttnGrad:
             large = torch.min(large, torch.full_like(large, half - 1))
             cls._buckets[key] = (ret + torch.where(k < max_exact, k, large)).reshape(-1).to(device)
         return cls._buckets[key]
+
+
+# ---------------------------------------------------------------------------------------------- wgrad on tcgen05
+class WgradTcJob(C.Structure):
+    _fields_ = [("kz", C.c_int32), ("n_taps", C.c_int32), ("qmin", C.c_int32), ("span", C.c_int32), ("m0", C.c_int32),
+                ("n0", C.c_int32), ("shift", C.c_int32 * 8), ("out_hi", C.c_int64 * 8), ("out_lo", C.c_int64 * 8)]
+
+
+class WgradTcParams(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("dy", C.c_void_p), ("dw", C.c_void_p),
+                ("B", C.c_int32), ("D", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+                ("Cx", C.c_int32), ("Cy", C.c_int32), ("m_valid", C.c_int32),
+                ("cx_off", C.c_int32), ("cx_n", C.c_int32), ("n_total", C.c_int32), ("n_off", C.c_int32), ("t_total", C.c_int32),
+                ("padw", C.c_int32), ("pz", C.c_int32), ("stack", C.c_int32), ("nx", C.c_int32), ("ncols", C.c_int32),
+                ("stages", C.c_int32), ("n_jobs", C.c_int32), ("jobs", C.c_void_p), ("split", C.c_int32), ("scale", C.c_float),
+                ("swap_lbo_sbo", C.c_int32), ("reserved0", C.c_int32)]
+
+
+_tc_bound = False
+
+
+def _bind_tc():
+    global _tc_bound
+    L = _lib.lib()
+    if not _tc_bound:
+        L.wdno_wgrad_tc.restype = C.c_int
+        L.wdno_wgrad_tc.argtypes = [C.POINTER(WgradTcParams), C.c_int, C.c_void_p]
+        L.wdno_wgrad_tc_smem_bytes.restype = C.c_int64
+        L.wdno_wgrad_tc_smem_bytes.argtypes = [C.POINTER(WgradTcParams), C.c_int]
+        _tc_bound = True
+    return L
+
+
+class WgradTC:
+    """tcgen05 weight gradient of one stride-1 'same' convolution (csrc/wgrad_tc.cu).  `supported()` says whether the layer
+    geometry fits (64 or a multiple of 128 output channels; a window of <= 64 or a multiple of 64 input channels)."""
+
+    SWAP = 0   # descriptor-stride convention (settled by tools/probe_wgrad_tc.py)
+
+    @staticmethod
+    def supported(cout, cin_window, KD, KH, KW):
+        if KD * KH * KW == 1:
+            return False                       # 1x1 layers: the mma.sync kernel (K loop too short to fill TMEM with taps)
+        if not (cout == 64 and KD > 1) and cout % 128:
+            return False
+        return cin_window <= 64 or cin_window % 64 == 0
+
+    def __init__(self, cout, KD, KH, KW, device):
+        self.cout, self.KD, self.KH, self.KW = cout, KD, KH, KW
+        self.device = torch.device(device)
+        self.stack = 1 if cout == 64 else 0
+        self._jobs = {}
+
+    def _job_table(self, Wp, cx_n):
+        key = (Wp, cx_n)
+        if key in self._jobs:
+            return self._jobs[key]
+        KD, KH, KW = self.KD, self.KH, self.KW
+        nx = min(64, (cx_n + 15) // 16 * 16)
+        per = max(1, min(8, 512 // 64))
+        taps = sorted(((ky - KH // 2) * Wp + (kx - KW // 2), ky, kx) for ky in range(KH) for kx in range(KW))
+        ngrp = (len(taps) + per - 1) // per
+        size = (len(taps) + ngrp - 1) // ngrp
+        groups = [taps[i:i + size] for i in range(0, len(taps), size)]
+        kzs = list(range(KD - 1, -1, -2)) if self.stack else list(range(KD))
+        m_tiles = [0] if self.stack else list(range(0, self.cout, 128))
+        n_tiles = list(range(0, cx_n, 64))
+        jobs = []
+        for kz in kzs:
+            for grp in groups:
+                for m0 in m_tiles:
+                    for n0 in n_tiles:
+                        j = WgradTcJob()
+                        j.kz, j.n_taps, j.m0, j.n0 = kz, len(grp), m0, n0
+                        j.qmin = grp[0][0]
+                        j.span = grp[-1][0] - grp[0][0]
+                        for i, (sh, ky, kx) in enumerate(grp):
+                            j.shift[i] = sh - grp[0][0]
+                            j.out_hi[i] = (kz * KH + ky) * KW + kx
+                            j.out_lo[i] = ((kz - 1) * KH + ky) * KW + kx if (self.stack and kz >= 1) else -1
+                        jobs.append(j)
+        arr = (WgradTcJob * len(jobs))(*jobs)
+        dev = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).clone().to(self.device)
+        self._jobs[key] = (dev, len(jobs), max(j.span for j in jobs), nx)
+        return self._jobs[key]
+
+    def __call__(self, x, dy, dw, scale, cx_off=0, cx_n=None, n_off=0, n_total=None, m_valid=None):
+        L = _bind_tc()
+        B, D, H, W, Cy = dy.shape
+        Cx = x.shape[-1]
+        cx_n = Cx - cx_off if cx_n is None else cx_n
+        n_total = cx_n if n_total is None else n_total
+        padw = self.KW // 2
+        jobs_dev, n_jobs, max_span, nx = self._job_table(W + padw, cx_n)
+        p = WgradTcParams()
+        p.x, p.dy, p.dw = x.data_ptr(), dy.data_ptr(), dw.data_ptr()
+        p.B, p.D, p.H, p.W, p.Cx, p.Cy = B, D, H, W, Cx, Cy
+        p.m_valid = Cy if m_valid is None else m_valid
+        p.cx_off, p.cx_n, p.n_total, p.n_off, p.t_total = cx_off, cx_n, n_total, n_off, self.KD * self.KH * self.KW
+        p.padw, p.pz, p.stack, p.nx, p.ncols = padw, self.KD // 2, self.stack, nx, 64
+        p.n_jobs, p.jobs = n_jobs, jobs_dev.data_ptr()
+        sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+        items = B * (D + (1 if self.stack else 0)) * ((H * (W + padw) + 127) // 128)
+        p.split = max(1, min(items, sms // n_jobs if n_jobs <= sms else 1))
+        p.scale, p.swap_lbo_sbo = scale, WgradTC.SWAP
+        p.stages = 3
+        if L.wdno_wgrad_tc_smem_bytes(C.byref(p), max_span) > 227 * 1024:
+            p.stages = 2
+        _lib.check(L.wdno_wgrad_tc(C.byref(p), max_span, _lib.current_stream_ptr()), "wgrad_tc")
+
+
+def colsum_f16(dy, out, scale):
+    Cc = dy.shape[-1]
+    _lib.check(_lib.lib().wdno_colsum_f16(_p(dy), dy.numel() // Cc, Cc, _p(out), float(scale), _lib.current_stream_ptr()), "colsum_f16")
