@@ -209,6 +209,14 @@ class ConvLayer:
         self.up2 = bool(getattr(fwd, "up2", False))   # nearest x2 up-sampling fused into the forward operand load
         dev = fwd.device
         self.wgrad = Wgrad(kind, tuple(weight.shape), dev)
+        # stride-1 'same' convolutions with 64 / 128k output channels: the tcgen05 weight-gradient kernel (csrc/wgrad_tc.cu);
+        # WDNO_WGRAD_TC=0 keeps every layer on the mma.sync kernel
+        self.wgrad_tc = None
+        import os
+        if kind == "conv" and not self.up2 and os.environ.get("WDNO_WGRAD_TC", "1") != "0":
+            w5 = self.wgrad
+            if all(WgradTC.supported(w5.cout, min(cs, w5.cin), w5.KD, w5.KH, w5.KW) for cs in self.src_channels):
+                self.wgrad_tc = WgradTC(w5.cout, w5.KD, w5.KH, w5.KW, dev)
         self.dgrad = []
         if need_dgrad:
             for w in self._dgrad_weights():
@@ -285,8 +293,13 @@ class ConvLayer:
         n_total = self.weight.shape[1] // (4 if self.kind == "unshuffle" else 1)
         for i, (src, cs) in enumerate(zip(srcs, self.src_channels)):
             real = min(cs, n_total - off)
-            self.wgrad(src, dy, gw, gb if i == 0 else None, scale, cx_off=0, cx_n=real, n_off=off, n_total=n_total,
-                       m_valid=self.weight.shape[0])
+            if self.wgrad_tc is not None:
+                self.wgrad_tc(src, dy, gw, scale, cx_off=0, cx_n=real, n_off=off, n_total=n_total, m_valid=self.weight.shape[0])
+                if i == 0 and gb is not None:
+                    colsum_f16(dy, gb, scale)
+            else:
+                self.wgrad(src, dy, gw, gb if i == 0 else None, scale, cx_off=0, cx_n=real, n_off=off, n_total=n_total,
+                           m_valid=self.weight.shape[0])
             off += cs
 
 
@@ -501,4 +514,5 @@ class WgradTC:
 
 def colsum_f16(dy, out, scale):
     Cc = dy.shape[-1]
+    assert out.dtype == torch.float32 and out.numel() >= Cc
     _lib.check(_lib.lib().wdno_colsum_f16(_p(dy), dy.numel() // Cc, Cc, _p(out), float(scale), _lib.current_stream_ptr()), "colsum_f16")
