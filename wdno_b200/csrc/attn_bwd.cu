@@ -21,8 +21,8 @@ namespace wdno {
 
 namespace {
 
-constexpr int kH = 4, kD = 32, kHid = 128, kQkv = 384;
-constexpr int TS = 33;   // padded fp32 row
+constexpr int kD = 32, kHid = 128, kQkv = 384;
+constexpr int TS = 36;   // padded fp32 row: 144 B, 16-byte aligned (float4 broadcast reads, conflict-free float4 row writes)
 
 struct SeqMap2 {
   long long inner, outerT, innerT, tokT;
@@ -109,11 +109,11 @@ __global__ void __launch_bounds__(128) short_attn_bwd_kernel(const __half* __res
       __syncwarp();   // the previous item's column pass is done with the tiles
       if (act) {
 #pragma unroll
-        for (int d = 0; d < 32; ++d) {
-          Q[lane * TS + d] = q[d];
-          K[lane * TS + d] = k[d];
-          V[lane * TS + d] = v[d];
-          G[lane * TS + d] = g[d];
+        for (int d = 0; d < 32; d += 4) {
+          *reinterpret_cast<float4*>(Q + lane * TS + d) = make_float4(q[d], q[d + 1], q[d + 2], q[d + 3]);
+          *reinterpret_cast<float4*>(K + lane * TS + d) = make_float4(k[d], k[d + 1], k[d + 2], k[d + 3]);
+          *reinterpret_cast<float4*>(V + lane * TS + d) = make_float4(v[d], v[d + 1], v[d + 2], v[d + 3]);
+          *reinterpret_cast<float4*>(G + lane * TS + d) = make_float4(g[d], g[d + 1], g[d + 2], g[d + 3]);
         }
       }
     }
@@ -126,7 +126,10 @@ __global__ void __launch_bounds__(128) short_attn_bwd_kernel(const __half* __res
       for (int j = 0; j < n; ++j) {
         float sc = 0.f;
 #pragma unroll
-        for (int d = 0; d < 32; ++d) sc = fmaf(q[d], K[j * TS + d], sc);
+        for (int d = 0; d < 32; d += 4) {
+          const float4 kv = *reinterpret_cast<const float4*>(K + j * TS + d);   // broadcast
+          sc = fmaf(q[d], kv.x, fmaf(q[d + 1], kv.y, fmaf(q[d + 2], kv.z, fmaf(q[d + 3], kv.w, sc))));
+        }
         if (bias != nullptr) sc += __ldg(bias + (static_cast<size_t>(h) * n + lane) * n + j);
         P[lane * TS + j] = sc;
         m = fmaxf(m, sc);
@@ -144,7 +147,10 @@ __global__ void __launch_bounds__(128) short_attn_bwd_kernel(const __half* __res
         P[lane * TS + j] = p;
         float dp = 0.f;
 #pragma unroll
-        for (int d = 0; d < 32; ++d) dp = fmaf(g[d], V[j * TS + d], dp);
+        for (int d = 0; d < 32; d += 4) {
+          const float4 vv = *reinterpret_cast<const float4*>(V + j * TS + d);
+          dp = fmaf(g[d], vv.x, fmaf(g[d + 1], vv.y, fmaf(g[d + 2], vv.z, fmaf(g[d + 3], vv.w, dp))));
+        }
         S[lane * TS + j] = dp;
         delta = fmaf(p, dp, delta);
       }
@@ -153,7 +159,13 @@ __global__ void __launch_bounds__(128) short_attn_bwd_kernel(const __half* __res
         S[lane * TS + j] = ds;
         Bacc[lane * TS + j] += ds;
 #pragma unroll
-        for (int d = 0; d < 32; ++d) dq[d] = fmaf(ds, K[j * TS + d], dq[d]);
+        for (int d = 0; d < 32; d += 4) {
+          const float4 kv = *reinterpret_cast<const float4*>(K + j * TS + d);
+          dq[d] = fmaf(ds, kv.x, dq[d]);
+          dq[d + 1] = fmaf(ds, kv.y, dq[d + 1]);
+          dq[d + 2] = fmaf(ds, kv.z, dq[d + 2]);
+          dq[d + 3] = fmaf(ds, kv.w, dq[d + 3]);
+        }
       }
     }
     __syncwarp();
@@ -165,9 +177,17 @@ __global__ void __launch_bounds__(128) short_attn_bwd_kernel(const __half* __res
       for (int i = 0; i < n; ++i) {
         const float ds = S[i * TS + lane], p = P[i * TS + lane];
 #pragma unroll
-        for (int d = 0; d < 32; ++d) {
-          dk[d] = fmaf(ds, Q[i * TS + d], dk[d]);
-          dv[d] = fmaf(p, G[i * TS + d], dv[d]);
+        for (int d = 0; d < 32; d += 4) {
+          const float4 qv = *reinterpret_cast<const float4*>(Q + i * TS + d);
+          const float4 gv = *reinterpret_cast<const float4*>(G + i * TS + d);
+          dk[d] = fmaf(ds, qv.x, dk[d]);
+          dk[d + 1] = fmaf(ds, qv.y, dk[d + 1]);
+          dk[d + 2] = fmaf(ds, qv.z, dk[d + 2]);
+          dk[d + 3] = fmaf(ds, qv.w, dk[d + 3]);
+          dv[d] = fmaf(p, gv.x, dv[d]);
+          dv[d + 1] = fmaf(p, gv.y, dv[d + 1]);
+          dv[d + 2] = fmaf(p, gv.z, dv[d + 2]);
+          dv[d + 3] = fmaf(p, gv.w, dv[d + 3]);
         }
       }
       // inverse rotation (the rotation matrix is orthogonal), then the q scale
@@ -327,22 +347,42 @@ __global__ void __launch_bounds__(128) la_bwd_kstat_kernel(const __half* __restr
   const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long img = blockIdx.x;
   const __half* kp = qkv + img * n_pos * static_cast<long long>(kQkv) + kHid + h * kD + lane;
-  float m = -INFINITY, l = 0.f;
-  for (int p = 0; p < n_pos; ++p) {
-    const float v = __half2float(__ldg(kp + static_cast<size_t>(p) * kQkv));
-    const float mn = fmaxf(m, v);
-    l = l * __expf(m - mn) + __expf(v - mn);
-    m = mn;
+  float mm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, ll[4] = {0.f, 0.f, 0.f, 0.f};
+  int p = 0;
+  for (; p + 4 <= n_pos; p += 4) {
+    float v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = __half2float(__ldg(kp + static_cast<size_t>(p + u) * kQkv));
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float mn = fmaxf(mm[u], v[u]);
+      ll[u] = ll[u] * __expf(mm[u] - mn) + __expf(v[u] - mn);
+      mm[u] = mn;
+    }
   }
+  for (; p < n_pos; ++p) {
+    const float v = __half2float(__ldg(kp + static_cast<size_t>(p) * kQkv));
+    const float mn = fmaxf(mm[0], v);
+    ll[0] = ll[0] * __expf(mm[0] - mn) + __expf(v - mn);
+    mm[0] = mn;
+  }
+  const float m = fmaxf(fmaxf(mm[0], mm[1]), fmaxf(mm[2], mm[3]));
+  float l = 0.f;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) l += (mm[u] == -INFINITY) ? 0.f : ll[u] * __expf(mm[u] - m);
   float* st = work + img * kLaWork + (h * 32 + lane) * 2;
   st[0] = m;
   st[1] = 1.f / l;
 }
 
+// (1) is latency bound when one warp walks all positions of an image serially; four independent (max, sum) chains per lane
 // (2) ctx[d][e] += sum_p k^[d] v[e],  dctx[d][e] += sum_p q^[d] dout[e]  over a chunk of positions.
-// block = 4 warps = 4 heads; lane = d; each lane accumulates its row d of both 32x32 matrices (64 registers).
+// block = 4 warps = 4 heads; lane = d; each lane accumulates its row d of both 32x32 matrices (64 registers); the per-position
+// vectors v and dout are staged in the warp's shared-memory row and read back as float4 broadcasts (8 loads instead of 32
+// shuffles each).
 __global__ void __launch_bounds__(128) la_bwd_ctx_kernel(const __half* __restrict__ qkv, const __half* __restrict__ dout,
                                                          float* __restrict__ work, int n_pos, int chunk, float scale) {
+  __shared__ __align__(16) float stv[4][2][2][32];   // [warp][buffer][v | dout][e]
   const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long img = blockIdx.y;
   float* wk = work + img * kLaWork;
@@ -357,6 +397,9 @@ __global__ void __launch_bounds__(128) la_bwd_ctx_kernel(const __half* __restric
     const float kr = __half2float(__ldg(row + kHid + lane));
     const float vr = __half2float(__ldg(row + 2 * kHid + lane));
     const float gr = __half2float(__ldg(dout + (img * n_pos + p) * static_cast<long long>(kHid) + h * kD + lane));
+    const int bf = p & 1;
+    stv[h][bf][0][lane] = vr;
+    stv[h][bf][1][lane] = gr;
     // q^ = softmax over d (lanes) * scale
     float mx = qr;
 #pragma unroll
@@ -367,10 +410,19 @@ __global__ void __launch_bounds__(128) la_bwd_ctx_kernel(const __half* __restric
     for (int sh = 16; sh > 0; sh >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, sh);
     const float qh = ex / sum * scale;
     const float kh = __expf(kr - km) * kil;
+    __syncwarp();
 #pragma unroll
-    for (int e = 0; e < 32; ++e) {
-      cx[e] = fmaf(kh, __shfl_sync(0xffffffffu, vr, e), cx[e]);
-      dc[e] = fmaf(qh, __shfl_sync(0xffffffffu, gr, e), dc[e]);
+    for (int e = 0; e < 32; e += 4) {
+      const float4 v4 = *reinterpret_cast<const float4*>(&stv[h][bf][0][e]);
+      const float4 g4 = *reinterpret_cast<const float4*>(&stv[h][bf][1][e]);
+      cx[e] = fmaf(kh, v4.x, cx[e]);
+      cx[e + 1] = fmaf(kh, v4.y, cx[e + 1]);
+      cx[e + 2] = fmaf(kh, v4.z, cx[e + 2]);
+      cx[e + 3] = fmaf(kh, v4.w, cx[e + 3]);
+      dc[e] = fmaf(qh, g4.x, dc[e]);
+      dc[e + 1] = fmaf(qh, g4.y, dc[e + 1]);
+      dc[e + 2] = fmaf(qh, g4.z, dc[e + 2]);
+      dc[e + 3] = fmaf(qh, g4.w, dc[e + 3]);
     }
   }
   float* cxo = wk + 4 * 32 * 2 + (h * 32 + lane) * 32;
@@ -382,11 +434,17 @@ __global__ void __launch_bounds__(128) la_bwd_ctx_kernel(const __half* __restric
   }
 }
 
-// (3) per position: dq, dk, dv.  block = 4 warps = 4 heads, lane = d (and = e for dv); ctx / dctx of the image in shared memory.
+// (3) per position: dq, dk, dv.  block = 4 warps = 4 heads, lane = d (and = e for dv); ctx / dctx of the image in shared memory,
+// the position's v / dout / k^ vectors staged per warp (float4 broadcast reads).
 __global__ void __launch_bounds__(128) la_bwd_pos_kernel(const __half* __restrict__ qkv, const __half* __restrict__ dout,
                                                          const float* __restrict__ work, __half* __restrict__ dqkv, int n_pos,
                                                          int chunk, float scale) {
-  __shared__ float cxs[4][32 * TS], dcs[4][32 * TS];
+  constexpr int TS2 = 36;
+  extern __shared__ __align__(16) float la_sm[];
+  float (*cxs)[32 * TS2] = reinterpret_cast<float (*)[32 * TS2]>(la_sm);                  // ctx   [4][32][36]
+  float (*dcs)[32 * TS2] = reinterpret_cast<float (*)[32 * TS2]>(la_sm + 4 * 32 * TS2);   // dctx
+  float (*dct)[32 * TS2] = reinterpret_cast<float (*)[32 * TS2]>(la_sm + 8 * 32 * TS2);   // dctx^T
+  float (*stv)[2][3][32] = reinterpret_cast<float (*)[2][3][32]>(la_sm + 12 * 32 * TS2);  // [warp][buffer][v | dout | k^][.]
   const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long img = blockIdx.y;
   const float* wk = work + img * kLaWork;
@@ -394,14 +452,15 @@ __global__ void __launch_bounds__(128) la_bwd_pos_kernel(const __half* __restric
   const float* cxi = wk + 4 * 32 * 2 + h * 32 * 32;
   const float* dci = cxi + 4 * 32 * 32;
   for (int i = lane; i < 32 * 32; i += 32) {
-    cxs[h][(i >> 5) * TS + (i & 31)] = cxi[i];
-    dcs[h][(i >> 5) * TS + (i & 31)] = dci[i];
+    cxs[h][(i >> 5) * TS2 + (i & 31)] = cxi[i];
+    dcs[h][(i >> 5) * TS2 + (i & 31)] = dci[i];
+    dct[h][(i & 31) * TS2 + (i >> 5)] = dci[i];
   }
   __syncwarp();
   // t[d] = sum_e dctx[d][e] ctx[d][e]  (= sum over n of k^ dk^)
   float td = 0.f;
 #pragma unroll
-  for (int e = 0; e < 32; ++e) td = fmaf(dcs[h][lane * TS + e], cxs[h][lane * TS + e], td);
+  for (int e = 0; e < 32; ++e) td = fmaf(dcs[h][lane * TS2 + e], cxs[h][lane * TS2 + e], td);
   const int p0 = blockIdx.x * chunk, p1 = min(n_pos, p0 + chunk);
   for (int p = p0; p < p1; ++p) {
     const long long tk = img * n_pos + p;
@@ -410,6 +469,11 @@ __global__ void __launch_bounds__(128) la_bwd_pos_kernel(const __half* __restric
     const float kr = __half2float(__ldg(row + kHid + lane));
     const float vr = __half2float(__ldg(row + 2 * kHid + lane));
     const float gr = __half2float(__ldg(dout + tk * kHid + h * kD + lane));
+    const float kh = __expf(kr - km) * kil;  // softmax over n
+    const int bf = p & 1;
+    stv[h][bf][0][lane] = vr;
+    stv[h][bf][1][lane] = gr;
+    stv[h][bf][2][lane] = kh;
     float mx = qr;
 #pragma unroll
     for (int sh = 16; sh > 0; sh >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, sh));
@@ -418,13 +482,19 @@ __global__ void __launch_bounds__(128) la_bwd_pos_kernel(const __half* __restric
 #pragma unroll
     for (int sh = 16; sh > 0; sh >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, sh);
     const float qs = ex / sum;               // softmax over d (unscaled)
-    const float kh = __expf(kr - km) * kil;  // softmax over n
+    __syncwarp();
     float dqh = 0.f, dkh = 0.f, dv = 0.f;
 #pragma unroll
-    for (int e = 0; e < 32; ++e) {
-      dqh = fmaf(cxs[h][lane * TS + e], __shfl_sync(0xffffffffu, gr, e), dqh);   // dq^[d] = sum_e ctx[d][e] dout[e]
-      dkh = fmaf(dcs[h][lane * TS + e], __shfl_sync(0xffffffffu, vr, e), dkh);   // dk^[d] = sum_e dctx[d][e] v[e]
-      dv = fmaf(dcs[h][e * TS + lane], __shfl_sync(0xffffffffu, kh, e), dv);     // dv[e=lane] = sum_d k^[d] dctx[d][e]
+    for (int e = 0; e < 32; e += 4) {
+      const float4 v4 = *reinterpret_cast<const float4*>(&stv[h][bf][0][e]);
+      const float4 g4 = *reinterpret_cast<const float4*>(&stv[h][bf][1][e]);
+      const float4 k4 = *reinterpret_cast<const float4*>(&stv[h][bf][2][e]);
+      const float4 c4 = *reinterpret_cast<const float4*>(&cxs[h][lane * TS2 + e]);
+      const float4 d4 = *reinterpret_cast<const float4*>(&dcs[h][lane * TS2 + e]);
+      const float4 t4 = *reinterpret_cast<const float4*>(&dct[h][lane * TS2 + e]);   // dctx[d = e..e+3][e' = lane]
+      dqh = fmaf(c4.x, g4.x, fmaf(c4.y, g4.y, fmaf(c4.z, g4.z, fmaf(c4.w, g4.w, dqh))));   // dq^[d] = sum_e ctx[d][e] dout[e]
+      dkh = fmaf(d4.x, v4.x, fmaf(d4.y, v4.y, fmaf(d4.z, v4.z, fmaf(d4.w, v4.w, dkh))));   // dk^[d] = sum_e dctx[d][e] v[e]
+      dv = fmaf(t4.x, k4.x, fmaf(t4.y, k4.y, fmaf(t4.z, k4.z, fmaf(t4.w, k4.w, dv))));     // dv[e'] = sum_d k^[d] dctx[d][e']
     }
     // softmax over d backward (q = scale * qs): dq_raw = scale * qs * (dq^ - sum_d qs dq^)
     float dot = qs * dqh;
@@ -505,7 +575,14 @@ extern "C" int wdno_linear_attn_bwd(const void* qkv, const void* d_out, void* dq
   const int nch = (n_pos + chunk - 1) / chunk;
   la_bwd_ctx_kernel<<<dim3(nch, static_cast<unsigned>(n_img)), 128, 0, st>>>(
       static_cast<const __half*>(qkv), static_cast<const __half*>(d_out), static_cast<float*>(work), n_pos, chunk, scale);
-  la_bwd_pos_kernel<<<dim3(nch, static_cast<unsigned>(n_img)), 128, 0, st>>>(
+  constexpr int kPosSmem = (12 * 32 * 36 + 4 * 2 * 3 * 32) * 4;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e2 = cudaFuncSetAttribute(la_bwd_pos_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPosSmem);
+    if (e2 != cudaSuccess) return set_cuda_error(e2, "linear_attn_bwd: cudaFuncSetAttribute");
+    configured = true;
+  }
+  la_bwd_pos_kernel<<<dim3(nch, static_cast<unsigned>(n_img)), 128, kPosSmem, st>>>(
       static_cast<const __half*>(qkv), static_cast<const __half*>(d_out), static_cast<const float*>(work),
       static_cast<__half*>(dqkv), n_pos, chunk, scale);
   return check_launch("linear_attn_bwd");

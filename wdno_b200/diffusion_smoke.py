@@ -428,14 +428,43 @@ class GaussianDiffusion(nn.Module):
         r.step.zero_()
         return r
 
+    def _bound_design(self, run, design_fn, design_guidance, low, init, init_u):
+        """the guidance callback bound to the runner's STATIC copies of (low, init, init_u): the closure -- and with it a
+        whole-step CUDA graph that captured it -- survives across sample() calls; a call only refreshes the buffers"""
+        if design_fn is None:
+            return None
+        dev = self.betas.device
+        st = run.static
+        if init_u is not None:
+            if st.get("init_u") is None or st["init_u"].shape != init_u.shape:
+                st["init_u"] = torch.empty(init_u.shape, dtype=torch.float32, device=dev)
+                run._design_key = None
+            st["init_u"].copy_(init_u, non_blocking=True)
+        else:
+            st["init_u"] = None
+        lo = st["low"] if low is not None and st.get("low") is not None else low
+        if lo is not None and lo is low:
+            if st.get("low_g") is None or st["low_g"].shape != low.shape:
+                st["low_g"] = torch.empty(low.shape, dtype=torch.float32, device=dev)
+                run._design_key = None
+            st["low_g"].copy_(low, non_blocking=True)
+            lo = st["low_g"]
+        key = (id(design_fn), design_guidance, lo is None)
+        if getattr(run, "_design_key", None) != key:
+            design, _ = self._guidance(design_fn, design_guidance, lo, st["init"], st["init_u"])
+            run._design, run._design_key, run._design_fn = design, key, design_fn
+            run._gg = None
+        return run._design
+
     @torch.no_grad()
     def ddim_sample(self, shape, N_upsample=0, design_fn=None, design_guidance="standard", init=None, init_u=None,
                     control=None, low=None, device=None):
         dev = self.betas.device
-        design, gs = self._guidance(design_fn, design_guidance, low, init, init_u)
+        _, gs = self._guidance(design_fn, design_guidance, low, init, init_u)
         assert init is not None
         run = self._runner("ddim", shape, N_upsample, init, control if self.is_condition_control else None,
                            low if self.is_super_model else None, gs)
+        design = self._bound_design(run, design_fn, design_guidance, low, init, init_u)
         run.x.copy_(self._randn(shape, dev))
         ops.apply_conditions(run.x, run.prog)
         n = len(run.times)
@@ -456,10 +485,11 @@ class GaussianDiffusion(nn.Module):
     def p_sample_loop(self, shape, N_upsample=0, design_fn=None, design_guidance="standard", return_all_timesteps=None,
                       init=None, init_u=None, control=None, low=None, device=None):
         dev = self.betas.device
-        design, gs = self._guidance(design_fn, design_guidance, low, init, init_u)
+        _, gs = self._guidance(design_fn, design_guidance, low, init, init_u)
         assert init is not None
         run = self._runner("ddpm", shape, N_upsample, init, control if self.is_condition_control else None,
                            low if self.is_super_model else None, gs)
+        design = self._bound_design(run, design_fn, design_guidance, low, init, init_u)
         run.x.copy_(self._randn(list(shape), dev))
         ops.apply_conditions(run.x, run.prog)
         for i, t in enumerate(run.times):
