@@ -391,38 +391,49 @@ __global__ void __launch_bounds__(128) la_bwd_ctx_kernel(const __half* __restric
 #pragma unroll
   for (int e = 0; e < 32; ++e) { cx[e] = 0.f; dc[e] = 0.f; }
   const int p0 = blockIdx.x * chunk, p1 = min(n_pos, p0 + chunk);
-  for (int p = p0; p < p1; ++p) {
-    const __half* row = qkv + (img * n_pos + p) * static_cast<long long>(kQkv) + h * kD;
-    const float qr = __half2float(__ldg(row + lane));
-    const float kr = __half2float(__ldg(row + kHid + lane));
-    const float vr = __half2float(__ldg(row + 2 * kHid + lane));
-    const float gr = __half2float(__ldg(dout + (img * n_pos + p) * static_cast<long long>(kHid) + h * kD + lane));
-    const int bf = p & 1;
-    stv[h][bf][0][lane] = vr;
-    stv[h][bf][1][lane] = gr;
-    // q^ = softmax over d (lanes) * scale
-    float mx = qr;
+  for (int pb = p0; pb < p1; pb += 4) {
+    // the loop is latency bound on its four 64-byte loads per position: fetch four positions at once
+    float qr4[4], kr4[4], vr4[4], gr4[4];
 #pragma unroll
-    for (int sh = 16; sh > 0; sh >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, sh));
-    const float ex = __expf(qr - mx);
-    float sum = ex;
+    for (int u = 0; u < 4; ++u) {
+      const int p = min(pb + u, p1 - 1);
+      const __half* row = qkv + (img * n_pos + p) * static_cast<long long>(kQkv) + h * kD;
+      qr4[u] = __half2float(__ldg(row + lane));
+      kr4[u] = __half2float(__ldg(row + kHid + lane));
+      vr4[u] = __half2float(__ldg(row + 2 * kHid + lane));
+      gr4[u] = __half2float(__ldg(dout + (img * n_pos + p) * static_cast<long long>(kHid) + h * kD + lane));
+    }
 #pragma unroll
-    for (int sh = 16; sh > 0; sh >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, sh);
-    const float qh = ex / sum * scale;
-    const float kh = __expf(kr - km) * kil;
-    __syncwarp();
+    for (int u = 0; u < 4; ++u) {
+      if (pb + u >= p1) break;
+      const float qr = qr4[u], kr = kr4[u];
+      const int bf = u & 1;
+      stv[h][bf][0][lane] = vr4[u];
+      stv[h][bf][1][lane] = gr4[u];
+      // q^ = softmax over d (lanes) * scale
+      float mx = qr;
 #pragma unroll
-    for (int e = 0; e < 32; e += 4) {
-      const float4 v4 = *reinterpret_cast<const float4*>(&stv[h][bf][0][e]);
-      const float4 g4 = *reinterpret_cast<const float4*>(&stv[h][bf][1][e]);
-      cx[e] = fmaf(kh, v4.x, cx[e]);
-      cx[e + 1] = fmaf(kh, v4.y, cx[e + 1]);
-      cx[e + 2] = fmaf(kh, v4.z, cx[e + 2]);
-      cx[e + 3] = fmaf(kh, v4.w, cx[e + 3]);
-      dc[e] = fmaf(qh, g4.x, dc[e]);
-      dc[e + 1] = fmaf(qh, g4.y, dc[e + 1]);
-      dc[e + 2] = fmaf(qh, g4.z, dc[e + 2]);
-      dc[e + 3] = fmaf(qh, g4.w, dc[e + 3]);
+      for (int sh = 16; sh > 0; sh >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, sh));
+      const float ex = __expf(qr - mx);
+      float sum = ex;
+#pragma unroll
+      for (int sh = 16; sh > 0; sh >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, sh);
+      const float qh = ex / sum * scale;
+      const float kh = __expf(kr - km) * kil;
+      __syncwarp();
+#pragma unroll
+      for (int e = 0; e < 32; e += 4) {
+        const float4 v4 = *reinterpret_cast<const float4*>(&stv[h][bf][0][e]);
+        const float4 g4 = *reinterpret_cast<const float4*>(&stv[h][bf][1][e]);
+        cx[e] = fmaf(kh, v4.x, cx[e]);
+        cx[e + 1] = fmaf(kh, v4.y, cx[e + 1]);
+        cx[e + 2] = fmaf(kh, v4.z, cx[e + 2]);
+        cx[e + 3] = fmaf(kh, v4.w, cx[e + 3]);
+        dc[e] = fmaf(qh, g4.x, dc[e]);
+        dc[e + 1] = fmaf(qh, g4.y, dc[e + 1]);
+        dc[e + 2] = fmaf(qh, g4.z, dc[e + 2]);
+        dc[e + 3] = fmaf(qh, g4.w, dc[e + 3]);
+      }
     }
   }
   float* cxo = wk + 4 * 32 * 2 + (h * 32 + lane) * 32;
@@ -462,50 +473,60 @@ __global__ void __launch_bounds__(128) la_bwd_pos_kernel(const __half* __restric
 #pragma unroll
   for (int e = 0; e < 32; ++e) td = fmaf(dcs[h][lane * TS2 + e], cxs[h][lane * TS2 + e], td);
   const int p0 = blockIdx.x * chunk, p1 = min(n_pos, p0 + chunk);
-  for (int p = p0; p < p1; ++p) {
-    const long long tk = img * n_pos + p;
-    const __half* row = qkv + tk * kQkv + h * kD;
-    const float qr = __half2float(__ldg(row + lane));
-    const float kr = __half2float(__ldg(row + kHid + lane));
-    const float vr = __half2float(__ldg(row + 2 * kHid + lane));
-    const float gr = __half2float(__ldg(dout + tk * kHid + h * kD + lane));
-    const float kh = __expf(kr - km) * kil;  // softmax over n
-    const int bf = p & 1;
-    stv[h][bf][0][lane] = vr;
-    stv[h][bf][1][lane] = gr;
-    stv[h][bf][2][lane] = kh;
-    float mx = qr;
+  for (int pb = p0; pb < p1; pb += 4) {
+    float qr4[4], kr4[4], vr4[4], gr4[4];
 #pragma unroll
-    for (int sh = 16; sh > 0; sh >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, sh));
-    const float ex = __expf(qr - mx);
-    float sum = ex;
-#pragma unroll
-    for (int sh = 16; sh > 0; sh >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, sh);
-    const float qs = ex / sum;               // softmax over d (unscaled)
-    __syncwarp();
-    float dqh = 0.f, dkh = 0.f, dv = 0.f;
-#pragma unroll
-    for (int e = 0; e < 32; e += 4) {
-      const float4 v4 = *reinterpret_cast<const float4*>(&stv[h][bf][0][e]);
-      const float4 g4 = *reinterpret_cast<const float4*>(&stv[h][bf][1][e]);
-      const float4 k4 = *reinterpret_cast<const float4*>(&stv[h][bf][2][e]);
-      const float4 c4 = *reinterpret_cast<const float4*>(&cxs[h][lane * TS2 + e]);
-      const float4 d4 = *reinterpret_cast<const float4*>(&dcs[h][lane * TS2 + e]);
-      const float4 t4 = *reinterpret_cast<const float4*>(&dct[h][lane * TS2 + e]);   // dctx[d = e..e+3][e' = lane]
-      dqh = fmaf(c4.x, g4.x, fmaf(c4.y, g4.y, fmaf(c4.z, g4.z, fmaf(c4.w, g4.w, dqh))));   // dq^[d] = sum_e ctx[d][e] dout[e]
-      dkh = fmaf(d4.x, v4.x, fmaf(d4.y, v4.y, fmaf(d4.z, v4.z, fmaf(d4.w, v4.w, dkh))));   // dk^[d] = sum_e dctx[d][e] v[e]
-      dv = fmaf(t4.x, k4.x, fmaf(t4.y, k4.y, fmaf(t4.z, k4.z, fmaf(t4.w, k4.w, dv))));     // dv[e'] = sum_d k^[d] dctx[d][e']
+    for (int u = 0; u < 4; ++u) {
+      const long long tk = img * n_pos + min(pb + u, p1 - 1);
+      const __half* row = qkv + tk * kQkv + h * kD;
+      qr4[u] = __half2float(__ldg(row + lane));
+      kr4[u] = __half2float(__ldg(row + kHid + lane));
+      vr4[u] = __half2float(__ldg(row + 2 * kHid + lane));
+      gr4[u] = __half2float(__ldg(dout + tk * kHid + h * kD + lane));
     }
-    // softmax over d backward (q = scale * qs): dq_raw = scale * qs * (dq^ - sum_d qs dq^)
-    float dot = qs * dqh;
 #pragma unroll
-    for (int sh = 16; sh > 0; sh >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, sh);
-    const float dq = scale * qs * (dqh - dot);
-    const float dk = kh * (dkh - td);
-    __half* ob = dqkv + tk * kQkv + h * kD + lane;
-    ob[0] = h_sat(dq);
-    ob[kHid] = h_sat(dk);
-    ob[2 * kHid] = h_sat(dv);
+    for (int u = 0; u < 4; ++u) {
+      if (pb + u >= p1) break;
+      const long long tk = img * n_pos + pb + u;
+      const float qr = qr4[u];
+      const float kh = __expf(kr4[u] - km) * kil;  // softmax over n
+      const int bf = u & 1;
+      stv[h][bf][0][lane] = vr4[u];
+      stv[h][bf][1][lane] = gr4[u];
+      stv[h][bf][2][lane] = kh;
+      float mx = qr;
+#pragma unroll
+      for (int sh = 16; sh > 0; sh >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, sh));
+      const float ex = __expf(qr - mx);
+      float sum = ex;
+#pragma unroll
+      for (int sh = 16; sh > 0; sh >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, sh);
+      const float qs = ex / sum;               // softmax over d (unscaled)
+      __syncwarp();
+      float dqh = 0.f, dkh = 0.f, dv = 0.f;
+#pragma unroll
+      for (int e = 0; e < 32; e += 4) {
+        const float4 v4 = *reinterpret_cast<const float4*>(&stv[h][bf][0][e]);
+        const float4 g4 = *reinterpret_cast<const float4*>(&stv[h][bf][1][e]);
+        const float4 k4 = *reinterpret_cast<const float4*>(&stv[h][bf][2][e]);
+        const float4 c4 = *reinterpret_cast<const float4*>(&cxs[h][lane * TS2 + e]);
+        const float4 d4 = *reinterpret_cast<const float4*>(&dcs[h][lane * TS2 + e]);
+        const float4 t4 = *reinterpret_cast<const float4*>(&dct[h][lane * TS2 + e]);   // dctx[d = e..e+3][e' = lane]
+        dqh = fmaf(c4.x, g4.x, fmaf(c4.y, g4.y, fmaf(c4.z, g4.z, fmaf(c4.w, g4.w, dqh))));   // dq^[d] = sum_e ctx[d][e] dout[e]
+        dkh = fmaf(d4.x, v4.x, fmaf(d4.y, v4.y, fmaf(d4.z, v4.z, fmaf(d4.w, v4.w, dkh))));   // dk^[d] = sum_e dctx[d][e] v[e]
+        dv = fmaf(t4.x, k4.x, fmaf(t4.y, k4.y, fmaf(t4.z, k4.z, fmaf(t4.w, k4.w, dv))));     // dv[e'] = sum_d k^[d] dctx[d][e']
+      }
+      // softmax over d backward (q = scale * qs): dq_raw = scale * qs * (dq^ - sum_d qs dq^)
+      float dot = qs * dqh;
+#pragma unroll
+      for (int sh = 16; sh > 0; sh >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, sh);
+      const float dq = scale * qs * (dqh - dot);
+      const float dk = kh * (dkh - td);
+      __half* ob = dqkv + tk * kQkv + h * kD + lane;
+      ob[0] = h_sat(dq);
+      ob[kHid] = h_sat(dk);
+      ob[2 * kHid] = h_sat(dv);
+    }
   }
 }
 
