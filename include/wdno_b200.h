@@ -186,6 +186,16 @@ int wdno_linattn_block(const void* x, void* y, const float* gamma, const void* w
                        const float* wout, const float* bias, void* work, int64_t n_img, int n_pos, int C,
                        float scale, float eps, void* stream);
 
+/* tcgen05 form of linattn_block (csrc/linattn_tc.cu; C = 64 or 128): same workspace, same result up to fp16 rounding.
+ * The LayerNorm gain is folded into the weight operands by the caller (W[:, c] * gamma[c]):
+ *   wq_canon  fp16 [C/8][128][8] : W_q diag(gamma) [128][C] in the UMMA K-major operand order (8-channel chunk, row, channel in chunk);
+ *   wkv_canon fp16 [C/8][256][8] : rows 0..127 = W_k diag(gamma) (head, d), rows 128..255 = W_v diag(gamma) (head, e).
+ * wdno_linattn_tc_supported() -> 1 when (n_img, n_pos, C) is inside its envelope, else 0 (use wdno_linattn_block). */
+int wdno_linattn_tc_supported(int64_t n_img, int n_pos, int C);
+int wdno_linattn_block_tc(const void* x, void* y, const void* wq_canon, const void* wkv_canon,
+                          const float* wout, const float* bias, void* work, int64_t n_img, int n_pos, int C,
+                          float scale, float eps, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * diffusion step algebra on the fp32 state [B,F,C,H,W] (Burgers: F=1).
  * reference: smoke/ddpm/diffusion_2d.py:689-699,723-754,769-785,851-933,970-976,988-1050 ;

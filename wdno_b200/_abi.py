@@ -28,6 +28,8 @@ SIGNATURES = {
     "wdno_softmax_attn": [P, P, P, P, P, L64, I, L64, L64, L64, L64, F, P],
     "wdno_linear_attn": [P, P, L64, I, F, P],
     "wdno_linattn_block": [P, P, P, P, P, P, P, P, L64, I, I, F, F, P],
+    "wdno_linattn_block_tc": [P, P, P, P, P, P, P, L64, I, I, F, F, P],
+    "wdno_linattn_tc_supported": [L64, I, I],
     "wdno_tattn_block_tc": [P, P, P, P, P, P, P, P, L64, I, L64, I, F, F, P],
     "wdno_tattn_block": [P, P, P, P, P, P, P, P, P, L64, I, L64, I, F, F, P],
     "wdno_ddim_step": [P, P, P, P, P, P, I, I, I, I, I, I, I, P],

@@ -46,6 +46,19 @@ class LinAttnBlock:
         assert self.wout.shape == (self.C, 128)
         self.scale = dim_head ** -0.5
         self._work = {}
+        # C = 64 / 128: every product on tcgen05 (csrc/linattn_tc.cu); WDNO_LINATTN_TC=0 keeps the mma.sync kernels
+        import os
+        self.tc = self.C in (64, 128) and os.environ.get("WDNO_LINATTN_TC", "1") != "0"
+        self._tc_ok = {}
+        if self.tc:
+            self.wq_c, self.wkv_c = (t.to(dev) for t in self._packed_canon())
+
+    def _packed_canon(self):
+        """UMMA canonical K-major operands [C/8][rows][8]: W_q (128 rows) and W_k | W_v (256 rows), LayerNorm gain folded in"""
+        gamma, w_qkv = self._src[0], self._src[1]
+        wq = w_qkv.detach().float().reshape(w_qkv.shape[0], -1) * gamma.detach().float().reshape(1, -1).to(w_qkv.device)   # [384, C]
+        canon = lambda w: w.reshape(w.shape[0], w.shape[1] // 8, 8).permute(1, 0, 2).contiguous().to(torch.float16)
+        return canon(wq[:128]), canon(wq[128:])
 
     def _packed(self):
         gamma, w_qkv, w_out, b_out = self._src
@@ -61,6 +74,9 @@ class LinAttnBlock:
         """re-pack from the live parameters into the existing device buffers (addresses stay valid for captured graphs)"""
         for dst, src in zip((self.gamma, self.wq, self.wkv, self.wout, self.bias), self._packed()):
             if dst is not None and dst.data_ptr() != src.data_ptr():
+                dst.copy_(src)
+        if self.tc:
+            for dst, src in zip((self.wq_c, self.wkv_c), self._packed_canon()):
                 dst.copy_(src)
 
     def __call__(self, x, eps=1e-5):
@@ -83,6 +99,14 @@ class LinAttnBlock:
         return y
 
     def _launch(self, L, x, y, key, n_img, n_pos, eps):
+        if self.tc:
+            if key not in self._tc_ok:
+                self._tc_ok[key] = L.wdno_linattn_tc_supported(n_img, n_pos, self.C) == 1
+            if self._tc_ok[key]:
+                _lib.check(L.wdno_linattn_block_tc(_p(x), _p(y), _p(self.wq_c), _p(self.wkv_c), _p(self.wout),
+                                                   _p(self.bias), _p(self._work[key]), n_img, n_pos, self.C, self.scale,
+                                                   float(eps), _lib.current_stream_ptr()), "linattn_block_tc")
+                return
         _lib.check(L.wdno_linattn_block(_p(x), _p(y), _p(self.gamma), _p(self.wq), _p(self.wkv), _p(self.wout), _p(self.bias),
                                         _p(self._work[key]), n_img, n_pos, self.C, self.scale, float(eps),
                                         _lib.current_stream_ptr()), "linattn_block")

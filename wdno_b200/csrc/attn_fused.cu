@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(128 * NPH, (NPH == 2) ? 2 : 4) la1_kernel(cons
 // mpack[img]: M[c][j] = scale * sum_e Wout[c][32h + e] ctx_h[d][e]  (j = 32h + d) in B-fragment order
 // [c/8][j/32][lane][8 halves] (see mma_sync.cuh).
 __global__ void __launch_bounds__(256) la_mid_kernel(const float* __restrict__ part, const float* __restrict__ wout,
-                                                     __half* __restrict__ mpack, int C, int nparts, float scale) {
+                                                     __half* __restrict__ mpack, int C, int nparts, float scale, int canon) {
   __shared__ float ctx[kLaHeads][kLaDh][kLaDh + 1];
   __shared__ float wts[4][kLaHid];  // per part: exp(m_i - m) * scale / z  for (h, d)
   pdl_trigger();
@@ -250,12 +250,28 @@ __global__ void __launch_bounds__(256) la_mid_kernel(const float* __restrict__ p
   }
   __syncthreads();
   // ctx[h][d][e] = sum_i S_i[h][d][e] * w_i[h][d]   (coalesced over e)
-  for (int idx = threadIdx.x; idx < kLaHeads * 32 * 32; idx += 256) {
-    const int h = idx >> 10, d = (idx >> 5) & 31, e = idx & 31;
-    float sacc = 0.f;
-    for (int i = 0; i < nparts; ++i)
-      sacc = fmaf(pimg[(static_cast<size_t>(i) * kLaHeads + h) * kLaPart + 64 + d * 32 + e], wts[i][h * 32 + d], sacc);
-    ctx[h][d][e] = sacc;
+  // all loads of four outputs are issued before the first use (the loop was one dependent global load per FMA: 45 % of the
+  // kernel's stall samples sat on its first FFMA)
+#pragma unroll
+  for (int k4 = 0; k4 < 4; ++k4) {
+    float pv[4][4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int idx = threadIdx.x + 256 * (k4 * 4 + k);
+      const int h = idx >> 10, de = idx & 1023;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        pv[k][i] = (i < nparts) ? __ldg(pimg + (static_cast<size_t>(i) * kLaHeads + h) * kLaPart + 64 + de) : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int idx = threadIdx.x + 256 * (k4 * 4 + k);
+      const int h = idx >> 10, d = (idx >> 5) & 31, e = idx & 31;
+      float sacc = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) sacc = fmaf(pv[k][i], wts[i][h * 32 + d], sacc);
+      ctx[h][d][e] = sacc;
+    }
   }
   __syncthreads();
   const int t = threadIdx.x & 127, chalf = threadIdx.x >> 7;
@@ -301,7 +317,9 @@ __global__ void __launch_bounds__(256) la_mid_kernel(const float* __restrict__ p
         s3 = fmaf(w4.w, cr[4 * e4 + 3], s3);
       }
       const int nt = c >> 3, gg = c & 7;
-      msm[((nt * 4 + (ks >> 1)) * 32 + (gg * 4 + qq)) * 8 + ((ks & 1) * 2 + reg) * 2 + half] = wdno::h_sat((s0 + s1) + (s2 + s3));
+      const __half mv = wdno::h_sat((s0 + s1) + (s2 + s3));
+      if (canon) msm[((j >> 3) * C + c) * 8 + (j & 7)] = mv;   // UMMA K-major B operand [128/8][C][8] (linattn_tc.cu)
+      else msm[((nt * 4 + (ks >> 1)) * 32 + (gg * 4 + qq)) * 8 + ((ks & 1) * 2 + reg) * 2 + half] = mv;
     }
   }
   __syncthreads();
@@ -1447,6 +1465,21 @@ static int launch_tattn(const __half* x, __half* y, const float* gamma, const ui
   return check_launch("tattn_block");
 }
 
+// merge + fold launch for the tcgen05 form (linattn_tc.cu): same kernel, M written as a UMMA operand when canon != 0
+int launch_la_mid(const float* part, const float* wout, void* mpack, int C, int nparts, float scale, int canon, int n_img,
+                  cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(la_mid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * kLaHid * 2);
+    if (e != cudaSuccess) return set_cuda_error(e, "la_mid: cudaFuncSetAttribute");
+    configured = true;
+  }
+  cudaError_t le = launch_pdl(la_mid_kernel, dim3(n_img), dim3(256), static_cast<size_t>(C * kLaHid * 2), st, part, wout, static_cast<__half*>(mpack), C,
+                              nparts, scale, canon);
+  if (le != cudaSuccess) return set_cuda_error(le, "la_mid: launch");
+  return WDNO_OK;
+}
+
 static int la_split(int n_pos) { return ((n_pos + 63) / 64 >= 16) ? 2 : 1; }
 
 template <int C>
@@ -1479,7 +1512,7 @@ static int launch_linattn(const __half* x, __half* y, const float* gamma, const 
     launch_pdl(la1_kernel<C, WS1, 2>, dim3(n_img * split), dim3(256), static_cast<size_t>(smem1), st, x, gamma, wkv, part, n_pos, split,
                eps);
   launch_pdl(la_mid_kernel, dim3(n_img), dim3(256), static_cast<size_t>(C * kLaHid * 2), st, static_cast<const float*>(part), wout,
-             mpack, C, nparts, scale);
+             mpack, C, nparts, scale, 0);
   static const bool use_warp = [] { const char* e = getenv("WDNO_LA2_WARP"); return !(e && e[0] == '0'); }();
   if (use_warp) {
     const int smem_w = 4 * (16 * (C + 8) + 2 * 16 * C) * 2;

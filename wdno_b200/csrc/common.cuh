@@ -21,6 +21,10 @@ int launch_short_attn_mma(const void* qkv, void* out, const float* bias, const f
 int launch_flash_attn_mma(const void* qkv, void* out, long long n_seq, int n_tok, long long inner, long long outerT,
                           long long innerT, long long tokT, float scale, cudaStream_t st);
 
+// attn_fused.cu: merge the context partials of the linear attention and fold to_out into them (canon: UMMA operand order)
+int launch_la_mid(const float* part, const float* wout, void* mpack, int C, int nparts, float scale, int canon, int n_img,
+                  cudaStream_t st);
+
 // dwt3d_stream.cu: streaming (register sliding-window) form of the fused 3-D transforms; return 1 = launched, 0 = shape or
 // alignment outside the envelope (use the tile kernels of dwt3d.cu), < 0 = error
 int launch_ana3d_stream(const float* x, float* const* bands8, long long band_bstride, long long B, int Nd, int Nh, int Nw, int nd,
