@@ -23,6 +23,8 @@
 #include <math.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "../../include/wdno_b200.h"
 #include "common.cuh"
 #include "cvt_sat.cuh"
@@ -145,10 +147,12 @@ __device__ __forceinline__ void ln_role(const __half* __restrict__ x, uint8_t* x
     uint8_t* xb = xn_base + buf * XNB;
 #pragma unroll
     for (int pb = 0; pb < PASSES; pb += BATCH) {
+      // one-pass statistics (sum, sum of squares of the fp16 inputs in fp32; var = E[x^2] - mean^2, clamped): one FFMA per
+      // element instead of a centring pass -- the producers share their issue slots with the row warps
       float f[BATCH][16], sum[BATCH], sq[BATCH];
 #pragma unroll
       for (int b = 0; b < BATCH; ++b) {
-        float sm[4] = {0.f, 0.f, 0.f, 0.f};
+        float sm[4] = {0.f, 0.f, 0.f, 0.f}, sqp[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int v = 0; v < 2; ++v) {
           const __half2* hh = reinterpret_cast<const __half2*>(&cur[pb + b][v]);
@@ -158,40 +162,34 @@ __device__ __forceinline__ void ln_role(const __half* __restrict__ x, uint8_t* x
             f[b][v * 8 + 2 * i] = tt.x;
             f[b][v * 8 + 2 * i + 1] = tt.y;
             sm[i] += tt.x + tt.y;
+            sqp[i] = fmaf(tt.x, tt.x, sqp[i]);
+            sqp[i] = fmaf(tt.y, tt.y, sqp[i]);
           }
         }
         sum[b] = (sm[0] + sm[1]) + (sm[2] + sm[3]);
+        sq[b] = (sqp[0] + sqp[1]) + (sqp[2] + sqp[3]);
         load(tn, pb + b);                           // registers of this pass are free: next tile's rows
       }
 #pragma unroll
       for (int o = 1; o < LPR; o <<= 1)
 #pragma unroll
-        for (int b = 0; b < BATCH; ++b) sum[b] += __shfl_xor_sync(0xffffffffu, sum[b], o);
-#pragma unroll
-      for (int b = 0; b < BATCH; ++b) {
-        const float mean = sum[b] * (1.0f / C);
-        float sqp[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          f[b][i] -= mean;
-          sqp[i & 3] = fmaf(f[b][i], f[b][i], sqp[i & 3]);
+        for (int b = 0; b < BATCH; ++b) {
+          sum[b] += __shfl_xor_sync(0xffffffffu, sum[b], o);
+          sq[b] += __shfl_xor_sync(0xffffffffu, sq[b], o);
         }
-        sq[b] = (sqp[0] + sqp[1]) + (sqp[2] + sqp[3]);
-      }
-#pragma unroll
-      for (int o = 1; o < LPR; o <<= 1)
-#pragma unroll
-        for (int b = 0; b < BATCH; ++b) sq[b] += __shfl_xor_sync(0xffffffffu, sq[b], o);
 #pragma unroll
       for (int b = 0; b < BATCH; ++b) {
         const int row = RPP * (pb + b) + rsub;
-        const float rstd = (row < t.nv) ? rsqrtf(sq[b] * (1.0f / C) + eps) : 0.f;
+        const float mean = sum[b] * (1.0f / C);
+        const float var = fmaxf(fmaf(-mean, mean, sq[b] * (1.0f / C)), 0.f);
+        const float rstd = (row < t.nv) ? rsqrtf(var + eps) : 0.f;
+        const float sh = -mean * rstd;
 #pragma unroll
         for (int v = 0; v < 2; ++v) {
           uint4 ov;
           uint32_t* o = reinterpret_cast<uint32_t*>(&ov);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) o[i] = pack2(f[b][v * 8 + 2 * i] * rstd, f[b][v * 8 + 2 * i + 1] * rstd);
+          for (int i = 0; i < 4; ++i) o[i] = pack2(fmaf(f[b][v * 8 + 2 * i], rstd, sh), fmaf(f[b][v * 8 + 2 * i + 1], rstd, sh));
           *reinterpret_cast<uint4*>(xb + ((q * 2 + v) * 128 + row) * 16) = ov;
         }
       }
@@ -414,53 +412,55 @@ __global__ void __launch_bounds__(kThreads, 1) la1_tc_kernel(const __half* __res
       ptx::tmem_ld_wait();
       ptx::tc_fence_before();
       ptx::mbar_arrive(&bars->a_empty[buf]);           // this half of the K^T row now lives in registers
-      const bool full = t.nv == 128;                    // warp-uniform: masks only on an image's last, partial tile
-      // ---- max over the tile's valid pixels: own 64 columns (four chains), then the other half through shared memory
-      float mxs[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-      if (full) {
-#pragma unroll
-        for (int c = 0; c < 32; ++c) mxs[c & 3] = fmaxf(mxs[c & 3], fmaxf(__uint_as_float(ra[c]), __uint_as_float(rb[c])));
-      } else {
+      // ---- max over the tile's valid pixels (own 64 columns, four chains; the other half through shared memory), then
+      //      ek = exp(k - max) -> fp16 chunks of 8 pixels (K-major A operand of the S product).  Two instantiations: the
+      //      column masks exist only in the one that handles an image's last, partial tile.
+      float* ex = exch + (buf * 2) * 128;
+      uint8_t* ekb = smem + Map::oEk + buf * (128 * 128 * 2);
+      float m_new = 0.f;
+      auto tile_body = [&](auto full_c) {
+        constexpr bool FULL = decltype(full_c)::value;
+        float mxs[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
-          mxs[c & 3] = fmaxf(mxs[c & 3], (c0 + c < t.nv) ? __uint_as_float(ra[c]) : -INFINITY);
-          mxs[c & 3] = fmaxf(mxs[c & 3], (c0 + 32 + c < t.nv) ? __uint_as_float(rb[c]) : -INFINITY);
+          const float va = (FULL || c0 + c < t.nv) ? __uint_as_float(ra[c]) : -INFINITY;
+          const float vb2 = (FULL || c0 + 32 + c < t.nv) ? __uint_as_float(rb[c]) : -INFINITY;
+          mxs[c & 3] = fmaxf(mxs[c & 3], fmaxf(va, vb2));
         }
-      }
-      const float mx = fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3]));
-      float* ex = exch + (buf * 2) * 128;
-      ex[hf * 128 + row] = mx;
-      pair_sync(qd);
-      const float m_new = fmaxf(m_run, fmaxf(mx, ex[(1 - hf) * 128 + row]));
-      z *= ex2((m_run - m_new) * kLog2e);
-      m_run = m_new;
-      // ---- ek = exp(k - max) -> fp16 chunks of 8 pixels (K-major A operand of the S product)
-      const float nb = -m_new * kLog2e;
-      uint8_t* ekb = smem + Map::oEk + buf * (128 * 128 * 2);
-      float zp[4] = {0.f, 0.f, 0.f, 0.f};
-      auto emit = [&](const uint32_t (&r)[32], int cb) {
+        const float mx = fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3]));
+        ex[hf * 128 + row] = mx;
+        pair_sync(qd);
+        m_new = fmaxf(m_run, fmaxf(mx, ex[(1 - hf) * 128 + row]));
+        z *= ex2((m_run - m_new) * kLog2e);
+        m_run = m_new;
+        const float nb = -m_new * kLog2e;
+        float zp[4] = {0.f, 0.f, 0.f, 0.f};
+        auto emit = [&](const uint32_t (&r)[32], int cb) {
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          uint4 ov;
-          uint32_t* o = reinterpret_cast<uint32_t*>(&ov);
+          for (int ch = 0; ch < 4; ++ch) {
+            uint4 ov;
+            uint32_t* o = reinterpret_cast<uint32_t*>(&ov);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int c = ch * 8 + 2 * i;
-            float e0 = ex2(fmaf(__uint_as_float(r[c]), kLog2e, nb));
-            float e1 = ex2(fmaf(__uint_as_float(r[c + 1]), kLog2e, nb));
-            if (!full) {
-              if (cb + c >= t.nv) e0 = 0.f;
-              if (cb + c + 1 >= t.nv) e1 = 0.f;
+            for (int i = 0; i < 4; ++i) {
+              const int c = ch * 8 + 2 * i;
+              float e0 = ex2(fmaf(__uint_as_float(r[c]), kLog2e, nb));
+              float e1 = ex2(fmaf(__uint_as_float(r[c + 1]), kLog2e, nb));
+              if (!FULL) {
+                if (cb + c >= t.nv) e0 = 0.f;
+                if (cb + c + 1 >= t.nv) e1 = 0.f;
+              }
+              zp[i] += e0 + e1;
+              o[i] = pack2(e0, e1);
             }
-            zp[i] += e0 + e1;
-            o[i] = pack2(e0, e1);
+            *reinterpret_cast<uint4*>(ekb + (((cb >> 3) + ch) * 128 + row) * 16) = ov;
           }
-          *reinterpret_cast<uint4*>(ekb + (((cb >> 3) + ch) * 128 + row) * 16) = ov;
-        }
+        };
+        emit(ra, c0);
+        emit(rb, c0 + 32);
+        z += (zp[0] + zp[1]) + (zp[2] + zp[3]);
       };
-      emit(ra, c0);
-      emit(rb, c0 + 32);
-      z += (zp[0] + zp[1]) + (zp[2] + zp[3]);
+      if (t.nv == 128) tile_body(std::true_type{});
+      else tile_body(std::false_type{});
       // ---- S of the previous tile
       if (j >= 1) {
         merge(j - 1);
