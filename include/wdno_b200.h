@@ -186,6 +186,13 @@ int wdno_linattn_block(const void* x, void* y, const float* gamma, const void* w
                        const float* wout, const float* bias, void* work, int64_t n_img, int n_pos, int C,
                        float scale, float eps, void* stream);
 
+/* all-tcgen05 form of tattn_block for C = 64 (csrc/tattn_row.cu): every product a 128-row UMMA, softmax in the registers of the
+ * thread that owns the accumulator row.  wqkv_canon fp16 [C/8][384][8] = W_qkv diag(gamma) and wout_canon fp16 [16][C][8] = W_out in
+ * the UMMA K-major operand order (the LayerNorm gain is folded into W_qkv by the caller); bias / rot_* as for wdno_tattn_block. */
+int wdno_tattn_block_row(const void* x, void* y, const void* wqkv_canon, const void* wout_canon, const float* bias,
+                         const float* rot_cos, const float* rot_sin, int64_t n_samples, int n_frames, int64_t hw, int C,
+                         float scale, float eps, void* stream);
+
 /* tcgen05 form of linattn_block (csrc/linattn_tc.cu; C = 64 or 128): same workspace, same result up to fp16 rounding.
  * The LayerNorm gain is folded into the weight operands by the caller (W[:, c] * gamma[c]):
  *   wq_canon  fp16 [C/8][128][8] : W_q diag(gamma) [128][C] in the UMMA K-major operand order (8-channel chunk, row, channel in chunk);

@@ -31,6 +31,7 @@ SIGNATURES = {
     "wdno_linattn_block_tc": [P, P, P, P, P, P, P, L64, I, I, F, F, P],
     "wdno_linattn_tc_supported": [L64, I, I],
     "wdno_tattn_block_tc": [P, P, P, P, P, P, P, P, L64, I, L64, I, F, F, P],
+    "wdno_tattn_block_row": [P, P, P, P, P, P, P, L64, I, L64, I, F, F, P],
     "wdno_tattn_block": [P, P, P, P, P, P, P, P, P, L64, I, L64, I, F, F, P],
     "wdno_ddim_step": [P, P, P, P, P, P, I, I, I, I, I, I, I, P],
     "wdno_ddpm_step": [P, P, P, P, P, P, I, I, I, I, I, I, I, P],

@@ -124,16 +124,25 @@ class TemporalBlock:
         assert w_qkv.shape[0] == 384 and self.C in (64, 128, 256) and tuple(w_out.shape[:2]) == (self.C, 128)
         self.gamma, self.wqk, self.wv, self.wo = (t.to(dev) for t in self._packed())
         self.scale = dim_head ** -0.5
-        # C = 64 (the full-resolution instances): projections on tcgen05 (csrc/tattn_tc.cu); WDNO_TATTN_TC=0 keeps the mma.sync kernel
+        # C = 64 (the full-resolution instances): WDNO_TATTN_TC=2 (default) every product on tcgen05, softmax per accumulator row
+        # (csrc/tattn_row.cu); =1 projections on tcgen05 + mma.sync attention (csrc/tattn_tc.cu); =0 the mma.sync kernel
         import os
-        self.tc = self.C == 64 and os.environ.get("WDNO_TATTN_TC", "1") != "0"
+        mode = os.environ.get("WDNO_TATTN_TC", "2")
+        self.tc = self.C == 64 and mode == "1"
+        self.row = self.C == 64 and mode not in ("0", "1")
         if self.tc:
             self.wqkv_c, self.wo_c = (t.to(dev) for t in self._packed_canon())
+        if self.row:
+            self.wqkv_g, self.wo_g = (t.to(dev) for t in self._packed_canon(fold_gamma=True))
 
-    def _packed_canon(self):
-        """UMMA canonical K-major operands: [K/8][rows][8]"""
-        _, w_qkv, w_out = self._src
+    def _packed_canon(self, fold_gamma=False):
+        """UMMA canonical K-major operands: [K/8][rows][8]; fold_gamma: W_qkv diag(gamma) (the row kernel normalises without gain)"""
+        gamma, w_qkv, w_out = self._src
         wq = w_qkv.detach().float().reshape(w_qkv.shape[0], -1)    # [384, C]
+        if fold_gamma:
+            # the row kernel also wants the attention scale and log2(e) (its softmax runs in base 2) in the q rows
+            wq = wq * gamma.detach().float().reshape(1, -1).to(wq.device)
+            wq = torch.cat([wq[:128] * (self.scale * 1.4426950408889634), wq[128:]])
         wo = w_out.detach().float().reshape(w_out.shape[0], -1)    # [C, 128]
         canon = lambda w: w.reshape(w.shape[0], w.shape[1] // 8, 8).permute(1, 0, 2).contiguous().to(torch.float16)
         return canon(wq), canon(wo)
@@ -152,6 +161,9 @@ class TemporalBlock:
         if self.tc:
             for dst, src in zip((self.wqkv_c, self.wo_c), self._packed_canon()):
                 dst.copy_(src)
+        if self.row:
+            for dst, src in zip((self.wqkv_g, self.wo_g), self._packed_canon(fold_gamma=True)):
+                dst.copy_(src)
 
     def __call__(self, x, bias=None, rot=None, eps=1e-5):
         """bias fp32 [4, D, D] or None; rot = (cos, sin) fp32 [D, 16] or None."""
@@ -167,6 +179,11 @@ class TemporalBlock:
         # algorithmic work (conv3d.py:262-353): one read + one write of the fp16 residual stream; projections + QK^T + PV
         with _timing.span("tattn_block", flops=2.0 * ntok * (self.C * 384 + 128 * self.C + 2 * 128 * D),
                           bytes=4.0 * ntok * self.C, meta=(self.C, B, D, H * W)):
+            if self.row:
+                _lib.check(_lib.lib().wdno_tattn_block_row(_p(x), _p(y), _p(self.wqkv_g), _p(self.wo_g), _p(bias), _p(rc), _p(rs),
+                                                           B, D, H * W, self.C, self.scale, float(eps),
+                                                           _lib.current_stream_ptr()), "tattn_block_row")
+                return y
             if self.tc:
                 _lib.check(_lib.lib().wdno_tattn_block_tc(_p(x), _p(y), _p(self.gamma), _p(self.wqkv_c), _p(self.wo_c), _p(bias),
                                                           _p(rc), _p(rs), B, D, H * W, self.C, self.scale, float(eps),
