@@ -65,3 +65,88 @@ def test_tattn_block_vs_oracle(C, B, D, H, W):
     got = got.float().cpu().permute(0, 4, 1, 2, 3)
     assert rel_l2(got - x, want - x) < 6e-3, rel_l2(got - x, want - x)
     assert rel_l2(got, want) < 1e-3
+
+
+def _torch_linattn(x, gamma, wqkv, wout, bout, eps=1e-5):
+    """fp64 restatement of conv3d.py:165-184,232-258 on [n_img, n, C] (the oracle module works on 5-D tensors)"""
+    mean = x.mean(-1, keepdim=True)
+    var = x.var(-1, unbiased=False, keepdim=True)
+    xn = (x - mean) / (var + eps).sqrt() * gamma
+    q, k, v = [t.reshape(t.shape[0], t.shape[1], 4, 32) for t in (xn @ wqkv.t()).chunk(3, dim=-1)]
+    q = q.softmax(dim=-1) * 32 ** -0.5
+    k = k.softmax(dim=1)
+    ctx = torch.einsum("inhd,inhe->ihde", k, v)
+    out = torch.einsum("ihde,inhd->inhe", ctx, q).reshape(x.shape[0], x.shape[1], 128)
+    return x + out @ wout.t() + bout
+
+
+@pytest.mark.parametrize("C,n_img,n", [(64, 200, 300), (128, 333, 400), (64, 151, 1000), (64, 1, 128), (128, 3, 129)])
+def test_linattn_tc_images_split_over_ctas(C, n_img, n):
+    """tcgen05 form (csrc/linattn_tc.cu): more images than SMs, so a CTA's tile range cuts images in two (two context partials
+    per image, one of them empty when the image fits), ragged last tiles, and the one-tile-per-image geometry.  Checked against
+    an fp64 restatement and against the mma.sync kernels on the same inputs."""
+    from wdno_b200.attn_fused import LinAttnBlock
+    torch.manual_seed(C + n)
+    gamma = 1 + 0.2 * torch.randn(C)
+    wqkv = torch.randn(384, C) * (2.0 / C ** 0.5)
+    wout = torch.randn(C, 128) * 0.1
+    bout = torch.randn(C) * 0.1
+    x = (torch.randn(n_img, 1, n, 1, C) * 1.5 + 0.2).half().cuda()
+    blk = LinAttnBlock(gamma, wqkv.reshape(384, C, 1, 1), wout.reshape(C, 128, 1, 1), bout, device="cuda")
+    assert blk.tc, "the tcgen05 path must be the default for C = 64 / 128"
+    got = blk(x).float().reshape(n_img, n, C)
+    old_env = os.environ.get("WDNO_LINATTN_TC")
+    os.environ["WDNO_LINATTN_TC"] = "0"
+    try:
+        ref_blk = LinAttnBlock(gamma, wqkv.reshape(384, C, 1, 1), wout.reshape(C, 128, 1, 1), bout, device="cuda")
+    finally:
+        if old_env is None:
+            del os.environ["WDNO_LINATTN_TC"]
+        else:
+            os.environ["WDNO_LINATTN_TC"] = old_env
+    assert not ref_blk.tc
+    other = ref_blk(x).float().reshape(n_img, n, C)
+    xf = x.float().reshape(n_img, n, C)
+    want = _torch_linattn(xf.double(), gamma.cuda().double(), wqkv.cuda().double(), wout.cuda().double(), bout.cuda().double()).float()
+    assert rel_l2(got - xf, want - xf) < 6e-3, rel_l2(got - xf, want - xf)
+    assert rel_l2(got, want) < 1e-3
+    assert rel_l2(got - xf, other - xf) < 4e-3        # two fp16-operand evaluations of the same block
+    assert not torch.isnan(got).any()
+
+
+@pytest.mark.parametrize("B,D,H,W", [(2, 24, 20, 20), (1, 24, 13, 11), (3, 32, 9, 9)])
+def test_tattn_row_multi_tile_and_variants_agree(B, D, H, W):
+    """all-tcgen05 temporal block (csrc/tattn_row.cu, the C = 64 default): several tiles per CTA, pixel counts that are not a
+    multiple of the 4-pixel tile, 32 frames; must agree with the two older kernels (WDNO_TATTN_TC=1 / 0) to fp16 round-off."""
+    from wdno_b200.attn_fused import TemporalBlock
+    C = 64
+    torch.manual_seed(D + H)
+    gamma = 1 + 0.2 * torch.randn(C)
+    wqkv = torch.randn(384, C) * (2.0 / C ** 0.5)
+    wout = torch.randn(C, 128) * 0.1
+    x = (torch.randn(B, D, H, W, C) * 1.5 + 0.2).half().cuda()
+    bias = (torch.randn(4, D, D) * 0.5).cuda()
+    freqs = 1.0 / (10000 ** (torch.arange(0, 32, 2).float() / 32))
+    ang = torch.arange(D, dtype=torch.float32)[:, None] * freqs[None, :]
+    rot = (ang.cos().contiguous().cuda(), ang.sin().contiguous().cuda())
+    outs = {}
+    old_env = os.environ.get("WDNO_TATTN_TC")
+    try:
+        for mode in ("2", "1", "0"):
+            if mode == "0" and (H * W) % 2:
+                continue                                  # the mma.sync pair kernel needs an even pixel count
+            os.environ["WDNO_TATTN_TC"] = mode
+            blk = TemporalBlock(gamma, wqkv, wout, device="cuda")
+            assert blk.row == (mode == "2") and blk.tc == (mode == "1")
+            outs[mode] = blk(x, bias=bias, rot=rot).float()
+    finally:
+        if old_env is None:
+            os.environ.pop("WDNO_TATTN_TC", None)
+        else:
+            os.environ["WDNO_TATTN_TC"] = old_env
+    xf = x.float()
+    for mode, o in outs.items():
+        assert not torch.isnan(o).any(), mode
+    assert rel_l2(outs["2"] - xf, outs["1"] - xf) < 4e-3, rel_l2(outs["2"] - xf, outs["1"] - xf)
+    if "0" in outs:
+        assert rel_l2(outs["2"] - xf, outs["0"] - xf) < 4e-3
