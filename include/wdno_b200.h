@@ -112,11 +112,15 @@ typedef struct {
   int32_t fold;           /* 1: the D planes of a "sample" are D independent samples of a 2-D layer folded into the depth
                              axis (KD == 1 only) so that ZT of them share every weight tile: GroupNorm coefficients and
                              statistics are indexed by b*D + z instead of b */
-  int32_t reserved0;
+  int32_t cluster;        /* 0 / 1: independent CTAs.  2: CTA pairs (thread-block clusters of 2) that fetch every weight tile ONCE with
+                             a multicast bulk copy; needs an even grid <= wdno_tapgemm_max_cluster_ctas(), an even number of
+                             (sample, plane group, tile) units and reuse == 0 */
 } wdno_tapgemm_params;
 
 /* bytes of dynamic shared memory the plan needs, or <0 */
 int64_t wdno_tapgemm_smem_bytes(const wdno_tapgemm_params* p);
+/* CTAs of 2-CTA clusters that can be resident at once with smem_bytes of dynamic shared memory each, or <0 */
+int wdno_tapgemm_max_cluster_ctas(int64_t smem_bytes);
 int wdno_tapgemm(const wdno_tapgemm_params* p, void* stream);
 
 /* Plain 1x1 convolution / Linear (no fused GroupNorm prologue or statistics): the HBM-bound layers -- ResnetBlock.res_conv

@@ -31,7 +31,7 @@ def test_exports_every_declared_symbol(lib):
 def test_struct_layouts_match_header():
     from wdno_b200 import _abi, _lib
     assert C.sizeof(_lib.Tap) == 8 and C.sizeof(_lib.KSet) == 24 and C.sizeof(_lib.NChunk) == 40
-    assert C.sizeof(_lib.TapGemmParams) == 256   # + strips, Wfull, fold, reserved0
+    assert C.sizeof(_lib.TapGemmParams) == 256   # + strips, Wfull, fold, cluster
     assert C.sizeof(_abi.CondOp) == 96
     from wdno_b200 import training
     assert C.sizeof(training.WgradGroup) == 56          # 5 + 3 int32, 3 int64

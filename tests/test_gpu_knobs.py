@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 KNOBS = [{}, {"WDNO_ZSTACK": "0"}, {"WDNO_FOLD": "0"}, {"WDNO_FOLD": "force"}, {"WDNO_CONV1X1": "0"}, {"WDNO_TATTN_WARP": "0"},
          {"WDNO_LA2_WARP": "0"}, {"WDNO_LA1_NPH": "2"}, {"WDNO_DWT3D_STREAM": "0"}, {"WDNO_DWT3D_FUSED": "0"}, {"WDNO_NTILE_BIG": "0"},
          {"WDNO_TIME_UNIFORM": "0"}, {"WDNO_PDL": "1"}, {"WDNO_TATTN_TC": "0"}, {"WDNO_TATTN_TC": "1"}, {"WDNO_LINATTN_TC": "0"},
-         {"WDNO_LINATTN_TC": "0", "WDNO_LA2_WARP": "0"}, {"WDNO_LINATTN_TC": "0", "WDNO_LA1_NPH": "2"}]
+         {"WDNO_LINATTN_TC": "0", "WDNO_LA2_WARP": "0"}, {"WDNO_LINATTN_TC": "0", "WDNO_LA1_NPH": "2"}, {"WDNO_CLUSTER": "1"}]
 
 
 @pytest.mark.parametrize("knob", KNOBS, ids=lambda k: ",".join(f"{a}={b}" for a, b in k.items()) or "defaults")

@@ -41,7 +41,7 @@ class TapGemmParams(C.Structure):
         ("NSLOT", C.c_int32), ("NBST", C.c_int32), ("S_pad", C.c_int32), ("grid", C.c_int32),
         ("TPS", C.c_int32), ("reuse", C.c_int32), ("n_taps", C.c_int32), ("bias_len", C.c_int32),
         ("n_sets", C.c_int32), ("zstack", C.c_int32), ("strips", C.c_int32), ("Wfull", C.c_int32),
-        ("fold", C.c_int32), ("reserved0", C.c_int32),
+        ("fold", C.c_int32), ("cluster", C.c_int32),
     ]
 
 
@@ -63,6 +63,8 @@ def lib():
     L.wdno_device_cc.restype = C.c_int
     L.wdno_tapgemm_smem_bytes.restype = C.c_int64
     L.wdno_tapgemm_smem_bytes.argtypes = [C.POINTER(TapGemmParams)]
+    L.wdno_tapgemm_max_cluster_ctas.restype = C.c_int
+    L.wdno_tapgemm_max_cluster_ctas.argtypes = [C.c_int64]
     L.wdno_tapgemm.restype = C.c_int
     L.wdno_tapgemm.argtypes = [C.POINTER(TapGemmParams), C.c_void_p]
     _bind_rest(L)

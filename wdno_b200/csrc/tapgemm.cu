@@ -35,7 +35,7 @@ constexpr int kThreads = (kEpiWarps + 2 + kProdWarps + kLoadWarps) * 32;
 constexpr int kProdThreads = kProdWarps * 32;
 constexpr int kLoadThreads = kLoadWarps * 32;
 constexpr int kMaxSlots = 12;
-constexpr int kMaxBStages = 8;
+constexpr int kMaxBStages = 4;
 constexpr int kBarBytes = 512;
 constexpr int kMaxTaps = 384;             // tap table copied to shared memory (7x7x7 = 343)
 constexpr int kStageRow = 144;             // epilogue staging: 128 B of fp16 columns + 16 B pad (row's global offset)
@@ -68,6 +68,7 @@ struct Bars {
   uint64_t raw_full[kMaxSlots];
   uint64_t b_full[kMaxBStages];
   uint64_t b_empty[kMaxBStages];
+  uint64_t b_peer[kMaxBStages];   // cluster mode, leader CTA: the peer's stage is free and its mbarrier armed
   uint64_t acc_full[2];
   uint64_t acc_empty[2];
   uint32_t tmem_base;
@@ -103,6 +104,21 @@ __device__ __forceinline__ Work decode_work(int w, int n_chunks, int ptiles, int
     k.xs0 = (r - k.b * strips) * strip_w;
   }
   return k;
+}
+
+// i-th work item of this CTA, or -1.  Default: blockIdx.x + i * gridDim.x.  Cluster mode (p.cluster == 2, CTA pairs that
+// share every weight tile through one multicast copy): the pair walks pair-items q = pair + i * n_pairs; both CTAs take the
+// same N-chunk (q % n_chunks) of two neighbouring position / plane units, so they consume the weight stream in lock step.
+__device__ __forceinline__ int work_at(const wdno_tapgemm_params& p, int i, int n_work) {
+  if (p.cluster != 2) {
+    const long long w = static_cast<long long>(blockIdx.x) + static_cast<long long>(i) * gridDim.x;
+    return w < n_work ? static_cast<int>(w) : -1;
+  }
+  const long long q = static_cast<long long>(blockIdx.x >> 1) + static_cast<long long>(i) * (gridDim.x >> 1);
+  if (2 * q >= n_work) return -1;
+  const int chunk = static_cast<int>(q % p.n_chunks);
+  const int rest = static_cast<int>(q / p.n_chunks) * 2 + static_cast<int>(blockIdx.x & 1u);
+  return chunk + p.n_chunks * rest;
 }
 
 // silu(v) = v * sigmoid(v) = 0.5 v (1 + tanh(v/2)): one MUFU op (tanh.approx.f32, rel. error 2^-11, i.e. the fp16 rounding
@@ -164,14 +180,15 @@ __device__ __forceinline__ void mma_role(const wdno_tapgemm_params& p, Bars* bar
   const uint32_t S_pad = static_cast<uint32_t>(p.S_pad);
   const uint32_t slot_u = (static_cast<uint32_t>(p.KC >> 3) * S_pad * 16u) >> 4;
   const uint32_t btile_u = (N * static_cast<uint32_t>(p.KC) * 2u) >> 4, bstage_u = btile_u * static_cast<uint32_t>(TPS);
-  const uint32_t a_lo0 = (ptx::smem_u32(slab_base) >> 4) + (S_pad << 16);  // start | LBO = S_pad*16 B
-  const uint32_t b_lo0 = (ptx::smem_u32(b_base) >> 4) + (N << 16);         // start | LBO = N*16 B
+  // (in a cluster launch the numeric shared address carries the CTA rank above bit 18: descriptors take the CTA-relative offset)
+  const uint32_t a_lo0 = ((ptx::smem_u32(slab_base) & 0x3FFFFu) >> 4) + (S_pad << 16);  // start | LBO = S_pad*16 B
+  const uint32_t b_lo0 = ((ptx::smem_u32(b_base) & 0x3FFFFu) >> 4) + (N << 16);         // start | LBO = N*16 B
   const uint32_t a_kstep = 2u * S_pad, b_kstep = 2u * N;
   uint32_t s0 = 0, sph = 0;   // ring slot / phase of plane 0 of the current K-set
   uint32_t bst = 0, bph = 0;  // weight stage / phase
   uint32_t acnt = 0;          // accumulator-buffer use counter
   PROF_DECL;
-  for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+  for (int wi = 0, w; (w = work_at(p, wi, n_work)) >= 0; ++wi) {
     const int nc0 = reuse ? 0 : (w % n_chunks);
     const int nc1 = reuse ? n_chunks : nc0 + 1;
     const uint32_t su = s0, suph = sph;  // ring position at the start of this work item
@@ -273,8 +290,9 @@ __device__ __forceinline__ void mma_role_zstack(const wdno_tapgemm_params& p, Ba
   const uint32_t S_pad = static_cast<uint32_t>(p.S_pad);
   const uint32_t slot_u = (static_cast<uint32_t>(p.KC >> 3) * S_pad * 16u) >> 4;
   const uint32_t btile_u = (rows * static_cast<uint32_t>(p.KC) * 2u) >> 4, bstage_u = btile_u * static_cast<uint32_t>(TPS);
-  const uint32_t a_lo0 = (ptx::smem_u32(slab_base) >> 4) + (S_pad << 16);  // start | LBO = S_pad*16 B
-  const uint32_t b_lo0 = (ptx::smem_u32(b_base) >> 4) + (rows << 16);      // start | LBO = rows*16 B
+  // (in a cluster launch the numeric shared address carries the CTA rank above bit 18: descriptors take the CTA-relative offset)
+  const uint32_t a_lo0 = ((ptx::smem_u32(slab_base) & 0x3FFFFu) >> 4) + (S_pad << 16);  // start | LBO = S_pad*16 B
+  const uint32_t b_lo0 = ((ptx::smem_u32(b_base) & 0x3FFFFu) >> 4) + (rows << 16);      // start | LBO = rows*16 B
   const uint32_t a_kstep = 2u * S_pad;
   constexpr uint32_t b_kstep = 2u * rows;
   const uint32_t id1 = ptx::make_idesc_f16(64, 0), id2 = ptx::make_idesc_f16(128, 0), id3 = ptx::make_idesc_f16(192, 0),
@@ -316,7 +334,7 @@ __device__ __forceinline__ void mma_role_zstack(const wdno_tapgemm_params& p, Ba
       if (++sj == nslot) sj = 0;
     }
   };
-  for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++acnt) {
+  for (int wi = 0, w; (w = work_at(p, wi, n_work)) >= 0; ++wi, ++acnt) {
     const wdno_nchunk ci = s_chunks[w % n_chunks];
     const uint32_t buf = acnt & 1u, aph = (acnt >> 1) & 1u;
     PROF_REGION(0, ptx::mbar_wait(&bars->acc_empty[buf], aph ^ 1u));
@@ -401,6 +419,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const wdno_tapgemm
     for (int i = 0; i < p.NBST; ++i) {
       ptx::mbar_init(&bars->b_full[i], 1);
       ptx::mbar_init(&bars->b_empty[i], 1);
+      ptx::mbar_init(&bars->b_peer[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&bars->acc_full[i], 1);
@@ -419,6 +438,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const wdno_tapgemm
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (p.cluster == 2) ptx::cluster_sync();   // the peer's mbarriers exist before the first multicast copy / remote arrive
   ptx::tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
   // everything above touched only plan constants (tables, bias) and on-chip state; activations, GroupNorm
@@ -445,7 +465,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const wdno_tapgemm
       if (p.src_mode == 1) { Hs = 2 * p.H; Ws = 2 * p.Wfull; }
       if (p.src_mode == 2) { Hs = p.H >> 1; Ws = p.Wfull >> 1; }
       uint32_t slot = 0, ph = 0;
-      for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+      for (int wi = 0, w; (w = work_at(p, wi, n_work)) >= 0; ++wi) {
         const Work wk = decode_work(w, p.n_chunks, ptiles, zgroups, p.reuse, p.strips, p.W);
         const wdno_nchunk ci = s_chunks[wk.nc0];
         const int q0 = wk.pt * 128 * p.PT + s_first;
@@ -520,13 +540,13 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const wdno_tapgemm
 
     // cursor over the sequence of plane jobs (work item, K-set, plane) this CTA produces
     struct Cursor {
-      int w, si, j, nset, set_begin;
+      int w, wi, si, j, nset, set_begin;
       uint32_t slot, ph;
       int b, z0, q0, xs0;
       int off[kIt];
     };
     auto load_work = [&](Cursor& cu) {
-      if (cu.w >= n_work) return;
+      if (cu.w < 0) return;
       const Work wk = decode_work(cu.w, p.n_chunks, ptiles, zgroups, p.reuse, p.strips, p.W);
       const wdno_nchunk ci = s_chunks[wk.nc0];  // with reuse every chunk shares chunk 0's K-sets
       cu.nset = ci.set_count;
@@ -544,7 +564,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const wdno_tapgemm
         cu.j = 0;
         if (++cu.si == cu.nset) {
           cu.si = 0;
-          cu.w += gridDim.x;
+          cu.w = work_at(p, ++cu.wi, n_work);
           load_work(cu);
         }
       }
@@ -628,14 +648,14 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const wdno_tapgemm
     };
 
     Cursor iss;
-    iss.w = blockIdx.x; iss.si = 0; iss.j = 0; iss.slot = 0; iss.ph = 0; iss.nset = 0; iss.set_begin = 0;
+    iss.wi = 0; iss.w = work_at(p, 0, n_work); iss.si = 0; iss.j = 0; iss.slot = 0; iss.ph = 0; iss.nset = 0; iss.set_begin = 0;
     iss.b = 0; iss.z0 = 0; iss.q0 = 0;
 #pragma unroll
     for (int i = 0; i < kIt; ++i) iss.off[i] = kSkip;
     load_work(iss);
     PROF_DECL;
     if (!any_act) {
-      while (iss.w < n_work) {
+      while (iss.w >= 0) {
         PROF_REGION(0, ptx::mbar_wait(&bars->slab_empty[iss.slot], iss.ph ^ 1u));
         issue(iss);
         ptx::cp_async_mbar_arrive_noinc(&bars->slab_full[iss.slot]);
@@ -643,7 +663,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const wdno_tapgemm
       }
     } else {
       // the loader warps fill the slot; transform it in place (each thread its own chunks) and publish
-      while (iss.w < n_work) {
+      while (iss.w >= 0) {
         PROF_REGION(0, ptx::mbar_wait(&bars->raw_full[iss.slot], iss.ph));
         PROF_REGION(3, transform(iss));
         ptx::fence_proxy_async_smem();
@@ -655,9 +675,16 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const wdno_tapgemm
   } else if (warp == kBWarp) {
     // ============================================================ B (weight tile) producer
     // warp-uniform control flow, one elected lane issues the bulk copies (TPS tiles per stage)
+    // Cluster mode (opt-in, WDNO_CLUSTER=1): all CTAs of a layer stream the SAME few hundred KB of weight tiles out of L2, again
+    // for every work item; a CTA pair fetches each tile once -- the leader (cluster rank 0) issues one multicast copy that
+    // lands at the same offset in both CTAs and completes the same-offset mbarrier in both.  The peer only arms its barrier and
+    // tells the leader (remote arrive) that its stage is free.  Measured neutral (256 -> 256 at 10 x 10: 170.5 vs 171.9 us,
+    // 64 -> 64 at 40 x 40: 44.6 vs 43.9 us): the weight stream out of L2 is NOT what holds these layers below the MMA rate.
     uint32_t bst = 0, bph = 0;
+    const bool clustered = p.cluster == 2;
+    const uint32_t crank = clustered ? ptx::cluster_ctarank() : 0u;
     PROF_DECL;
-    for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+    for (int wi = 0, w; (w = work_at(p, wi, n_work)) >= 0; ++wi) {
       const Work wk = decode_work(w, p.n_chunks, ptiles, zgroups, p.reuse);
       for (int nc = wk.nc0; nc < wk.nc1; ++nc) {
         const wdno_nchunk ci = s_chunks[nc];
@@ -665,10 +692,24 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const wdno_tapgemm
         for (int i = 0; i < ci.n_tiles; i += p.TPS) {  // the plan guarantees TPS | taps of every kz group
           const uint32_t cnt = static_cast<uint32_t>(p.TPS);
           PROF_REGION(0, ptx::mbar_wait(&bars->b_empty[bst], bph ^ 1u));
-          if (ptx::elect_one()) {
-            ptx::mbar_arrive_expect_tx(&bars->b_full[bst], cnt * btile_bytes);
-            ptx::bulk_g2s(b_base + static_cast<size_t>(bst) * bstage_bytes, wsrc + static_cast<size_t>(i) * btile_bytes,
-                          cnt * btile_bytes, &bars->b_full[bst]);
+          if (!clustered) {
+            if (ptx::elect_one()) {
+              ptx::mbar_arrive_expect_tx(&bars->b_full[bst], cnt * btile_bytes);
+              ptx::bulk_g2s(b_base + static_cast<size_t>(bst) * bstage_bytes, wsrc + static_cast<size_t>(i) * btile_bytes,
+                            cnt * btile_bytes, &bars->b_full[bst]);
+            }
+          } else if (crank != 0u) {
+            if (ptx::elect_one()) {
+              ptx::mbar_arrive_expect_tx(&bars->b_full[bst], cnt * btile_bytes);
+              ptx::mbar_arrive_remote(&bars->b_peer[bst], 0u);
+            }
+          } else {
+            PROF_REGION(1, ptx::mbar_wait_cluster(&bars->b_peer[bst], bph));
+            if (ptx::elect_one()) {
+              ptx::mbar_arrive_expect_tx(&bars->b_full[bst], cnt * btile_bytes);
+              ptx::bulk_g2s_multicast(b_base + static_cast<size_t>(bst) * bstage_bytes, wsrc + static_cast<size_t>(i) * btile_bytes,
+                                      cnt * btile_bytes, &bars->b_full[bst], static_cast<uint16_t>(3));
+            }
           }
           __syncwarp();
           if (++bst == static_cast<uint32_t>(p.NBST)) { bst = 0; bph ^= 1u; }
@@ -714,7 +755,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const wdno_tapgemm
     const bool has_bias = p.bias != nullptr, has_stats = p.stats != nullptr;
     uint32_t acnt = 0;
     PROF_DECL;
-    for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+    for (int wi = 0, w; (w = work_at(p, wi, n_work)) >= 0; ++wi) {
       const Work wk = decode_work(w, p.n_chunks, ptiles, zgroups, p.reuse, p.strips, p.W);
       const int o0 = wk.pt * 128 * p.PT;
       const int z0 = wk.zg * p.ZT;
@@ -908,6 +949,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const wdno_tapgemm
   // ---------------------------------------------------------------- teardown
   ptx::tc_fence_before();
   __syncthreads();
+  if (p.cluster == 2) ptx::cluster_sync();   // neither CTA of a pair leaves while the other may still signal it
   if (warp == kMmaWarp) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, 512);
@@ -958,6 +1000,15 @@ static int validate(const wdno_tapgemm_params* p) {
   if (p->n_chunks > kMaxChunks) return set_error(WDNO_E_INVALID, "tapgemm: more than 32 N-chunks");
   if (p->n_sets < 1 || p->n_sets > kMaxSets) return set_error(WDNO_E_INVALID, "tapgemm: n_sets must be in [1,128]");
   if (p->bias && (p->bias_len < 1 || p->bias_len > kMaxBias)) return set_error(WDNO_E_INVALID, "tapgemm: bias_len must be in [1,1024]");
+  if (p->NBST > kMaxBStages) return set_error(WDNO_E_INVALID, "tapgemm: more than 4 weight stages");
+  if (p->cluster != 0 && p->cluster != 1 && p->cluster != 2) return set_error(WDNO_E_INVALID, "tapgemm: cluster must be 0, 1 or 2");
+  if (p->cluster == 2) {
+    const long long positions = static_cast<long long>(p->H) * p->Wp;
+    const long long ptiles = (positions + 128 * p->PT - 1) / (128 * p->PT);
+    const long long units = static_cast<long long>(p->B) * p->strips * ((p->D + p->ZT - 1) / p->ZT) * ptiles;
+    if (p->reuse || (units & 1) || (p->grid & 1))
+      return set_error(WDNO_E_INVALID, "tapgemm: CTA pairs need an even grid, an even number of (sample, plane group, tile) units and no slab reuse");
+  }
   return WDNO_OK;
 }
 
@@ -989,8 +1040,50 @@ extern "C" int wdno_tapgemm(const wdno_tapgemm_params* p, void* stream) {
     if (e != cudaSuccess) return wdno::set_cuda_error(e, "tapgemm: cudaFuncSetAttribute");
     configured = 227 * 1024;
   }
-  cudaError_t le = wdno::launch_pdl(wdno::tapgemm_kernel, dim3(p->grid), dim3(wdno::kThreads), static_cast<size_t>(smem),
-                                    static_cast<cudaStream_t>(stream), *p);
+  cudaError_t le;
+  if (p->cluster == 2) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(p->grid);
+    cfg.blockDim = dim3(wdno::kThreads);
+    cfg.dynamicSmemBytes = static_cast<size_t>(smem);
+    cfg.stream = static_cast<cudaStream_t>(stream);
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = wdno::pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 2;
+    le = cudaLaunchKernelEx(&cfg, wdno::tapgemm_kernel, *p);
+  } else {
+    le = wdno::launch_pdl(wdno::tapgemm_kernel, dim3(p->grid), dim3(wdno::kThreads), static_cast<size_t>(smem),
+                          static_cast<cudaStream_t>(stream), *p);
+  }
   if (le != cudaSuccess) return wdno::set_cuda_error(le, "tapgemm: launch");
   return wdno::check_launch("tapgemm");
+}
+
+// CTAs of 2-CTA clusters that can be resident at once with `smem_bytes` of dynamic shared memory each (the persistent grid of a
+// cluster-mode plan must not exceed it: a pair that does not fit would run as a second wave)
+extern "C" int wdno_tapgemm_max_cluster_ctas(int64_t smem_bytes) {
+  if (smem_bytes < 0 || smem_bytes > 227 * 1024) return WDNO_E_INVALID;
+  cudaError_t e = cudaFuncSetAttribute(wdno::tapgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) return wdno::set_cuda_error(e, "tapgemm: cudaFuncSetAttribute");
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * wdno::num_sms());
+  cfg.blockDim = dim3(wdno::kThreads);
+  cfg.dynamicSmemBytes = static_cast<size_t>(smem_bytes);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  e = cudaOccupancyMaxActiveClusters(&n, wdno::tapgemm_kernel, &cfg);
+  if (e != cudaSuccess) return wdno::set_cuda_error(e, "tapgemm: cudaOccupancyMaxActiveClusters");
+  return 2 * n;
 }

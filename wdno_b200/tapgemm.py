@@ -29,6 +29,18 @@ def _device_bytes(ctypes_array, device):
     return t.to(device)
 
 
+_CLUSTER_CAP = {}
+
+
+def _cluster_cta_cap(smem_bytes):
+    """CTAs of 2-CTA clusters resident at once (cached per shared-memory size; 0 when the query fails)"""
+    key = int(smem_bytes)
+    if key not in _CLUSTER_CAP:
+        n = _lib.lib().wdno_tapgemm_max_cluster_ctas(key)
+        _CLUSTER_CAP[key] = max(0, int(n))
+    return _CLUSTER_CAP[key]
+
+
 def _round_up(a, b):
     return (a + b - 1) // b * b
 
@@ -498,7 +510,25 @@ class TapGemm:
         p.n_sets = pk["n_sets"]
         p.zstack = zstack
         p.grid = max(1, min(n_work, sms))
+        p.cluster = 0
+        # WDNO_CLUSTER=1 (opt-in): CTA pairs (clusters of 2) share the weight stream -- every tile is fetched from L2 once per pair by
+        # a multicast copy.  Built to test whether the layers that need 15-16 B/clk/SM of weight tiles are held back by the L2
+        # (every SM pulls the same lines); measured neutral on the 256 -> 256 and 64 -> 64 layers, so it stays off.
+        units = n_work // (1 if reuse else pk["n_chunks"])
+        if (os.environ.get("WDNO_CLUSTER", "0") == "1" and not reuse and not fold and units % 2 == 0 and n_work >= 4
+                and self.device.type == "cuda"):
+            smem = self._smem_estimate(KC, S_pad, NSLOT, NBST, TPS, zstack)
+            cap = _cluster_cta_cap(smem)
+            grid = min(n_work, cap) & ~1
+            if grid >= 2 and grid >= (p.grid * 9) // 10:       # keep (almost) every SM busy
+                p.grid = grid
+                p.cluster = 2
         return p
+
+    def _smem_estimate(self, KC, S_pad, NSLOT, NBST, TPS, zstack):
+        slot = (KC // 8) * S_pad * 16
+        tile = self.N * KC * 2 * (self.KD if zstack else 1)
+        return _BAR_BYTES + _round_up(NSLOT * slot, 128) + NBST * TPS * tile
 
     # ------------------------------------------------------------------ launch
     def __call__(self, src0, src1=None, *, coef0=None, coef1=None, out=None, resid=None, stats=None,
