@@ -92,12 +92,14 @@ def test_linattn_tc_images_split_over_ctas(C, n_img, n):
     wout = torch.randn(C, 128) * 0.1
     bout = torch.randn(C) * 0.1
     x = (torch.randn(n_img, 1, n, 1, C) * 1.5 + 0.2).half().cuda()
-    blk = LinAttnBlock(gamma, wqkv.reshape(384, C, 1, 1), wout.reshape(C, 128, 1, 1), bout, device="cuda")
-    assert blk.tc, "the tcgen05 path must be the default for C = 64 / 128"
-    got = blk(x).float().reshape(n_img, n, C)
     old_env = os.environ.get("WDNO_LINATTN_TC")
-    os.environ["WDNO_LINATTN_TC"] = "0"
     try:
+        os.environ["WDNO_LINATTN_TC"] = "force"          # also for the few-image geometries the planner leaves to the mma.sync kernels
+        blk = LinAttnBlock(gamma, wqkv.reshape(384, C, 1, 1), wout.reshape(C, 128, 1, 1), bout, device="cuda")
+        assert blk.tc
+        got = blk(x).float().reshape(n_img, n, C)
+        assert all(blk._tc_ok.values()), "the tcgen05 kernels must have run"
+        os.environ["WDNO_LINATTN_TC"] = "0"
         ref_blk = LinAttnBlock(gamma, wqkv.reshape(384, C, 1, 1), wout.reshape(C, 128, 1, 1), bout, device="cuda")
     finally:
         if old_env is None:

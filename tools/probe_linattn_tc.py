@@ -37,7 +37,7 @@ def run(name):
     wout = torch.randn(C, 128) * 0.1
     bout = torch.randn(C) * 0.1
     x = (torch.randn(n_img, 1, n, 1, C) * 1.5 + 0.2).half().cuda()
-    os.environ["WDNO_LINATTN_TC"] = "1"
+    os.environ["WDNO_LINATTN_TC"] = "force"
     tc = LinAttnBlock(gamma, wqkv.reshape(384, C, 1, 1), wout.reshape(C, 128, 1, 1), bout, device="cuda")
     os.environ["WDNO_LINATTN_TC"] = "0"
     old = LinAttnBlock(gamma, wqkv.reshape(384, C, 1, 1), wout.reshape(C, 128, 1, 1), bout, device="cuda")

@@ -49,6 +49,7 @@ class LinAttnBlock:
         # C = 64 / 128: every product on tcgen05 (csrc/linattn_tc.cu); WDNO_LINATTN_TC=0 keeps the mma.sync kernels
         import os
         self.tc = self.C in (64, 128) and os.environ.get("WDNO_LINATTN_TC", "1") != "0"
+        self._tc_force = os.environ.get("WDNO_LINATTN_TC", "1") == "force"
         self._tc_ok = {}
         if self.tc:
             self.wq_c, self.wkv_c = (t.to(dev) for t in self._packed_canon())
@@ -101,7 +102,10 @@ class LinAttnBlock:
     def _launch(self, L, x, y, key, n_img, n_pos, eps):
         if self.tc:
             if key not in self._tc_ok:
-                self._tc_ok[key] = L.wdno_linattn_tc_supported(n_img, n_pos, self.C) == 1
+                # one persistent CTA walks whole images: with fewer images than half the SMs the mma.sync kernels (which split
+                # an image over many blocks) fill the machine better (6 images: 69 vs 47 us); WDNO_LINATTN_TC=force overrides
+                enough = n_img >= 74 or self._tc_force
+                self._tc_ok[key] = enough and L.wdno_linattn_tc_supported(n_img, n_pos, self.C) == 1
             if self._tc_ok[key]:
                 _lib.check(L.wdno_linattn_block_tc(_p(x), _p(y), _p(self.wq_c), _p(self.wkv_c), _p(self.wout),
                                                    _p(self.bias), _p(self._work[key]), n_img, n_pos, self.C, self.scale,
