@@ -69,14 +69,16 @@ def test_c3_batch16_forward_vs_fp32_oracle_per_layer_and_rows():
     e_out = rel_l2(y, yo)
     assert e_out < 4e-3, e_out
     del taps_e, taps_o
-    # row i of the batch-16 run vs the batch-1 run of row i: same kernels, plans may differ (fp32 partial-sum grouping)
+    # row i of the batch-16 run vs the batch-1 run of row i: plans may differ (fp32 partial-sum grouping), and the linear
+    # attention runs on the tcgen05 kernels at batch 16 but on the mma.sync ones at batch 1 (fewer images than half the SMs):
+    # two fp16-operand evaluations of the same network, 1.0e-3 apart (5e-4 when both runs use the same kernels)
     rows, bit_equal = [], 0
     with torch.no_grad():
         for i in (0, 7, 15):
             yi = m.engine().forward(x[i:i + 1].contiguous(), t[i:i + 1].contiguous())
             rows.append(rel_l2(yi[0], y[i]))
             bit_equal += int(torch.equal(yi[0], y[i]))
-    assert max(rows) < 1e-3, rows
+    assert max(rows) < 2e-3, rows
     _record("c3_b16_forward", dict(rel_l2_out=e_out, worst_layer=worst, row_vs_batch1=rows, rows_bit_equal=bit_equal))
 
 
@@ -94,7 +96,7 @@ def test_c4_batch16_forward_vs_fp32_oracle():
         assert e < 4e-3, e
         y1 = m.engine().forward(x[5:6].contiguous(), t[5:6].contiguous())
         r = rel_l2(y1[0], y[5])
-    assert r < 1e-3, r
+    assert r < 2e-3, r                         # batch 1 runs the linear attention on the mma.sync kernels (see the C3 test)
     _record("c4_b16_forward", dict(rel_l2_out=e, row_vs_batch1=r))
 
 
