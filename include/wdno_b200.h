@@ -192,7 +192,9 @@ int wdno_linattn_block(const void* x, void* y, const float* gamma, const void* w
 
 /* all-tcgen05 form of tattn_block for C = 64 (csrc/tattn_row.cu): every product a 128-row UMMA, softmax in the registers of the
  * thread that owns the accumulator row.  wqkv_canon fp16 [C/8][384][8] = W_qkv diag(gamma) and wout_canon fp16 [16][C][8] = W_out in
- * the UMMA K-major operand order (the LayerNorm gain is folded into W_qkv by the caller); bias / rot_* as for wdno_tattn_block. */
+ * the UMMA K-major operand order.  The caller folds into W_qkv (a) the LayerNorm gain (all rows) and (b) scale * log2(e) into the
+ * q rows 0..127 -- the kernel's softmax runs in base 2 and multiplies nothing at run time; the `scale` argument is therefore not
+ * applied again (kept for signature symmetry with wdno_tattn_block).  bias / rot_* as for wdno_tattn_block (natural-log units). */
 int wdno_tattn_block_row(const void* x, void* y, const void* wqkv_canon, const void* wout_canon, const float* bias,
                          const float* rot_cos, const float* rot_sin, int64_t n_samples, int n_frames, int64_t hw, int C,
                          float scale, float eps, void* stream);

@@ -8,16 +8,16 @@
 //            row thread: running max over the pixels, ek = exp(k - max) -> fp16, written as 16-byte chunks of 8 pixels =
 //            the UMMA canonical K-major layout (K = pixels) of the NEXT product  S[(h,d) x (h',e)] = ek v^T  (all head pairs
 //            in one M = N = 128 MMA; the thread keeps the 32 columns of its own head) merged into a register-resident
-//            (max, sum, S[32]) per row.  k, v, ek never leave the SM.
+//            (max, sum, S) per row (each of the two warps of a lane quarter keeps 16 of the 32 columns).  k, v, ek never leave the SM.
 //   la2_tc : Q[pixel x (h,d)] = xn Wq^T (M = 128 pixels): row thread = pixel, per-head softmax over 32 columns in registers
 //            -> fp16 A operand -> Y[pixel x C] = q M_img^T (M_img = scale * W_out blockdiag(ctx^T) from la_mid) -> warp-local
-//            transpose through shared memory -> + bias + residual -> 128-byte coalesced row stores.
+//            transpose through shared memory -> + bias + residual -> coalesced 64-byte row segments.
 // Both kernels are persistent (one CTA per SM walks a contiguous range of 128-pixel tiles) and warp-specialised:
 //   warps 0-3 LayerNorm producers (16 channels per lane, next tile prefetched in registers, output = UMMA operand tiles),
 //   warps 4-11 accumulator-row consumers: TWO warps per TMEM lane quarter (= warp % 4), each owning one half of the columns
 //   (ncu of the one-warp-per-quarter version: that warp ran at IPC 0.18, a pure latency chain), warp 12 = MMA issuer; mbarrier
-//   rings between them, so the LayerNorm of tile i+1/i+2, the MMAs of tile i+1 and the exponentials of tile i overlap.  Floor: 128 x 128 MUFU.EX2 per tile
-//   = 1024 cycles per SM sub-partition; the tensor pipe needs 1024 (la1) / 640 (la2) cycles per tile and runs beside it.
+//   rings between them, so the LayerNorm of tile i+1/i+2, the MMAs of tile i+1 and the exponentials of tile i overlap.
+//   Floor: 128 x 128 MUFU.EX2 per tile = 1024 cycles per SM sub-partition; the tensor pipe needs 1024 (la1) / 640 (la2) cycles per tile and runs beside it.
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math.h>

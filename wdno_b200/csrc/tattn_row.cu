@@ -453,6 +453,7 @@ __global__ void __launch_bounds__(kThreads, 1) tattn_row_kernel(const __half* __
 
 }  // namespace wdno
 
+// `scale` is NOT applied here: the caller folds scale * log2(e) into the q rows of wqkv_canon (include/wdno_b200.h)
 extern "C" int wdno_tattn_block_row(const void* x, void* y, const void* wqkv_canon, const void* wout_canon, const float* bias,
                                     const float* rot_cos, const float* rot_sin, int64_t n_samples, int n_frames, int64_t hw, int C,
                                     float scale, float eps, void* stream) {
