@@ -152,3 +152,46 @@ def test_tattn_row_multi_tile_and_variants_agree(B, D, H, W):
     assert rel_l2(outs["2"] - xf, outs["1"] - xf) < 4e-3, rel_l2(outs["2"] - xf, outs["1"] - xf)
     if "0" in outs:
         assert rel_l2(outs["2"] - xf, outs["0"] - xf) < 4e-3
+
+
+def test_tcgen05_attention_blocks_one_pass_layernorm_with_offset_inputs():
+    """The tcgen05 blocks take the LayerNorm statistics in one pass (E[x^2] - mean^2 in fp32).  Inputs with
+    |mean| / sigma = 40 per pixel (far beyond a residual stream) must still meet the block tolerance: against the fp64 restatement for
+    the linear block, against the centring mma.sync kernel for the temporal block.  The output projection is scaled up so that the
+    attention branch (not the fp16 rounding of x + branch at |x| = 4) is what the comparison sees."""
+    from wdno_b200.attn_fused import LinAttnBlock, TemporalBlock
+    C = 64
+    torch.manual_seed(11)
+    gamma = 1 + 0.2 * torch.randn(C)
+    wqkv = torch.randn(384, C) * (2.0 / C ** 0.5)
+    wout = torch.randn(C, 128) * 2.0
+    bout = torch.randn(C) * 0.1
+    # linear attention: 160 images x 200 pixels
+    x = (torch.randn(160, 1, 200, 1, C) * 0.1 + 4.0).half().cuda()
+    blk = LinAttnBlock(gamma, wqkv.reshape(384, C, 1, 1), wout.reshape(C, 128, 1, 1), bout, device="cuda")
+    got = blk(x).float().reshape(160, 200, C)
+    assert blk.tc and all(blk._tc_ok.values())
+    xf = x.float().reshape(160, 200, C)
+    want = _torch_linattn(xf.double(), gamma.cuda().double(), wqkv.cuda().double(), wout.cuda().double(), bout.cuda().double()).float()
+    assert rel_l2(got - xf, want - xf) < 6e-3, rel_l2(got - xf, want - xf)
+    # temporal attention: row kernel vs the centring mma.sync kernel
+    D = 24
+    xt = (torch.randn(2, D, 10, 10, C) * 0.1 + 4.0).half().cuda()
+    bias = (torch.randn(4, D, D) * 0.5).cuda()
+    freqs = 1.0 / (10000 ** (torch.arange(0, 32, 2).float() / 32))
+    ang = torch.arange(D, dtype=torch.float32)[:, None] * freqs[None, :]
+    rot = (ang.cos().contiguous().cuda(), ang.sin().contiguous().cuda())
+    old_env = os.environ.get("WDNO_TATTN_TC")
+    try:
+        os.environ["WDNO_TATTN_TC"] = "2"
+        row = TemporalBlock(gamma, wqkv, wout, device="cuda")
+        os.environ["WDNO_TATTN_TC"] = "0"
+        ref = TemporalBlock(gamma, wqkv, wout, device="cuda")
+    finally:
+        if old_env is None:
+            os.environ.pop("WDNO_TATTN_TC", None)
+        else:
+            os.environ["WDNO_TATTN_TC"] = old_env
+    assert row.row and not ref.row and not ref.tc
+    a, b = row(xt, bias=bias, rot=rot).float(), ref(xt, bias=bias, rot=rot).float()
+    assert rel_l2(a - xt.float(), b - xt.float()) < 6e-3, rel_l2(a - xt.float(), b - xt.float())
