@@ -384,6 +384,17 @@ class TapGemm:
             # 2-D layers are weight-stream heavy: keep >= 3 weight stages in flight before spending shared memory on
             # slab slots beyond the minimum; 3-D layers (tuned on the smoke U-Net): slots first
             top = min(12, want_slots)
+            if not two_d and os.environ.get("WDNO_FIT_ORDER", "taps") == "taps":
+                # 3-D layers: taps per weight stage first, slab slots second.  Every stage costs the issuing thread a
+                # tcgen05.commit (~67 issue cycles, tools/micro/mma_commit_cost.cu) and an mbarrier round trip, and a stage of one
+                # tap is only ZT*PT*KS MMAs long; 256 -> 256 at 10 x 10: TPS 1 / 6 slots 179.3 us, TPS 3 / 4 slots 163.4 us
+                # (tools/sweep_generic.py).  Two stages in flight are enough for the L2-resident weight stream.
+                for tps in divs:
+                    for nslot in range(top, min_slots - 1, -1):
+                        for nbst in ((2,) if tps > 1 else (4, 3, 2)):
+                            if _BAR_BYTES + _round_up(nslot * slot, 128) + nbst * tps * btile(KC) <= _SMEM_LIMIT:
+                                return S_pad, nslot, nbst, tps
+                return None
             for min_b, low in (((3, min(top, min_slots + 1)), (2, min_slots)) if two_d else ((2, min_slots),)):
                 for nslot in range(top, low - 1, -1):
                     for tps in divs:
