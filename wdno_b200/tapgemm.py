@@ -481,7 +481,13 @@ class TapGemm:
                     if two_d:
                         # weight tiles of one item stream from L2 at ~10 B/cycle/SM (measured on the 8x8 Burgers layers)
                         mma_part = max(mma_part, ntaps * ctot * self.N * 2 // 10)
-                    per_item = mma_part + 3000 + P * (ctot // KC) * 800 * PT
+                    if two_d or os.environ.get("WDNO_FIT_ORDER", "taps") != "taps":
+                        per_item = mma_part + 3000 + P * (ctot // KC) * 800 * PT
+                    else:
+                        # 3-D layers, re-fitted in round 2 (tools/sweep_generic.py): a weight stage costs the issuing thread ~300
+                        # cycles (commit + mbarrier round trip + the burst it cannot overlap), a plane of a K-set ~200
+                        stages = ntaps * (ctot // KC) // f[3]
+                        per_item = mma_part + 3000 + P * (ctot // KC) * 200 * PT + stages * 300
                     est = waves * per_item
                     score = (-est, min(f[1] - P, 2), KC)  # then prefer a full ring (P+2 slots) and the larger KC
                     if best is None or score > best[0]:
